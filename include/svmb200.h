@@ -1,0 +1,166 @@
+/*
+ * svmb200.h -- C ABI of the B200-native kernel-SVM dual training path.
+ *
+ * This is the drop-in boundary for ONE hot path of dmeoli/optiml (a pure-Python/NumPy library):
+ *   SVC/SVR(dual=True, reg_intercept=True, optimizer=ProjectedGradient).fit / decision_function
+ * with LinearKernel / PolyKernel / GaussianKernel.  The reference has no FFI seam of its own; the
+ * seam is the NumPy call sites listed beside each entry point (paths relative to the reference
+ * repository root).  A binding only needs ctypes/cffi: plain pointers, sizes and doubles, no
+ * framework types.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a non-zero code on failure; svmb200_last_error()
+ *     then returns a thread-local, NUL-terminated description (CUDA / NCCL error text included);
+ *   - there is NO CPU fallback: without a CUDA device (or with a non-sm_100 device) the compute
+ *     entry points fail with SVMB200_ERR_CUDA;
+ *   - "dptr" arguments are device pointers obtained from svmb200_malloc on the same context;
+ *     "host" arguments are ordinary host pointers (pinned or pageable);
+ *   - all matrices are FP64, row-major; "ld" is the row stride in elements;
+ *   - one context == one GPU == one CUDA stream; multi-GPU runs use one process (context) per GPU
+ *     and exchange the per-iteration product shards with one NCCL all-gather (svmb200_comm_*).
+ */
+#ifndef SVMB200_H
+#define SVMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVMB200_OK 0
+#define SVMB200_ERR_ARG 1     /* invalid argument */
+#define SVMB200_ERR_CUDA 2    /* CUDA runtime / driver error, or no usable device */
+#define SVMB200_ERR_NCCL 3    /* NCCL error or libnccl not loadable */
+#define SVMB200_ERR_STATE 4   /* call sequence error */
+
+/* kernel ids: optiml/ml/svm/kernels.py:40 (LinearKernel), :54 (PolyKernel), :98 (GaussianKernel) */
+#define SVMB200_KERNEL_LINEAR 0
+#define SVMB200_KERNEL_POLY 1
+#define SVMB200_KERNEL_GAUSSIAN 2
+
+/* Hessian layouts understood by the solver */
+#define SVMB200_HESSIAN_PLAIN 0 /* Q is the n x n matrix itself, nvars = n (SVC; generic BCQP)      */
+#define SVMB200_HESSIAN_SVR 1   /* resident matrix is M = K+1 (n x n); Q = [[M,-M],[-M,M]], nvars=2n */
+
+/* solver status, optiml/opti/_base.py:76 and projected_gradient.py:100-106 */
+#define SVMB200_STATUS_UNKNOWN 0
+#define SVMB200_STATUS_OPTIMAL 1
+#define SVMB200_STATUS_STOPPED 2
+
+typedef struct svmb200_ctx svmb200_ctx;
+typedef struct svmb200_pg svmb200_pg;
+
+const char* svmb200_last_error(void);
+const char* svmb200_version(void);
+
+/* ---- context, memory, multi-GPU plumbing ------------------------------------------------- */
+int svmb200_device_count(int* count);
+int svmb200_ctx_create(int device, svmb200_ctx** out);
+int svmb200_ctx_destroy(svmb200_ctx* ctx);
+int svmb200_ctx_info(svmb200_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes,
+                     size_t* total_bytes);
+int svmb200_malloc(svmb200_ctx* ctx, size_t bytes, void** dptr);
+int svmb200_free(svmb200_ctx* ctx, void* dptr);
+int svmb200_memset(svmb200_ctx* ctx, void* dptr, int value, size_t bytes);
+int svmb200_h2d(svmb200_ctx* ctx, void* dptr, const void* host, size_t bytes);
+int svmb200_d2h(svmb200_ctx* ctx, void* host, const void* dptr, size_t bytes);
+int svmb200_d2d(svmb200_ctx* ctx, void* dst, const void* src, size_t bytes);
+int svmb200_sync(svmb200_ctx* ctx);
+int svmb200_host_alloc_pinned(size_t bytes, void** host);
+int svmb200_host_free_pinned(void* host);
+/* CUDA-event timing on the context's stream (used by bench.py; torch events do not see this stream) */
+int svmb200_timer_start(svmb200_ctx* ctx);
+int svmb200_timer_stop_ms(svmb200_ctx* ctx, float* ms); /* records, synchronises, returns elapsed */
+/* number of kernels this library launched on the context since creation */
+int svmb200_launch_count(svmb200_ctx* ctx, uint64_t* launches);
+
+/* NCCL: rank 0 calls svmb200_comm_unique_id and broadcasts the 128 bytes by any means
+ * (the Python host uses torch.distributed); every rank then calls svmb200_comm_init. */
+int svmb200_comm_unique_id(void* id128);
+int svmb200_comm_init(svmb200_ctx* ctx, const void* id128, int rank, int nranks);
+int svmb200_comm_destroy(svmb200_ctx* ctx);
+
+/* ---- K1: Gram / Hessian build ------------------------------------------------------------
+ * Replaces  kernels.py:49-51 (linear), :91-95 (poly), :125-129 (gaussian, via sklearn
+ * euclidean_distances) fused with  ml/svm/_base.py:554,628 (SVC: Q = K o yy^T + yy^T) or
+ * :1098-1099,1178 (SVR: M = K + 1; the 2x2 sign pattern is applied by the solver).
+ *
+ * out[i - row0][j] = s_i s_j ( k(A_i, B_j) + bias ),  i in [row0, row0+nrows), j in [0, nb)
+ *   k = <a,b>                              (LINEAR)
+ *     = (gamma <a,b> + coef0) ^ degree     (POLY)
+ *     = exp(-gamma max(0, |a|^2+|b|^2-2<a,b>)), distance forced to 0 where i == j if `same` (GAUSSIAN)
+ * dA: na x d (ld = lda), dB: nb x d (ld = ldb); pass dB = dA and same = 1 for the training Gram.
+ * dsign_a / dsign_b: +-1.0 per row, or NULL (= +1).  Columns [nb, ldo) of `out` are zero-filled
+ * (the solver streams whole padded rows).  ldo must be a multiple of 2.
+ * Tiled FP64 tensor-core contraction (mma.sync DMMA), operands staged by TMA.                 */
+int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int64_t lda, const double* dB, int64_t nb,
+                 int64_t ldb, int64_t d, int same, int kernel, double gamma, double coef0, double degree,
+                 const double* dsign_a, const double* dsign_b, double bias, int64_t row0, int64_t nrows,
+                 double* dout, int64_t ldo);
+/* helper: leading dimension the library wants for an n-column streamed matrix */
+int64_t svmb200_padded_ld(int64_t ncols);
+
+/* ---- K2: streaming matrix-vector product ---------------------------------------------------
+ * dw[row0 + i] = sum_j dQ[i][j] * du[j], i in [0, nrows).  du must hold ld elements (pad = 0).
+ * Replaces the three products of projected_gradient.py:82,121 (opti/_base.py:282,291).          */
+int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw);
+
+/* ---- K2+K3(+K4): projected-gradient solve of the box-constrained QP -------------------------
+ * Replaces  BoxConstrainedQuadraticOptimizer.__init__ (opti/constrained/_base.py:59-73) +
+ * ProjectedGradient.minimize (opti/constrained/projected_gradient.py:76-143).
+ *
+ * The context's rank owns rows [row0, row0+nrows) of the n x n resident matrix dQ (ld).  With a
+ * communicator attached every rank must call the same sequence; row shards must be
+ * ceil(n/nranks) rows per rank in rank order (the last may be shorter).
+ * Host vectors q, lb, ub, x0 have nvars = n (PLAIN) or 2n (SVR) elements; lb may be NULL (= 0),
+ * x0 may be NULL (= (lb+ub)/2).                                                               */
+int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
+                      int hessian, const double* q_host, const double* lb_host, const double* ub_host,
+                      const double* x0_host, double eps, int64_t max_iter, svmb200_pg** out);
+/* Advance by at most `max_new` iterations (< 0: run to termination; 0: only evaluate the state at
+ * the current callback point, i.e. f, |d| and the stopping tests).  The callback point of the
+ * reference (projected_gradient.py:95-98) is reached once per iteration; the state visible after
+ * svmb200_pg_run returns is the state AT a callback point: x, f(x), g(x), |projected gradient|.  */
+int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, int* status);
+int svmb200_pg_state(svmb200_pg* pg, double* x_host, double* g_host, double* f, double* ng);
+/* f and |d| at every callback point so far: (iter+1) values each (train_loss_history, ml/svm/_base.py:289-293) */
+int svmb200_pg_history(svmb200_pg* pg, double* f_hist_host, double* ng_hist_host, int64_t* count);
+/* timing of the last svmb200_pg_run: device milliseconds and number of Q passes (matvec launches) */
+int svmb200_pg_stats(svmb200_pg* pg, float* ms, int64_t* passes, float* matvec_ms);
+/* when on, every K2 launch of svmb200_pg_run is bracketed by CUDA events (matvec_ms above) */
+int svmb200_pg_set_profile(svmb200_pg* pg, int on);
+int svmb200_pg_device_x(svmb200_pg* pg, double** dx); /* device pointer of the iterate (nvars)     */
+int svmb200_pg_destroy(svmb200_pg* pg);
+
+/* ---- K5: masked product for the intercept ---------------------------------------------------
+ * Replaces the Python loop  ml/svm/_base.py:877-880 / :1433-1437:
+ * v[i] = sum_m M[i][m] * beta[m] over the rank's rows (all-gathered when a communicator is attached),
+ * beta = host vector of n coefficients (alpha masked to the support set; SVR: alpha+ - alpha-).
+ * The caller finishes b = mean_n (y_n - (s_n v_n - sum(beta s))) on the host (O(n)).           */
+int svmb200_masked_product(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0,
+                           int64_t nrows, const double* beta_host, double* v_host);
+
+/* ---- K6: decision function --------------------------------------------------------------------
+ * Replaces  ml/svm/_base.py:284-287:  out[j] = sum_i dual_coef[i] k(SV_i, X_j) + b, computed in
+ * column chunks without materialising the nsv x m kernel matrix on the host.                    */
+int svmb200_decision(svmb200_ctx* ctx, const double* sv_host, int64_t nsv, const double* dual_coef_host,
+                     const double* x_host, int64_t m, int64_t d, int kernel, double gamma, double coef0,
+                     double degree, double intercept, double* out_host);
+
+/* ---- host-pointer convenience entry points (what a reference-side binding would call) ------- */
+/* kernels.py Kernel.__call__(X, Y=None): out is nx x ny row-major on the host. y_host NULL => Y is X */
+int svmb200_kernel_matrix_host(svmb200_ctx* ctx, const double* x_host, int64_t nx, const double* y_host,
+                               int64_t ny, int64_t d, int kernel, double gamma, double coef0, double degree,
+                               double* out_host);
+/* ProjectedGradient(quad=Quadratic(Q,q), ub, lb, x).minimize() on a host-resident Q (n x n, ld = n) */
+int svmb200_bcqp_pg_host(svmb200_ctx* ctx, const double* Q_host, const double* q_host, const double* lb_host,
+                         const double* ub_host, const double* x0_host, int64_t n, double eps, int64_t max_iter,
+                         double* x_out, double* g_out, double* f_hist, double* ng_hist, int64_t* iter,
+                         int* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVMB200_H */

@@ -1,0 +1,130 @@
+"""ctypes binding of the svmb200 C ABI (include/svmb200.h).
+
+The shared library is built in-tree by ``optiml_b200/csrc/build.py`` (nvcc, sm_100a).  There is no
+fallback: if the library is missing, or no B200-class GPU is visible, every compute call raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_lib', 'libsvmb200.so')
+
+KERNEL_LINEAR, KERNEL_POLY, KERNEL_GAUSSIAN = 0, 1, 2
+HESSIAN_PLAIN, HESSIAN_SVR = 0, 1
+STATUS = {0: 'unknown', 1: 'optimal', 2: 'stopped'}
+
+c_dp = C.POINTER(C.c_double)
+c_vp = C.c_void_p
+i64 = C.c_int64
+
+# name -> (argtypes); every function returns int unless listed in _NON_STATUS
+PROTOTYPES = {
+    'svmb200_device_count': [C.POINTER(C.c_int)],
+    'svmb200_ctx_create': [C.c_int, C.POINTER(c_vp)],
+    'svmb200_ctx_destroy': [c_vp],
+    'svmb200_ctx_info': [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t),
+                         C.POINTER(C.c_size_t)],
+    'svmb200_malloc': [c_vp, C.c_size_t, C.POINTER(c_vp)],
+    'svmb200_free': [c_vp, c_vp],
+    'svmb200_memset': [c_vp, c_vp, C.c_int, C.c_size_t],
+    'svmb200_h2d': [c_vp, c_vp, c_vp, C.c_size_t],
+    'svmb200_d2h': [c_vp, c_vp, c_vp, C.c_size_t],
+    'svmb200_d2d': [c_vp, c_vp, c_vp, C.c_size_t],
+    'svmb200_sync': [c_vp],
+    'svmb200_host_alloc_pinned': [C.c_size_t, C.POINTER(c_vp)],
+    'svmb200_host_free_pinned': [c_vp],
+    'svmb200_timer_start': [c_vp],
+    'svmb200_timer_stop_ms': [c_vp, C.POINTER(C.c_float)],
+    'svmb200_launch_count': [c_vp, C.POINTER(C.c_uint64)],
+    'svmb200_comm_unique_id': [c_vp],
+    'svmb200_comm_init': [c_vp, c_vp, C.c_int, C.c_int],
+    'svmb200_comm_destroy': [c_vp],
+    'svmb200_gram': [c_vp, c_vp, i64, i64, c_vp, i64, i64, i64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                     c_vp, c_vp, C.c_double, i64, i64, c_vp, i64],
+    'svmb200_matvec': [c_vp, c_vp, i64, i64, c_vp, c_vp],
+    'svmb200_pg_create': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, i64,
+                          C.POINTER(c_vp)],
+    'svmb200_pg_run': [c_vp, i64, C.POINTER(i64), C.POINTER(C.c_int)],
+    'svmb200_pg_state': [c_vp, c_vp, c_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    'svmb200_pg_history': [c_vp, c_vp, c_vp, C.POINTER(i64)],
+    'svmb200_pg_stats': [c_vp, C.POINTER(C.c_float), C.POINTER(i64), C.POINTER(C.c_float)],
+    'svmb200_pg_set_profile': [c_vp, C.c_int],
+    'svmb200_pg_device_x': [c_vp, C.POINTER(c_vp)],
+    'svmb200_pg_destroy': [c_vp],
+    'svmb200_masked_product': [c_vp, c_vp, i64, i64, i64, i64, c_vp, c_vp],
+    'svmb200_decision': [c_vp, c_vp, i64, c_vp, c_vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_double,
+                         C.c_double, c_vp],
+    'svmb200_kernel_matrix_host': [c_vp, c_vp, i64, c_vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                   c_vp],
+    'svmb200_bcqp_pg_host': [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i64, C.c_double, i64, c_vp, c_vp, c_vp, c_vp,
+                             C.POINTER(i64), C.POINTER(C.c_int)],
+}
+_NON_STATUS = {
+    'svmb200_last_error': ([], C.c_char_p),
+    'svmb200_version': ([], C.c_char_p),
+    'svmb200_padded_ld': ([i64], i64),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeError(RuntimeError):
+    """Raised when a svmb200 call fails; carries the library's error text."""
+
+
+def load_library():
+    """Load libsvmb200.so (once).  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f'{LIB_PATH} not found: build it with `python -m optiml_b200.csrc.build` '
+                              '(or __graft_entry__.build()); optiml_b200 has no CPU fallback')
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        for name, (argtypes, restype) in _NON_STATUS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = lib
+        return lib
+
+
+def exported_symbols():
+    return sorted(list(PROTOTYPES) + list(_NON_STATUS))
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = load_library().svmb200_last_error().decode(errors='replace')
+        raise NativeError(f'{what or "svmb200"} failed (code {rc}): {msg}')
+
+
+def call(name, *args):
+    lib = load_library()
+    check(getattr(lib, name)(*args), name)
+
+
+def as_f64(a, copy=False):
+    a = np.array(a, dtype=np.float64, order='C', copy=True) if copy else np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def ptr(a):
+    """void* of a C-contiguous float64 ndarray (or None)."""
+    if a is None:
+        return None
+    assert a.flags['C_CONTIGUOUS'] and a.dtype == np.float64
+    return a.ctypes.data_as(c_vp)
+
+
+def padded_ld(ncols):
+    return int(load_library().svmb200_padded_ld(int(ncols)))

@@ -1,0 +1,66 @@
+// Shared declarations for the svmb200 library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/svmb200.h"
+
+struct svmb200_ctx {
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    // NCCL (loaded lazily through dlopen, see comm.cu)
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+    // cached TMA encoder (driver entry point fetched at run time: no link-time libcuda dependency)
+    void* encode_tiled = nullptr;
+};
+
+void svmb200_set_error(const char* fmt, ...);
+
+#define SVM_CHECK_ARG(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            svmb200_set_error("%s: %s", __func__, msg);            \
+            return SVMB200_ERR_ARG;                                \
+        }                                                          \
+    } while (0)
+
+#define SVM_CUDA(call)                                                                                 \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            svmb200_set_error("%s:%d %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return SVMB200_ERR_CUDA;                                                                   \
+        }                                                                                              \
+    } while (0)
+
+#define SVM_TRY(call)              \
+    do {                           \
+        int rc__ = (call);         \
+        if (rc__ != SVMB200_OK) return rc__; \
+    } while (0)
+
+static inline int svm_use(svmb200_ctx* ctx) {
+    if (!ctx) {
+        svmb200_set_error("null context");
+        return SVMB200_ERR_ARG;
+    }
+    SVM_CUDA(cudaSetDevice(ctx->device));
+    return SVMB200_OK;
+}
+
+static inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// internal cross-file entry points
+int svm_comm_allgather(svmb200_ctx* ctx, double* dbuf, int64_t count_per_rank);  // in place, on ctx->stream
+int svm_launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw,
+                      const int* d_done);

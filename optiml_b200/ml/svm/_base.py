@@ -1,0 +1,308 @@
+"""sklearn-compatible SVM estimators for the dual, box-constrained formulation, trained on the GPU.
+
+Host mirror of optiml/ml/svm/_base.py restricted to the branch
+``dual=True, reg_intercept=True, loss in {hinge, epsilon_insensitive}, optimizer=<BCQP solver>``:
+same constructor keywords (sklearn ``clone``/``get_params`` work), same validation errors, same
+fitted attributes.  Every other branch of the reference (primal losses, SMO, string QP solvers,
+Lagrangian duals) raises ``NotImplementedError`` -- they are different algorithms and out of scope.
+
+Where the reference builds K, Q = K o yy' + yy' and three more n x n temporaries on the host
+(ml/svm/_base.py:552-554, 628; opti/_base.py:243), here the Hessian is produced directly in HBM by
+the fused Gram kernel, row-sharded over the GPUs of the job, and never visits the host.
+"""
+import ctypes as C
+
+import numpy as np
+from sklearn.base import BaseEstimator, ClassifierMixin, RegressorMixin
+from sklearn.preprocessing import LabelBinarizer
+
+from .kernels import gaussian, Kernel, LinearKernel, _dense_f64
+from .losses import (squared_hinge, squared_epsilon_insensitive, Hinge, SquaredHinge, EpsilonInsensitive,
+                     SquaredEpsilonInsensitive)
+from ... import _native as N
+from ...opti import Optimizer, Quadratic
+from ...opti.constrained import BoxConstrainedQuadraticOptimizer, ProjectedGradient
+from ...runtime import DeviceHessian, default_context
+
+_SCOPE = ('optiml_b200 implements the dual formulation with reg_intercept=True solved by a '
+          'BoxConstrainedQuadraticOptimizer (ProjectedGradient); {} is outside that path')
+
+
+class SVM(BaseEstimator):
+    """Common constructor / decision function (optiml/ml/svm/_base.py:26-293)."""
+
+    def __init__(self, loss=None, kernel=gaussian, C=1, rho=1, mu=1, fit_intercept=True, intercept_scaling=1,
+                 reg_intercept=False, dual=False, optimizer=None, master_solver='clarabel', learning_rate='auto',
+                 momentum_type='none', momentum=0.9, max_iter=1000, max_f_eval=15000, tol=1e-4, batch_size=None,
+                 shuffle=True, random_state=None, early_stopping=False, validation_split=0., patience=5,
+                 verbose=False, master_verbose=False):
+        self.loss = loss
+        if not isinstance(kernel, Kernel):
+            raise TypeError(f'{kernel} is not an allowed kernel function')
+        self.kernel = kernel
+        if not C > 0:
+            raise ValueError('C must be > 0')
+        self.C = C
+        if not rho > 0:
+            raise ValueError('rho must be > 0')
+        self.rho = rho
+        if not mu > 0:
+            raise ValueError('mu must be > 0')
+        self.mu = mu
+        if not isinstance(fit_intercept, bool):
+            raise ValueError('fit_intercept mu be a boolean value')
+        self.fit_intercept = fit_intercept
+        self.intercept_scaling = intercept_scaling
+        if not isinstance(reg_intercept, bool):
+            raise ValueError('reg_intercept mu be a boolean value')
+        self.reg_intercept = reg_intercept
+        if not isinstance(dual, bool):
+            raise ValueError('dual must be a boolean value')
+        self.dual = dual
+        if not self.dual and not (isinstance(optimizer, type) and issubclass(optimizer, Optimizer)) \
+                and optimizer is not None:
+            raise TypeError(f'{optimizer} is not an allowed optimization method')
+        self.optimizer = optimizer
+        self.master_solver = master_solver
+        self.learning_rate = learning_rate
+        self.max_iter = max_iter
+        self.max_f_eval = max_f_eval
+        self.momentum_type = momentum_type
+        self.momentum = momentum
+        if not tol > 0:
+            raise ValueError('tol must be > 0')
+        self.tol = tol
+        self.batch_size = batch_size
+        self.shuffle = shuffle
+        self.random_state = random_state
+        self.early_stopping = early_stopping
+        self.validation_split = validation_split
+        self.patience = patience
+        self.verbose = verbose
+        self.master_verbose = master_verbose
+        if not self.dual or isinstance(self.kernel, LinearKernel):
+            self.coef_ = np.zeros(0)
+        self.intercept_ = 0.
+        self.support_ = np.zeros(0)
+        self.support_vectors_ = np.zeros(0)
+        if self.dual:
+            self.alphas_ = np.zeros(0)
+            self.dual_coef_ = np.zeros(0)
+        if not isinstance(optimizer, str):
+            self.train_loss_history = []
+
+    # ------------------------------------------------------------------ shared pieces of fit
+    def _bcqp_solver_class(self):
+        """The solver class to instantiate; mirrors the dispatch of ml/svm/_base.py:559-636."""
+        opt = self.optimizer
+        if isinstance(opt, BoxConstrainedQuadraticOptimizer):
+            opt = type(opt)  # refit of an estimator whose ``optimizer`` was replaced by the fitted instance
+        if not self.dual:
+            raise NotImplementedError(_SCOPE.format('dual=False (primal formulation)'))
+        if isinstance(opt, str) or opt is None:
+            raise NotImplementedError(_SCOPE.format(f'optimizer={opt!r}'))
+        if not (isinstance(opt, type) and issubclass(opt, BoxConstrainedQuadraticOptimizer)):
+            raise NotImplementedError(_SCOPE.format(f'optimizer={opt}'))
+        if not self.reg_intercept:
+            # ml/svm/_base.py:621-624, 1171-1174: no BCQP solver handles the equality constraint
+            raise NotImplementedError
+        return opt
+
+    def _build_hessian(self, X, signs, layout):
+        """K1: Gram matrix + bias (+ label signs) straight into this rank's row shard in HBM."""
+        ctx = default_context()
+        n, d = X.shape
+        kid, gamma, coef0, degree = self.kernel.gram_spec(X)
+        dX = ctx.upload_matrix(X)
+        dS = ctx.upload_vector(signs) if signs is not None else None
+        H = DeviceHessian(ctx, n, layout)
+        sp = C.c_void_p(dS.dptr) if dS is not None else None
+        N.call('svmb200_gram', ctx.handle, C.c_void_p(dX.dptr), n, dX.ld, C.c_void_p(dX.dptr), n, dX.ld, d, 1, kid,
+               gamma, coef0, degree, sp, sp, 1.0, H.row0, H.nrows, C.c_void_p(H.matrix.dptr), H.ld)
+        ctx.sync()
+        dX.release()
+        if dS is not None:
+            dS.release()
+        return H
+
+    def _solve(self, solver_cls, ub):
+        return solver_cls(quad=self.obj, ub=ub, tol=self.tol, max_iter=self.max_iter,
+                          callback=self._store_train_info, verbose=self.verbose).minimize()
+
+    def decision_function(self, X):
+        """ml/svm/_base.py:284-287.  ``gamma='scale'`` is resolved from ``support_vectors_`` (the first
+        argument of the reference's kernel call), not from the training matrix."""
+        if self.dual and not isinstance(self.kernel, LinearKernel):
+            X, _ = _dense_f64(X, None)
+            sv = np.ascontiguousarray(self.support_vectors_, dtype=np.float64)
+            coef = np.ascontiguousarray(self.dual_coef_, dtype=np.float64)
+            kid, gamma, coef0, degree = self.kernel.gram_spec(sv)
+            out = np.empty(X.shape[0])
+            N.call('svmb200_decision', default_context().handle, N.ptr(sv), sv.shape[0], N.ptr(coef), N.ptr(X),
+                   X.shape[0], X.shape[1], kid, gamma, coef0, degree, float(self.intercept_), N.ptr(out))
+            return out
+        return np.dot(X, self.coef_) + self.intercept_
+
+    def _store_train_info(self, opt):
+        self.train_loss_history.append(opt.f_x)
+
+    _store_train_info._svmb200_history_only = True
+
+
+class SVC(ClassifierMixin, SVM):
+    """C-Support Vector Classification, dual hinge-loss problem (optiml/ml/svm/_base.py:354-885)."""
+
+    def __init__(self, loss=squared_hinge, kernel=gaussian, C=1, rho=1, mu=1, fit_intercept=True,
+                 intercept_scaling=1, reg_intercept=False, dual=False, optimizer=None, master_solver='clarabel',
+                 learning_rate='auto', momentum_type='none', momentum=0.9, max_iter=1000, max_f_eval=15000, tol=1e-4,
+                 batch_size=None, shuffle=True, random_state=None, early_stopping=False, validation_split=0.,
+                 patience=5, verbose=False, master_verbose=False):
+        super(SVC, self).__init__(loss=loss, kernel=kernel, C=C, rho=rho, mu=mu, fit_intercept=fit_intercept,
+                                  intercept_scaling=intercept_scaling, reg_intercept=reg_intercept, dual=dual,
+                                  optimizer=optimizer, master_solver=master_solver, learning_rate=learning_rate,
+                                  momentum_type=momentum_type, momentum=momentum, max_iter=max_iter,
+                                  max_f_eval=max_f_eval, tol=tol, batch_size=batch_size, shuffle=shuffle,
+                                  random_state=random_state, early_stopping=early_stopping,
+                                  validation_split=validation_split, patience=patience, verbose=verbose,
+                                  master_verbose=master_verbose)
+        if not getattr(loss, '_loss_type', None) == 'classifier':
+            raise TypeError(f'{loss} is not an allowed SVC loss function')
+        self.lb = LabelBinarizer(neg_label=-1)
+
+    def fit(self, X, y):
+        self.lb.fit(y)
+        if len(self.lb.classes_) > 2:
+            raise ValueError('use OneVsOneClassifier or OneVsRestClassifier from sklearn.multiclass '
+                             'to train a model over more than two labels')
+        y = self.lb.transform(y).ravel()
+        solver_cls = self._bcqp_solver_class()
+        if self.loss == SquaredHinge:
+            raise NotImplementedError  # ml/svm/_base.py:771-774
+        if self.loss != Hinge:
+            raise TypeError(f'{self.loss} is not an allowed loss')
+        X, _ = _dense_f64(X, None)
+        n = len(y)
+        ys = y.astype(np.float64)
+
+        # Q = K o yy' + yy'  (ml/svm/_base.py:552-554, 628), q = -1, 0 <= alpha <= C
+        self.obj = Quadratic(self._build_hessian(X, ys, 'plain'), -np.ones(n))
+        ub = np.ones(n) * self.C
+        self.optimizer = self._solve(solver_cls, ub)
+        self.alphas_ = self.optimizer.x
+
+        # support set, dual coefficients, intercept (ml/svm/_base.py:867-880)
+        sv = self.alphas_ > 1e-6
+        self.support_ = np.arange(n)[sv]
+        self.support_vectors_, sv_y, alphas = X[sv], y[sv], self.alphas_[sv]
+        self.dual_coef_ = alphas * sv_y
+        if isinstance(self.kernel, LinearKernel):
+            self.coef_ = np.dot(self.dual_coef_, self.support_vectors_)
+        # K5: sum_m dual_coef_m K[n, m] for every n from ONE masked pass over the resident
+        # Q = s_n s_m (K + 1):  s_n (Q beta)_n = sum_m dual_coef_m K[n, m] + sum_m dual_coef_m
+        v = self.obj.device_hessian().product(np.where(sv, self.alphas_, 0.))
+        k_dot = ys[sv] * v[sv] - np.sum(self.dual_coef_)
+        self.intercept_ = float(np.sum(sv_y - k_dot)) / len(alphas)
+        return self
+
+    def predict(self, X):
+        return self.lb.inverse_transform(self.decision_function(X))
+
+
+class SVR(RegressorMixin, SVM):
+    """Epsilon-Support Vector Regression, dual eps-insensitive problem (ml/svm/_base.py:888-1442)."""
+
+    def __init__(self, loss=squared_epsilon_insensitive, epsilon=0.1, kernel=gaussian, C=1, rho=1, mu=1,
+                 fit_intercept=True, intercept_scaling=1, reg_intercept=False, dual=False, optimizer=None,
+                 master_solver='clarabel', learning_rate='auto', momentum_type='none', momentum=0.9, max_iter=1000,
+                 max_f_eval=15000, tol=1e-4, batch_size=None, shuffle=True, random_state=None, early_stopping=False,
+                 validation_split=0., patience=5, verbose=False, master_verbose=False):
+        super(SVR, self).__init__(loss=loss, kernel=kernel, C=C, rho=rho, mu=mu, fit_intercept=fit_intercept,
+                                  intercept_scaling=intercept_scaling, reg_intercept=reg_intercept, dual=dual,
+                                  optimizer=optimizer, master_solver=master_solver, learning_rate=learning_rate,
+                                  momentum_type=momentum_type, momentum=momentum, max_iter=max_iter,
+                                  max_f_eval=max_f_eval, tol=tol, batch_size=batch_size, shuffle=shuffle,
+                                  random_state=random_state, early_stopping=early_stopping,
+                                  validation_split=validation_split, patience=patience, verbose=verbose,
+                                  master_verbose=master_verbose)
+        if not getattr(loss, '_loss_type', None) == 'regressor':
+            raise TypeError(f'{loss} is not an allowed SVR loss function')
+        if not epsilon >= 0:
+            raise ValueError('epsilon must be >= 0')
+        self.epsilon = epsilon
+
+    def fit(self, X, y):
+        y = np.asarray(y)
+        targets = y.shape[1] if y.ndim > 1 else 1
+        if targets > 1:
+            raise ValueError('use sklearn.multioutput.MultiOutputRegressor '
+                             'to train a model over more than one target')
+        solver_cls = self._bcqp_solver_class()
+        if self.loss == SquaredEpsilonInsensitive:
+            raise NotImplementedError  # ml/svm/_base.py:1325-1328
+        if self.loss != EpsilonInsensitive:
+            raise TypeError(f'{self.loss} is not an allowed loss')
+        X, _ = _dense_f64(X, None)
+        y = y.astype(np.float64).ravel()
+        n = len(y)
+
+        # Q = [[K, -K], [-K, K]] + ee', e = [1, -1]  (ml/svm/_base.py:1098-1100, 1126, 1178): only
+        # M = K + 1 (n x n) is resident, the solver applies the block signs
+        self.obj = Quadratic(self._build_hessian(X, None, 'svr'), np.hstack((-y, y)) + self.epsilon)
+        ub = np.ones(2 * n) * self.C
+        self.optimizer = self._solve(solver_cls, ub)
+        self.alphas_ = self.optimizer.x
+        alphas_p, alphas_n = np.split(self.alphas_, 2)
+
+        # ml/svm/_base.py:1423-1437
+        sv = np.logical_or(alphas_p > 1e-6, alphas_n > 1e-6)
+        self.support_ = np.arange(n)[sv]
+        self.support_vectors_, sv_y = X[sv], y[sv]
+        self.dual_coef_ = alphas_p[sv] - alphas_n[sv]
+        if isinstance(self.kernel, LinearKernel):
+            self.coef_ = np.dot(self.dual_coef_, self.support_vectors_)
+        beta = np.where(sv, alphas_p - alphas_n, 0.)
+        v = self.obj.device_hessian().product(np.concatenate((beta, np.zeros(n))))[:n]  # (K + 1) beta
+        k_dot = v[sv] - np.sum(self.dual_coef_)
+        self.intercept_ = (float(np.sum(sv_y - k_dot)) - self.epsilon) / len(sv_y)
+        return self
+
+    def predict(self, X):
+        return self.decision_function(X)
+
+
+class DualSVC(SVC):
+    """``SVC`` preset to the path this package accelerates: hinge loss, dual problem with the intercept
+    regularised, ProjectedGradient on the GPU (the name BASELINE.json uses)."""
+
+    def __init__(self, loss=Hinge, kernel=gaussian, C=1, rho=1, mu=1, fit_intercept=True, intercept_scaling=1,
+                 reg_intercept=True, dual=True, optimizer=ProjectedGradient, master_solver='clarabel',
+                 learning_rate='auto', momentum_type='none', momentum=0.9, max_iter=1000, max_f_eval=15000, tol=1e-4,
+                 batch_size=None, shuffle=True, random_state=None, early_stopping=False, validation_split=0.,
+                 patience=5, verbose=False, master_verbose=False):
+        super(DualSVC, self).__init__(loss=loss, kernel=kernel, C=C, rho=rho, mu=mu, fit_intercept=fit_intercept,
+                                      intercept_scaling=intercept_scaling, reg_intercept=reg_intercept, dual=dual,
+                                      optimizer=optimizer, master_solver=master_solver, learning_rate=learning_rate,
+                                      momentum_type=momentum_type, momentum=momentum, max_iter=max_iter,
+                                      max_f_eval=max_f_eval, tol=tol, batch_size=batch_size, shuffle=shuffle,
+                                      random_state=random_state, early_stopping=early_stopping,
+                                      validation_split=validation_split, patience=patience, verbose=verbose,
+                                      master_verbose=master_verbose)
+
+
+class DualSVR(SVR):
+    """``SVR`` preset: eps-insensitive loss, dual problem, ProjectedGradient on the GPU."""
+
+    def __init__(self, loss=EpsilonInsensitive, epsilon=0.1, kernel=gaussian, C=1, rho=1, mu=1, fit_intercept=True,
+                 intercept_scaling=1, reg_intercept=True, dual=True, optimizer=ProjectedGradient,
+                 master_solver='clarabel', learning_rate='auto', momentum_type='none', momentum=0.9, max_iter=1000,
+                 max_f_eval=15000, tol=1e-4, batch_size=None, shuffle=True, random_state=None, early_stopping=False,
+                 validation_split=0., patience=5, verbose=False, master_verbose=False):
+        super(DualSVR, self).__init__(loss=loss, epsilon=epsilon, kernel=kernel, C=C, rho=rho, mu=mu,
+                                      fit_intercept=fit_intercept, intercept_scaling=intercept_scaling,
+                                      reg_intercept=reg_intercept, dual=dual, optimizer=optimizer,
+                                      master_solver=master_solver, learning_rate=learning_rate,
+                                      momentum_type=momentum_type, momentum=momentum, max_iter=max_iter,
+                                      max_f_eval=max_f_eval, tol=tol, batch_size=batch_size, shuffle=shuffle,
+                                      random_state=random_state, early_stopping=early_stopping,
+                                      validation_split=validation_split, patience=patience, verbose=verbose,
+                                      master_verbose=master_verbose)

@@ -1,0 +1,91 @@
+"""Kernel functors (reference: optiml/ml/svm/kernels.py).  ``kernel(X, Y=None)`` returns the Gram
+matrix as a host ndarray, computed by the CUDA Gram kernel (csrc/gram.cu); the estimators use
+``gram_spec`` instead and keep the training Gram matrix in HBM."""
+import ctypes as C
+
+import numpy as np
+from sklearn.base import BaseEstimator
+from sklearn.metrics.pairwise import check_pairwise_arrays
+
+from ... import _native as N
+from ...runtime import default_context
+
+
+def _check_gamma(gamma):
+    if isinstance(gamma, str):
+        if gamma not in ('scale', 'auto'):
+            raise ValueError(f'unknown gamma type {gamma}')
+    elif not gamma > 0:
+        raise ValueError('gamma must be > 0')
+
+
+def _dense_f64(X, Y):
+    """sklearn's pairwise validation (2-D, finite, matching feature counts), then dense float64:
+    sparse / float32 inputs are converted (the reference keeps float32 Grams in float32)."""
+    same = Y is None or Y is X
+    X, Y = check_pairwise_arrays(X, None if same else Y, accept_sparse='csr')
+    dense = [np.ascontiguousarray(A.toarray() if hasattr(A, 'toarray') else A, dtype=np.float64) for A in (X, Y)]
+    return dense[0], (None if same else dense[1])
+
+
+class Kernel(BaseEstimator):
+    """Base class: a kernel maps two sample sets to their Gram matrix (kernels.py:9-37)."""
+
+    kernel_id = None
+
+    def resolve_gamma(self, X):
+        """'scale' -> 1/(d * X.var()), 'auto' -> 1/d, evaluated on the FIRST argument of the call
+        exactly as kernels.py:93-94 / 127-128 do (host NumPy, so the value is bit-identical)."""
+        gamma = getattr(self, 'gamma', None)
+        if gamma is None:
+            return 1.
+        return (1. / (X.shape[1] * X.var()) if gamma == 'scale' else
+                1. / X.shape[1] if gamma == 'auto' else gamma)
+
+    def gram_spec(self, X):
+        """(kernel_id, gamma, coef0, degree) for a call whose first argument is X."""
+        return (self.kernel_id, float(self.resolve_gamma(X)), float(getattr(self, 'coef0', 0.)),
+                float(getattr(self, 'degree', 1)))
+
+    def __call__(self, X, Y=None):
+        if self.kernel_id is None:
+            raise NotImplementedError
+        X, Y = _dense_f64(X, Y)
+        kid, gamma, coef0, degree = self.gram_spec(X)
+        ny = X.shape[0] if Y is None else Y.shape[0]
+        out = np.empty((X.shape[0], ny))
+        N.call('svmb200_kernel_matrix_host', default_context().handle, N.ptr(X), X.shape[0], N.ptr(Y), ny, X.shape[1],
+               kid, gamma, coef0, degree, N.ptr(out))
+        return out
+
+
+class LinearKernel(Kernel):
+    """K(X, Y) = <X, Y>  (kernels.py:40-51)."""
+    kernel_id = N.KERNEL_LINEAR
+
+
+class PolyKernel(Kernel):
+    """K(X, Y) = (gamma <X, Y> + coef0) ** degree  (kernels.py:54-95)."""
+    kernel_id = N.KERNEL_POLY
+
+    def __init__(self, degree=3, gamma='scale', coef0=0.):
+        if not degree > 0:
+            raise ValueError('degree must be > 0')
+        self.degree = degree
+        _check_gamma(gamma)
+        self.gamma = gamma
+        self.coef0 = coef0
+
+
+class GaussianKernel(Kernel):
+    """K(X, Y) = exp(-gamma ||X - Y||^2)  (kernels.py:98-129)."""
+    kernel_id = N.KERNEL_GAUSSIAN
+
+    def __init__(self, gamma='scale'):
+        _check_gamma(gamma)
+        self.gamma = gamma
+
+
+linear = LinearKernel()
+poly = PolyKernel()
+gaussian = GaussianKernel()

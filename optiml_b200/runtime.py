@@ -1,0 +1,235 @@
+"""Device runtime of the host mirror: one context (GPU + stream) per process, device-resident
+matrices and the multi-GPU plumbing.
+
+Multi-GPU model: one process per GPU (``torchrun``); ``torch.distributed`` is used only to agree on
+the NCCL unique id, the per-iteration exchange itself is an ``ncclAllGather`` issued by the C
+library on its own stream (csrc/comm.cu).
+"""
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import _native as N
+
+_default_ctx = None
+
+
+class Context:
+    """Owns a ``svmb200_ctx`` (one GPU, one stream)."""
+
+    def __init__(self, device=None):
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0'))
+        count = C.c_int(0)
+        N.call('svmb200_device_count', C.byref(count))
+        h = C.c_void_p()
+        N.call('svmb200_ctx_create', int(device) % max(count.value, 1), C.byref(h))
+        self.handle = h
+        self.device = int(device)
+        self.rank, self.nranks = 0, 1
+        self._finalizer = weakref.finalize(self, N.load_library().svmb200_ctx_destroy, h)
+
+    # ---------------------------------------------------------------- memory
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        N.call('svmb200_malloc', self.handle, int(nbytes), C.byref(p))
+        return p.value
+
+    def free(self, dptr):
+        if dptr:
+            N.call('svmb200_free', self.handle, C.c_void_p(dptr))
+
+    def memset(self, dptr, value, nbytes):
+        N.call('svmb200_memset', self.handle, C.c_void_p(dptr), int(value), int(nbytes))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        N.call('svmb200_h2d', self.handle, C.c_void_p(dptr), arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+
+    def d2h(self, arr, dptr):
+        assert arr.flags['C_CONTIGUOUS']
+        N.call('svmb200_d2h', self.handle, arr.ctypes.data_as(C.c_void_p), C.c_void_p(dptr), arr.nbytes)
+
+    def sync(self):
+        N.call('svmb200_sync', self.handle)
+
+    def timer_start(self):
+        N.call('svmb200_timer_start', self.handle)
+
+    def timer_stop_ms(self):
+        ms = C.c_float(0)
+        N.call('svmb200_timer_stop_ms', self.handle, C.byref(ms))
+        return float(ms.value)
+
+    def launch_count(self):
+        n = C.c_uint64(0)
+        N.call('svmb200_launch_count', self.handle, C.byref(n))
+        return int(n.value)
+
+    def info(self):
+        sm, ma, mi = C.c_int(0), C.c_int(0), C.c_int(0)
+        fr, to = C.c_size_t(0), C.c_size_t(0)
+        N.call('svmb200_ctx_info', self.handle, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(fr), C.byref(to))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), free_bytes=fr.value, total_bytes=to.value)
+
+    # ---------------------------------------------------------------- multi-GPU
+    def attach_communicator(self, rank, nranks, unique_id):
+        """Join the NCCL communicator described by ``unique_id`` (128 bytes from rank 0)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        N.call('svmb200_comm_init', self.handle, C.cast(buf, C.c_void_p), int(rank), int(nranks))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    @staticmethod
+    def new_unique_id():
+        buf = C.create_string_buffer(128)
+        N.call('svmb200_comm_unique_id', C.cast(buf, C.c_void_p))
+        return buf.raw
+
+    def row_shard(self, n):
+        """Rows [row0, row0+nrows) of an n-row matrix owned by this rank: ceil(n/P) rows per rank."""
+        return shard_rows(n, self.rank, self.nranks)
+
+    # ---------------------------------------------------------------- matrices
+    def upload_matrix(self, X):
+        """Copy a host matrix to the device with an even leading dimension (16-byte row stride)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        n, d = X.shape
+        ld = d + (d & 1)
+        if ld != d:
+            Xp = np.zeros((n, ld))
+            Xp[:, :d] = X
+            X = Xp
+        m = DeviceMatrix(self, n, d, ld)
+        self.h2d(m.dptr, X)
+        return m
+
+    def upload_vector(self, v, length=None):
+        v = np.ascontiguousarray(v, dtype=np.float64).ravel()
+        length = len(v) if length is None else int(length)
+        out = DeviceMatrix(self, 1, length, max(length, 2))
+        self.memset(out.dptr, 0, out.nbytes)
+        self.h2d(out.dptr, v)
+        return out
+
+
+def shard_rows(n, rank, nranks):
+    rpr = -(-int(n) // int(nranks))
+    row0 = min(int(n), rank * rpr)
+    return row0, max(0, min(rpr, int(n) - row0))
+
+
+class DeviceMatrix:
+    """A row-major FP64 matrix in HBM (rows x cols, leading dimension ld)."""
+
+    def __init__(self, ctx, rows, cols, ld):
+        self.ctx, self.rows, self.cols, self.ld = ctx, int(rows), int(cols), int(ld)
+        self.nbytes = max(self.rows, 1) * self.ld * 8
+        self.dptr = ctx.malloc(self.nbytes)
+        self._finalizer = weakref.finalize(self, _free_quiet, ctx, self.dptr)
+
+    def release(self):
+        self._finalizer()
+        self.dptr = None
+
+    def to_host(self):
+        buf = np.empty((self.rows, self.ld))
+        self.ctx.d2h(buf, self.dptr)
+        return np.ascontiguousarray(buf[:, :self.cols])
+
+
+def _free_quiet(ctx, dptr):
+    try:
+        ctx.free(dptr)
+    except Exception:  # interpreter shutdown / context already gone
+        pass
+
+
+class DeviceHessian:
+    """Row shard [row0, row0+nrows) of the n x n matrix the solver streams every iteration.
+
+    ``layout='plain'``: the matrix is Q itself.  ``layout='svr'``: the matrix is M = K + 1 and the
+    Hessian is [[M, -M], [-M, M]] (ml/svm/_base.py:1098-1099, 1178 of the reference) -- the 2n x 2n
+    matrix is never materialised on the device.
+    """
+
+    def __init__(self, ctx, n, layout='plain', matrix=None, row0=None, nrows=None):
+        self.ctx, self.n, self.layout = ctx, int(n), layout
+        if row0 is None:
+            row0, nrows = ctx.row_shard(n)
+        self.row0, self.nrows = int(row0), int(nrows)
+        self.ld = N.padded_ld(n)
+        self.matrix = matrix if matrix is not None else DeviceMatrix(ctx, self.nrows, self.n, self.ld)
+
+    @property
+    def nvars(self):
+        return 2 * self.n if self.layout == 'svr' else self.n
+
+    @classmethod
+    def from_host(cls, ctx, Q):
+        """Upload (this rank's rows of) a host-resident square matrix."""
+        Q = np.asarray(Q, dtype=np.float64)
+        n = Q.shape[0]
+        h = cls(ctx, n, 'plain')
+        block = np.zeros((max(h.nrows, 1), h.ld))
+        block[:h.nrows, :n] = Q[h.row0:h.row0 + h.nrows]
+        ctx.h2d(h.matrix.dptr, block)
+        return h
+
+    def shard_to_host(self):
+        buf = np.empty((max(self.nrows, 1), self.ld))
+        self.ctx.d2h(buf, self.matrix.dptr)
+        return np.ascontiguousarray(buf[:self.nrows, :self.n])
+
+    def to_host(self):
+        """Materialise the full Hessian on the host (debug / parity / API compatibility only)."""
+        M = self.shard_to_host()
+        if self.ctx.nranks > 1:
+            import torch.distributed as dist
+            parts = [None] * self.ctx.nranks
+            dist.all_gather_object(parts, M)
+            M = np.vstack(parts)
+        if self.layout == 'svr':
+            return np.vstack((np.hstack((M, -M)), np.hstack((-M, M))))
+        return M
+
+    def product(self, v):
+        """Q @ v through the streaming matvec kernel (all ranks get the full result)."""
+        v = np.asarray(v, dtype=np.float64).ravel()
+        if self.layout == 'svr':
+            beta = v[:self.n] - v[self.n:]
+        else:
+            beta = v
+        beta = np.ascontiguousarray(beta)
+        out = np.empty(self.n)
+        N.call('svmb200_masked_product', self.ctx.handle, C.c_void_p(self.matrix.dptr), self.n, self.ld, self.row0,
+               self.nrows, N.ptr(beta), N.ptr(out))
+        return np.concatenate((out, -out)) if self.layout == 'svr' else out
+
+    def release(self):
+        self.matrix.release()
+
+
+def default_context():
+    """Process-wide context.  Under ``torchrun`` (torch.distributed initialised, world size > 1) the
+    context joins an NCCL communicator whose id is broadcast through torch.distributed."""
+    global _default_ctx
+    if _default_ctx is not None:
+        return _default_ctx
+    ctx = Context()
+    import sys
+    if 'torch' in sys.modules:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            rank, world = dist.get_rank(), dist.get_world_size()
+            box = [Context.new_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ctx.attach_communicator(rank, world, box[0])
+    _default_ctx = ctx
+    return ctx
+
+
+def set_default_context(ctx):
+    global _default_ctx
+    _default_ctx = ctx
