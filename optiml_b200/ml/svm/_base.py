@@ -108,26 +108,30 @@ class SVM(BaseEstimator):
             raise NotImplementedError
         return opt
 
-    def _build_hessian(self, X, signs, layout):
-        """K1: Gram matrix + bias (+ label signs) straight into this rank's row shard in HBM."""
+    def _build_hessian(self, X, signs, layout, X_device=None):
+        """K1: Gram matrix + bias (+ label signs) straight into this rank's row shard in HBM.
+        ``X_device`` (a DeviceMatrix already holding X) skips the host->device copy of X."""
         ctx = default_context()
         n, d = X.shape
         kid, gamma, coef0, degree = self.kernel.gram_spec(X)
-        dX = ctx.upload_matrix(X)
+        dX = X_device if X_device is not None else ctx.upload_matrix(X)
         dS = ctx.upload_vector(signs) if signs is not None else None
         H = DeviceHessian(ctx, n, layout)
         sp = C.c_void_p(dS.dptr) if dS is not None else None
         N.call('svmb200_gram', ctx.handle, C.c_void_p(dX.dptr), n, dX.ld, C.c_void_p(dX.dptr), n, dX.ld, d, 1, kid,
                gamma, coef0, degree, sp, sp, 1.0, H.row0, H.nrows, C.c_void_p(H.matrix.dptr), H.ld)
         ctx.sync()
-        dX.release()
+        if X_device is None:
+            dX.release()
         if dS is not None:
             dS.release()
         return H
 
     def _solve(self, solver_cls, ub):
-        return solver_cls(quad=self.obj, ub=ub, tol=self.tol, max_iter=self.max_iter,
-                          callback=self._store_train_info, verbose=self.verbose).minimize()
+        solver = solver_cls(quad=self.obj, ub=ub, tol=self.tol, max_iter=self.max_iter,
+                            callback=self._store_train_info, verbose=self.verbose)
+        solver.profile = bool(getattr(self, 'profile_matvec', False))  # CUDA events around every K2 launch
+        return solver.minimize()
 
     def decision_function(self, X):
         """ml/svm/_base.py:284-287.  ``gamma='scale'`` is resolved from ``support_vectors_`` (the first
@@ -169,7 +173,7 @@ class SVC(ClassifierMixin, SVM):
             raise TypeError(f'{loss} is not an allowed SVC loss function')
         self.lb = LabelBinarizer(neg_label=-1)
 
-    def fit(self, X, y):
+    def fit(self, X, y, X_device=None):
         self.lb.fit(y)
         if len(self.lb.classes_) > 2:
             raise ValueError('use OneVsOneClassifier or OneVsRestClassifier from sklearn.multiclass '
@@ -185,7 +189,7 @@ class SVC(ClassifierMixin, SVM):
         ys = y.astype(np.float64)
 
         # Q = K o yy' + yy'  (ml/svm/_base.py:552-554, 628), q = -1, 0 <= alpha <= C
-        self.obj = Quadratic(self._build_hessian(X, ys, 'plain'), -np.ones(n))
+        self.obj = Quadratic(self._build_hessian(X, ys, 'plain', X_device), -np.ones(n))
         ub = np.ones(n) * self.C
         self.optimizer = self._solve(solver_cls, ub)
         self.alphas_ = self.optimizer.x
@@ -230,7 +234,7 @@ class SVR(RegressorMixin, SVM):
             raise ValueError('epsilon must be >= 0')
         self.epsilon = epsilon
 
-    def fit(self, X, y):
+    def fit(self, X, y, X_device=None):
         y = np.asarray(y)
         targets = y.shape[1] if y.ndim > 1 else 1
         if targets > 1:
@@ -247,7 +251,7 @@ class SVR(RegressorMixin, SVM):
 
         # Q = [[K, -K], [-K, K]] + ee', e = [1, -1]  (ml/svm/_base.py:1098-1100, 1126, 1178): only
         # M = K + 1 (n x n) is resident, the solver applies the block signs
-        self.obj = Quadratic(self._build_hessian(X, None, 'svr'), np.hstack((-y, y)) + self.epsilon)
+        self.obj = Quadratic(self._build_hessian(X, None, 'svr', X_device), np.hstack((-y, y)) + self.epsilon)
         ub = np.ones(2 * n) * self.C
         self.optimizer = self._solve(solver_cls, ub)
         self.alphas_ = self.optimizer.x

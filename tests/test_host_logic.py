@@ -1,0 +1,105 @@
+"""CPU-only checks: the C-ABI library builds/loads and exports every symbol of include/svmb200.h, the
+host mirror validates arguments like the reference, sharding arithmetic, loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    with open(os.path.join(ROOT, 'include', 'svmb200.h')) as fh:
+        text = fh.read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(svmb200_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    import __graft_entry__ as entry
+    lib_path = entry.build()
+    assert os.path.exists(lib_path)
+    from optiml_b200 import _native
+    lib = _native.load_library()
+    names = header_functions()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), f'{name} declared in include/svmb200.h but not exported'
+    # and every bound prototype is declared in the header
+    assert set(_native.exported_symbols()) <= set(names)
+    assert lib.svmb200_version().decode().startswith('svmb200')
+    assert _native.padded_ld(50000) == 50000 and _native.padded_ld(1001) == 1008
+
+
+def test_no_cpu_fallback_without_gpu():
+    import shutil
+    if shutil.which('nvidia-smi') and os.path.exists('/dev/nvidia0'):
+        pytest.skip('a GPU is present')
+    from optiml_b200 import _native
+    from optiml_b200.ml.svm import DualSVC
+    with pytest.raises(_native.NativeError):
+        DualSVC().fit(np.random.default_rng(0).standard_normal((8, 2)), [0, 1] * 4)
+
+
+def test_constructor_validation_matches_reference():
+    from optiml_b200.ml.svm import SVC, SVR, DualSVC, DualSVR
+    from optiml_b200.ml.svm.kernels import GaussianKernel, PolyKernel
+    from optiml_b200.ml.svm.losses import hinge, epsilon_insensitive, squared_hinge
+    from optiml_b200.opti.constrained import ProjectedGradient
+    with pytest.raises(TypeError):
+        SVC(loss=hinge, kernel='rbf')  # ml/svm/_base.py:214-215
+    for bad in (dict(C=0), dict(rho=0), dict(mu=-1), dict(tol=0), dict(fit_intercept=1), dict(reg_intercept=0),
+                dict(dual='yes')):
+        with pytest.raises(ValueError):
+            DualSVC(**bad)
+    with pytest.raises(TypeError):
+        SVC(loss=epsilon_insensitive)  # :417-418
+    with pytest.raises(TypeError):
+        SVR(loss=hinge)  # :959-960
+    with pytest.raises(ValueError):
+        DualSVR(epsilon=-1)  # :961-962
+    with pytest.raises(ValueError):
+        PolyKernel(degree=0)
+    with pytest.raises(ValueError):
+        GaussianKernel(gamma='bogus')
+    with pytest.raises(ValueError):
+        GaussianKernel(gamma=-1.)
+    m = SVC(loss=hinge, dual=True, reg_intercept=True, optimizer=ProjectedGradient)
+    assert m.alphas_.size == 0 and m.intercept_ == 0. and m.train_loss_history == []
+    assert not hasattr(m, 'coef_')  # only for linear kernels / primal (:259-261)
+    with pytest.raises(NotImplementedError):
+        SVC(loss=squared_hinge).fit(np.zeros((4, 2)), [0, 1, 0, 1])  # primal path is out of scope
+    from sklearn.base import clone
+    assert clone(DualSVR(C=2, epsilon=0.2)).epsilon == 0.2
+
+
+def test_gamma_resolution_follows_first_argument():
+    from optiml_b200.ml.svm.kernels import GaussianKernel, PolyKernel, LinearKernel
+    X = np.random.default_rng(0).standard_normal((10, 4))
+    assert GaussianKernel().resolve_gamma(X) == 1. / (4 * X.var())
+    assert PolyKernel(gamma='auto').resolve_gamma(X) == 0.25
+    assert GaussianKernel(gamma=0.7).gram_spec(X) == (2, 0.7, 0., 1.)
+    assert PolyKernel(degree=2, coef0=1.).gram_spec(X)[2:] == (1., 2.)
+    assert LinearKernel().gram_spec(X)[0] == 0
+
+
+def test_row_sharding():
+    from optiml_b200.runtime import shard_rows
+    for n in (1, 7, 8, 50000, 120000, 1001):
+        for P in (1, 2, 3, 4, 8):
+            shards = [shard_rows(n, r, P) for r in range(P)]
+            rpr = -(-n // P)
+            assert sum(s[1] for s in shards) == n
+            assert all(s[0] == min(n, r * rpr) for r, s in enumerate(shards))
+            assert all(0 <= s[1] <= rpr for s in shards)
+
+
+def test_product_path_does_not_import_oracle():
+    """the oracle is test infrastructure: nothing under optiml_b200/ may reference it"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'optiml_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                with open(os.path.join(dirpath, f)) as fh:
+                    src = fh.read()
+                assert 'oracle' not in src.lower() or f == 'configs.py', f'{f} mentions the oracle'
