@@ -81,6 +81,10 @@ int svmb200_launch_count(svmb200_ctx* ctx, uint64_t* launches);
 int svmb200_comm_unique_id(void* id128);
 int svmb200_comm_init(svmb200_ctx* ctx, const void* id128, int rank, int nranks);
 int svmb200_comm_destroy(svmb200_ctx* ctx);
+/* Row partition used by every sharded entry point: rank r owns rows [row0, row0+nrows) of an n-row
+ * matrix, ceil(n/nranks) rounded up to a multiple of 8 rows per rank (the last ranks may get fewer,
+ * possibly none).  Aligned shard boundaries keep every reduction shape independent of nranks. */
+int svmb200_shard_rows(int64_t n, int rank, int nranks, int64_t* row0, int64_t* nrows);
 
 /* ---- K1: Gram / Hessian build ------------------------------------------------------------
  * Replaces  kernels.py:49-51 (linear), :91-95 (poly), :125-129 (gaussian, via sklearn
@@ -112,8 +116,8 @@ int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld
  * ProjectedGradient.minimize (opti/constrained/projected_gradient.py:76-143).
  *
  * The context's rank owns rows [row0, row0+nrows) of the n x n resident matrix dQ (ld).  With a
- * communicator attached every rank must call the same sequence; row shards must be
- * ceil(n/nranks) rows per rank in rank order (the last may be shorter).
+ * communicator attached every rank must call the same sequence; row shards must be the ones
+ * svmb200_shard_rows returns.
  * Host vectors q, lb, ub, x0 have nvars = n (PLAIN) or 2n (SVR) elements; lb may be NULL (= 0),
  * x0 may be NULL (= (lb+ub)/2).                                                               */
 int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,

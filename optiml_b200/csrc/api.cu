@@ -60,6 +60,7 @@ extern "C" int svmb200_ctx_destroy(svmb200_ctx* ctx) {
     svmb200_comm_destroy(ctx);
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
+        svm_release_matvec_scratch(ctx);
         cudaStreamDestroy(ctx->stream);
     }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

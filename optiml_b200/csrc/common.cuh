@@ -22,6 +22,8 @@ struct svmb200_ctx {
     int rank = 0, nranks = 1;
     // cached TMA encoder (driver entry point fetched at run time: no link-time libcuda dependency)
     void* encode_tiled = nullptr;
+    // segment partials / tickets of the streaming matvec (grown on demand, pg.cu)
+    void* matvec_scratch = nullptr;
 };
 
 void svmb200_set_error(const char* fmt, ...);
@@ -62,5 +64,6 @@ static inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b 
 
 // internal cross-file entry points
 int svm_comm_allgather(svmb200_ctx* ctx, double* dbuf, int64_t count_per_rank);  // in place, on ctx->stream
+void svm_release_matvec_scratch(svmb200_ctx* ctx);
 int svm_launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw,
                       const int* d_done);

@@ -6,23 +6,41 @@
 //          max_t = largest feasible step ; den = d'Qd ; t = den<=1e-16 ? max_t : min(-g'd/den, max_t)
 //          x += t d ; iter += 1
 // The reference streams Q three times per iteration.  Here Q is streamed ONCE per iteration:
-//   w = Q d  (K2),  den = d'w,  g <- g + t w,  f = x'(g+q)/2,  -g'd == d'd  (K3).
-// All O(n) work runs in one 8-CTA thread-block cluster (distributed-shared-memory reduction for
-// den, global partials for the reductions that are only consumed one kernel later).
+//   w = Q u  (K2; u = d, or d+ - d- for the SVR block Hessian),  den = u'w,  g <- g + t w,
+//   f = x'(g+q)/2,  -g'd == d'd  (K3).
+//
+// Every reduction has a fixed shape that depends on the problem size only -- never on the number of
+// GPUs, the grid or the arrival order -- so the iterate is bit-identical for 1, 2, 4 and 8 GPUs.
 #include "common.cuh"
-#include <cooperative_groups.h>
 #include <math.h>
 
-namespace cg = cooperative_groups;
-
 // ------------------------------------------------------------------------------------------ K2
-// One CTA owns R consecutive rows and walks the whole (padded) row length; every thread issues
-// R*U independent 128-bit streaming loads per step (L1 no-allocate: Q is touched once per pass),
-// the vector operand u comes through L1/L2.  Per-row reduction order depends only on (NT, U, ld),
-// never on the number of GPUs, so row results are bit-identical for any row sharding.
-constexpr int MV_R = 8;
+// Work item = MV_R consecutive rows x one column segment of MV_SEG doubles.  Every thread keeps
+// MV_R*MV_U independent 128-bit streaming loads in flight (L1 no-allocate: Q is touched once per
+// pass); the vector operand comes through L1/L2.  The CTA that finishes a row block last (atomic
+// ticket) adds the segment partials in segment order, stores w and the block's share of u'w.
+// Segmenting keeps the grid at >= 12 waves even for a 1/8 row shard (tail effect) and keeps every
+// work item at 256 KB.
+constexpr int MV_R = 4;
 constexpr int MV_NT = 256;
-constexpr int MV_U = 2;
+constexpr int MV_U = 4;
+constexpr int MV_SEG = 8192;
+constexpr int MV_MINB = 3;
+constexpr int ROW_ALIGN = 8;  // row shards start on multiples of this (>= MV_R), see svmb200_shard_rows
+
+struct MatvecArgs {
+    const double* Q;        // nrows x ld shard
+    long long ld, nrows;
+    const double* u;        // ld entries, zero beyond n
+    double* w;              // nrows results
+    double* wpart;          // nseg x nrows_pad segment partials (unused when nseg == 1)
+    long long nrows_pad;
+    unsigned* tickets;      // one per row block, zero on entry, zero again on exit
+    const double* u_rows;   // u at this shard's rows (u + row0), or null
+    double* denpart;        // one per row block: sum_r u_rows[r] * w[r], or null
+    int nseg;
+    const int* done;
+};
 
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
     double2 r;
@@ -30,27 +48,29 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
     return r;
 }
 
-template <int R, int NT, int U>
-__global__ void __launch_bounds__(NT) matvec_rows_kernel(const double* __restrict__ Q, long long ld, long long nrows,
-                                                         const double* __restrict__ u, double* __restrict__ w,
-                                                         const int* __restrict__ done) {
-    if (done != nullptr && *done) return;
-    const long long row_base = (long long)blockIdx.x * R;
-    const int nvec = (int)(ld >> 1);
-    const double2* __restrict__ u2 = reinterpret_cast<const double2*>(u);
+__global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const MatvecArgs a) {
+    if (a.done != nullptr && *a.done) return;
+    constexpr int R = MV_R, NT = MV_NT, U = MV_U;
+    const long long rb = blockIdx.x / a.nseg;
+    const int seg = blockIdx.x % a.nseg;
+    const long long row_base = rb * R;
+    const long long c0 = (long long)seg * MV_SEG;
+    long long c1 = c0 + MV_SEG;
+    if (c1 > a.ld) c1 = a.ld;
+    const int nvec = (int)((c1 - c0) >> 1);
+    const double2* __restrict__ u2 = reinterpret_cast<const double2*>(a.u + c0);
     const double2* rows[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         long long rr = row_base + r;
-        if (rr >= nrows) rr = nrows - 1;  // clamp: read a valid row, result discarded below
-        rows[r] = reinterpret_cast<const double2*>(Q + rr * ld);
+        if (rr >= a.nrows) rr = a.nrows - 1;  // clamp: read a valid row, result discarded below
+        rows[r] = reinterpret_cast<const double2*>(a.Q + rr * a.ld + c0);
     }
     double acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
 
     int c = threadIdx.x;
-    // full steps: all U column groups in range
     for (; c + (U - 1) * NT < nvec; c += U * NT) {
         double2 qv[U][R];
         double2 uv[U];
@@ -70,12 +90,11 @@ __global__ void __launch_bounds__(NT) matvec_rows_kernel(const double* __restric
             }
         }
     }
-    // tail
     for (; c < nvec; c += NT) {
         double2 qv[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) qv[r] = ld_stream_f64x2(rows[r] + c);
-        double2 uv = __ldg(u2 + c);
+        const double2 uv = __ldg(u2 + c);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             acc[r] = fma(qv[r].x, uv.x, acc[r]);
@@ -84,6 +103,7 @@ __global__ void __launch_bounds__(NT) matvec_rows_kernel(const double* __restric
     }
     // warp butterfly, then fixed-order sum over warps
     __shared__ double red[NT / 32][R];
+    __shared__ unsigned is_last;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         double v = acc[r];
@@ -97,17 +117,74 @@ __global__ void __launch_bounds__(NT) matvec_rows_kernel(const double* __restric
         for (int r = 0; r < R; ++r) red[wid][r] = acc[r];
     }
     __syncthreads();
+    double v = 0.0;
+    const long long rr = row_base + threadIdx.x;  // meaningful for threadIdx.x < R
     if (threadIdx.x < R) {
-        double v = 0.0;
 #pragma unroll
         for (int k = 0; k < NT / 32; ++k) v += red[k][threadIdx.x];
-        long long rr = row_base + threadIdx.x;
-        if (rr < nrows) w[rr] = v;
+    }
+    if (a.nseg > 1) {
+        if (threadIdx.x < R && rr < a.nrows) a.wpart[(size_t)seg * a.nrows_pad + rr] = v;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicInc(&a.tickets[rb], (unsigned)(a.nseg - 1)) == (unsigned)(a.nseg - 1));
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        if (threadIdx.x < R && rr < a.nrows) {
+            v = 0.0;
+            for (int s = 0; s < a.nseg; ++s) v += __ldcg(&a.wpart[(size_t)s * a.nrows_pad + rr]);
+        }
+    }
+    if (threadIdx.x < 32) {
+        double dv = 0.0;
+        if (threadIdx.x < R && rr < a.nrows) {
+            a.w[rr] = v;
+            if (a.u_rows != nullptr) dv = __dmul_rn(a.u_rows[rr], v);
+        }
+        if (a.denpart != nullptr) {
+            // ((p0 + p1) + p2) + p3 : fixed order over the rows of the block
+            double tot = __shfl_sync(0xffffffffu, dv, 0);
+#pragma unroll
+            for (int r = 1; r < R; ++r) tot = __dadd_rn(tot, __shfl_sync(0xffffffffu, dv, r));
+            if (threadIdx.x == 0) a.denpart[rb] = tot;
+        }
     }
 }
 
-int svm_launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw,
-                      const int* d_done) {
+struct MatvecScratch {
+    double* wpart = nullptr;
+    unsigned* tickets = nullptr;
+    size_t wpart_elems = 0, ticket_elems = 0;
+};
+
+static int matvec_scratch_reserve(svmb200_ctx* ctx, MatvecScratch& s, int64_t nrows, int64_t ld) {
+    const int nseg = (int)((ld + MV_SEG - 1) / MV_SEG);
+    const size_t nrows_pad = (size_t)round_up64(nrows, 16);
+    const size_t need_w = nseg > 1 ? (size_t)nseg * nrows_pad : 0;
+    const size_t need_t = (size_t)((nrows + MV_R - 1) / MV_R);
+    if (need_w > s.wpart_elems) {
+        SVM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (s.wpart) cudaFree(s.wpart);
+        s.wpart = nullptr;
+        s.wpart_elems = 0;
+        SVM_CUDA(cudaMalloc(&s.wpart, need_w * sizeof(double)));
+        s.wpart_elems = need_w;
+    }
+    if (need_t > s.ticket_elems) {
+        SVM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (s.tickets) cudaFree(s.tickets);
+        s.tickets = nullptr;
+        s.ticket_elems = 0;
+        SVM_CUDA(cudaMalloc(&s.tickets, need_t * sizeof(unsigned)));
+        SVM_CUDA(cudaMemsetAsync(s.tickets, 0, need_t * sizeof(unsigned), ctx->stream));
+        s.ticket_elems = need_t;
+    }
+    return SVMB200_OK;
+}
+
+static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw,
+                         const double* du_rows, double* ddenpart, const int* d_done) {
     if (nrows <= 0) return SVMB200_OK;
     if (ld % 2 != 0 || ld <= 0) {
         svmb200_set_error("matvec: ld must be a positive multiple of 2");
@@ -117,12 +194,46 @@ int svm_launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t
         svmb200_set_error("matvec: operands must be 16-byte aligned");
         return SVMB200_ERR_ARG;
     }
-    const unsigned grid = (unsigned)((nrows + MV_R - 1) / MV_R);
-    matvec_rows_kernel<MV_R, MV_NT, MV_U><<<grid, MV_NT, 0, ctx->stream>>>(dQ, (long long)ld, (long long)nrows, du, dw,
-                                                                           d_done);
+    if (!ctx->matvec_scratch) ctx->matvec_scratch = new MatvecScratch();
+    MatvecScratch& s = *static_cast<MatvecScratch*>(ctx->matvec_scratch);
+    SVM_TRY(matvec_scratch_reserve(ctx, s, nrows, ld));
+    MatvecArgs a;
+    a.Q = dQ;
+    a.ld = ld;
+    a.nrows = nrows;
+    a.u = du;
+    a.w = dw;
+    a.wpart = s.wpart;
+    a.nrows_pad = round_up64(nrows, 16);
+    a.tickets = s.tickets;
+    a.u_rows = du_rows;
+    a.denpart = ddenpart;
+    a.nseg = (int)((ld + MV_SEG - 1) / MV_SEG);
+    a.done = d_done;
+    const int64_t nrb = (nrows + MV_R - 1) / MV_R;
+    if (nrb * a.nseg >= (1ll << 31)) {
+        svmb200_set_error("matvec: grid too large");
+        return SVMB200_ERR_ARG;
+    }
+    matvec_seg_kernel<<<(unsigned)(nrb * a.nseg), MV_NT, 0, ctx->stream>>>(a);
     ctx->launches++;
     SVM_CUDA(cudaGetLastError());
     return SVMB200_OK;
+}
+
+void svm_release_matvec_scratch(svmb200_ctx* ctx) {
+    if (ctx->matvec_scratch) {
+        MatvecScratch* s = static_cast<MatvecScratch*>(ctx->matvec_scratch);
+        if (s->wpart) cudaFree(s->wpart);
+        if (s->tickets) cudaFree(s->tickets);
+        delete s;
+        ctx->matvec_scratch = nullptr;
+    }
+}
+
+int svm_launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw,
+                      const int* d_done) {
+    return launch_matvec(ctx, dQ, nrows, ld, du, dw, nullptr, nullptr, d_done);
 }
 
 extern "C" int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du,
@@ -131,12 +242,31 @@ extern "C" int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows,
     return svm_launch_matvec(ctx, dQ, nrows, ld, du, dw, nullptr);
 }
 
+static int64_t rows_per_rank(int64_t n, int nranks) { return round_up64((n + nranks - 1) / nranks, ROW_ALIGN); }
+
+extern "C" int svmb200_shard_rows(int64_t n, int rank, int nranks, int64_t* row0, int64_t* nrows) {
+    SVM_CHECK_ARG(n >= 0 && nranks >= 1 && rank >= 0 && rank < nranks && row0 && nrows, "bad argument");
+    const int64_t rpr = rows_per_rank(n, nranks);
+    int64_t r0 = (int64_t)rank * rpr;
+    if (r0 > n) r0 = n;
+    int64_t nr = n - r0;
+    if (nr > rpr) nr = rpr;
+    *row0 = r0;
+    *nrows = nr;
+    return SVMB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ K3
-constexpr int VP_CL = 8;      // CTAs per cluster (portable maximum)
-constexpr int VP_NT = 1024;   // threads per CTA
+// Grid-wide vector phase, no inter-CTA synchronisation: a CTA first reduces (redundantly, in a fixed
+// order) the per-row-block shares of u'w written by K2 and the per-CTA partials of |d|^2, x'(g+q) and
+// max_t written by the previous K3 launch, takes the step on its slice, and leaves its own partials
+// for the next launch.
+constexpr int VP_NT = 256;
+constexpr int VP_MAXC = 128;   // at most this many CTAs (fixed: the reduction shape must not follow the GPU)
+constexpr int VP_ELEMS = 512;  // target elements per CTA
 
 struct PGDeviceState {
-    long long iter;  // iterations completed (== index of the state whose f/ng are stored below)
+    long long iter;  // index of the state whose f/ng are stored below
     int done;
     int status;
     double f, ng, s, maxt, t, den;
@@ -144,13 +274,16 @@ struct PGDeviceState {
 
 struct VecArgs {
     double *x, *g, *d, *u;
-    const double *q, *lb, *ub, *w;
-    double *part_s, *part_f, *part_mt;  // VP_CL entries each
+    const double *q, *lb, *ub;
+    const double* gathered;  // per rank: [rpr results w | rpr/MV_R shares of u'w]
+    long long rpr, stride;
+    double* part;            // 3 x VP_MAXC : |d|^2, x'(g+q), max_t per CTA
     double *hist_f, *hist_ng;
     long long hist_cap;
     PGDeviceState* st;
-    long long n;         // matrix dimension
-    int svr;             // 0: nvars = n ; 1: nvars = 2n, Q = [[M,-M],[-M,M]]
+    long long n;   // matrix dimension
+    int svr;       // 0: nvars = n ; 1: nvars = 2n, Q = [[M,-M],[-M,M]]
+    int nctas;
     double eps;
     long long max_iter;
 };
@@ -159,7 +292,7 @@ enum { VP_INIT = 0, VP_STEP = 1, VP_FINALISE = 2 };
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 __device__ __forceinline__ double warp_min(double v) {
@@ -168,13 +301,41 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
+struct Quad {
+    double a, b, c, m;  // three sums and one min
+};
+
+// all threads receive the block-wide result; fixed tree: lanes (butterfly), then warps in order
+__device__ __forceinline__ Quad block_reduce(Quad v, double (*sm)[4]) {
+    v.a = warp_sum(v.a);
+    v.b = warp_sum(v.b);
+    v.c = warp_sum(v.c);
+    v.m = warp_min(v.m);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();  // protect sm from the previous use
+    if (lane == 0) {
+        sm[wid][0] = v.a;
+        sm[wid][1] = v.b;
+        sm[wid][2] = v.c;
+        sm[wid][3] = v.m;
+    }
+    __syncthreads();
+    Quad r;
+    r.a = r.b = r.c = 0.0;
+    r.m = INFINITY;
+#pragma unroll
+    for (int i = 0; i < VP_NT / 32; ++i) {
+        r.a = __dadd_rn(r.a, sm[i][0]);
+        r.b = __dadd_rn(r.b, sm[i][1]);
+        r.c = __dadd_rn(r.c, sm[i][2]);
+        r.m = fmin(r.m, sm[i][3]);
+    }
+    return r;
+}
+
 // element-wise pieces, written with explicit round-to-nearest intrinsics so that nvcc cannot
 // contract them into FMAs: NumPy rounds t*d and x + (t*d) separately (projected_gradient.py:129).
 __device__ __forceinline__ double axpy_rn(double a, double x, double y) { return __dadd_rn(y, __dmul_rn(a, x)); }
-
-struct TailAcc {
-    double s, f, mt;
-};
 
 __device__ __forceinline__ double project_dir(double g, double x, double lb, double ub) {
     // projected_gradient.py:83-87
@@ -184,44 +345,50 @@ __device__ __forceinline__ double project_dir(double g, double x, double lb, dou
     return d;
 }
 
-__device__ __forceinline__ void tail_accumulate(TailAcc& a, double d, double x, double g, double q, double lb, double ub) {
-    a.s = __dadd_rn(a.s, __dmul_rn(d, d));
-    a.f = __dadd_rn(a.f, __dmul_rn(x, __dadd_rn(g, q)));
+__device__ __forceinline__ void tail_accumulate(Quad& a, double d, double x, double g, double q, double lb, double ub) {
+    a.a = __dadd_rn(a.a, __dmul_rn(d, d));
+    a.b = __dadd_rn(a.b, __dmul_rn(x, __dadd_rn(g, q)));
     // projected_gradient.py:111-114 (correctly rounded IEEE division, exact min)
-    if (d > 0.0) a.mt = fmin(a.mt, __ddiv_rn(__dsub_rn(ub, x), d));
-    else if (d < 0.0) a.mt = fmin(a.mt, __ddiv_rn(__dsub_rn(lb, x), d));
+    if (d > 0.0) a.m = fmin(a.m, __ddiv_rn(__dsub_rn(ub, x), d));
+    else if (d < 0.0) a.m = fmin(a.m, __ddiv_rn(__dsub_rn(lb, x), d));
 }
 
 template <int MODE>
-__global__ void __cluster_dims__(VP_CL, 1, 1) __launch_bounds__(VP_NT, 1) pg_vector_kernel(VecArgs a, long long k) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned crank = cluster.block_rank();
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    __shared__ double sm_a[VP_NT / 32], sm_b[VP_NT / 32], sm_c[VP_NT / 32];
-    __shared__ double sm_den;  // this CTA's partial of d'w, read by the peers through DSMEM
-    __shared__ double sm_peer[VP_CL];
-
+__global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const long long k) {
+    __shared__ double sm[VP_NT / 32][4];
     PGDeviceState* st = a.st;
-    if (st->done) return;  // set by an earlier kernel: uniform over the cluster
-
+    // `done` is raised inside the stop branch below, which every CTA of that launch takes anyway;
+    // a CTA that starts late and already sees the flag returns here instead -- same outcome.
+    if (*reinterpret_cast<volatile int*>(&st->done)) return;
+    const int tid = threadIdx.x;
     const long long n = a.n;
-    const long long chunk = (n + VP_CL - 1) / VP_CL;
-    const long long j0 = crank * chunk;
+    const long long chunk = (n + a.nctas - 1) / a.nctas;
+    const long long j0 = (long long)blockIdx.x * chunk;
     const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
+    const long long bpr = a.rpr / MV_R;  // row blocks per rank
 
     double t = 0.0;
     if (MODE != VP_INIT) {
-        // ---- finalise the state reached by the previous kernel: reductions in fixed CTA order
-        double s = 0.0, f2 = 0.0, mt = INFINITY;
-#pragma unroll
-        for (int r = 0; r < VP_CL; ++r) {
-            s = __dadd_rn(s, a.part_s[r]);
-            f2 = __dadd_rn(f2, a.part_f[r]);
-            mt = fmin(mt, a.part_mt[r]);
+        // ---- reductions over the whole problem, identical in every CTA
+        Quad r;
+        r.a = r.b = r.c = 0.0;
+        r.m = INFINITY;
+        if (tid < a.nctas) {
+            r.a = a.part[tid];
+            r.b = a.part[VP_MAXC + tid];
+            r.m = a.part[2 * VP_MAXC + tid];
         }
-        const double f = 0.5 * f2;
+        if (MODE == VP_STEP) {
+            const long long nblk = (n + MV_R - 1) / MV_R;
+            for (long long b = tid; b < nblk; b += VP_NT) {
+                const long long rk = b / bpr;
+                r.c = __dadd_rn(r.c, a.gathered[rk * a.stride + a.rpr + (b - rk * bpr)]);
+            }
+        }
+        r = block_reduce(r, sm);
+        const double s = r.a, f = 0.5 * r.b, mt = r.m, den = r.c;
         const double ng = sqrt(s);
-        if (crank == 0 && tid == 0) {
+        if (blockIdx.x == 0 && tid == 0) {
             if (k < a.hist_cap) {
                 a.hist_f[k] = f;
                 a.hist_ng[k] = ng;
@@ -236,7 +403,7 @@ __global__ void __cluster_dims__(VP_CL, 1, 1) __launch_bounds__(VP_NT, 1) pg_vec
         if (ng <= a.eps) stop = SVMB200_STATUS_OPTIMAL;          // projected_gradient.py:100-102
         else if (k >= a.max_iter) stop = SVMB200_STATUS_STOPPED;  // projected_gradient.py:104-106
         if (stop) {
-            if (crank == 0 && tid == 0) {
+            if (blockIdx.x == 0 && tid == 0) {
                 st->status = stop;
                 __threadfence();
                 st->done = 1;
@@ -244,47 +411,21 @@ __global__ void __cluster_dims__(VP_CL, 1, 1) __launch_bounds__(VP_NT, 1) pg_vec
             return;
         }
         if (MODE == VP_FINALISE) return;
-
-        // ---- den = d'Qd = d'w  (projected_gradient.py:121)
-        double dp = 0.0;
-        for (long long j = j0 + tid; j < j1; j += VP_NT) {
-            const double wj = a.w[j];
-            if (a.svr) {
-                // w_full = [w ; -w], d = [d1 ; d2]  =>  d'w_full = sum (d1_j - d2_j) w_j = sum u_j w_j
-                dp = __dadd_rn(dp, __dmul_rn(a.u[j], wj));
-            } else {
-                dp = __dadd_rn(dp, __dmul_rn(a.d[j], wj));
-            }
-        }
-        dp = warp_sum(dp);
-        if (lane == 0) sm_a[wid] = dp;
-        __syncthreads();
-        if (tid == 0) {
-            double v = 0.0;
-            for (int i = 0; i < VP_NT / 32; ++i) v = __dadd_rn(v, sm_a[i]);
-            sm_den = v;
-        }
-        cluster.sync();
-        if (tid < VP_CL) sm_peer[tid] = *cluster.map_shared_rank(&sm_den, tid);
-        __syncthreads();
-        double den = 0.0;
-#pragma unroll
-        for (int r = 0; r < VP_CL; ++r) den = __dadd_rn(den, sm_peer[r]);
-        // projected_gradient.py:123-127 ; -g'd equals d'd term by term, so the numerator is s
+        // projected_gradient.py:121-127 ; -g'd equals d'd term by term, so the numerator is s
         t = (den <= 1e-16) ? mt : fmin(__ddiv_rn(s, den), mt);
-        if (crank == 0 && tid == 0) {
+        if (blockIdx.x == 0 && tid == 0) {
             st->t = t;
             st->den = den;
         }
     }
 
     // ---- x += t d ; g += t w ; new direction, partial reductions for the next state
-    TailAcc acc;
-    acc.s = 0.0;
-    acc.f = 0.0;
-    acc.mt = INFINITY;
+    Quad acc;
+    acc.a = acc.b = acc.c = 0.0;
+    acc.m = INFINITY;
     for (long long j = j0 + tid; j < j1; j += VP_NT) {
-        const double wj = a.w[j];
+        const long long rk = j / a.rpr;
+        const double wj = a.gathered[rk * a.stride + (j - rk * a.rpr)];
         double x = a.x[j], q = a.q[j], g;
         if (MODE == VP_INIT) {
             g = __dadd_rn(wj, q);  // g = Q x0 + q  (opti/_base.py:291)
@@ -318,28 +459,12 @@ __global__ void __cluster_dims__(VP_CL, 1, 1) __launch_bounds__(VP_NT, 1) pg_vec
         }
         a.u[j] = uj;
     }
-    acc.s = warp_sum(acc.s);
-    acc.f = warp_sum(acc.f);
-    acc.mt = warp_min(acc.mt);
-    if (lane == 0) {
-        sm_a[wid] = acc.s;
-        sm_b[wid] = acc.f;
-        sm_c[wid] = acc.mt;
-    }
-    __syncthreads();
+    acc = block_reduce(acc, sm);
     if (tid == 0) {
-        double s = 0.0, f = 0.0, mt = INFINITY;
-        for (int i = 0; i < VP_NT / 32; ++i) {
-            s = __dadd_rn(s, sm_a[i]);
-            f = __dadd_rn(f, sm_b[i]);
-            mt = fmin(mt, sm_c[i]);
-        }
-        a.part_s[crank] = s;
-        a.part_f[crank] = f;
-        a.part_mt[crank] = mt;
-        if (crank == 0 && MODE != VP_INIT) st->iter = k + 1;
+        a.part[blockIdx.x] = acc.a;
+        a.part[VP_MAXC + blockIdx.x] = acc.b;
+        a.part[2 * VP_MAXC + blockIdx.x] = acc.m;
     }
-    if (MODE == VP_STEP) cluster.sync();  // keep sm_den alive until every peer has read it
 }
 
 // ------------------------------------------------------------------------------------------ driver
@@ -352,7 +477,9 @@ struct svmb200_pg {
     int64_t max_iter = 1000;
     int64_t hist_cap = 0;
     // device buffers
-    double *x = nullptr, *g = nullptr, *d = nullptr, *u = nullptr, *w = nullptr;
+    double *x = nullptr, *g = nullptr, *d = nullptr, *u = nullptr, *w = nullptr;  // w: gathered [P][stride]
+    int64_t stride = 0;  // rows_per_rank results + rows_per_rank / MV_R shares of u'w
+    int nctas = 1;
     double *q = nullptr, *lb = nullptr, *ub = nullptr;
     double *part = nullptr, *hist_f = nullptr, *hist_ng = nullptr;
     PGDeviceState* st = nullptr;
@@ -365,6 +492,7 @@ struct svmb200_pg {
     int64_t last_passes = 0;
     bool profile = false;
     std::vector<cudaEvent_t> mv_ev;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // own events: the context's pair belongs to svmb200_timer_*
 };
 
 static VecArgs make_vec_args(svmb200_pg* pg) {
@@ -376,10 +504,11 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
     a.q = pg->q;
     a.lb = pg->lb;
     a.ub = pg->ub;
-    a.w = pg->w;
-    a.part_s = pg->part;
-    a.part_f = pg->part + VP_CL;
-    a.part_mt = pg->part + 2 * VP_CL;
+    a.gathered = pg->w;
+    a.rpr = pg->rows_per_rank;
+    a.stride = pg->stride;
+    a.part = pg->part;
+    a.nctas = pg->nctas;
     a.hist_f = pg->hist_f;
     a.hist_ng = pg->hist_ng;
     a.hist_cap = pg->hist_cap;
@@ -394,7 +523,7 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
 template <int MODE>
 static int launch_vec(svmb200_pg* pg, long long k) {
     VecArgs a = make_vec_args(pg);
-    pg_vector_kernel<MODE><<<VP_CL, VP_NT, 0, pg->ctx->stream>>>(a, k);
+    pg_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
     pg->ctx->launches++;
     SVM_CUDA(cudaGetLastError());
     return SVMB200_OK;
@@ -409,13 +538,15 @@ static int pg_product(svmb200_pg* pg, bool timed) {
         SVM_CUDA(cudaEventCreate(&e1));
         SVM_CUDA(cudaEventRecord(e0, ctx->stream));
     }
-    SVM_TRY(svm_launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, pg->w + pg->row0, &pg->st->done));
+    double* wshard = pg->w + (size_t)ctx->rank * pg->stride;
+    SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wshard, pg->u + pg->row0, wshard + pg->rows_per_rank,
+                          &pg->st->done));
     if (e1) {
         SVM_CUDA(cudaEventRecord(e1, ctx->stream));
         pg->mv_ev.push_back(e0);
         pg->mv_ev.push_back(e1);
     }
-    if (ctx->nranks > 1) SVM_TRY(svm_comm_allgather(ctx, pg->w, pg->rows_per_rank));
+    if (ctx->nranks > 1) SVM_TRY(svm_comm_allgather(ctx, pg->w, pg->stride));
     pg->last_passes++;
     return SVMB200_OK;
 }
@@ -424,6 +555,8 @@ extern "C" int svmb200_pg_destroy(svmb200_pg* pg) {
     if (!pg) return SVMB200_OK;
     if (pg->ctx) cudaSetDevice(pg->ctx->device);
     for (cudaEvent_t e : pg->mv_ev) cudaEventDestroy(e);
+    if (pg->ev0) cudaEventDestroy(pg->ev0);
+    if (pg->ev1) cudaEventDestroy(pg->ev1);
     double* bufs[] = {pg->x, pg->g, pg->d, pg->u, pg->w, pg->q, pg->lb, pg->ub, pg->part, pg->hist_f, pg->hist_ng};
     for (double* b : bufs)
         if (b) cudaFree(b);
@@ -445,15 +578,11 @@ extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
     SVM_CHECK_ARG(hessian == SVMB200_HESSIAN_PLAIN || hessian == SVMB200_HESSIAN_SVR, "bad hessian layout");
     SVM_CHECK_ARG(max_iter > 0, "max_iter must be > 0");  // opti/_base.py:73-74
     const int P = ctx->nranks;
-    const int64_t rpr = (n + P - 1) / P;
-    if (P > 1) {
-        const int64_t exp_row0 = (int64_t)ctx->rank * rpr;
-        int64_t exp_rows = n - exp_row0;
-        if (exp_rows > rpr) exp_rows = rpr;
-        if (exp_rows < 0) exp_rows = 0;
-        SVM_CHECK_ARG(row0 == exp_row0 && nrows == exp_rows, "row shard does not match ceil(n/nranks) partition");
-    } else {
-        SVM_CHECK_ARG(row0 == 0 && nrows == n, "single-rank solve needs the whole matrix");
+    const int64_t rpr = rows_per_rank(n, P);
+    {
+        int64_t exp_row0 = 0, exp_rows = 0;
+        SVM_TRY(svmb200_shard_rows(n, ctx->rank, P, &exp_row0, &exp_rows));
+        SVM_CHECK_ARG(row0 == exp_row0 && nrows == exp_rows, "row shard does not match svmb200_shard_rows");
     }
     svmb200_pg* pg = new svmb200_pg();
     pg->ctx = ctx;
@@ -465,6 +594,10 @@ extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
     pg->svr = hessian == SVMB200_HESSIAN_SVR;
     pg->nvars = pg->svr ? 2 * n : n;
     pg->rows_per_rank = rpr;
+    pg->stride = rpr + rpr / MV_R;
+    pg->nctas = (int)((n + VP_ELEMS - 1) / VP_ELEMS);
+    if (pg->nctas > VP_MAXC) pg->nctas = VP_MAXC;
+    if (pg->nctas < 1) pg->nctas = 1;
     pg->eps = eps;
     pg->max_iter = max_iter;
     pg->hist_cap = max_iter + 1 < (1ll << 24) ? max_iter + 1 : (1ll << 24);
@@ -489,16 +622,19 @@ extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
     PG_CUDA(cudaMalloc(&pg->lb, nv));
     PG_CUDA(cudaMalloc(&pg->ub, nv));
     PG_CUDA(cudaMalloc(&pg->u, (size_t)ld * sizeof(double)));
-    PG_CUDA(cudaMalloc(&pg->w, (size_t)(rpr * P) * sizeof(double)));
-    PG_CUDA(cudaMalloc(&pg->part, 3 * VP_CL * sizeof(double)));
+    PG_CUDA(cudaMalloc(&pg->w, (size_t)(pg->stride * P) * sizeof(double)));
+    PG_CUDA(cudaMalloc(&pg->part, 3 * VP_MAXC * sizeof(double)));
     PG_CUDA(cudaMalloc(&pg->hist_f, (size_t)pg->hist_cap * sizeof(double)));
     PG_CUDA(cudaMalloc(&pg->hist_ng, (size_t)pg->hist_cap * sizeof(double)));
     PG_CUDA(cudaMalloc(&pg->st, sizeof(PGDeviceState)));
     PG_CUDA(cudaMallocHost(&pg->st_host, sizeof(PGDeviceState)));
+    PG_CUDA(cudaEventCreate(&pg->ev0));
+    PG_CUDA(cudaEventCreate(&pg->ev1));
     cudaStream_t s = ctx->stream;
     PG_CUDA(cudaMemsetAsync(pg->st, 0, sizeof(PGDeviceState), s));
     PG_CUDA(cudaMemsetAsync(pg->u, 0, (size_t)ld * sizeof(double), s));
-    PG_CUDA(cudaMemsetAsync(pg->w, 0, (size_t)(rpr * P) * sizeof(double), s));
+    PG_CUDA(cudaMemsetAsync(pg->w, 0, (size_t)(pg->stride * P) * sizeof(double), s));
+    PG_CUDA(cudaMemsetAsync(pg->part, 0, 3 * VP_MAXC * sizeof(double), s));
     PG_CUDA(cudaMemsetAsync(pg->d, 0, nv, s));
     PG_CUDA(cudaMemsetAsync(pg->g, 0, nv, s));
     // bounds / start point: opti/constrained/_base.py:61-65 (lb = 0, x0 = (lb+ub)/2)
@@ -538,7 +674,7 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
     pg->mv_ev.clear();
     pg->last_passes = 0;
     pg->last_ms = pg->last_mv_ms = 0.f;
-    SVM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    SVM_CUDA(cudaEventRecord(pg->ev0, ctx->stream));
     if (!pg->finished) {
         const bool to_end = max_new < 0;
         int64_t budget = to_end ? (pg->max_iter - pg->k_next) : max_new;
@@ -562,9 +698,9 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
             SVM_TRY(pg_poll(pg));
         }
     }
-    SVM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    SVM_CUDA(cudaEventSynchronize(ctx->ev1));
-    SVM_CUDA(cudaEventElapsedTime(&pg->last_ms, ctx->ev0, ctx->ev1));
+    SVM_CUDA(cudaEventRecord(pg->ev1, ctx->stream));
+    SVM_CUDA(cudaEventSynchronize(pg->ev1));
+    SVM_CUDA(cudaEventElapsedTime(&pg->last_ms, pg->ev0, pg->ev1));
     for (size_t i = 0; i + 1 < pg->mv_ev.size(); i += 2) {
         float ms = 0.f;
         SVM_CUDA(cudaEventElapsedTime(&ms, pg->mv_ev[i], pg->mv_ev[i + 1]));
@@ -631,7 +767,12 @@ extern "C" int svmb200_masked_product(svmb200_ctx* ctx, const double* dQ, int64_
     SVM_CHECK_ARG(dQ && beta_host && v_host, "null argument");
     SVM_CHECK_ARG(ld >= n && ld % 2 == 0, "ld must be >= n and even");
     const int P = ctx->nranks;
-    const int64_t rpr = (n + P - 1) / P;
+    const int64_t rpr = rows_per_rank(n, P);
+    {
+        int64_t exp_row0 = 0, exp_rows = 0;
+        SVM_TRY(svmb200_shard_rows(n, ctx->rank, P, &exp_row0, &exp_rows));
+        SVM_CHECK_ARG(row0 == exp_row0 && nrows == exp_rows, "row shard does not match svmb200_shard_rows");
+    }
     double *du = nullptr, *dw = nullptr;
     SVM_CUDA(cudaMalloc(&du, (size_t)ld * sizeof(double)));
     if (cudaMalloc(&dw, (size_t)(rpr * P) * sizeof(double)) != cudaSuccess) {
@@ -644,7 +785,7 @@ extern "C" int svmb200_masked_product(svmb200_ctx* ctx, const double* dQ, int64_
     cudaMemsetAsync(du, 0, (size_t)ld * sizeof(double), s);
     cudaMemsetAsync(dw, 0, (size_t)(rpr * P) * sizeof(double), s);
     cudaMemcpyAsync(du, beta_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s);
-    rc = svm_launch_matvec(ctx, dQ, nrows, ld, du, dw + row0, nullptr);
+    rc = svm_launch_matvec(ctx, dQ, nrows, ld, du, dw + (size_t)ctx->rank * rpr, nullptr);
     if (rc == SVMB200_OK && P > 1) rc = svm_comm_allgather(ctx, dw, rpr);
     if (rc == SVMB200_OK) {
         cudaMemcpyAsync(v_host, dw, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);

@@ -111,8 +111,10 @@ class SVM(BaseEstimator):
     def _build_hessian(self, X, signs, layout, X_device=None):
         """K1: Gram matrix + bias (+ label signs) straight into this rank's row shard in HBM.
         ``X_device`` (a DeviceMatrix already holding X) skips the host->device copy of X."""
+        import time
         ctx = default_context()
         n, d = X.shape
+        t0 = time.perf_counter()
         kid, gamma, coef0, degree = self.kernel.gram_spec(X)
         dX = X_device if X_device is not None else ctx.upload_matrix(X)
         dS = ctx.upload_vector(signs) if signs is not None else None
@@ -125,13 +127,18 @@ class SVM(BaseEstimator):
             dX.release()
         if dS is not None:
             dS.release()
+        self.fit_times_ = {'gram_s': time.perf_counter() - t0}  # gamma + upload + Gram kernel (wall clock)
         return H
 
     def _solve(self, solver_cls, ub):
         solver = solver_cls(quad=self.obj, ub=ub, tol=self.tol, max_iter=self.max_iter,
                             callback=self._store_train_info, verbose=self.verbose)
         solver.profile = bool(getattr(self, 'profile_matvec', False))  # CUDA events around every K2 launch
-        return solver.minimize()
+        import time
+        t0 = time.perf_counter()
+        solver.minimize()
+        self.fit_times_['solve_s'] = time.perf_counter() - t0
+        return solver
 
     def decision_function(self, X):
         """ml/svm/_base.py:284-287.  ``gamma='scale'`` is resolved from ``support_vectors_`` (the first

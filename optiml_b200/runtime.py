@@ -29,17 +29,36 @@ class Context:
         self.handle = h
         self.device = int(device)
         self.rank, self.nranks = 0, 1
+        # large device buffers (the Hessian shard) are recycled between fits: cudaMalloc/cudaFree of
+        # tens of GB costs ~0.1 s each, more than the Gram build itself
+        self._pool = {}
         self._finalizer = weakref.finalize(self, N.load_library().svmb200_ctx_destroy, h)
 
     # ---------------------------------------------------------------- memory
+    POOL_MIN_BYTES = 64 << 20
+
     def malloc(self, nbytes):
+        cached = self._pool.get(int(nbytes))
+        if cached:
+            return cached.pop()
         p = C.c_void_p()
         N.call('svmb200_malloc', self.handle, int(nbytes), C.byref(p))
         return p.value
 
-    def free(self, dptr):
-        if dptr:
-            N.call('svmb200_free', self.handle, C.c_void_p(dptr))
+    def free(self, dptr, nbytes=0):
+        if not dptr:
+            return
+        if nbytes >= self.POOL_MIN_BYTES and sum(len(v) for v in self._pool.values()) < 2:
+            self._pool.setdefault(int(nbytes), []).append(dptr)  # keep for the next fit
+            return
+        N.call('svmb200_free', self.handle, C.c_void_p(dptr))
+
+    def trim(self):
+        """Return pooled buffers to the driver."""
+        for lst in self._pool.values():
+            for dptr in lst:
+                N.call('svmb200_free', self.handle, C.c_void_p(dptr))
+        self._pool = {}
 
     def memset(self, dptr, value, nbytes):
         N.call('svmb200_memset', self.handle, C.c_void_p(dptr), int(value), int(nbytes))
@@ -88,7 +107,7 @@ class Context:
         return buf.raw
 
     def row_shard(self, n):
-        """Rows [row0, row0+nrows) of an n-row matrix owned by this rank: ceil(n/P) rows per rank."""
+        """Rows [row0, row0+nrows) of an n-row matrix owned by this rank."""
         return shard_rows(n, self.rank, self.nranks)
 
     # ---------------------------------------------------------------- matrices
@@ -115,9 +134,10 @@ class Context:
 
 
 def shard_rows(n, rank, nranks):
-    rpr = -(-int(n) // int(nranks))
-    row0 = min(int(n), rank * rpr)
-    return row0, max(0, min(rpr, int(n) - row0))
+    """(row0, nrows) of rank's shard: the partition of svmb200_shard_rows (single source of truth)."""
+    r0, nr = C.c_int64(0), C.c_int64(0)
+    N.call('svmb200_shard_rows', int(n), int(rank), int(nranks), C.byref(r0), C.byref(nr))
+    return int(r0.value), int(nr.value)
 
 
 class DeviceMatrix:
@@ -127,7 +147,7 @@ class DeviceMatrix:
         self.ctx, self.rows, self.cols, self.ld = ctx, int(rows), int(cols), int(ld)
         self.nbytes = max(self.rows, 1) * self.ld * 8
         self.dptr = ctx.malloc(self.nbytes)
-        self._finalizer = weakref.finalize(self, _free_quiet, ctx, self.dptr)
+        self._finalizer = weakref.finalize(self, _free_quiet, ctx, self.dptr, self.nbytes)
 
     def release(self):
         self._finalizer()
@@ -139,9 +159,9 @@ class DeviceMatrix:
         return np.ascontiguousarray(buf[:, :self.cols])
 
 
-def _free_quiet(ctx, dptr):
+def _free_quiet(ctx, dptr, nbytes=0):
     try:
-        ctx.free(dptr)
+        ctx.free(dptr, nbytes)
     except Exception:  # interpreter shutdown / context already gone
         pass
 
