@@ -232,16 +232,20 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    iters_total, mv_ms, mv_launches, pg_ms = 0, 0.0, 0, 0.0
+    iters_total, mv_ms, mv_launches, pg_ms, comm_ms, vec_ms, step_s = 0, 0.0, 0, 0.0, 0.0, 0.0, []
     ctx.timer_start()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
+        ts = time.perf_counter()
         m = make_model().fit(X, y, X_device=dX)
         iters_total += m.optimizer.iter
         mv_ms += m.optimizer.matvec_ms
+        comm_ms += m.optimizer.comm_ms
+        vec_ms += m.optimizer.vector_ms
         mv_launches += m.optimizer.q_passes
         pg_ms += m.optimizer.device_ms
         m.obj.release()
+        step_s.append(round(time.perf_counter() - ts, 4))
     barrier()
     dev_ms = ctx.timer_stop_ms()
     wall_s = time.perf_counter() - t_wall
@@ -293,8 +297,11 @@ def run_b200(args):
         'hbm_gbps_pg_loop': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9,
         'frac_of_8TBps_nominal': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9 / world / 8000.0,
         'iters_per_step': iters_total / args.steps, 'status': status, 'f_x': fx, 'n_sv': nsv,
-        'wall_s_value_leg': wall_s,
-        'roofline': {'bound': 'hbm', 'kernel': 'matvec_rows_kernel (K2)', 'achieved': achieved, 'peak': peak,
+        'wall_s_value_leg': wall_s, 'step_wall_s': step_s,
+        'per_iteration_us': {'matvec': 1e3 * mv_ms / max(mv_launches, 1), 'allgather': 1e3 * comm_ms / max(mv_launches, 1),
+                             'vector_phase': 1e3 * vec_ms / max(mv_launches, 1),
+                             'pg_loop_total': 1e3 * pg_ms / max(mv_launches, 1)},
+        'roofline': {'bound': 'hbm', 'kernel': 'matvec_seg_kernel (K2)', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                      'bytes_per_launch': bytes_per_launch, 'avg_launch_ms': mv_avg_ms, 'launches_timed': mv_launches},
         'e2e': {'value': e2e_iters / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),

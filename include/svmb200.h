@@ -82,7 +82,7 @@ int svmb200_comm_unique_id(void* id128);
 int svmb200_comm_init(svmb200_ctx* ctx, const void* id128, int rank, int nranks);
 int svmb200_comm_destroy(svmb200_ctx* ctx);
 /* Row partition used by every sharded entry point: rank r owns rows [row0, row0+nrows) of an n-row
- * matrix, ceil(n/nranks) rounded up to a multiple of 8 rows per rank (the last ranks may get fewer,
+ * matrix, ceil(n/nranks) rounded up to a multiple of 64 rows per rank (the last ranks may get fewer,
  * possibly none).  Aligned shard boundaries keep every reduction shape independent of nranks. */
 int svmb200_shard_rows(int64_t n, int rank, int nranks, int64_t* row0, int64_t* nrows);
 
@@ -133,8 +133,10 @@ int svmb200_pg_state(svmb200_pg* pg, double* x_host, double* g_host, double* f, 
 int svmb200_pg_history(svmb200_pg* pg, double* f_hist_host, double* ng_hist_host, int64_t* count);
 /* timing of the last svmb200_pg_run: device milliseconds and number of Q passes (matvec launches) */
 int svmb200_pg_stats(svmb200_pg* pg, float* ms, int64_t* passes, float* matvec_ms);
-/* when on, every K2 launch of svmb200_pg_run is bracketed by CUDA events (matvec_ms above) */
+/* when on, every iteration of svmb200_pg_run is bracketed by CUDA events: K2 (matvec_ms above),
+ * the all-gather and K3; svmb200_pg_stats_ex returns the three sums of the last run */
 int svmb200_pg_set_profile(svmb200_pg* pg, int on);
+int svmb200_pg_stats_ex(svmb200_pg* pg, float* matvec_ms, float* comm_ms, float* vector_ms);
 int svmb200_pg_device_x(svmb200_pg* pg, double** dx); /* device pointer of the iterate (nvars)     */
 int svmb200_pg_destroy(svmb200_pg* pg);
 

@@ -53,6 +53,7 @@ PROTOTYPES = {
     'svmb200_pg_history': [c_vp, c_vp, c_vp, C.POINTER(i64)],
     'svmb200_pg_stats': [c_vp, C.POINTER(C.c_float), C.POINTER(i64), C.POINTER(C.c_float)],
     'svmb200_pg_set_profile': [c_vp, C.c_int],
+    'svmb200_pg_stats_ex': [c_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)],
     'svmb200_pg_device_x': [c_vp, C.POINTER(c_vp)],
     'svmb200_pg_destroy': [c_vp],
     'svmb200_masked_product': [c_vp, c_vp, i64, i64, i64, i64, c_vp, c_vp],

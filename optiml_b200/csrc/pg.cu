@@ -17,27 +17,29 @@
 // ------------------------------------------------------------------------------------------ K2
 // Work item = MV_R consecutive rows x one column segment of MV_SEG doubles.  Every thread keeps
 // MV_R*MV_U independent 128-bit streaming loads in flight (L1 no-allocate: Q is touched once per
-// pass); the vector operand comes through L1/L2.  The CTA that finishes a row block last (atomic
-// ticket) adds the segment partials in segment order, stores w and the block's share of u'w.
-// Segmenting keeps the grid at >= 12 waves even for a 1/8 row shard (tail effect) and keeps every
-// work item at 256 KB.
+// pass); the vector operand comes through L1/L2.  Rows are grouped by MV_GROUP (64): the CTA that
+// finishes a group last (one atomic ticket per group) adds the segment partials of its 64 rows in
+// segment order, stores w and the group's share of u'w.  Segmenting keeps the grid at >= 20 waves
+// even for a 1/8 row shard (tail effect) and every work item at 256 KB.
 constexpr int MV_R = 4;
 constexpr int MV_NT = 256;
 constexpr int MV_U = 4;
 constexpr int MV_SEG = 8192;
 constexpr int MV_MINB = 3;
-constexpr int ROW_ALIGN = 8;  // row shards start on multiples of this (>= MV_R), see svmb200_shard_rows
+constexpr int MV_GROUP = 64;            // rows per group (one u'w share per group)
+constexpr int ROW_ALIGN = MV_GROUP;     // row shards start on multiples of this, see svmb200_shard_rows
+constexpr int MV_BPG = MV_GROUP / MV_R;  // row blocks per group
 
 struct MatvecArgs {
     const double* Q;        // nrows x ld shard
     long long ld, nrows;
     const double* u;        // ld entries, zero beyond n
     double* w;              // nrows results
-    double* wpart;          // nseg x nrows_pad segment partials (unused when nseg == 1)
+    double* wpart;          // nseg x nrows_pad segment partials
     long long nrows_pad;
-    unsigned* tickets;      // one per row block, zero on entry, zero again on exit
+    unsigned* tickets;      // one per group, zero on entry, zero again on exit
     const double* u_rows;   // u at this shard's rows (u + row0), or null
-    double* denpart;        // one per row block: sum_r u_rows[r] * w[r], or null
+    double* denpart;        // one per group: sum over the group's rows of u_rows[r] * w[r], or null
     int nseg;
     const int* done;
 };
@@ -51,104 +53,110 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
 __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const MatvecArgs a) {
     if (a.done != nullptr && *a.done) return;
     constexpr int R = MV_R, NT = MV_NT, U = MV_U;
-    const long long rb = blockIdx.x / a.nseg;
-    const int seg = blockIdx.x % a.nseg;
-    const long long row_base = rb * R;
-    const long long c0 = (long long)seg * MV_SEG;
-    long long c1 = c0 + MV_SEG;
-    if (c1 > a.ld) c1 = a.ld;
-    const int nvec = (int)((c1 - c0) >> 1);
-    const double2* __restrict__ u2 = reinterpret_cast<const double2*>(a.u + c0);
-    const double2* rows[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        long long rr = row_base + r;
-        if (rr >= a.nrows) rr = a.nrows - 1;  // clamp: read a valid row, result discarded below
-        rows[r] = reinterpret_cast<const double2*>(a.Q + rr * a.ld + c0);
-    }
-    double acc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.0;
-
-    int c = threadIdx.x;
-    for (; c + (U - 1) * NT < nvec; c += U * NT) {
-        double2 qv[U][R];
-        double2 uv[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) qv[j][r] = ld_stream_f64x2(rows[r] + c + j * NT);
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) uv[j] = __ldg(u2 + c + j * NT);
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                acc[r] = fma(qv[j][r].x, uv[j].x, acc[r]);
-                acc[r] = fma(qv[j][r].y, uv[j].y, acc[r]);
-            }
-        }
-    }
-    for (; c < nvec; c += NT) {
-        double2 qv[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) qv[r] = ld_stream_f64x2(rows[r] + c);
-        const double2 uv = __ldg(u2 + c);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            acc[r] = fma(qv[r].x, uv.x, acc[r]);
-            acc[r] = fma(qv[r].y, uv.y, acc[r]);
-        }
-    }
-    // warp butterfly, then fixed-order sum over warps
+    const unsigned items_per_group = (unsigned)(MV_BPG * a.nseg);
+    const unsigned group = blockIdx.x / items_per_group;
+    const unsigned within = blockIdx.x - group * items_per_group;
+    const unsigned rb_in_group = within / (unsigned)a.nseg;
+    const int seg = (int)(within - rb_in_group * (unsigned)a.nseg);
+    const long long row_base = (long long)group * MV_GROUP + (long long)rb_in_group * R;
     __shared__ double red[NT / 32][R];
     __shared__ unsigned is_last;
+
+    if (row_base < a.nrows) {
+        const long long c0 = (long long)seg * MV_SEG;
+        long long c1 = c0 + MV_SEG;
+        if (c1 > a.ld) c1 = a.ld;
+        const int nvec = (int)((c1 - c0) >> 1);
+        const double2* __restrict__ u2 = reinterpret_cast<const double2*>(a.u + c0);
+        const double2* rows[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        double v = acc[r];
+        for (int r = 0; r < R; ++r) {
+            long long rr = row_base + r;
+            if (rr >= a.nrows) rr = a.nrows - 1;  // clamp: read a valid row, result discarded below
+            rows[r] = reinterpret_cast<const double2*>(a.Q + rr * a.ld + c0);
+        }
+        double acc[R];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        acc[r] = v;
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) {
+        for (int r = 0; r < R; ++r) acc[r] = 0.0;
+
+        int c = threadIdx.x;
+        for (; c + (U - 1) * NT < nvec; c += U * NT) {
+            double2 qv[U][R];
+            double2 uv[U];
 #pragma unroll
-        for (int r = 0; r < R; ++r) red[wid][r] = acc[r];
-    }
-    __syncthreads();
-    double v = 0.0;
-    const long long rr = row_base + threadIdx.x;  // meaningful for threadIdx.x < R
-    if (threadIdx.x < R) {
+            for (int j = 0; j < U; ++j) {
 #pragma unroll
-        for (int k = 0; k < NT / 32; ++k) v += red[k][threadIdx.x];
-    }
-    if (a.nseg > 1) {
-        if (threadIdx.x < R && rr < a.nrows) a.wpart[(size_t)seg * a.nrows_pad + rr] = v;
-        __threadfence();
+                for (int r = 0; r < R; ++r) qv[j][r] = ld_stream_f64x2(rows[r] + c + j * NT);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) uv[j] = __ldg(u2 + c + j * NT);
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    acc[r] = fma(qv[j][r].x, uv[j].x, acc[r]);
+                    acc[r] = fma(qv[j][r].y, uv[j].y, acc[r]);
+                }
+            }
+        }
+        for (; c < nvec; c += NT) {
+            double2 qv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) qv[r] = ld_stream_f64x2(rows[r] + c);
+            const double2 uv = __ldg(u2 + c);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acc[r] = fma(qv[r].x, uv.x, acc[r]);
+                acc[r] = fma(qv[r].y, uv.y, acc[r]);
+            }
+        }
+        // warp butterfly, then fixed-order sum over warps
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double v = acc[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[r] = v;
+        }
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) red[wid][r] = acc[r];
+        }
         __syncthreads();
-        if (threadIdx.x == 0) is_last = (atomicInc(&a.tickets[rb], (unsigned)(a.nseg - 1)) == (unsigned)(a.nseg - 1));
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-        if (threadIdx.x < R && rr < a.nrows) {
-            v = 0.0;
-            for (int s = 0; s < a.nseg; ++s) v += __ldcg(&a.wpart[(size_t)s * a.nrows_pad + rr]);
+        if (threadIdx.x < R && row_base + threadIdx.x < a.nrows) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < NT / 32; ++k) v += red[k][threadIdx.x];
+            a.wpart[(size_t)seg * a.nrows_pad + row_base + threadIdx.x] = v;
         }
     }
-    if (threadIdx.x < 32) {
+    // ---- one ticket per group; the last arriver combines the group
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicInc(&a.tickets[group], items_per_group - 1) == items_per_group - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < MV_GROUP) {
+        const long long rr = (long long)group * MV_GROUP + threadIdx.x;
         double dv = 0.0;
-        if (threadIdx.x < R && rr < a.nrows) {
+        if (rr < a.nrows) {
+            double v = 0.0;
+            for (int s = 0; s < a.nseg; ++s) v += __ldcg(&a.wpart[(size_t)s * a.nrows_pad + rr]);
             a.w[rr] = v;
             if (a.u_rows != nullptr) dv = __dmul_rn(a.u_rows[rr], v);
         }
         if (a.denpart != nullptr) {
-            // ((p0 + p1) + p2) + p3 : fixed order over the rows of the block
-            double tot = __shfl_sync(0xffffffffu, dv, 0);
+            // fixed tree over the 64 rows: butterfly inside each warp, then warp 0 + warp 1
 #pragma unroll
-            for (int r = 1; r < R; ++r) tot = __dadd_rn(tot, __shfl_sync(0xffffffffu, dv, r));
-            if (threadIdx.x == 0) a.denpart[rb] = tot;
+            for (int o = 16; o > 0; o >>= 1) dv = __dadd_rn(dv, __shfl_xor_sync(0xffffffffu, dv, o));
+            if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = dv;
         }
+    }
+    if (a.denpart != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) a.denpart[group] = __dadd_rn(red[0][0], red[0][1]);
     }
 }
 
@@ -161,8 +169,8 @@ struct MatvecScratch {
 static int matvec_scratch_reserve(svmb200_ctx* ctx, MatvecScratch& s, int64_t nrows, int64_t ld) {
     const int nseg = (int)((ld + MV_SEG - 1) / MV_SEG);
     const size_t nrows_pad = (size_t)round_up64(nrows, 16);
-    const size_t need_w = nseg > 1 ? (size_t)nseg * nrows_pad : 0;
-    const size_t need_t = (size_t)((nrows + MV_R - 1) / MV_R);
+    const size_t need_w = (size_t)nseg * nrows_pad;
+    const size_t need_t = (size_t)((nrows + MV_GROUP - 1) / MV_GROUP);
     if (need_w > s.wpart_elems) {
         SVM_CUDA(cudaStreamSynchronize(ctx->stream));
         if (s.wpart) cudaFree(s.wpart);
@@ -210,12 +218,13 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
     a.denpart = ddenpart;
     a.nseg = (int)((ld + MV_SEG - 1) / MV_SEG);
     a.done = d_done;
-    const int64_t nrb = (nrows + MV_R - 1) / MV_R;
-    if (nrb * a.nseg >= (1ll << 31)) {
+    const int64_t ngroups = (nrows + MV_GROUP - 1) / MV_GROUP;
+    const int64_t nitems = ngroups * MV_BPG * a.nseg;
+    if (nitems >= (1ll << 31)) {
         svmb200_set_error("matvec: grid too large");
         return SVMB200_ERR_ARG;
     }
-    matvec_seg_kernel<<<(unsigned)(nrb * a.nseg), MV_NT, 0, ctx->stream>>>(a);
+    matvec_seg_kernel<<<(unsigned)nitems, MV_NT, 0, ctx->stream>>>(a);
     ctx->launches++;
     SVM_CUDA(cudaGetLastError());
     return SVMB200_OK;
@@ -275,7 +284,7 @@ struct PGDeviceState {
 struct VecArgs {
     double *x, *g, *d, *u;
     const double *q, *lb, *ub;
-    const double* gathered;  // per rank: [rpr results w | rpr/MV_R shares of u'w]
+    const double* gathered;  // per rank: [rpr results w | rpr/MV_GROUP shares of u'w]
     long long rpr, stride;
     double* part;            // 3 x VP_MAXC : |d|^2, x'(g+q), max_t per CTA
     double *hist_f, *hist_ng;
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     const long long chunk = (n + a.nctas - 1) / a.nctas;
     const long long j0 = (long long)blockIdx.x * chunk;
     const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
-    const long long bpr = a.rpr / MV_R;  // row blocks per rank
+    const unsigned rpr = (unsigned)a.rpr, gpr = rpr / MV_GROUP;  // rows / groups per rank (n < 2^31)
 
     double t = 0.0;
     if (MODE != VP_INIT) {
@@ -379,10 +388,18 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
             r.m = a.part[2 * VP_MAXC + tid];
         }
         if (MODE == VP_STEP) {
-            const long long nblk = (n + MV_R - 1) / MV_R;
-            for (long long b = tid; b < nblk; b += VP_NT) {
-                const long long rk = b / bpr;
-                r.c = __dadd_rn(r.c, a.gathered[rk * a.stride + a.rpr + (b - rk * bpr)]);
+            // u'w: one share per 64-row group, thread-strided in global group order
+            const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
+            for (unsigned b0 = tid; b0 < ngrp; b0 += 4 * VP_NT) {
+                double v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned b = b0 + e * VP_NT;
+                    const unsigned rk = b / gpr;
+                    v[e] = b < ngrp ? a.gathered[(size_t)rk * a.stride + rpr + (b - rk * gpr)] : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) r.c = __dadd_rn(r.c, v[e]);
             }
         }
         r = block_reduce(r, sm);
@@ -424,8 +441,8 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     acc.a = acc.b = acc.c = 0.0;
     acc.m = INFINITY;
     for (long long j = j0 + tid; j < j1; j += VP_NT) {
-        const long long rk = j / a.rpr;
-        const double wj = a.gathered[rk * a.stride + (j - rk * a.rpr)];
+        const unsigned rk = (unsigned)j / rpr;
+        const double wj = a.gathered[(size_t)rk * a.stride + ((unsigned)j - rk * rpr)];
         double x = a.x[j], q = a.q[j], g;
         if (MODE == VP_INIT) {
             g = __dadd_rn(wj, q);  // g = Q x0 + q  (opti/_base.py:291)
@@ -478,7 +495,7 @@ struct svmb200_pg {
     int64_t hist_cap = 0;
     // device buffers
     double *x = nullptr, *g = nullptr, *d = nullptr, *u = nullptr, *w = nullptr;  // w: gathered [P][stride]
-    int64_t stride = 0;  // rows_per_rank results + rows_per_rank / MV_R shares of u'w
+    int64_t stride = 0;  // rows_per_rank results + rows_per_rank / MV_GROUP shares of u'w
     int nctas = 1;
     double *q = nullptr, *lb = nullptr, *ub = nullptr;
     double *part = nullptr, *hist_f = nullptr, *hist_ng = nullptr;
@@ -488,7 +505,7 @@ struct svmb200_pg {
     int64_t k_next = 0;     // next iteration whose STEP kernel has not been enqueued
     bool finished = false;  // device reported done
     // stats of the last run
-    float last_ms = 0.f, last_mv_ms = 0.f;
+    float last_ms = 0.f, last_mv_ms = 0.f, last_comm_ms = 0.f, last_vec_ms = 0.f;
     int64_t last_passes = 0;
     bool profile = false;
     std::vector<cudaEvent_t> mv_ev;
@@ -532,21 +549,24 @@ static int launch_vec(svmb200_pg* pg, long long k) {
 static int pg_product(svmb200_pg* pg, bool timed) {
     // w[row0 : row0+nrows] = Q_shard u, then all ranks exchange their shards (K4)
     svmb200_ctx* ctx = pg->ctx;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     if (timed && pg->profile) {
         SVM_CUDA(cudaEventCreate(&e0));
         SVM_CUDA(cudaEventCreate(&e1));
+        SVM_CUDA(cudaEventCreate(&e2));
         SVM_CUDA(cudaEventRecord(e0, ctx->stream));
     }
     double* wshard = pg->w + (size_t)ctx->rank * pg->stride;
     SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wshard, pg->u + pg->row0, wshard + pg->rows_per_rank,
                           &pg->st->done));
-    if (e1) {
-        SVM_CUDA(cudaEventRecord(e1, ctx->stream));
+    if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
+    if (ctx->nranks > 1) SVM_TRY(svm_comm_allgather(ctx, pg->w, pg->stride));
+    if (e2) {
+        SVM_CUDA(cudaEventRecord(e2, ctx->stream));
         pg->mv_ev.push_back(e0);
         pg->mv_ev.push_back(e1);
+        pg->mv_ev.push_back(e2);
     }
-    if (ctx->nranks > 1) SVM_TRY(svm_comm_allgather(ctx, pg->w, pg->stride));
     pg->last_passes++;
     return SVMB200_OK;
 }
@@ -594,7 +614,7 @@ extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
     pg->svr = hessian == SVMB200_HESSIAN_SVR;
     pg->nvars = pg->svr ? 2 * n : n;
     pg->rows_per_rank = rpr;
-    pg->stride = rpr + rpr / MV_R;
+    pg->stride = rpr + rpr / MV_GROUP;
     pg->nctas = (int)((n + VP_ELEMS - 1) / VP_ELEMS);
     if (pg->nctas > VP_MAXC) pg->nctas = VP_MAXC;
     if (pg->nctas < 1) pg->nctas = 1;
@@ -673,7 +693,7 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
     for (cudaEvent_t e : pg->mv_ev) cudaEventDestroy(e);
     pg->mv_ev.clear();
     pg->last_passes = 0;
-    pg->last_ms = pg->last_mv_ms = 0.f;
+    pg->last_ms = pg->last_mv_ms = pg->last_comm_ms = pg->last_vec_ms = 0.f;
     SVM_CUDA(cudaEventRecord(pg->ev0, ctx->stream));
     if (!pg->finished) {
         const bool to_end = max_new < 0;
@@ -686,6 +706,12 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
             for (int64_t i = 0; i < nb; ++i) {
                 SVM_TRY(pg_product(pg, true));
                 SVM_TRY(launch_vec<VP_STEP>(pg, pg->k_next));
+                if (pg->profile) {
+                    cudaEvent_t e3 = nullptr;
+                    SVM_CUDA(cudaEventCreate(&e3));
+                    SVM_CUDA(cudaEventRecord(e3, ctx->stream));
+                    pg->mv_ev.push_back(e3);
+                }
                 pg->k_next++;
             }
             budget -= nb;
@@ -701,10 +727,14 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
     SVM_CUDA(cudaEventRecord(pg->ev1, ctx->stream));
     SVM_CUDA(cudaEventSynchronize(pg->ev1));
     SVM_CUDA(cudaEventElapsedTime(&pg->last_ms, pg->ev0, pg->ev1));
-    for (size_t i = 0; i + 1 < pg->mv_ev.size(); i += 2) {
+    for (size_t i = 0; i + 3 < pg->mv_ev.size(); i += 4) {
         float ms = 0.f;
         SVM_CUDA(cudaEventElapsedTime(&ms, pg->mv_ev[i], pg->mv_ev[i + 1]));
         pg->last_mv_ms += ms;
+        SVM_CUDA(cudaEventElapsedTime(&ms, pg->mv_ev[i + 1], pg->mv_ev[i + 2]));
+        pg->last_comm_ms += ms;
+        SVM_CUDA(cudaEventElapsedTime(&ms, pg->mv_ev[i + 2], pg->mv_ev[i + 3]));
+        pg->last_vec_ms += ms;
     }
     if (iter) *iter = pg->st_host->iter;
     if (status) *status = pg->st_host->done ? pg->st_host->status : SVMB200_STATUS_UNKNOWN;
@@ -745,6 +775,14 @@ extern "C" int svmb200_pg_stats(svmb200_pg* pg, float* ms, int64_t* passes, floa
     if (ms) *ms = pg->last_ms;
     if (passes) *passes = pg->last_passes;
     if (matvec_ms) *matvec_ms = pg->last_mv_ms;
+    return SVMB200_OK;
+}
+
+extern "C" int svmb200_pg_stats_ex(svmb200_pg* pg, float* matvec_ms, float* comm_ms, float* vector_ms) {
+    SVM_CHECK_ARG(pg != nullptr, "null solver");
+    if (matvec_ms) *matvec_ms = pg->last_mv_ms;
+    if (comm_ms) *comm_ms = pg->last_comm_ms;
+    if (vector_ms) *vector_ms = pg->last_vec_ms;
     return SVMB200_OK;
 }
 

@@ -108,3 +108,6 @@ class ProjectedGradient(BoxConstrainedQuadraticOptimizer):
         ms, passes, mv = C.c_float(0), C.c_int64(0), C.c_float(0)
         N.call('svmb200_pg_stats', h, C.byref(ms), C.byref(passes), C.byref(mv))
         self.device_ms, self.q_passes, self.matvec_ms = float(ms.value), int(passes.value), float(mv.value)
+        cm, vm = C.c_float(0), C.c_float(0)
+        N.call('svmb200_pg_stats_ex', h, C.byref(mv), C.byref(cm), C.byref(vm))
+        self.comm_ms, self.vector_ms = float(cm.value), float(vm.value)

@@ -89,7 +89,7 @@ def test_row_sharding():
     for n in (1, 7, 8, 50000, 120000, 1001):
         for P in (1, 2, 3, 4, 8):
             shards = [shard_rows(n, r, P) for r in range(P)]
-            rpr = -(-(-(-n // P)) // 8) * 8  # ceil(n/P) rounded up to a multiple of 8
+            rpr = -(-(-(-n // P)) // 64) * 64  # ceil(n/P) rounded up to a multiple of 64
             assert sum(s[1] for s in shards) == n
             assert all(s[0] == min(n, r * rpr) for r, s in enumerate(shards))
             assert all(0 <= s[1] <= rpr for s in shards)
