@@ -243,11 +243,19 @@ def default_context():
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             rank, world = dist.get_rank(), dist.get_world_size()
-            box = [Context.new_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
-            ctx.attach_communicator(rank, world, box[0])
+            ctx.attach_communicator(rank, world, broadcast_unique_id(dist, Context.new_unique_id))
     _default_ctx = ctx
     return ctx
+
+
+def broadcast_unique_id(dist, make_id):
+    """Rank 0 creates the 128-byte NCCL id, every rank receives it through torch.distributed."""
+    box = [make_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    uid = bytes(box[0])
+    if len(uid) != 128:
+        raise ValueError('NCCL unique id must be 128 bytes')
+    return uid
 
 
 def set_default_context(ctx):
