@@ -290,7 +290,7 @@ def run_b200(args):
         'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'{args.config} DualSVC GaussianKernel C=1 n={n} d={d} max_iter={args.max_iter} '
-                               f'(make_classification random_state=0)', 'parallelism': f'row-block x{world}',
+                               f'(make_classification random_state=0)', 'parallelism': f'row-block x{world}', 'exchange': ctx.exchange,
                    'l2': f'inputs larger than L2: Q shard = {8.0 * n * n / world / 1e9:.2f} GB per GPU, streamed once '
                          'per iteration'},
         'fit_s': dev_ms / args.steps / 1e3, 'pg_its_per_s': iters_total / (pg_ms / 1e3),

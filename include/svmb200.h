@@ -81,6 +81,15 @@ int svmb200_launch_count(svmb200_ctx* ctx, uint64_t* launches);
 int svmb200_comm_unique_id(void* id128);
 int svmb200_comm_init(svmb200_ctx* ctx, const void* id128, int rank, int nranks);
 int svmb200_comm_destroy(svmb200_ctx* ctx);
+/* Optional fused exchange over NVLink peer memory (replaces the per-iteration ncclAllGather of the
+ * solver): every rank exports an arena (svmb200_comm_p2p_export returns its 64-byte CUDA IPC handle),
+ * the handles of all ranks, concatenated in rank order, are passed to svmb200_comm_p2p_attach.  The
+ * matvec kernel then stores its results directly into every peer's arena and raises a per-rank flag
+ * there; the vector kernel waits on the flags.  Without it (or if IPC mapping fails) NCCL is used. */
+int svmb200_comm_p2p_export(svmb200_ctx* ctx, size_t arena_bytes, void* handle64);
+int svmb200_comm_p2p_attach(svmb200_ctx* ctx, const void* handles, int nranks);
+int svmb200_comm_p2p_enabled(svmb200_ctx* ctx, int* enabled);
+int svmb200_comm_p2p_disable(svmb200_ctx* ctx); /* all ranks must agree: call it everywhere if any rank failed to attach */
 /* Row partition used by every sharded entry point: rank r owns rows [row0, row0+nrows) of an n-row
  * matrix, ceil(n/nranks) rounded up to a multiple of 64 rows per rank (the last ranks may get fewer,
  * possibly none).  Aligned shard boundaries keep every reduction shape independent of nranks. */

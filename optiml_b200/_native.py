@@ -42,6 +42,10 @@ PROTOTYPES = {
     'svmb200_comm_unique_id': [c_vp],
     'svmb200_comm_init': [c_vp, c_vp, C.c_int, C.c_int],
     'svmb200_comm_destroy': [c_vp],
+    'svmb200_comm_p2p_export': [c_vp, C.c_size_t, c_vp],
+    'svmb200_comm_p2p_attach': [c_vp, c_vp, C.c_int],
+    'svmb200_comm_p2p_enabled': [c_vp, C.POINTER(C.c_int)],
+    'svmb200_comm_p2p_disable': [c_vp],
     'svmb200_shard_rows': [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)],
     'svmb200_gram': [c_vp, c_vp, i64, i64, c_vp, i64, i64, i64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                      c_vp, c_vp, C.c_double, i64, i64, c_vp, i64],

@@ -90,8 +90,87 @@ extern "C" int svmb200_comm_init(svmb200_ctx* ctx, const void* id128, int rank, 
     return SVMB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-memory arena for the fused matvec + exchange (K2 writes into every peer, K3 waits on flags).
+extern "C" int svmb200_comm_p2p_export(svmb200_ctx* ctx, size_t arena_bytes, void* handle64) {
+    SVM_TRY(svm_use(ctx));
+    SVM_CHECK_ARG(handle64 != nullptr && arena_bytes >= (1u << 20), "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    if (ctx->arena) {
+        svmb200_set_error("arena already exported");
+        return SVMB200_ERR_STATE;
+    }
+    SVM_CUDA(cudaMalloc(&ctx->arena, arena_bytes));
+    SVM_CUDA(cudaMemset(ctx->arena, 0, arena_bytes));
+    ctx->arena_bytes = arena_bytes;
+    cudaIpcMemHandle_t h;
+    SVM_CUDA(cudaIpcGetMemHandle(&h, ctx->arena));
+    memcpy(handle64, &h, sizeof(h));
+    return SVMB200_OK;
+}
+
+extern "C" int svmb200_comm_p2p_attach(svmb200_ctx* ctx, const void* handles, int nranks) {
+    SVM_TRY(svm_use(ctx));
+    SVM_CHECK_ARG(handles != nullptr && nranks == ctx->nranks && nranks <= SVM_MAX_RANKS, "bad argument");
+    if (!ctx->arena) {
+        svmb200_set_error("call svmb200_comm_p2p_export first");
+        return SVMB200_ERR_STATE;
+    }
+    for (int r = 0; r < nranks; ++r) {
+        if (r == ctx->rank) {
+            ctx->peer_arena[r] = ctx->arena;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            svmb200_set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+            for (int q = 0; q < r; ++q)
+                if (q != ctx->rank && ctx->peer_arena[q]) {
+                    cudaIpcCloseMemHandle(ctx->peer_arena[q]);
+                    ctx->peer_arena[q] = nullptr;
+                }
+            return SVMB200_ERR_CUDA;
+        }
+        ctx->peer_arena[r] = static_cast<unsigned char*>(p);
+    }
+    ctx->p2p_enabled = true;
+    ctx->xseq = 0;
+    return SVMB200_OK;
+}
+
+extern "C" int svmb200_comm_p2p_disable(svmb200_ctx* ctx) {
+    SVM_CHECK_ARG(ctx != nullptr, "null argument");
+    ctx->p2p_enabled = false;  // keep the mappings; the solver falls back to ncclAllGather
+    return SVMB200_OK;
+}
+
+extern "C" int svmb200_comm_p2p_enabled(svmb200_ctx* ctx, int* enabled) {
+    SVM_CHECK_ARG(ctx != nullptr && enabled != nullptr, "null argument");
+    *enabled = ctx->p2p_enabled ? 1 : 0;
+    return SVMB200_OK;
+}
+
+static void p2p_release(svmb200_ctx* ctx) {
+    for (int r = 0; r < SVM_MAX_RANKS; ++r) {
+        if (ctx->peer_arena[r] && ctx->peer_arena[r] != ctx->arena) cudaIpcCloseMemHandle(ctx->peer_arena[r]);
+        ctx->peer_arena[r] = nullptr;
+    }
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    ctx->p2p_enabled = false;
+}
+
 extern "C" int svmb200_comm_destroy(svmb200_ctx* ctx) {
     if (!ctx) return SVMB200_OK;
+    if (ctx->arena) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        p2p_release(ctx);
+    }
     if (ctx->nccl_comm && g_nccl.CommDestroy) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);

@@ -10,6 +10,8 @@
 
 #include "../../include/svmb200.h"
 
+constexpr int SVM_MAX_RANKS = 16;
+
 struct svmb200_ctx {
     int device = -1;
     int sm_count = 0;
@@ -24,7 +26,19 @@ struct svmb200_ctx {
     void* encode_tiled = nullptr;
     // segment partials / tickets of the streaming matvec (grown on demand, pg.cu)
     void* matvec_scratch = nullptr;
+    // fused exchange over NVLink peer memory (comm.cu): every rank owns an arena that all peers map
+    // through CUDA IPC; K2 stores its results straight into every peer's arena and raises a flag there
+    bool p2p_enabled = false;
+    unsigned char* arena = nullptr;               // local arena
+    size_t arena_bytes = 0;
+    unsigned char* peer_arena[SVM_MAX_RANKS] = {};  // peer_arena[r] = rank r's arena as mapped here (self: local)
+    unsigned long long xseq = 0;                  // number of fused exchanges issued so far (same on all ranks)
 };
+
+// arena layout
+constexpr size_t ARENA_FLAGS_OFF = 0;      // unsigned long long flag[SVM_MAX_RANKS]: last sequence number completed by rank r
+constexpr size_t ARENA_LOCAL_OFF = 256;    // unsigned rank_done ; unsigned fault
+constexpr size_t ARENA_DATA_OFF = 1024;    // two gathered buffers (double-buffered by sequence parity)
 
 void svmb200_set_error(const char* fmt, ...);
 

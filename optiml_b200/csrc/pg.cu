@@ -42,7 +42,24 @@ struct MatvecArgs {
     double* denpart;        // one per group: sum over the group's rows of u_rows[r] * w[r], or null
     int nseg;
     const int* done;
+    // fused exchange (nranks_x > 0): the group combiner stores w / u'w shares into every rank's gathered
+    // buffer; the CTA that completes the shard's last group publishes `seq` in every rank's flag word
+    int nranks_x;
+    unsigned ngroups;
+    unsigned* rank_done;                         // local counter of finished groups (self-resetting)
+    unsigned long long seq;
+    double* peer_w[SVM_MAX_RANKS];               // this rank's slot in rank r's gathered buffer
+    unsigned long long* peer_flag[SVM_MAX_RANKS];  // this rank's flag word in rank r's arena
 };
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
     double2 r;
@@ -144,7 +161,11 @@ __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const Matvec
         if (rr < a.nrows) {
             double v = 0.0;
             for (int s = 0; s < a.nseg; ++s) v += __ldcg(&a.wpart[(size_t)s * a.nrows_pad + rr]);
-            a.w[rr] = v;
+            if (a.nranks_x > 0) {
+                for (int p = 0; p < a.nranks_x; ++p) a.peer_w[p][rr] = v;  // NVLink stores (one slot is local)
+            } else {
+                a.w[rr] = v;
+            }
             if (a.u_rows != nullptr) dv = __dmul_rn(a.u_rows[rr], v);
         }
         if (a.denpart != nullptr) {
@@ -156,7 +177,27 @@ __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const Matvec
     }
     if (a.denpart != nullptr) {
         __syncthreads();
-        if (threadIdx.x == 0) a.denpart[group] = __dadd_rn(red[0][0], red[0][1]);
+        if (threadIdx.x == 0) {
+            const double tot = __dadd_rn(red[0][0], red[0][1]);
+            if (a.nranks_x > 0) {
+                const size_t off = (size_t)(a.denpart - a.w) + group;  // share slot relative to the w slot
+                for (int p = 0; p < a.nranks_x; ++p) a.peer_w[p][off] = tot;
+            } else {
+                a.denpart[group] = tot;
+            }
+        }
+    }
+    if (a.nranks_x > 0) {
+        // publish: data stores -> system fence -> local count; the last group's CTA raises the flags
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(a.rank_done, 1u) == a.ngroups - 1) {
+                *a.rank_done = 0;
+                __threadfence_system();
+                for (int p = 0; p < a.nranks_x; ++p) st_release_sys_u64(a.peer_flag[p], a.seq);
+            }
+        }
     }
 }
 
@@ -191,9 +232,39 @@ static int matvec_scratch_reserve(svmb200_ctx* ctx, MatvecScratch& s, int64_t nr
     return SVMB200_OK;
 }
 
+// a rank that owns no rows (n small, many ranks) still has to announce "my (empty) shard is done"
+__global__ void publish_flags_kernel(const int* done, int nranks, unsigned long long seq,
+                                     unsigned long long* f0, unsigned long long* f1, unsigned long long* f2,
+                                     unsigned long long* f3, unsigned long long* f4, unsigned long long* f5,
+                                     unsigned long long* f6, unsigned long long* f7, unsigned long long* f8,
+                                     unsigned long long* f9, unsigned long long* f10, unsigned long long* f11,
+                                     unsigned long long* f12, unsigned long long* f13, unsigned long long* f14,
+                                     unsigned long long* f15) {
+    if (done != nullptr && *done) return;
+    unsigned long long* f[SVM_MAX_RANKS] = {f0, f1, f2, f3, f4, f5, f6, f7, f8, f9, f10, f11, f12, f13, f14, f15};
+    if (threadIdx.x < nranks) st_release_sys_u64(f[threadIdx.x], seq);
+}
+
+struct ExchangeTargets {
+    int nranks = 0;
+    unsigned long long seq = 0;
+    unsigned* rank_done = nullptr;
+    double* peer_w[SVM_MAX_RANKS] = {};
+    unsigned long long* peer_flag[SVM_MAX_RANKS] = {};
+};
+
 static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw,
-                         const double* du_rows, double* ddenpart, const int* d_done) {
-    if (nrows <= 0) return SVMB200_OK;
+                         const double* du_rows, double* ddenpart, const int* d_done,
+                         const ExchangeTargets* xt = nullptr) {
+    if (nrows <= 0 && xt == nullptr) return SVMB200_OK;
+    if (nrows <= 0) {
+        unsigned long long* const* f = xt->peer_flag;
+        publish_flags_kernel<<<1, 32, 0, ctx->stream>>>(d_done, xt->nranks, xt->seq, f[0], f[1], f[2], f[3], f[4], f[5],
+                                                        f[6], f[7], f[8], f[9], f[10], f[11], f[12], f[13], f[14], f[15]);
+        ctx->launches++;
+        SVM_CUDA(cudaGetLastError());
+        return SVMB200_OK;
+    }
     if (ld % 2 != 0 || ld <= 0) {
         svmb200_set_error("matvec: ld must be a positive multiple of 2");
         return SVMB200_ERR_ARG;
@@ -219,6 +290,19 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
     a.nseg = (int)((ld + MV_SEG - 1) / MV_SEG);
     a.done = d_done;
     const int64_t ngroups = (nrows + MV_GROUP - 1) / MV_GROUP;
+    a.nranks_x = 0;
+    a.ngroups = (unsigned)ngroups;
+    a.rank_done = nullptr;
+    a.seq = 0;
+    if (xt != nullptr) {
+        a.nranks_x = xt->nranks;
+        a.rank_done = xt->rank_done;
+        a.seq = xt->seq;
+        for (int r = 0; r < xt->nranks; ++r) {
+            a.peer_w[r] = xt->peer_w[r];
+            a.peer_flag[r] = xt->peer_flag[r];
+        }
+    }
     const int64_t nitems = ngroups * MV_BPG * a.nseg;
     if (nitems >= (1ll << 31)) {
         svmb200_set_error("matvec: grid too large");
@@ -295,6 +379,11 @@ struct VecArgs {
     int nctas;
     double eps;
     long long max_iter;
+    // fused exchange: wait until every rank has published `wait_seq` in this rank's flag words
+    const unsigned long long* flags;
+    unsigned long long wait_seq;
+    int nranks_wait;
+    int* fault;
 };
 
 enum { VP_INIT = 0, VP_STEP = 1, VP_FINALISE = 2 };
@@ -370,6 +459,22 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     // a CTA that starts late and already sees the flag returns here instead -- same outcome.
     if (*reinterpret_cast<volatile int*>(&st->done)) return;
     const int tid = threadIdx.x;
+    if (MODE != VP_FINALISE && a.nranks_wait > 0) {
+        // peers store their product shards straight into this GPU's memory (K2); spin (bounded) on the
+        // per-rank flag words, then order the data loads behind the acquire
+        if (tid < a.nranks_wait) {
+            unsigned long long t0 = 0, now = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (ld_acquire_sys_u64(a.flags + tid) < a.wait_seq) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > 20000000000ull) {  // 20 s: a peer died; flag the fault and stop the solve
+                    *a.fault = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
     const long long n = a.n;
     const long long chunk = (n + a.nctas - 1) / a.nctas;
     const long long j0 = (long long)blockIdx.x * chunk;
@@ -496,6 +601,8 @@ struct svmb200_pg {
     // device buffers
     double *x = nullptr, *g = nullptr, *d = nullptr, *u = nullptr, *w = nullptr;  // w: gathered [P][stride]
     int64_t stride = 0;  // rows_per_rank results + rows_per_rank / MV_GROUP shares of u'w
+    bool p2p = false;           // fused exchange through the peer arena instead of ncclAllGather
+    unsigned long long cur_seq = 0;  // sequence number of the product the next vector kernel consumes
     int nctas = 1;
     double *q = nullptr, *lb = nullptr, *ub = nullptr;
     double *part = nullptr, *hist_f = nullptr, *hist_ng = nullptr;
@@ -522,6 +629,19 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
     a.lb = pg->lb;
     a.ub = pg->ub;
     a.gathered = pg->w;
+    a.flags = nullptr;
+    a.wait_seq = 0;
+    a.nranks_wait = 0;
+    a.fault = nullptr;
+    if (pg->p2p) {
+        svmb200_ctx* ctx = pg->ctx;
+        const size_t bufbytes = (size_t)pg->stride * ctx->nranks * sizeof(double);
+        a.gathered = reinterpret_cast<const double*>(ctx->arena + ARENA_DATA_OFF + (pg->cur_seq & 1) * bufbytes);
+        a.flags = reinterpret_cast<const unsigned long long*>(ctx->arena + ARENA_FLAGS_OFF);
+        a.wait_seq = pg->cur_seq;
+        a.nranks_wait = ctx->nranks;
+        a.fault = reinterpret_cast<int*>(ctx->arena + ARENA_LOCAL_OFF + 8);
+    }
     a.rpr = pg->rows_per_rank;
     a.stride = pg->stride;
     a.part = pg->part;
@@ -556,11 +676,30 @@ static int pg_product(svmb200_pg* pg, bool timed) {
         SVM_CUDA(cudaEventCreate(&e2));
         SVM_CUDA(cudaEventRecord(e0, ctx->stream));
     }
-    double* wshard = pg->w + (size_t)ctx->rank * pg->stride;
-    SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wshard, pg->u + pg->row0, wshard + pg->rows_per_rank,
-                          &pg->st->done));
-    if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
-    if (ctx->nranks > 1) SVM_TRY(svm_comm_allgather(ctx, pg->w, pg->stride));
+    if (pg->p2p) {
+        // K2 + K4 fused: results go straight into every rank's gathered buffer (parity = seq & 1)
+        ExchangeTargets xt;
+        xt.nranks = ctx->nranks;
+        xt.seq = ++ctx->xseq;
+        pg->cur_seq = xt.seq;
+        xt.rank_done = reinterpret_cast<unsigned*>(ctx->arena + ARENA_LOCAL_OFF);
+        const size_t bufbytes = (size_t)pg->stride * ctx->nranks * sizeof(double);
+        const size_t slot = ARENA_DATA_OFF + (xt.seq & 1) * bufbytes + (size_t)ctx->rank * pg->stride * sizeof(double);
+        for (int r = 0; r < ctx->nranks; ++r) {
+            xt.peer_w[r] = reinterpret_cast<double*>(ctx->peer_arena[r] + slot);
+            xt.peer_flag[r] = reinterpret_cast<unsigned long long*>(ctx->peer_arena[r] + ARENA_FLAGS_OFF) + ctx->rank;
+        }
+        double* wlocal = reinterpret_cast<double*>(ctx->arena + slot);
+        SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wlocal, pg->u + pg->row0,
+                              wlocal + pg->rows_per_rank, &pg->st->done, &xt));
+        if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
+    } else {
+        double* wshard = pg->w + (size_t)ctx->rank * pg->stride;
+        SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wshard, pg->u + pg->row0,
+                              wshard + pg->rows_per_rank, &pg->st->done));
+        if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
+        if (ctx->nranks > 1) SVM_TRY(svm_comm_allgather(ctx, pg->w, pg->stride));
+    }
     if (e2) {
         SVM_CUDA(cudaEventRecord(e2, ctx->stream));
         pg->mv_ev.push_back(e0);
@@ -615,6 +754,8 @@ extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
     pg->nvars = pg->svr ? 2 * n : n;
     pg->rows_per_rank = rpr;
     pg->stride = rpr + rpr / MV_GROUP;
+    pg->p2p = ctx->p2p_enabled && P > 1 &&
+              ARENA_DATA_OFF + 2 * (size_t)pg->stride * P * sizeof(double) <= ctx->arena_bytes;
     pg->nctas = (int)((n + VP_ELEMS - 1) / VP_ELEMS);
     if (pg->nctas > VP_MAXC) pg->nctas = VP_MAXC;
     if (pg->nctas < 1) pg->nctas = 1;
@@ -683,6 +824,14 @@ static int pg_poll(svmb200_pg* pg) {
     SVM_CUDA(cudaMemcpyAsync(pg->st_host, pg->st, sizeof(PGDeviceState), cudaMemcpyDeviceToHost, pg->ctx->stream));
     SVM_CUDA(cudaStreamSynchronize(pg->ctx->stream));
     if (pg->st_host->done) pg->finished = true;
+    if (pg->p2p) {
+        int fault = 0;
+        SVM_CUDA(cudaMemcpy(&fault, pg->ctx->arena + ARENA_LOCAL_OFF + 8, sizeof(int), cudaMemcpyDeviceToHost));
+        if (fault) {
+            svmb200_set_error("peer exchange timed out: a rank stopped publishing its product shard");
+            return SVMB200_ERR_STATE;
+        }
+    }
     return SVMB200_OK;
 }
 

@@ -100,6 +100,40 @@ class Context:
         N.call('svmb200_comm_init', self.handle, C.cast(buf, C.c_void_p), int(rank), int(nranks))
         self.rank, self.nranks = int(rank), int(nranks)
 
+    def enable_peer_exchange(self, dist, arena_bytes=64 << 20):
+        """Map every rank's exchange arena (CUDA IPC over NVLink) so that the matvec kernel can store its
+        shard straight into all peers.  Falls back to the NCCL all-gather if any rank cannot map."""
+        buf = C.create_string_buffer(64)
+        ok = True
+        try:
+            N.call('svmb200_comm_p2p_export', self.handle, int(arena_bytes), C.cast(buf, C.c_void_p))
+        except N.NativeError:
+            ok = False
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, buf.raw if ok else None)
+        if any(h is None for h in handles):
+            N.call('svmb200_comm_p2p_disable', self.handle)
+            return False
+        blob = C.create_string_buffer(b''.join(handles), 64 * self.nranks)
+        try:
+            N.call('svmb200_comm_p2p_attach', self.handle, C.cast(blob, C.c_void_p), self.nranks)
+        except N.NativeError:
+            ok = False
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, ok)
+        self.peer_exchange = all(flags)
+        if not self.peer_exchange:
+            N.call('svmb200_comm_p2p_disable', self.handle)  # every rank must take the same path
+        return self.peer_exchange
+
+    @property
+    def exchange(self):
+        if self.nranks == 1:
+            return 'none'
+        en = C.c_int(0)
+        N.call('svmb200_comm_p2p_enabled', self.handle, C.byref(en))
+        return 'p2p' if en.value else 'nccl'
+
     @staticmethod
     def new_unique_id():
         buf = C.create_string_buffer(128)
@@ -244,6 +278,8 @@ def default_context():
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             rank, world = dist.get_rank(), dist.get_world_size()
             ctx.attach_communicator(rank, world, broadcast_unique_id(dist, Context.new_unique_id))
+            if os.environ.get('SVMB200_EXCHANGE', 'p2p').lower() != 'nccl':
+                ctx.enable_peer_exchange(dist)
     _default_ctx = ctx
     return ctx
 

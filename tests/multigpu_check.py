@@ -31,6 +31,8 @@ def main():
 
     ctx = runtime.default_context()
     assert ctx.nranks == world and ctx.rank == rank
+    if rank == 0:
+        print(f'[multigpu N={world}] exchange = {ctx.exchange}', flush=True)
     cases = [
         ('C1', None, lambda: DualSVC(kernel=GaussianKernel(), C=1)),
         ('C4', 8192 + 37, lambda: DualSVC(kernel=GaussianKernel(), C=1, max_iter=200)),
