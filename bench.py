@@ -36,6 +36,12 @@ METRIC = 'DualSVC Gaussian n=50k d=128 C=1: projected-gradient iterations/s over
 UNIT = 'PG it/s'
 
 
+def metric_name(config, n, d):
+    if config == 'C4' and n == 50000:
+        return METRIC
+    return f'DualSVC Gaussian n={n} d={d} C=1 ({config}): projected-gradient iterations/s over the whole fit'
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -147,7 +153,8 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_full = args.n or 50000
+    from optiml_b200.configs import CONFIGS
+    n_full = args.n or CONFIGS[args.config]['n']
     n_sample = min(n_full, 16000)
     vals = []
     for i in range(args.warmup + args.steps):
@@ -159,10 +166,11 @@ def run_reference(args):
     sample = (f'first {n_sample} rows of {args.config} (n={n_full}); NumPy oracle = reference algorithm '
               f'(Gram + 20 PG iterations, 3 passes over Q each); it/s scaled by ({n_sample}/{n_full})^2 '
               f'to the full problem, whole-fit equivalent incl. Gram')
-    line = {'impl': 'reference', 'metric': METRIC, 'value': its, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+    line = {'impl': 'reference', 'metric': metric_name(args.config, n_full, CONFIGS[args.config]['d']), 'value': its, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'{args.config} DualSVC GaussianKernel C=1 n={n_full} d=128 max_iter={args.max_iter}',
+            'config': {'workload': f'{args.config} DualSVC GaussianKernel C=1 n={n_full} d={CONFIGS[args.config]["d"]} '
+                                   f'max_iter={args.max_iter}',
                        'sample': sample},
             'cpu_baseline': {'value': its, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port', 'sample': sample,
                              'pg_only_its': float(np.mean([v['its_full_pg_only'] for v in vals]))},
@@ -286,7 +294,7 @@ def run_b200(args):
         if tj.get('n') == n and tj.get('n_gpus', 1) == world:
             traffic = tj.get('dram_bytes_per_launch')
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': metric_name(args.config, n, d), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'{args.config} DualSVC GaussianKernel C=1 n={n} d={d} max_iter={args.max_iter} '
