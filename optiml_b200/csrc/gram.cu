@@ -4,27 +4,40 @@
 // sklearn euclidean_distances: D = -2AB' + |a|^2 + |b|^2, max(D,0), diag = 0 when B is A) fused with
 // optiml/ml/svm/_base.py:554,628 (Q = K o yy' + yy') / :1098-1099,1178 (M = K + 1).
 //
-// Structure (sm_100a): persistent CTAs, one 128x128 output tile at a time.
-//   warp 8      : TMA producer -- cp.async.bulk.tensor 2D boxes of 128 rows x 16 doubles (128 B,
-//                 SWIZZLE_128B) for A and B into a 4-stage shared-memory ring, mbarrier full/empty.
-//   warps 0..7  : FP64 tensor-core contraction, mma.sync.m8n8k4 (DMMA; tcgen05 has no f64 kind),
-//                 64x32 accumulator block per warp in registers, fused exp/pow/sign/bias epilogue,
-//                 128-bit stores.  The producer keeps prefetching the next tile during the epilogue.
+// Structure (sm_100a): persistent CTAs of three warpgroups, 128x64 output tiles.
+//   warpgroup 2 : TMA producers -- warp 8 / warp 9 (one elected lane each) feed one 4-stage ring per
+//                 consumer group with cp.async.bulk.tensor 2D boxes (A: 128 rows x 16 doubles, B: 64 x 16,
+//                 128 B inner extent, SWIZZLE_128B), mbarrier full/empty; registers handed back with
+//                 setmaxnreg.dec.
+//   warpgroups 0,1 : two consumer groups, one 128x64 tile each: FP64 tensor-core contraction
+//                 (mma.sync.m8n8k4 -> DMMA; tcgen05 has no f64 kind; 64x32 accumulator block per warp,
+//                 setmaxnreg.inc to 232 registers) followed by the fused exp/pow/sign/bias epilogue.
+//                 DMMA and vector FP64 share ONE execution unit on B200 (scripts/fp64_probe.cu), so the
+//                 epilogue cannot hide behind the other group's contraction; by default the two groups
+//                 change phase together (named barrier), ping-pong and free-running are kept as measured
+//                 alternatives (SVMB200_GRAM_EXCLUSIVE=1/0).
 // Shared-memory reads are bank-conflict free: with the 128B swizzle the 16-byte chunk c of row r
 // lives at chunk c^(r&7); the four k-slots of an m8n8k4 fragment are mapped to chunks {s, s+4}
 // (s = k-step), so the 16 lanes of a half-warp hit 16 distinct 8-byte bank pairs.
 #include "common.cuh"
 #include <cudaTypedefs.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
-constexpr int MMA_WARPS = 8;
-constexpr int GRAM_THREADS = (MMA_WARPS + 1) * 32;
-constexpr int TILE_BYTES = BM * BK * 8;            // 16 KB per operand per stage
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;        // 32 KB
-constexpr int GRAM_SMEM = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8;
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
+constexpr int GROUP_WARPS = 4;                      // warps per consumer group
+constexpr int GRAM_THREADS = 384;                   // 2 consumer warpgroups + 1 producer warpgroup
+constexpr int A_BYTES = BM * BK * 8;                // 16 KB
+constexpr int B_BYTES = BN * BK * 8;                // 8 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 24 KB
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;    // 96 KB per consumer group
+constexpr int OPND_DOUBLES = 2 * BM + 2 * BN;         // per group: |a|^2, s_a for 128 rows; |b|^2, s_b for 64 columns
+constexpr int GRAM_SMEM = 2 * RING_BYTES + 1024 + 4 * STAGES * 8 + 2 * OPND_DOUBLES * 8;
+constexpr int BAR_GROUP0 = 1;                       // named barriers 1,2: "group g may use the tensor pipe"
+constexpr int BAR_PHASE = 5;                        // named barrier 5: both groups change phase together (lockstep)
+constexpr int BAR_LOCAL0 = 3;                       // named barriers 3,4: group-local sync around the operand staging
 
 struct GramArgs {
     const double* norm_a;  // |a_i|^2 per row of A (gaussian) or null
@@ -38,6 +51,7 @@ struct GramArgs {
     int kchunks;
     int tiles_m, tiles_n;
     int same;
+    int exclusive;  // 0: groups run free; 1: ping-pong on the tensor pipe; 2: lockstep phases (see kernel)
     double gamma, coef0, degree, bias;
 };
 
@@ -77,23 +91,51 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// The transcendental bodies are kept out of line: the epilogue is unrolled 64x per thread (static
-// accumulator indices) and 64 inlined copies of exp()/pow() would not fit the instruction cache.
-__device__ __noinline__ double exp_outofline(double x) { return exp(x); }
+// pow() stays out of line (the poly epilogue is unrolled 64x per thread and pow is ~300 instructions).
 __device__ __noinline__ double pow_outofline(double x, double y) { return pow(x, y); }
 
-template <int KERNEL>
-__device__ __forceinline__ double kernel_epilogue(double dot, double na, double nb, bool diag, const GramArgs& p) {
-    if (KERNEL == SVMB200_KERNEL_LINEAR) return dot;
-    if (KERNEL == SVMB200_KERNEL_POLY) {
-        // (gamma * <a,b> + coef0) ** degree with separately rounded product and sum (NumPy semantics)
-        return pow_outofline(__dadd_rn(__dmul_rn(p.gamma, dot), p.coef0), p.degree);
+// exp(x), x <= 0, for the Gaussian epilogue, evaluated for EIGHT independent arguments in lock-step so
+// that the FP64 unit sees 8 independent dependency chains (a scalar exp() is one chain of dependent DFMAs,
+// 9.4 cycles each).  Classic scheme: k = rint(x log2 e) through the 1.5*2^52 trick, r = x - k ln2 (hi/lo
+// split), degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 6e-18), then 2^k in two exact steps
+// (2^(k+1000) on the exponent field, times 2^-1000) so that results in the denormal range are rounded once
+// and everything below underflows to 0 -- no branch, no call.  <= 1.5 ulp; exp8(0) == 1 exactly.
+__device__ __forceinline__ void exp8(const double (&x)[8], double (&out)[8]) {
+    constexpr double L2E = 1.4426950408889634074, MAGIC = 6755399441055744.0;
+    constexpr double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    constexpr double TWO_M1000 = 9.33263618503218878990e-302;  // 2^-1000
+    double r[8], p[8];
+    int k[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const double xe = fmax(x[e], -800.0);  // exp(-800) == 0 in FP64; keeps k in range
+        double t = fma(xe, L2E, MAGIC);
+        k[e] = __double2loint(t);
+        t -= MAGIC;
+        r[e] = fma(t, -LN2_HI, xe);
+        r[e] = fma(t, -LN2_LO, r[e]);
+        p[e] = 1.0 / 6227020800.0;  // 1/13!
     }
-    // gaussian: D = (-2<a,b> + |a|^2) + |b|^2 ; clamp ; exact zero on the diagonal of a self-Gram
-    double dist = __dadd_rn(__dadd_rn(-2.0 * dot, na), nb);
-    dist = fmax(dist, 0.0);
-    if (diag) dist = 0.0;
-    return exp_outofline(__dmul_rn(-p.gamma, dist));
+    constexpr double C[13] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
+                              1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600};
+#pragma unroll
+    for (int j = 12; j >= 0; --j) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p[e] = fma(p[e], r[e], C[j]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        out[e] = __hiloint2double(__double2hiint(p[e]) + ((k[e] + 1000) << 20), __double2loint(p[e])) * TWO_M1000;
+}
+
+__device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 template <int KERNEL>
@@ -102,16 +144,15 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment required by the 128B swizzle pattern
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * RING_BYTES);  // [group][full x STAGES | empty x STAGES]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, MMA_WARPS);
-        }
+        for (int gq = 0; gq < 2; ++gq)
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(smem_u32(bars + gq * 2 * STAGES + s), 1);
+                mbar_init(smem_u32(bars + gq * 2 * STAGES + STAGES + s), GROUP_WARPS);
+            }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -119,14 +160,18 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     const int ntiles = p.tiles_m * p.tiles_n;
 
-    if (warp == MMA_WARPS) {
-        // ===================== TMA producer (one elected lane) =====================
-        if (lane == 0) {
+    if (warp >= 2 * GROUP_WARPS) {
+        // ===================== TMA producers: warp 8 -> ring 0, warp 9 -> ring 1 =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int grp = warp - 2 * GROUP_WARPS;
+        if (grp < 2 && lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+            const uint32_t ring = smem_u32(smem) + grp * RING_BYTES;
+            const uint32_t full0 = smem_u32(bars + grp * 2 * STAGES), empty0 = full0 + 8 * STAGES;
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
                 const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
                 const int arow = (int)p.row0 + tm * BM;
                 const int brow = tn * BN;
@@ -134,9 +179,9 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t fb = full0 + 8 * stage;
                     mbar_expect_tx(fb, STAGE_BYTES);
-                    const uint32_t dst = smem_base + stage * STAGE_BYTES;
+                    const uint32_t dst = ring + stage * STAGE_BYTES;
                     tma_load_2d(dst, &map_a, fb, kc * BK, arow);
-                    tma_load_2d(dst + TILE_BYTES, &map_b, fb, kc * BK, brow);
+                    tma_load_2d(dst + A_BYTES, &map_b, fb, kc * BK, brow);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -147,26 +192,69 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         return;
     }
 
-    // ===================== DMMA consumers =====================
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps -> 64 x 32 per warp
+    // ===================== consumer groups (ping-pong) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int grp = warp / GROUP_WARPS;           // 0 or 1
+    const int wg = warp % GROUP_WARPS;
+    const int wm = wg >> 1, wn = wg & 1;          // 2 x 2 warps -> 64 x 32 per warp
     const int g = lane >> 2, t = lane & 3;
     // byte offset of this lane's k-slot inside a 128-byte row, before the per-step XOR
     const int hi = (t >> 1) * 4, sub = (t & 1) * 8;
+    const unsigned char* ring = smem + grp * RING_BYTES;
+    const uint32_t full0 = smem_u32(bars + grp * 2 * STAGES), empty0 = full0 + 8 * STAGES;
+    // per-tile epilogue operands, staged with cp.async while the contraction runs
+    double* opnd = reinterpret_cast<double*>(smem + 2 * RING_BYTES + 4 * STAGES * 8) + grp * OPND_DOUBLES;
+    double* sm_na = opnd;
+    double* sm_sa = opnd + BM;
+    double* sm_nb = opnd + 2 * BM;
+    double* sm_sb = opnd + 2 * BM + BN;
+    const int gt = threadIdx.x - grp * GROUP_WARPS * 32;  // thread index inside the group
     int stage = 0;
     uint32_t phase = 0;
+    // group 1 lets group 0 go first
+    if (p.exclusive == 1 && grp == 1) named_bar_arrive(BAR_GROUP0 + 0, 2 * GROUP_WARPS * 32);
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+    // exclusive == 2: LOCKSTEP -- both groups contract together, then run their epilogues together.  DMMA and
+    // vector FP64 share one execution unit on this part (scripts/fp64_probe.cu: mixed = sum of both), and a DMMA
+    // holds it for 16 cycles, so an epilogue that runs beside the other group's contraction gets one FP64 issue
+    // per DMMA and crawls; phases of the same kind must run together.
+    const bool lockstep = p.exclusive == 2;
+    const bool pingpong = p.exclusive == 1;
+    const int rounds = (ntiles - (int)blockIdx.x + 2 * (int)gridDim.x - 1) / (2 * (int)gridDim.x);  // tiles of group 0
+    for (int round = 0; round < rounds; ++round) {
+        const int tile = blockIdx.x + (2 * round + grp) * gridDim.x;
+        const bool has_tile = tile < ntiles;
+        const int tm = has_tile ? tile / p.tiles_n : 0, tn = has_tile ? tile % p.tiles_n : 0;
         double acc[8][4][2];
+        if (has_tile) {
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
+        // stage |a|^2, s_a (128 rows) and |b|^2, s_b (64 columns) of this tile: asynchronous 8-byte copies
+        {
+            const long long i = p.row0 + (long long)tm * BM + gt;
+            const bool rok = i < p.row0 + p.nrows;
+            if (KERNEL == SVMB200_KERNEL_GAUSSIAN && rok) cp_async_8(sm_na + gt, p.norm_a + i);
+            else sm_na[gt] = 0.0;
+            if (p.sign_a != nullptr && rok) cp_async_8(sm_sa + gt, p.sign_a + i);
+            else sm_sa[gt] = 1.0;
+            if (gt < BN) {
+                const long long c = (long long)tn * BN + gt;
+                const bool cok = c < p.nb;
+                if (KERNEL == SVMB200_KERNEL_GAUSSIAN && cok) cp_async_8(sm_nb + gt, p.norm_b + c);
+                else sm_nb[gt] = 0.0;
+                if (p.sign_b != nullptr && cok) cp_async_8(sm_sb + gt, p.sign_b + c);
+                else sm_sb[gt] = 1.0;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        // wait for the tensor pipe (the other group has finished its contraction)
+        if (pingpong) named_bar_sync(BAR_GROUP0 + grp, 2 * GROUP_WARPS * 32);
         for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(full0 + 8 * stage, phase);
-            const unsigned char* sa = smem + stage * STAGE_BYTES + (wm * 64 + g) * 128;
-            const unsigned char* sb = smem + stage * STAGE_BYTES + TILE_BYTES + (wn * 32 + g) * 128;
+            const unsigned char* sa = ring + stage * STAGE_BYTES + (wm * 64 + g) * 128;
+            const unsigned char* sb = ring + stage * STAGE_BYTES + A_BYTES + (wn * 32 + g) * 128;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int off = (((s + hi) ^ g) << 4) + sub;
@@ -187,27 +275,63 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 phase ^= 1;
             }
         }
+        // hand the tensor pipe to the other group if it still has a tile to contract
+        // (contractions alternate: this CTA's tile list is split even/odd between the groups, so the other
+        // group's next contraction is the tile one grid stride after ours)
+        if (pingpong && tile + (int)gridDim.x < ntiles) named_bar_arrive(BAR_GROUP0 + (grp ^ 1), 2 * GROUP_WARPS * 32);
+        }  // has_tile (contraction)
+        if (lockstep) named_bar_sync(BAR_PHASE, 2 * GROUP_WARPS * 32);
+        if (has_tile) {
 
         // ---- fused epilogue: kernel function, bias, label signs, 128-bit stores
         const long long col_base = (long long)tn * BN + wn * 32 + 2 * t;
-        double nbv[4][2], sbv[4][2];
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        named_bar_sync(BAR_LOCAL0 + grp, GROUP_WARPS * 32);  // every thread's staged operands are visible
+        double nbv[4][2];
+        unsigned sbh[4][2];  // sign bit of s_b
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const long long c = col_base + ni * 8 + e;
-                const bool ok = c < p.nb;
-                nbv[ni][e] = (KERNEL == SVMB200_KERNEL_GAUSSIAN && ok) ? p.norm_b[c] : 0.0;
-                sbv[ni][e] = (p.sign_b != nullptr && ok) ? p.sign_b[c] : 1.0;
+                const int cl = wn * 32 + 2 * t + ni * 8 + e;
+                nbv[ni][e] = sm_nb[cl];
+                sbh[ni][e] = (unsigned)__double2hiint(sm_sb[cl]) & 0x80000000u;
             }
         }
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi) {
             const long long i = p.row0 + (long long)tm * BM + wm * 64 + mi * 8 + g;  // row of A
             if (i >= p.row0 + p.nrows) continue;
-            const double na = (KERNEL == SVMB200_KERNEL_GAUSSIAN) ? p.norm_a[i] : 0.0;
-            const double sa_i = (p.sign_a != nullptr) ? p.sign_a[i] : 1.0;
+            const int rl = wm * 64 + mi * 8 + g;
+            const unsigned sah = (unsigned)__double2hiint(sm_sa[rl]) & 0x80000000u;
             double* orow = p.out + (i - p.row0) * p.ldo;
+            double val[8];
+            if (KERNEL == SVMB200_KERNEL_GAUSSIAN) {
+                // D = (-2<a,b> + |a|^2) + |b|^2 ; clamp ; exact zero on the diagonal of a self-Gram
+                const double na = sm_na[rl];
+                double x[8];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double dist = __dadd_rn(fma(-2.0, acc[mi][ni][e], na), nbv[ni][e]);  // -2<a,b> is exact
+                        dist = fmax(dist, 0.0);
+                        if (p.same && (i == col_base + ni * 8 + e)) dist = 0.0;
+                        x[ni * 2 + e] = __dmul_rn(-p.gamma, dist);
+                    }
+                exp8(x, val);
+            } else if (KERNEL == SVMB200_KERNEL_POLY) {
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)  // separately rounded product and sum (NumPy semantics)
+                        val[ni * 2 + e] = pow_outofline(__dadd_rn(__dmul_rn(p.gamma, acc[mi][ni][e]), p.coef0), p.degree);
+            } else {
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) val[ni * 2 + e] = acc[mi][ni][e];
+            }
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
                 const long long c = col_base + ni * 8;
@@ -216,17 +340,21 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 double* ve = reinterpret_cast<double*>(&v);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    double val = 0.0;
+                    double o = 0.0;
                     if (c + e < p.nb) {
-                        val = kernel_epilogue<KERNEL>(acc[mi][ni][e], na, nbv[ni][e], p.same && (i == c + e), p);
-                        if (p.bias != 0.0) val = __dadd_rn(val, p.bias);
-                        val = __dmul_rn(val, __dmul_rn(sa_i, sbv[ni][e]));
+                        o = val[ni * 2 + e];
+                        if (p.bias != 0.0) o = __dadd_rn(o, p.bias);
+                        // times s_a s_b = +-1: flip the sign bit (integer pipe, not the shared FP64 unit)
+                        o = __hiloint2double(__double2hiint(o) ^ (int)(sah ^ sbh[ni][e]), __double2loint(o));
                     }
-                    ve[e] = val;
+                    ve[e] = o;
                 }
                 *reinterpret_cast<double2*>(orow + c) = v;
             }
         }
+        named_bar_sync(BAR_LOCAL0 + grp, GROUP_WARPS * 32);  // operands free for the next tile's staging
+        }  // has_tile (epilogue)
+        if (lockstep) named_bar_sync(BAR_PHASE, 2 * GROUP_WARPS * 32);
     }
 }
 
@@ -244,7 +372,8 @@ __global__ void row_sqnorm_kernel(const double* __restrict__ X, long long n, lon
     if (lane == 0) out[row] = s;
 }
 
-int make_tensor_map(svmb200_ctx* ctx, CUtensorMap* map, const double* base, int64_t rows, int64_t d, int64_t ld) {
+int make_tensor_map(svmb200_ctx* ctx, CUtensorMap* map, const double* base, int64_t rows, int64_t d, int64_t ld,
+                    int box_rows) {
     if (!ctx->encode_tiled) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -258,7 +387,7 @@ int make_tensor_map(svmb200_ctx* ctx, CUtensorMap* map, const double* base, int6
     auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ctx->encode_tiled);
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -303,6 +432,7 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
     SVM_CHECK_ARG(ldo >= nb && ldo % 2 == 0, "ldo must be even and >= nb");
     SVM_CHECK_ARG(row0 >= 0 && nrows >= 0 && row0 + nrows <= na, "row range outside A");
     SVM_CHECK_ARG(kernel >= SVMB200_KERNEL_LINEAR && kernel <= SVMB200_KERNEL_GAUSSIAN, "unknown kernel id");
+    SVM_CHECK_ARG(kernel != SVMB200_KERNEL_GAUSSIAN || gamma >= 0.0, "gamma must be >= 0 for the gaussian kernel");
     SVM_CHECK_ARG(na < (1ll << 31) && nb < (1ll << 31) && d < (1ll << 31), "dimension too large");
     if (nrows == 0) return SVMB200_OK;
 
@@ -326,8 +456,8 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
     }
     int rc = SVMB200_OK;
     CUtensorMap ma, mb;
-    rc = make_tensor_map(ctx, &ma, dA, na, d, lda);
-    if (rc == SVMB200_OK) rc = make_tensor_map(ctx, &mb, dB, nb, d, ldb);
+    rc = make_tensor_map(ctx, &ma, dA, na, d, lda, BM);
+    if (rc == SVMB200_OK) rc = make_tensor_map(ctx, &mb, dB, nb, d, ldb, BN);
     if (rc == SVMB200_OK) {
         GramArgs a;
         a.norm_a = norm_a;
@@ -343,6 +473,11 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
         a.tiles_m = (int)((nrows + BM - 1) / BM);
         a.tiles_n = (int)((ldo + BN - 1) / BN);
         a.same = same;
+        {
+            // hand-over only pays when there is an epilogue to hide (gaussian / poly); SVMB200_GRAM_EXCLUSIVE overrides
+            const char* ev = getenv("SVMB200_GRAM_EXCLUSIVE");
+            a.exclusive = ev ? atoi(ev) : (kernel != SVMB200_KERNEL_LINEAR ? 2 : 0);
+        }
         a.gamma = gamma;
         a.coef0 = coef0;
         a.degree = degree;
