@@ -174,8 +174,19 @@ def test_full_size_c2_c3_properties(golden):
         g_fresh = m.obj.jacobian(m.alphas_)
         assert np.abs(g_fresh - m.optimizer.g_x).max() <= 1e-8 * max(1., np.abs(g_fresh).max())
         if os.path.exists(os.path.join(GOLDEN, gold + '.npz')):
-            g = golden(gold)
-            assert np.abs(fh[:10] - g['f_hist'][:10]).max() <= 1e-9 * np.abs(g['f_hist'][:10]).max()
+            g = golden(gold)  # the reference's own full-size run (198 s / 270 s on 8 host cores)
+            assert np.array_equal(m.support_, g['support'])
+            if cfg == 'C3':
+                # stable trajectory: north_star's bar at full size
+                assert np.abs(m.alphas_ - g['alphas']).max() <= 1e-8
+                assert np.abs(fh - g['f_hist']).max() <= 1e-9 * np.abs(g['f_hist']).max()
+                assert abs(m.intercept_ - float(g['intercept'])) <= 1e-8
+                assert np.abs(m.coef_ - g['coef']).max() <= 1e-8 * np.abs(g['coef']).max()
+                assert np.abs(m.decision_function(X[:256]) - g['decision']).max() <= 1e-7
+            else:
+                # C2 leaves the reference's trajectory after ~100 iterations (chaotic regime)
+                assert np.abs(fh[:60] - g['f_hist'][:60]).max() <= 1e-9 * np.abs(g['f_hist'][:60]).max()
+                assert fh[-1] <= g['f_hist'][-1] * 1.1
         m.obj.release()
 
 
