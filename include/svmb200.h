@@ -132,12 +132,21 @@ int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld
 int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
                       int hessian, const double* q_host, const double* lb_host, const double* ub_host,
                       const double* x0_host, double eps, int64_t max_iter, svmb200_pg** out);
+/* Frank-Wolfe on the same problem / same handle type (widening): replaces FrankWolfe.minimize
+ * (opti/constrained/frank_wolfe.py:88-165).  `t` in [0,1) is the stabilisation parameter.  The second history
+ * array of svmb200_pg_history then holds the relative gap, svmb200_pg_state's `ng` the last gap. */
+int svmb200_fw_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
+                      int hessian, const double* q_host, const double* lb_host, const double* ub_host,
+                      const double* x0_host, double eps, int64_t max_iter, double t, svmb200_pg** out);
 /* Advance by at most `max_new` iterations (< 0: run to termination; 0: only evaluate the state at
  * the current callback point, i.e. f, |d| and the stopping tests).  The callback point of the
  * reference (projected_gradient.py:95-98) is reached once per iteration; the state visible after
  * svmb200_pg_run returns is the state AT a callback point: x, f(x), g(x), |projected gradient|.  */
 int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, int* status);
 int svmb200_pg_state(svmb200_pg* pg, double* x_host, double* g_host, double* f, double* ng);
+/* scalars of the last evaluated state: {f, |d| (PG) or gap (FW), |d|^2 (PG) or best lower bound (FW), max_t,
+ * last step, last d'Qd} */
+int svmb200_pg_scalars(svmb200_pg* pg, double* vals6);
 /* f and |d| at every callback point so far: (iter+1) values each (train_loss_history, ml/svm/_base.py:289-293) */
 int svmb200_pg_history(svmb200_pg* pg, double* f_hist_host, double* ng_hist_host, int64_t* count);
 /* timing of the last svmb200_pg_run: device milliseconds and number of Q passes (matvec launches) */

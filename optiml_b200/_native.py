@@ -52,8 +52,11 @@ PROTOTYPES = {
     'svmb200_matvec': [c_vp, c_vp, i64, i64, c_vp, c_vp],
     'svmb200_pg_create': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, i64,
                           C.POINTER(c_vp)],
+    'svmb200_fw_create': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, i64, C.c_double,
+                          C.POINTER(c_vp)],
     'svmb200_pg_run': [c_vp, i64, C.POINTER(i64), C.POINTER(C.c_int)],
     'svmb200_pg_state': [c_vp, c_vp, c_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    'svmb200_pg_scalars': [c_vp, c_vp],
     'svmb200_pg_history': [c_vp, c_vp, c_vp, C.POINTER(i64)],
     'svmb200_pg_stats': [c_vp, C.POINTER(C.c_float), C.POINTER(i64), C.POINTER(C.c_float)],
     'svmb200_pg_set_profile': [c_vp, C.c_int],

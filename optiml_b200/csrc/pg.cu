@@ -363,6 +363,7 @@ struct PGDeviceState {
     int done;
     int status;
     double f, ng, s, maxt, t, den;
+    double best_lb;  // Frank-Wolfe: best lower bound so far
 };
 
 struct VecArgs {
@@ -379,6 +380,7 @@ struct VecArgs {
     int nctas;
     double eps;
     long long max_iter;
+    double fw_t;  // Frank-Wolfe stabilisation parameter t in [0, 1)
     // fused exchange: wait until every rank has published `wait_seq` in this rank's flag words
     const unsigned long long* flags;
     unsigned long long wait_seq;
@@ -589,12 +591,173 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     }
 }
 
+// ------------------------------------------------------------------------------------------ K3' Frank-Wolfe
+// Vector phase of the reference's FrankWolfe.minimize (optiml/opti/constrained/frank_wolfe.py:88-165), same
+// structure as pg_vector_kernel: y = ub where g < 0 else lb; lower bound f + g'(y-x); relative gap against the
+// best bound; d = y - x (y clipped to x +- t(ub-lb) when stabilised); a = den<=1e-16 ? 1 : min(-g'd/den, 1).
+// Partials per CTA: x'(g+q), g'(y-x) with the UNclipped y, g'd.  History slot 2 holds the gap.
+__device__ __forceinline__ void fw_direction(double g, double x, double lb, double ub, double t, double& d, double& gy) {
+    const double y = (g < 0.0) ? ub : lb;                       // frank_wolfe.py:100
+    gy = __dmul_rn(g, __dsub_rn(y, x));                          // term of g'(y - x), frank_wolfe.py:104
+    double yc = y;
+    if (t > 0.0) {                                               // frank_wolfe.py:128-130
+        const double radius = __dmul_rn(t, __dsub_rn(ub, lb));
+        yc = fmin(fmax(y, __dsub_rn(x, radius)), __dadd_rn(x, radius));
+    }
+    d = __dsub_rn(yc, x);                                        // frank_wolfe.py:135
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const long long k) {
+    __shared__ double sm[VP_NT / 32][4];
+    PGDeviceState* st = a.st;
+    if (*reinterpret_cast<volatile int*>(&st->done)) return;
+    const int tid = threadIdx.x;
+    if (MODE != VP_FINALISE && a.nranks_wait > 0) {
+        if (tid < a.nranks_wait) {
+            unsigned long long t0 = 0, now = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (ld_acquire_sys_u64(a.flags + tid) < a.wait_seq) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > 20000000000ull) {
+                    *a.fault = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const long long n = a.n;
+    const long long chunk = (n + a.nctas - 1) / a.nctas;
+    const long long j0 = (long long)blockIdx.x * chunk;
+    const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
+    const unsigned rpr = (unsigned)a.rpr, gpr = rpr / MV_GROUP;
+
+    double step = 0.0;
+    if (MODE != VP_INIT) {
+        Quad r;
+        r.a = r.b = r.c = 0.0;
+        r.m = 0.0;  // used as a fourth SUM here (g'd), not a min
+        double gd_part = 0.0;
+        if (tid < a.nctas) {
+            r.a = a.part[tid];                 // x'(g+q)
+            r.b = a.part[VP_MAXC + tid];       // g'(y-x)
+            gd_part = a.part[2 * VP_MAXC + tid];  // g'd
+        }
+        if (MODE == VP_STEP) {
+            const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
+            for (unsigned b0 = tid; b0 < ngrp; b0 += 4 * VP_NT) {
+                double v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned b = b0 + e * VP_NT;
+                    const unsigned rk = b / gpr;
+                    v[e] = b < ngrp ? a.gathered[(size_t)rk * a.stride + rpr + (b - rk * gpr)] : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) r.c = __dadd_rn(r.c, v[e]);
+            }
+        }
+        // reduce g'd through the sum slot of a second Quad (block_reduce's fourth slot is a min)
+        Quad r2;
+        r2.a = gd_part;
+        r2.b = r2.c = 0.0;
+        r2.m = INFINITY;
+        r = block_reduce(r, sm);
+        r2 = block_reduce(r2, sm);
+        const double f = 0.5 * r.a, gy = r.b, den = r.c, gd = r2.a;
+        const double lbv = __dadd_rn(f, gy);
+        const double prev_best = (k == 0) ? -INFINITY : st->best_lb;  // written by the previous launch
+        const double best = lbv > prev_best ? lbv : prev_best;        // frank_wolfe.py:105-106
+        const double gap = __ddiv_rn(__dsub_rn(f, best), fmax(fabs(f), 1.0));  // frank_wolfe.py:109
+        if (blockIdx.x == 0 && tid == 0) {
+            if (k < a.hist_cap) {
+                a.hist_f[k] = f;
+                a.hist_ng[k] = gap;
+            }
+            st->f = f;
+            st->ng = gap;
+            st->s = best;
+            st->best_lb = best;  // idempotent (max): a CTA that starts late and reads the new value computes the same
+            st->iter = k;
+        }
+        int stop = 0;
+        if (gap <= a.eps) stop = SVMB200_STATUS_OPTIMAL;          // frank_wolfe.py:120-122
+        else if (k >= a.max_iter) stop = SVMB200_STATUS_STOPPED;  // frank_wolfe.py:124-126
+        if (stop) {
+            if (blockIdx.x == 0 && tid == 0) {
+                st->status = stop;
+                __threadfence();
+                st->done = 1;
+            }
+            return;
+        }
+        if (MODE == VP_FINALISE) return;  // best_lb is committed by the STEP launch of the same k
+        step = (den <= 1e-16) ? 1.0 : fmin(__ddiv_rn(-gd, den), 1.0);  // frank_wolfe.py:145-149
+        if (blockIdx.x == 0 && tid == 0) {
+            st->t = step;
+            st->den = den;
+        }
+    }
+    Quad acc;
+    acc.a = acc.b = acc.c = 0.0;
+    acc.m = INFINITY;
+    for (long long j = j0 + tid; j < j1; j += VP_NT) {
+        const unsigned rk = (unsigned)j / rpr;
+        const double wj = a.gathered[(size_t)rk * a.stride + ((unsigned)j - rk * rpr)];
+        double x = a.x[j], q = a.q[j], g;
+        if (MODE == VP_INIT) {
+            g = __dadd_rn(wj, q);
+        } else {
+            x = axpy_rn(step, a.d[j], x);
+            g = axpy_rn(step, wj, a.g[j]);
+            a.x[j] = x;
+        }
+        a.g[j] = g;
+        double dn, gyj;
+        fw_direction(g, x, a.lb[j], a.ub[j], a.fw_t, dn, gyj);
+        a.d[j] = dn;
+        acc.a = __dadd_rn(acc.a, __dmul_rn(x, __dadd_rn(g, q)));
+        acc.b = __dadd_rn(acc.b, gyj);
+        acc.c = __dadd_rn(acc.c, __dmul_rn(g, dn));
+        double uj = dn;
+        if (a.svr) {
+            const long long i2 = j + n;
+            double x2 = a.x[i2], q2 = a.q[i2], g2;
+            if (MODE == VP_INIT) {
+                g2 = __dadd_rn(-wj, q2);
+            } else {
+                x2 = axpy_rn(step, a.d[i2], x2);
+                g2 = axpy_rn(step, -wj, a.g[i2]);
+                a.x[i2] = x2;
+            }
+            a.g[i2] = g2;
+            double dn2, gy2;
+            fw_direction(g2, x2, a.lb[i2], a.ub[i2], a.fw_t, dn2, gy2);
+            a.d[i2] = dn2;
+            acc.a = __dadd_rn(acc.a, __dmul_rn(x2, __dadd_rn(g2, q2)));
+            acc.b = __dadd_rn(acc.b, gy2);
+            acc.c = __dadd_rn(acc.c, __dmul_rn(g2, dn2));
+            uj = __dsub_rn(dn, dn2);
+        }
+        a.u[j] = uj;
+    }
+    acc = block_reduce(acc, sm);
+    if (tid == 0) {
+        a.part[blockIdx.x] = acc.a;
+        a.part[VP_MAXC + blockIdx.x] = acc.b;
+        a.part[2 * VP_MAXC + blockIdx.x] = acc.c;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ driver
 struct svmb200_pg {
     svmb200_ctx* ctx = nullptr;
     const double* dQ = nullptr;
     int64_t n = 0, ld = 0, row0 = 0, nrows = 0, nvars = 0, rows_per_rank = 0;
     int svr = 0;
+    int solver = 0;      // 0: projected gradient, 1: Frank-Wolfe
+    double fw_t = 0.0;   // Frank-Wolfe stabilisation parameter
     double eps = 1e-6;
     int64_t max_iter = 1000;
     int64_t hist_cap = 0;
@@ -654,13 +817,15 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
     a.svr = pg->svr;
     a.eps = pg->eps;
     a.max_iter = pg->max_iter;
+    a.fw_t = pg->fw_t;
     return a;
 }
 
 template <int MODE>
 static int launch_vec(svmb200_pg* pg, long long k) {
     VecArgs a = make_vec_args(pg);
-    pg_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
+    if (pg->solver == 1) fw_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
+    else pg_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
     pg->ctx->launches++;
     SVM_CUDA(cudaGetLastError());
     return SVMB200_OK;
@@ -725,9 +890,26 @@ extern "C" int svmb200_pg_destroy(svmb200_pg* pg) {
     return SVMB200_OK;
 }
 
+static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows, int hessian,
+                       const double* q_host, const double* lb_host, const double* ub_host, const double* x0_host,
+                       double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out);
+
 extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
                                  int hessian, const double* q_host, const double* lb_host, const double* ub_host,
                                  const double* x0_host, double eps, int64_t max_iter, svmb200_pg** out) {
+    return bcqp_create(ctx, dQ, n, ld, row0, nrows, hessian, q_host, lb_host, ub_host, x0_host, eps, max_iter, 0, 0.0, out);
+}
+
+extern "C" int svmb200_fw_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
+                                 int hessian, const double* q_host, const double* lb_host, const double* ub_host,
+                                 const double* x0_host, double eps, int64_t max_iter, double t, svmb200_pg** out) {
+    SVM_CHECK_ARG(t >= 0.0 && t < 1.0, "t has to lie in [0, 1)");  // frank_wolfe.py:84-85
+    return bcqp_create(ctx, dQ, n, ld, row0, nrows, hessian, q_host, lb_host, ub_host, x0_host, eps, max_iter, 1, t, out);
+}
+
+static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows, int hessian,
+                       const double* q_host, const double* lb_host, const double* ub_host, const double* x0_host,
+                       double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out) {
     SVM_TRY(svm_use(ctx));
     SVM_CHECK_ARG(out != nullptr, "out is null");
     *out = nullptr;
@@ -760,6 +942,8 @@ extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
     if (pg->nctas > VP_MAXC) pg->nctas = VP_MAXC;
     if (pg->nctas < 1) pg->nctas = 1;
     pg->eps = eps;
+    pg->solver = solver;
+    pg->fw_t = fw_t;
     pg->max_iter = max_iter;
     pg->hist_cap = max_iter + 1 < (1ll << 24) ? max_iter + 1 : (1ll << 24);
     const size_t nv = (size_t)pg->nvars * sizeof(double);
@@ -901,6 +1085,21 @@ extern "C" int svmb200_pg_state(svmb200_pg* pg, double* x_host, double* g_host, 
     SVM_CUDA(cudaStreamSynchronize(s));
     if (f) *f = pg->st_host->f;
     if (ng) *ng = pg->st_host->ng;
+    return SVMB200_OK;
+}
+
+extern "C" int svmb200_pg_scalars(svmb200_pg* pg, double* vals6) {
+    SVM_CHECK_ARG(pg != nullptr && vals6 != nullptr, "null argument");
+    SVM_TRY(svm_use(pg->ctx));
+    cudaStream_t s = pg->ctx->stream;
+    SVM_CUDA(cudaMemcpyAsync(pg->st_host, pg->st, sizeof(PGDeviceState), cudaMemcpyDeviceToHost, s));
+    SVM_CUDA(cudaStreamSynchronize(s));
+    vals6[0] = pg->st_host->f;
+    vals6[1] = pg->st_host->ng;
+    vals6[2] = pg->st_host->s;
+    vals6[3] = pg->st_host->maxt;
+    vals6[4] = pg->st_host->t;
+    vals6[5] = pg->st_host->den;
     return SVMB200_OK;
 }
 

@@ -1,0 +1,122 @@
+"""Shared host driver of the device-resident box-constrained QP solvers (ProjectedGradient, FrankWolfe).
+
+Both reference solvers have the same outer shape (projected_gradient.py:76-143, frank_wolfe.py:88-165):
+evaluate f, g and a direction, call the callback, test two stopping criteria, take an exact line-search
+step.  On the device that is one streaming pass over Q plus one vector kernel per iteration
+(csrc/pg.cu); this mixin only decides how often the host looks at the state.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ... import _native as N
+
+
+class DeviceLoopMixin:
+    # subclasses set these
+    _create_symbol = None          # C entry point that builds the solver handle
+    _verbose_header = ''
+
+    def _extra_create_args(self):
+        return ()
+
+    def _print_iteration(self, scalars):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ device solver handle
+    def _create(self, profile=False):
+        H = self.f.device_hessian()
+        n = H.nvars
+        if self.ub.size != n or self.lb.size != n or self.x.size != n:
+            raise ValueError('bounds / start point size does not match with Q')
+        q, lb, ub, x0 = (np.ascontiguousarray(v, dtype=np.float64) for v in (self.f.q, self.lb, self.ub, self.x))
+        h = C.c_void_p()
+        N.call(self._create_symbol, H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows,
+               N.HESSIAN_SVR if H.layout == 'svr' else N.HESSIAN_PLAIN, N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0),
+               float(self.eps), int(self.max_iter), *self._extra_create_args(), C.byref(h))
+        if profile:
+            N.call('svmb200_pg_set_profile', h, 1)
+        return h, n
+
+    @staticmethod
+    def _run(h, max_new):
+        it, st = C.c_int64(0), C.c_int(0)
+        N.call('svmb200_pg_run', h, int(max_new), C.byref(it), C.byref(st))
+        return int(it.value), N.STATUS[st.value]
+
+    def _pull_state(self, h, n):
+        x, g = np.empty(n), np.empty(n)
+        f, ng = C.c_double(0), C.c_double(0)
+        N.call('svmb200_pg_state', h, N.ptr(x), N.ptr(g), C.byref(f), C.byref(ng))
+        self.x, self.g_x, self.f_x = x, g, float(f.value)
+        return float(ng.value)
+
+    @staticmethod
+    def _scalars(h):
+        vals = np.zeros(6)
+        N.call('svmb200_pg_scalars', h, N.ptr(vals))
+        return vals
+
+    def _history_only_callback(self):
+        """True when nothing has to run on the host between iterations: no callback, or the estimators' own
+        ``_store_train_info`` (ml/svm/_base.py:289-293) which only appends f_x."""
+        cb = self._callback
+        return cb is None or getattr(cb, '_svmb200_history_only', False) or \
+            getattr(getattr(cb, '__func__', None), '_svmb200_history_only', False)
+
+    def minimize(self):
+        if self.verbose:
+            print(self._verbose_header, end='')
+        profile = bool(getattr(self, 'profile', False))
+        h, n = self._create(profile)
+        try:
+            if self._history_only_callback() and not self.verbose and self.f.ndim > 3:
+                self._minimize_resident(h, n)
+            else:
+                self._minimize_stepwise(h, n)
+            self._collect_stats(h)
+        finally:
+            N.load_library().svmb200_pg_destroy(h)
+        if self.verbose:
+            print('\n')
+        return self
+
+    def _minimize_resident(self, h, n):
+        # whole loop on the device; f at every callback point comes back in one copy
+        self.iter, self.status = self._run(h, -1)
+        self._pull_state(h, n)
+        cnt = C.c_int64(0)
+        f_hist, second = np.empty(self.iter + 1), np.empty(self.iter + 1)
+        N.call('svmb200_pg_history', h, N.ptr(f_hist), N.ptr(second), C.byref(cnt))
+        self.f_hist, self.ng_hist = f_hist[:cnt.value], second[:cnt.value]
+        if self._callback is not None:
+            # replay the history-only callback: one call per callback point, in order
+            final_f, final_iter = self.f_x, self.iter
+            for k, fk in enumerate(self.f_hist):
+                self.iter, self.f_x = k, float(fk)
+                self._callback(self, *self.callback_args)
+            self.iter, self.f_x = final_iter, final_f
+
+    def _minimize_stepwise(self, h, n):
+        # generic callbacks / verbose / ndim <= 3 histories: synchronise at every callback point
+        self.iter, status = self._run(h, 0)
+        while True:
+            self._pull_state(h, n)
+            if self.is_verbose():
+                self._print_iteration(self._scalars(h))
+            try:
+                self.callback()
+            except StopIteration:
+                break
+            if status != 'unknown':
+                self.status = status
+                break
+            self.iter, status = self._run(h, 1)
+
+    def _collect_stats(self, h):
+        ms, passes, mv = C.c_float(0), C.c_int64(0), C.c_float(0)
+        N.call('svmb200_pg_stats', h, C.byref(ms), C.byref(passes), C.byref(mv))
+        self.device_ms, self.q_passes, self.matvec_ms = float(ms.value), int(passes.value), float(mv.value)
+        cm, vm = C.c_float(0), C.c_float(0)
+        N.call('svmb200_pg_stats_ex', h, C.byref(mv), C.byref(cm), C.byref(vm))
+        self.comm_ms, self.vector_ms = float(cm.value), float(vm.value)

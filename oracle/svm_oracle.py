@@ -156,6 +156,60 @@ def projected_gradient(Q, q, ub, lb=None, x0=None, eps=1e-6, max_iter=1000, pass
     return res
 
 
+def frank_wolfe(Q, q, ub, lb=None, x0=None, t=0., eps=1e-6, max_iter=1000, passes=3, callback=None):
+    """optiml/opti/constrained/frank_wolfe.py:88-165 (start point opti/constrained/_base.py:59-65).
+    ``passes`` as in :func:`projected_gradient`.  ``ng_hist`` holds the relative gap."""
+    Q = np.asarray(Q, dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64)
+    ub = np.asarray(ub, dtype=np.float64)
+    lb = np.zeros_like(ub) if lb is None else np.asarray(lb, dtype=np.float64)
+    x = ((lb + ub) / 2) if x0 is None else np.array(x0, dtype=np.float64)
+    res = PGResult()
+    res.status, res.iter, res.n_clipped = 'unknown', 0, 0
+    f_hist, gap_hist = [], []
+    best_lb = -np.inf
+    g = Q @ x + q if passes == 1 else None
+    while True:
+        if passes == 3:
+            f_x = 0.5 * x @ Q @ x + q @ x
+            g = Q @ x + q
+        else:
+            f_x = 0.5 * (x @ (g + q))
+        y = np.where(g < 0, ub, lb)
+        lbv = f_x + g.dot(y - x)
+        if lbv > best_lb:
+            best_lb = lbv
+        gap = (f_x - best_lb) / max(abs(f_x), 1)
+        f_hist.append(f_x)
+        gap_hist.append(gap)
+        if callback is not None:
+            callback(res.iter, x, f_x, gap)
+        if gap <= eps:
+            res.status = 'optimal'
+            break
+        if res.iter >= max_iter:
+            res.status = 'stopped'
+            break
+        if t > 0:
+            radius = t * (ub - lb)
+            y = np.clip(y, x - radius, x + radius)
+        d = y - x
+        w = Q @ d if passes == 1 else d.dot(Q)
+        den = w.dot(d)
+        if den <= 1e-16:
+            a = 1
+        else:
+            a = min(-g.dot(d) / den, 1)
+            res.n_clipped += int(a == 1)
+        x += a * d
+        if passes == 1:
+            g = g + a * w
+        res.iter += 1
+    res.x, res.f_x, res.g_x = x, f_x, g
+    res.f_hist, res.ng_hist = np.array(f_hist), np.array(gap_hist)
+    return res
+
+
 # ----------------------------------------------------------------------------- estimators
 
 

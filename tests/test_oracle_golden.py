@@ -130,3 +130,16 @@ def test_c2_c3_c4_small(golden):
     g = golden('c4small_svc_gaussian')
     spec, X, y = make_config('C4', n=1200)
     _check_fit(O.svc_dual_fit(X, y, kind='gaussian', C=2.5, max_iter=300), g)
+
+
+@pytest.mark.parametrize('key,p,t', [('p2', 'p2', 0.), ('p5', 'p5', 0.), ('p64', 'p64', 0.), ('p200', 'p200', 0.),
+                                     ('p64_t05', 'p64', 0.5)])
+def test_frank_wolfe_three_pass_bit_exact(golden, key, p, t):
+    """widening: the oracle's Frank-Wolfe vs the reference's FrankWolfe.minimize"""
+    g, fw = golden('bcqp'), golden('frank_wolfe')
+    lb = g[p + '_lb'] if p + '_lb' in g else None
+    r = O.frank_wolfe(g[p + '_Q'], g[p + '_q'], g[p + '_ub'], lb=lb, t=t, passes=3)
+    assert r.iter == int(fw[key + '_iter']) and r.status == str(fw[key + '_status'])
+    assert np.array_equal(r.x, fw[key + '_x'])
+    assert np.array_equal(r.f_hist, fw[key + '_f_hist'])
+    assert np.array_equal(r.g_x, fw[key + '_g'])
