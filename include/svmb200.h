@@ -39,6 +39,9 @@ extern "C" {
 #define SVMB200_KERNEL_LINEAR 0
 #define SVMB200_KERNEL_POLY 1
 #define SVMB200_KERNEL_GAUSSIAN 2
+/* widening: kernels.py:166 (SigmoidKernel), :132 (LaplacianKernel) */
+#define SVMB200_KERNEL_SIGMOID 3
+#define SVMB200_KERNEL_LAPLACIAN 4
 
 /* Hessian layouts understood by the solver */
 #define SVMB200_HESSIAN_PLAIN 0 /* Q is the n x n matrix itself, nvars = n (SVC; generic BCQP)      */
@@ -104,6 +107,8 @@ int svmb200_shard_rows(int64_t n, int rank, int nranks, int64_t* row0, int64_t* 
  *   k = <a,b>                              (LINEAR)
  *     = (gamma <a,b> + coef0) ^ degree     (POLY)
  *     = exp(-gamma max(0, |a|^2+|b|^2-2<a,b>)), distance forced to 0 where i == j if `same` (GAUSSIAN)
+ *     = tanh(gamma <a,b> + coef0)                                                              (SIGMOID)
+ *     = exp(-gamma sum_k |a_k - b_k|)   (LAPLACIAN; CUDA-core pairwise kernel, not a contraction)
  * dA: na x d (ld = lda), dB: nb x d (ld = ldb); pass dB = dA and same = 1 for the training Gram.
  * dsign_a / dsign_b: +-1.0 per row, or NULL (= +1).  Columns [nb, ldo) of `out` are zero-filled
  * (the solver streams whole padded rows).  ldo must be a multiple of 2.

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_lib', 'libsvmb200.so')
 
-KERNEL_LINEAR, KERNEL_POLY, KERNEL_GAUSSIAN = 0, 1, 2
+KERNEL_LINEAR, KERNEL_POLY, KERNEL_GAUSSIAN, KERNEL_SIGMOID, KERNEL_LAPLACIAN = 0, 1, 2, 3, 4
 HESSIAN_PLAIN, HESSIAN_SVR = 0, 1
 STATUS = {0: 'unknown', 1: 'optimal', 2: 'stopped'}
 

@@ -93,6 +93,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 
 // pow() stays out of line (the poly epilogue is unrolled 64x per thread and pow is ~300 instructions).
 __device__ __noinline__ double pow_outofline(double x, double y) { return pow(x, y); }
+__device__ __noinline__ double tanh_outofline(double x) { return tanh(x); }
 
 // exp(x), x <= 0, for the Gaussian epilogue, evaluated for EIGHT independent arguments in lock-step so
 // that the FP64 unit sees 8 independent dependency chains (a scalar exp() is one chain of dependent DFMAs,
@@ -326,6 +327,12 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                     for (int e = 0; e < 2; ++e)  // separately rounded product and sum (NumPy semantics)
                         val[ni * 2 + e] = pow_outofline(__dadd_rn(__dmul_rn(p.gamma, acc[mi][ni][e]), p.coef0), p.degree);
+            } else if (KERNEL == SVMB200_KERNEL_SIGMOID) {
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)  // kernels.py:197-201
+                        val[ni * 2 + e] = tanh_outofline(__dadd_rn(__dmul_rn(p.gamma, acc[mi][ni][e]), p.coef0));
             } else {
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni)
@@ -355,6 +362,112 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         named_bar_sync(BAR_LOCAL0 + grp, GROUP_WARPS * 32);  // operands free for the next tile's staging
         }  // has_tile (epilogue)
         if (lockstep) named_bar_sync(BAR_PHASE, 2 * GROUP_WARPS * 32);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Laplacian kernel (widening): k(a,b) = exp(-gamma * sum_k |a_k - b_k|)
+// (optiml/ml/svm/kernels.py:159-163 -> sklearn manhattan_distances -> scipy cdist 'cityblock': a sequential
+// sum over k).  Not a contraction: CUDA-core tile kernel, 128x128 outputs per CTA, 8x8 per thread, operands
+// staged (transposed) in shared memory 16 features at a time, the same k order as the reference so the
+// distances are bit-identical; exp8 epilogue, bias, label signs, zero pad columns as in gram_kernel.
+constexpr int LT = 128, LKC = 16, LPAD = 2, LAP_THREADS = 256;
+
+struct LapArgs {
+    const double *A, *B;
+    long long lda, ldb, na, nb, d;
+    const double *sign_a, *sign_b;
+    double* out;
+    long long ldo, row0, nrows;
+    double gamma, bias;
+};
+
+__global__ void __launch_bounds__(LAP_THREADS) laplacian_kernel(const LapArgs p) {
+    __shared__ __align__(16) double As[LKC][LT + LPAD];
+    __shared__ __align__(16) double Bs[LKC][LT + LPAD];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const long long i0 = p.row0 + (long long)blockIdx.y * LT;   // first row of A in this tile
+    const long long j0 = (long long)blockIdx.x * LT;            // first row of B (= output column)
+    double acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+    double ra[8], rb[8];
+    auto fetch = [&](long long kc) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = tid + j * LAP_THREADS, row = e >> 4, k = e & 15;
+            const long long ia = i0 + row, jb = j0 + row, kk = kc + k;
+            ra[j] = (ia < p.row0 + p.nrows && kk < p.d) ? p.A[ia * p.lda + kk] : 0.0;
+            rb[j] = (jb < p.nb && kk < p.d) ? p.B[jb * p.ldb + kk] : 0.0;
+        }
+    };
+    fetch(0);
+    for (long long kc = 0; kc < p.d; kc += LKC) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = tid + j * LAP_THREADS, row = e >> 4, k = e & 15;
+            As[k][row] = ra[j];
+            Bs[k][row] = rb[j];
+        }
+        __syncthreads();
+        if (kc + LKC < p.d) fetch(kc + LKC);  // next chunk's global loads overlap the arithmetic below
+#pragma unroll 4
+        for (int k = 0; k < LKC; ++k) {
+            double a[8], b[8];
+#pragma unroll
+            for (int r = 0; r < 8; r += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&As[k][ty * 8 + r]);
+                a[r] = v.x;
+                a[r + 1] = v.y;
+                const double2 w = *reinterpret_cast<const double2*>(&Bs[k][tx * 8 + r]);
+                b[r] = w.x;
+                b[r + 1] = w.y;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = __dadd_rn(acc[r][c], fabs(__dsub_rn(a[r], b[c])));
+        }
+    }
+    // epilogue
+    unsigned sbh[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const long long col = j0 + tx * 8 + c;
+        sbh[c] = (p.sign_b != nullptr && col < p.nb) ? ((unsigned)__double2hiint(p.sign_b[col]) & 0x80000000u) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const long long i = i0 + ty * 8 + r;
+        if (i >= p.row0 + p.nrows) continue;
+        const unsigned sah = (p.sign_a != nullptr) ? ((unsigned)__double2hiint(p.sign_a[i]) & 0x80000000u) : 0u;
+        double x[8], val[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = __dmul_rn(-p.gamma, acc[r][c]);
+        exp8(x, val);
+        double* orow = p.out + (i - p.row0) * p.ldo;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            const long long col = j0 + tx * 8 + c;
+            if (col >= p.ldo) continue;
+            double2 v;
+            double* ve = reinterpret_cast<double*>(&v);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double o = 0.0;
+                if (col + e < p.nb) {
+                    o = val[c + e];
+                    if (p.bias != 0.0) o = __dadd_rn(o, p.bias);
+                    o = __hiloint2double(__double2hiint(o) ^ (int)(sah ^ sbh[c + e]), __double2loint(o));
+                }
+                ve[e] = o;
+            }
+            *reinterpret_cast<double2*>(orow + col) = v;
+        }
     }
 }
 
@@ -431,10 +544,36 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
                       (reinterpret_cast<uintptr_t>(dout) & 15) == 0, "matrices must be 16-byte aligned");
     SVM_CHECK_ARG(ldo >= nb && ldo % 2 == 0, "ldo must be even and >= nb");
     SVM_CHECK_ARG(row0 >= 0 && nrows >= 0 && row0 + nrows <= na, "row range outside A");
-    SVM_CHECK_ARG(kernel >= SVMB200_KERNEL_LINEAR && kernel <= SVMB200_KERNEL_GAUSSIAN, "unknown kernel id");
-    SVM_CHECK_ARG(kernel != SVMB200_KERNEL_GAUSSIAN || gamma >= 0.0, "gamma must be >= 0 for the gaussian kernel");
+    SVM_CHECK_ARG(kernel >= SVMB200_KERNEL_LINEAR && kernel <= SVMB200_KERNEL_LAPLACIAN, "unknown kernel id");
+    SVM_CHECK_ARG((kernel != SVMB200_KERNEL_GAUSSIAN && kernel != SVMB200_KERNEL_LAPLACIAN) || gamma >= 0.0,
+                  "gamma must be >= 0 for the gaussian / laplacian kernels");
     SVM_CHECK_ARG(na < (1ll << 31) && nb < (1ll << 31) && d < (1ll << 31), "dimension too large");
     if (nrows == 0) return SVMB200_OK;
+
+    if (kernel == SVMB200_KERNEL_LAPLACIAN) {
+        LapArgs a;
+        a.A = dA;
+        a.B = dB;
+        a.lda = lda;
+        a.ldb = ldb;
+        a.na = na;
+        a.nb = nb;
+        a.d = d;
+        a.sign_a = dsign_a;
+        a.sign_b = dsign_b;
+        a.out = dout;
+        a.ldo = ldo;
+        a.row0 = row0;
+        a.nrows = nrows;
+        a.gamma = gamma;
+        a.bias = bias;
+        dim3 grid((unsigned)((ldo + LT - 1) / LT), (unsigned)((nrows + LT - 1) / LT));
+        SVM_CHECK_ARG(grid.y <= 65535, "row range too large for one launch");
+        laplacian_kernel<<<grid, LAP_THREADS, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        SVM_CUDA(cudaGetLastError());
+        return SVMB200_OK;
+    }
 
     double *norm_a = nullptr, *norm_b = nullptr;
     if (kernel == SVMB200_KERNEL_GAUSSIAN) {
@@ -484,6 +623,7 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
         a.bias = bias;
         if (kernel == SVMB200_KERNEL_LINEAR) rc = launch_gram<SVMB200_KERNEL_LINEAR>(ctx, ma, mb, a);
         else if (kernel == SVMB200_KERNEL_POLY) rc = launch_gram<SVMB200_KERNEL_POLY>(ctx, ma, mb, a);
+        else if (kernel == SVMB200_KERNEL_SIGMOID) rc = launch_gram<SVMB200_KERNEL_SIGMOID>(ctx, ma, mb, a);
         else rc = launch_gram<SVMB200_KERNEL_GAUSSIAN>(ctx, ma, mb, a);
     }
     if (norm_a || norm_b) {

@@ -86,6 +86,27 @@ class GaussianKernel(Kernel):
         self.gamma = gamma
 
 
+class LaplacianKernel(Kernel):
+    """K(X, Y) = exp(-gamma ||X - Y||_1)  (kernels.py:132-163; widening)."""
+    kernel_id = N.KERNEL_LAPLACIAN
+
+    def __init__(self, gamma='scale'):
+        _check_gamma(gamma)
+        self.gamma = gamma
+
+
+class SigmoidKernel(Kernel):
+    """K(X, Y) = tanh(gamma <X, Y> + coef0)  (kernels.py:166-201; widening)."""
+    kernel_id = N.KERNEL_SIGMOID
+
+    def __init__(self, gamma='scale', coef0=0.):
+        _check_gamma(gamma)
+        self.gamma = gamma
+        self.coef0 = coef0
+
+
 linear = LinearKernel()
 poly = PolyKernel()
 gaussian = GaussianKernel()
+laplacian = LaplacianKernel()
+sigmoid = SigmoidKernel()

@@ -53,12 +53,14 @@ def load_reference():
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     from optiml.ml.svm import SVC, SVR
-    from optiml.ml.svm.kernels import GaussianKernel, PolyKernel, LinearKernel, gaussian, poly, linear
+    from optiml.ml.svm.kernels import (GaussianKernel, PolyKernel, LinearKernel, LaplacianKernel, SigmoidKernel,
+                                       gaussian, poly, linear)
     from optiml.ml.svm.losses import hinge, epsilon_insensitive
     from optiml.opti import Quadratic
     from optiml.opti.constrained import ProjectedGradient, FrankWolfe
     ns = types.SimpleNamespace(SVC=SVC, SVR=SVR, GaussianKernel=GaussianKernel, PolyKernel=PolyKernel,
-                               LinearKernel=LinearKernel, gaussian=gaussian, poly=poly, linear=linear,
+                               LinearKernel=LinearKernel, LaplacianKernel=LaplacianKernel,
+                               SigmoidKernel=SigmoidKernel, gaussian=gaussian, poly=poly, linear=linear,
                                hinge=hinge, epsilon_insensitive=epsilon_insensitive, Quadratic=Quadratic,
                                ProjectedGradient=ProjectedGradient, FrankWolfe=FrankWolfe)
     ns.generate_box_constrained_quadratic = _load_bcqp_generator()

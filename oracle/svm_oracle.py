@@ -74,7 +74,36 @@ def gaussian_kernel(X, Y=None, gamma='scale'):
     return np.exp(-g * squared_distances(X, Y))
 
 
+def manhattan_distances(X, Y=None):
+    """sklearn manhattan_distances (dense) = scipy cdist 'cityblock': s += |u_k - v_k|, k ascending."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = X if Y is None else np.asarray(Y, dtype=np.float64)
+    D = np.zeros((X.shape[0], Y.shape[0]))
+    for k in range(X.shape[1]):
+        D += np.abs(X[:, k, None] - Y[None, :, k])
+    return D
+
+
+def laplacian_kernel(X, Y=None, gamma='scale'):
+    """optiml/ml/svm/kernels.py:159-163  K = exp(-gamma * ||x - y||_1)  (widening 8f-2)."""
+    X = np.asarray(X, dtype=np.float64)
+    g = resolve_gamma(gamma, X)
+    return np.exp(-g * manhattan_distances(X, Y))
+
+
+def sigmoid_kernel(X, Y=None, gamma='scale', coef0=0.):
+    """optiml/ml/svm/kernels.py:197-201  K = tanh(gamma X Y^T + coef0)  (widening 8f-2)."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = X if Y is None else np.asarray(Y, dtype=np.float64)
+    g = resolve_gamma(gamma, X)
+    return np.tanh(g * (X @ Y.T) + coef0)
+
+
 def kernel_matrix(kind, X, Y=None, degree=3, gamma='scale', coef0=0.):
+    if kind == 'laplacian':
+        return laplacian_kernel(X, Y, gamma=gamma)
+    if kind == 'sigmoid':
+        return sigmoid_kernel(X, Y, gamma=gamma, coef0=coef0)
     if kind == 'linear':
         return linear_kernel(X, Y)
     if kind == 'poly':

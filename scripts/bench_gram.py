@@ -8,7 +8,8 @@ from optiml_b200.runtime import default_context
 from oracle import svm_oracle as O
 
 ctx = default_context()
-for cfg, n, kid, kind in (('C4', 50000, 2, 'gaussian'), ('C3', 20000, 0, 'linear'), ('C2', 10000, 1, 'poly'), ('C1', 2000, 2, 'gaussian')):
+for cfg, n, kid, kind in (('C4', 50000, 2, 'gaussian'), ('C3', 20000, 0, 'linear'), ('C2', 10000, 1, 'poly'), ('C1', 2000, 2, 'gaussian'),
+                          ('C4', 50000, 4, 'laplacian'), ('C4', 50000, 3, 'sigmoid')):
     spec, X, y = make_config(cfg, n=n)
     d = X.shape[1]
     gamma = 1. / (d * X.var())
@@ -29,6 +30,7 @@ for cfg, n, kid, kind in (('C4', 50000, 2, 'gaussian'), ('C3', 20000, 0, 'linear
     want = O.kernel_matrix(kind, X[r0:r0 + 128], X, gamma=gamma, degree=3)
     if kind == 'gaussian':
         want[np.arange(128), np.arange(r0, r0 + 128)] = 1.0
+    flops = 2.0 * n * n * d
     err = np.abs(rows[:, :n] - want) / (np.abs(want) + 1e-3 * np.abs(want).max())
     print(f'{cfg} n={n} d={d} {kind}: {ms:.3f} ms  {2.0*n*n*d/ms/1e9:.2f} TFLOP/s  write {8.0*n*ld/ms/1e6:.0f} GB/s  max rel err {err.max():.2e}', flush=True)
     ctx.free(dQ); dX.release()

@@ -80,3 +80,50 @@ def test_kernel_input_validation():
     # ints are promoted to float64, float32 is computed in FP64
     Ki = PolyKernel(gamma=1.)(np.arange(12).reshape(4, 3))
     assert Ki.dtype == np.float64 and Ki[1, 2] == float(np.dot([3, 4, 5], [6, 7, 8])) ** 3
+
+
+# ---- widening: Laplacian (CUDA-core pairwise kernel) and Sigmoid (tanh epilogue)
+def extra_kernels():
+    from optiml_b200.ml.svm.kernels import LaplacianKernel, SigmoidKernel
+    return {'lap_scale': (LaplacianKernel(), dict(kind='laplacian')),
+            'lap_g03': (LaplacianKernel(gamma=0.3), dict(kind='laplacian', gamma=0.3)),
+            'sig_scale': (SigmoidKernel(), dict(kind='sigmoid')),
+            'sig_g01_c05': (SigmoidKernel(gamma=0.01, coef0=0.5), dict(kind='sigmoid', gamma=0.01, coef0=0.5))}
+
+
+@pytest.mark.parametrize('name', ['lap_scale', 'lap_g03', 'sig_scale', 'sig_g01_c05'])
+def test_extra_kernel_golden(golden, name):
+    g, ex = golden('kernels'), golden('kernels_extra')
+    k, _ = extra_kernels()[name]
+    assert_gram_close(k(g['X']), ex[name + '_XX'])
+    assert_gram_close(k(g['X'], g['Y']), ex[name + '_XY'])
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 1), (129, 127, 17), (257, 1, 33), (130, 300, 100), (383, 129, 16)])
+@pytest.mark.parametrize('name', ['lap_scale', 'sig_scale'])
+def test_extra_kernel_ragged_shapes_vs_oracle(shape, name):
+    nx, ny, d = shape
+    rng = np.random.default_rng(nx * 1000 + ny + d)
+    X = rng.standard_normal((nx, d)) + 0.5
+    Y = rng.standard_normal((ny, d)) - 0.25
+    k, kw = extra_kernels()[name]
+    kw = dict(kw)
+    kind = kw.pop('kind')
+    assert_gram_close(k(X, Y), O.kernel_matrix(kind, X, Y, **kw))
+    assert_gram_close(k(X), O.kernel_matrix(kind, X, None, **kw))
+
+
+@pytest.mark.parametrize('name,kern', [('lap', 'LaplacianKernel'), ('sig', 'SigmoidKernel')])
+def test_extra_kernel_svc_fit(golden, name, kern):
+    from optiml_b200.ml.svm import SVC
+    from optiml_b200.ml.svm import kernels as K
+    from optiml_b200.ml.svm.losses import hinge
+    from optiml_b200.opti.constrained import FrankWolfe
+    iris, ex = golden('iris_ovr'), golden('kernels_extra')
+    kernel = K.LaplacianKernel() if name == 'lap' else K.SigmoidKernel(gamma=0.05, coef0=0.)
+    m = SVC(loss=hinge, kernel=kernel, reg_intercept=True, dual=True, optimizer=FrankWolfe, max_iter=300).fit(
+        iris['X_train'], (iris['y_train'] == 0).astype(int))
+    assert np.abs(m.alphas_ - ex[f'iris_{name}_alphas']).max() <= 1e-8
+    assert np.array_equal(m.support_, ex[f'iris_{name}_support'])
+    assert abs(m.intercept_ - float(ex[f'iris_{name}_intercept'])) <= 1e-8
+    assert np.abs(m.decision_function(iris['X_test']) - ex[f'iris_{name}_decision']).max() <= 1e-8

@@ -143,3 +143,14 @@ def test_frank_wolfe_three_pass_bit_exact(golden, key, p, t):
     assert np.array_equal(r.x, fw[key + '_x'])
     assert np.array_equal(r.f_hist, fw[key + '_f_hist'])
     assert np.array_equal(r.g_x, fw[key + '_g'])
+
+
+@pytest.mark.parametrize('name,kw', [('lap_scale', dict(kind='laplacian')), ('lap_g03', dict(kind='laplacian', gamma=0.3)),
+                                     ('sig_scale', dict(kind='sigmoid')), ('sig_g01_c05', dict(kind='sigmoid', gamma=0.01, coef0=0.5))])
+def test_extra_kernels_bit_exact(golden, name, kw):
+    """widening: Laplacian / Sigmoid kernels vs the reference"""
+    g, ex = golden('kernels'), golden('kernels_extra')
+    kw = dict(kw)
+    kind = kw.pop('kind')
+    assert np.array_equal(O.kernel_matrix(kind, g['X'], None, **kw), ex[name + '_XX'])
+    assert np.array_equal(O.kernel_matrix(kind, g['X'], g['Y'], **kw), ex[name + '_XY'])
