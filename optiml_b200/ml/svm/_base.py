@@ -152,7 +152,22 @@ class SVM(BaseEstimator):
             N.call('svmb200_decision', default_context().handle, N.ptr(sv), sv.shape[0], N.ptr(coef), N.ptr(X),
                    X.shape[0], X.shape[1], kid, gamma, coef0, degree, float(self.intercept_), N.ptr(out))
             return out
-        return np.dot(X, self.coef_) + self.intercept_
+        # linear dual / primal form X @ coef_ + b (ml/svm/_base.py:287): streaming matvec over the rows of X
+        X, _ = _dense_f64(X, None)
+        ctx = default_context()
+        dX = ctx.upload_matrix(X)
+        dcoef = ctx.upload_vector(self.coef_, length=dX.ld)
+        dout = ctx.malloc(8 * X.shape[0])
+        out = np.empty(X.shape[0])
+        try:
+            N.call('svmb200_matvec', ctx.handle, C.c_void_p(dX.dptr), X.shape[0], dX.ld, C.c_void_p(dcoef.dptr),
+                   C.c_void_p(dout))
+            ctx.d2h(out, dout)
+        finally:
+            ctx.free(dout)
+            dX.release()
+            dcoef.release()
+        return out + self.intercept_
 
     def _store_train_info(self, opt):
         self.train_loss_history.append(opt.f_x)

@@ -242,11 +242,21 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) mv_tma(const double* __rest
 struct Result { const char* name; double gbs; float ms; };
 static std::vector<Result> results;
 
+static int g_sustain = 0;
 template <typename F>
 void timeit(const char* name, double bytes, F launch, int reps = 10) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 3; ++i) launch();
     CK(cudaDeviceSynchronize());
+    if (g_sustain > 0) {
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < g_sustain; ++i) launch();
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("%-60s SUSTAINED x%d: %8.4f ms/launch  %7.1f GB/s\n", name, g_sustain, ms / g_sustain, bytes / (ms / g_sustain) / 1e6);
+        fflush(stdout);
+        return;
+    }
     float best = 1e30f, tot = 0;
     for (int i = 0; i < reps; ++i) {
         CK(cudaEventRecord(e0)); launch(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
@@ -291,34 +301,19 @@ int main(int argc, char** argv) {
     for (int pass = 0; pass < 2; ++pass) {
         const long long nrows = pass == 0 ? 50000 : 6250;
         const char* tag = pass == 0 ? "[20GB]" : "[2.5GB]";
-        run_ldg<8, 256, 2, 16>(tag, Q, ld, nrows, u, w, wpart, cnt, 0);      // round-1 first kernel
-        run_ldg<4, 256, 4, 16, 0, 0, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
-        run_ldg<4, 256, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
-        run_ldg<4, 256, 4, 16, 0, 0, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
-        run_ldg<4, 256, 4, 16, 0, 0, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        g_sustain = 0;
         run_ldg<4, 256, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<8, 256, 2, 16, 0, 0, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 0);
-        run_ldg<8, 256, 2, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 0);
-        run_ldg<8, 256, 2, 16, 0, 0, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 0);
-        run_ldg<8, 256, 2, 16, 0, 0, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
-        run_ldg<8, 256, 2, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
-        run_ldg<8, 256, 2, 16, 0, 0, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
-        run_ldg<8, 256, 2, 16, 0, 0, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<8, 256, 2, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<8, 256, 2, 16, 0, 0, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<4, 128, 4, 32, 0, 0, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<4, 128, 4, 32, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        g_sustain = pass == 0 ? 400 : 2000;
+        run_ldg<4, 256, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<4, 256, 4, 16, 0, 1, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
         run_ldg<4, 128, 4, 32, 0, 0, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<4, 128, 4, 32, 0, 0, 6>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<4, 128, 8, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
         run_ldg<4, 128, 8, 16, 0, 0, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<4, 128, 8, 16, 0, 0, 6>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<8, 128, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<8, 128, 4, 16, 0, 0, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<8, 128, 4, 16, 0, 0, 6>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
-        run_ldg<4, 256, 2, 32, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
-        run_ldg<4, 256, 4, 16, 1, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
-        run_ldg<4, 256, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
+        run_ldg<8, 256, 2, 16, 0, 0, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<4, 256, 4, 16, 0, 0, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_tma<4, 1024, 3, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192, 2);
+        run_tma<8, 512, 3, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192, 2);
+        run_tma<4, 1024, 3, 2>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192, 2);
+        run_ldg<4, 256, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
     }
     return 0;
 }
