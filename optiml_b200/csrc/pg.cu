@@ -55,6 +55,9 @@ struct MatvecArgs {
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -194,8 +197,10 @@ __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const Matvec
         if (threadIdx.x == 0) {
             if (atomicAdd(a.rank_done, 1u) == a.ngroups - 1) {
                 *a.rank_done = 0;
+                // ONE system fence, then relaxed flag stores (fence + relaxed store is a release pattern): a
+                // st.release per peer would be a fence each, i.e. one NVLink round trip per peer in sequence
                 __threadfence_system();
-                for (int p = 0; p < a.nranks_x; ++p) st_release_sys_u64(a.peer_flag[p], a.seq);
+                for (int p = 0; p < a.nranks_x; ++p) st_relaxed_sys_u64(a.peer_flag[p], a.seq);
             }
         }
     }
