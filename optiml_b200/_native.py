@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libsvmb200.so')
+LIB_PATH = os.environ.get('SVMB200_LIB') or os.path.join(_HERE, '_lib', 'libsvmb200.so')
 
 KERNEL_LINEAR, KERNEL_POLY, KERNEL_GAUSSIAN, KERNEL_SIGMOID, KERNEL_LAPLACIAN = 0, 1, 2, 3, 4
 HESSIAN_PLAIN, HESSIAN_SVR = 0, 1

@@ -42,26 +42,36 @@ struct MatvecArgs {
     double* denpart;        // one per group: sum over the group's rows of u_rows[r] * w[r], or null
     int nseg;
     const int* done;
-    // fused exchange (nranks_x > 0): the group combiner stores w / u'w shares into every rank's gathered
-    // buffer; the CTA that completes the shard's last group publishes `seq` in every rank's flag word
+    // fused exchange (nranks_x > 0): the group combiner stores w / u'w shares straight into every rank's
+    // gathered buffer as self-validating 16-byte entries {lo32 | tag, hi32 | tag} (two single-copy-atomic
+    // 8-byte words, tag = sequence number of the product): no fence, no flag, no counter -- the reader
+    // spins on the entry it needs until both tags match (the "LL" idea of NCCL, widened to FP64)
     int nranks_x;
-    unsigned ngroups;
-    unsigned* rank_done;                         // local counter of finished groups (self-resetting)
-    unsigned long long seq;
-    double* peer_w[SVM_MAX_RANKS];               // this rank's slot in rank r's gathered buffer
-    unsigned long long* peer_flag[SVM_MAX_RANKS];  // this rank's flag word in rank r's arena
+    unsigned tag;
+    ulonglong2* peer_w[SVM_MAX_RANKS];           // this rank's slot in rank r's gathered buffer
 };
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t)
+                 : "memory");
 }
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+// bounded spin (20 s: a peer died) -> fault flag; the host turns it into an error
+__device__ __forceinline__ double ll_load(const ulonglong2* p, unsigned tag, int* fault) {
+    unsigned long long w0, w1, t0 = 0, now = 0;
+    for (unsigned spins = 0;; ++spins) {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+        if ((spins & 1023u) == 1023u) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) {
+                *fault = 1;
+                break;
+            }
+        }
+    }
+    return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
 }
 
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const Matvec
             double v = 0.0;
             for (int s = 0; s < a.nseg; ++s) v += __ldcg(&a.wpart[(size_t)s * a.nrows_pad + rr]);
             if (a.nranks_x > 0) {
-                for (int p = 0; p < a.nranks_x; ++p) a.peer_w[p][rr] = v;  // NVLink stores (one slot is local)
+                for (int p = 0; p < a.nranks_x; ++p) ll_store(a.peer_w[p] + rr, v, a.tag);  // NVLink stores (one is local)
             } else {
                 a.w[rr] = v;
             }
@@ -184,23 +194,9 @@ __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const Matvec
             const double tot = __dadd_rn(red[0][0], red[0][1]);
             if (a.nranks_x > 0) {
                 const size_t off = (size_t)(a.denpart - a.w) + group;  // share slot relative to the w slot
-                for (int p = 0; p < a.nranks_x; ++p) a.peer_w[p][off] = tot;
+                for (int p = 0; p < a.nranks_x; ++p) ll_store(a.peer_w[p] + off, tot, a.tag);
             } else {
                 a.denpart[group] = tot;
-            }
-        }
-    }
-    if (a.nranks_x > 0) {
-        // publish: data stores -> system fence -> local count; the last group's CTA raises the flags
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (atomicAdd(a.rank_done, 1u) == a.ngroups - 1) {
-                *a.rank_done = 0;
-                // ONE system fence, then relaxed flag stores (fence + relaxed store is a release pattern): a
-                // st.release per peer would be a fence each, i.e. one NVLink round trip per peer in sequence
-                __threadfence_system();
-                for (int p = 0; p < a.nranks_x; ++p) st_relaxed_sys_u64(a.peer_flag[p], a.seq);
             }
         }
     }
@@ -237,39 +233,16 @@ static int matvec_scratch_reserve(svmb200_ctx* ctx, MatvecScratch& s, int64_t nr
     return SVMB200_OK;
 }
 
-// a rank that owns no rows (n small, many ranks) still has to announce "my (empty) shard is done"
-__global__ void publish_flags_kernel(const int* done, int nranks, unsigned long long seq,
-                                     unsigned long long* f0, unsigned long long* f1, unsigned long long* f2,
-                                     unsigned long long* f3, unsigned long long* f4, unsigned long long* f5,
-                                     unsigned long long* f6, unsigned long long* f7, unsigned long long* f8,
-                                     unsigned long long* f9, unsigned long long* f10, unsigned long long* f11,
-                                     unsigned long long* f12, unsigned long long* f13, unsigned long long* f14,
-                                     unsigned long long* f15) {
-    if (done != nullptr && *done) return;
-    unsigned long long* f[SVM_MAX_RANKS] = {f0, f1, f2, f3, f4, f5, f6, f7, f8, f9, f10, f11, f12, f13, f14, f15};
-    if (threadIdx.x < nranks) st_release_sys_u64(f[threadIdx.x], seq);
-}
-
 struct ExchangeTargets {
     int nranks = 0;
-    unsigned long long seq = 0;
-    unsigned* rank_done = nullptr;
-    double* peer_w[SVM_MAX_RANKS] = {};
-    unsigned long long* peer_flag[SVM_MAX_RANKS] = {};
+    unsigned tag = 0;
+    ulonglong2* peer_w[SVM_MAX_RANKS] = {};
 };
 
 static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw,
                          const double* du_rows, double* ddenpart, const int* d_done,
                          const ExchangeTargets* xt = nullptr) {
-    if (nrows <= 0 && xt == nullptr) return SVMB200_OK;
-    if (nrows <= 0) {
-        unsigned long long* const* f = xt->peer_flag;
-        publish_flags_kernel<<<1, 32, 0, ctx->stream>>>(d_done, xt->nranks, xt->seq, f[0], f[1], f[2], f[3], f[4], f[5],
-                                                        f[6], f[7], f[8], f[9], f[10], f[11], f[12], f[13], f[14], f[15]);
-        ctx->launches++;
-        SVM_CUDA(cudaGetLastError());
-        return SVMB200_OK;
-    }
+    if (nrows <= 0) return SVMB200_OK;  // an empty shard has nothing to compute or to send
     if (ld % 2 != 0 || ld <= 0) {
         svmb200_set_error("matvec: ld must be a positive multiple of 2");
         return SVMB200_ERR_ARG;
@@ -296,17 +269,11 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
     a.done = d_done;
     const int64_t ngroups = (nrows + MV_GROUP - 1) / MV_GROUP;
     a.nranks_x = 0;
-    a.ngroups = (unsigned)ngroups;
-    a.rank_done = nullptr;
-    a.seq = 0;
+    a.tag = 0;
     if (xt != nullptr) {
         a.nranks_x = xt->nranks;
-        a.rank_done = xt->rank_done;
-        a.seq = xt->seq;
-        for (int r = 0; r < xt->nranks; ++r) {
-            a.peer_w[r] = xt->peer_w[r];
-            a.peer_flag[r] = xt->peer_flag[r];
-        }
+        a.tag = xt->tag;
+        for (int r = 0; r < xt->nranks; ++r) a.peer_w[r] = xt->peer_w[r];
     }
     const int64_t nitems = ngroups * MV_BPG * a.nseg;
     if (nitems >= (1ll << 31)) {
@@ -386,12 +353,15 @@ struct VecArgs {
     double eps;
     long long max_iter;
     double fw_t;  // Frank-Wolfe stabilisation parameter t in [0, 1)
-    // fused exchange: wait until every rank has published `wait_seq` in this rank's flag words
-    const unsigned long long* flags;
-    unsigned long long wait_seq;
-    int nranks_wait;
+    // fused exchange: `gathered_ll` (tagged 16-byte entries, see ll_store) replaces `gathered`
+    const ulonglong2* gathered_ll;
+    unsigned tag;
     int* fault;
 };
+
+__device__ __forceinline__ double gathered_at(const VecArgs& a, size_t idx) {
+    return a.gathered_ll != nullptr ? ll_load(a.gathered_ll + idx, a.tag, a.fault) : a.gathered[idx];
+}
 
 enum { VP_INIT = 0, VP_STEP = 1, VP_FINALISE = 2 };
 
@@ -466,22 +436,6 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     // a CTA that starts late and already sees the flag returns here instead -- same outcome.
     if (*reinterpret_cast<volatile int*>(&st->done)) return;
     const int tid = threadIdx.x;
-    if (MODE != VP_FINALISE && a.nranks_wait > 0) {
-        // peers store their product shards straight into this GPU's memory (K2); spin (bounded) on the
-        // per-rank flag words, then order the data loads behind the acquire
-        if (tid < a.nranks_wait) {
-            unsigned long long t0 = 0, now = 0;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            while (ld_acquire_sys_u64(a.flags + tid) < a.wait_seq) {
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (now - t0 > 20000000000ull) {  // 20 s: a peer died; flag the fault and stop the solve
-                    *a.fault = 1;
-                    break;
-                }
-            }
-        }
-        __syncthreads();
-    }
     const long long n = a.n;
     const long long chunk = (n + a.nctas - 1) / a.nctas;
     const long long j0 = (long long)blockIdx.x * chunk;
@@ -508,7 +462,7 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
                 for (int e = 0; e < 4; ++e) {
                     const unsigned b = b0 + e * VP_NT;
                     const unsigned rk = b / gpr;
-                    v[e] = b < ngrp ? a.gathered[(size_t)rk * a.stride + rpr + (b - rk * gpr)] : 0.0;
+                    v[e] = b < ngrp ? gathered_at(a, (size_t)rk * a.stride + rpr + (b - rk * gpr)) : 0.0;
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) r.c = __dadd_rn(r.c, v[e]);
@@ -554,7 +508,7 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     acc.m = INFINITY;
     for (long long j = j0 + tid; j < j1; j += VP_NT) {
         const unsigned rk = (unsigned)j / rpr;
-        const double wj = a.gathered[(size_t)rk * a.stride + ((unsigned)j - rk * rpr)];
+        const double wj = gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
         double x = a.x[j], q = a.q[j], g;
         if (MODE == VP_INIT) {
             g = __dadd_rn(wj, q);  // g = Q x0 + q  (opti/_base.py:291)
@@ -618,20 +572,6 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
     PGDeviceState* st = a.st;
     if (*reinterpret_cast<volatile int*>(&st->done)) return;
     const int tid = threadIdx.x;
-    if (MODE != VP_FINALISE && a.nranks_wait > 0) {
-        if (tid < a.nranks_wait) {
-            unsigned long long t0 = 0, now = 0;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            while (ld_acquire_sys_u64(a.flags + tid) < a.wait_seq) {
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (now - t0 > 20000000000ull) {
-                    *a.fault = 1;
-                    break;
-                }
-            }
-        }
-        __syncthreads();
-    }
     const long long n = a.n;
     const long long chunk = (n + a.nctas - 1) / a.nctas;
     const long long j0 = (long long)blockIdx.x * chunk;
@@ -657,7 +597,7 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
                 for (int e = 0; e < 4; ++e) {
                     const unsigned b = b0 + e * VP_NT;
                     const unsigned rk = b / gpr;
-                    v[e] = b < ngrp ? a.gathered[(size_t)rk * a.stride + rpr + (b - rk * gpr)] : 0.0;
+                    v[e] = b < ngrp ? gathered_at(a, (size_t)rk * a.stride + rpr + (b - rk * gpr)) : 0.0;
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) r.c = __dadd_rn(r.c, v[e]);
@@ -709,7 +649,7 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
     acc.m = INFINITY;
     for (long long j = j0 + tid; j < j1; j += VP_NT) {
         const unsigned rk = (unsigned)j / rpr;
-        const double wj = a.gathered[(size_t)rk * a.stride + ((unsigned)j - rk * rpr)];
+        const double wj = gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
         double x = a.x[j], q = a.q[j], g;
         if (MODE == VP_INIT) {
             g = __dadd_rn(wj, q);
@@ -787,6 +727,8 @@ struct svmb200_pg {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // own events: the context's pair belongs to svmb200_timer_*
 };
 
+static unsigned exchange_tag(unsigned long long seq) { return (unsigned)(seq % 0xfffffffful) + 1u; }  // never 0
+
 static VecArgs make_vec_args(svmb200_pg* pg) {
     VecArgs a;
     a.x = pg->x;
@@ -797,17 +739,14 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
     a.lb = pg->lb;
     a.ub = pg->ub;
     a.gathered = pg->w;
-    a.flags = nullptr;
-    a.wait_seq = 0;
-    a.nranks_wait = 0;
+    a.gathered_ll = nullptr;
+    a.tag = 0;
     a.fault = nullptr;
     if (pg->p2p) {
         svmb200_ctx* ctx = pg->ctx;
-        const size_t bufbytes = (size_t)pg->stride * ctx->nranks * sizeof(double);
-        a.gathered = reinterpret_cast<const double*>(ctx->arena + ARENA_DATA_OFF + (pg->cur_seq & 1) * bufbytes);
-        a.flags = reinterpret_cast<const unsigned long long*>(ctx->arena + ARENA_FLAGS_OFF);
-        a.wait_seq = pg->cur_seq;
-        a.nranks_wait = ctx->nranks;
+        const size_t bufbytes = (size_t)pg->stride * ctx->nranks * sizeof(ulonglong2);
+        a.gathered_ll = reinterpret_cast<const ulonglong2*>(ctx->arena + ARENA_DATA_OFF + (pg->cur_seq & 1) * bufbytes);
+        a.tag = exchange_tag(pg->cur_seq);
         a.fault = reinterpret_cast<int*>(ctx->arena + ARENA_LOCAL_OFF + 8);
     }
     a.rpr = pg->rows_per_rank;
@@ -850,18 +789,16 @@ static int pg_product(svmb200_pg* pg, bool timed) {
         // K2 + K4 fused: results go straight into every rank's gathered buffer (parity = seq & 1)
         ExchangeTargets xt;
         xt.nranks = ctx->nranks;
-        xt.seq = ++ctx->xseq;
-        pg->cur_seq = xt.seq;
-        xt.rank_done = reinterpret_cast<unsigned*>(ctx->arena + ARENA_LOCAL_OFF);
-        const size_t bufbytes = (size_t)pg->stride * ctx->nranks * sizeof(double);
-        const size_t slot = ARENA_DATA_OFF + (xt.seq & 1) * bufbytes + (size_t)ctx->rank * pg->stride * sizeof(double);
-        for (int r = 0; r < ctx->nranks; ++r) {
-            xt.peer_w[r] = reinterpret_cast<double*>(ctx->peer_arena[r] + slot);
-            xt.peer_flag[r] = reinterpret_cast<unsigned long long*>(ctx->peer_arena[r] + ARENA_FLAGS_OFF) + ctx->rank;
-        }
-        double* wlocal = reinterpret_cast<double*>(ctx->arena + slot);
-        SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wlocal, pg->u + pg->row0,
-                              wlocal + pg->rows_per_rank, &pg->st->done, &xt));
+        const unsigned long long seq = ++ctx->xseq;
+        pg->cur_seq = seq;
+        xt.tag = exchange_tag(seq);
+        const size_t bufbytes = (size_t)pg->stride * ctx->nranks * sizeof(ulonglong2);
+        const size_t slot = ARENA_DATA_OFF + (seq & 1) * bufbytes + (size_t)ctx->rank * pg->stride * sizeof(ulonglong2);
+        for (int r = 0; r < ctx->nranks; ++r) xt.peer_w[r] = reinterpret_cast<ulonglong2*>(ctx->peer_arena[r] + slot);
+        // the plain pointers only carry the slot geometry (w at [0, rpr), shares at [rpr, stride)) in this mode
+        double* geom = reinterpret_cast<double*>(ctx->arena);
+        SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, geom, pg->u + pg->row0, geom + pg->rows_per_rank,
+                              &pg->st->done, &xt));
         if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
     } else {
         double* wshard = pg->w + (size_t)ctx->rank * pg->stride;
@@ -942,7 +879,7 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     pg->rows_per_rank = rpr;
     pg->stride = rpr + rpr / MV_GROUP;
     pg->p2p = ctx->p2p_enabled && P > 1 &&
-              ARENA_DATA_OFF + 2 * (size_t)pg->stride * P * sizeof(double) <= ctx->arena_bytes;
+              ARENA_DATA_OFF + 2 * (size_t)pg->stride * P * sizeof(ulonglong2) <= ctx->arena_bytes;
     pg->nctas = (int)((n + VP_ELEMS - 1) / VP_ELEMS);
     if (pg->nctas > VP_MAXC) pg->nctas = VP_MAXC;
     if (pg->nctas < 1) pg->nctas = 1;
