@@ -87,8 +87,9 @@ int svmb200_comm_destroy(svmb200_ctx* ctx);
 /* Optional fused exchange over NVLink peer memory (replaces the per-iteration ncclAllGather of the
  * solver): every rank exports an arena (svmb200_comm_p2p_export returns its 64-byte CUDA IPC handle),
  * the handles of all ranks, concatenated in rank order, are passed to svmb200_comm_p2p_attach.  The
- * matvec kernel then stores its results directly into every peer's arena and raises a per-rank flag
- * there; the vector kernel waits on the flags.  Without it (or if IPC mapping fails) NCCL is used. */
+ * matvec kernel then stores its results directly into every peer's arena as self-validating tagged
+ * 16-byte entries (no fence, no flag); the vector kernel spins on the entries it reads.  Without it
+ * (or if IPC mapping fails) NCCL is used. */
 int svmb200_comm_p2p_export(svmb200_ctx* ctx, size_t arena_bytes, void* handle64);
 int svmb200_comm_p2p_attach(svmb200_ctx* ctx, const void* handles, int nranks);
 int svmb200_comm_p2p_enabled(svmb200_ctx* ctx, int* enabled);

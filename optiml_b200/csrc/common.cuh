@@ -27,7 +27,7 @@ struct svmb200_ctx {
     // segment partials / tickets of the streaming matvec (grown on demand, pg.cu)
     void* matvec_scratch = nullptr;
     // fused exchange over NVLink peer memory (comm.cu): every rank owns an arena that all peers map
-    // through CUDA IPC; K2 stores its results straight into every peer's arena and raises a flag there
+    // through CUDA IPC; K2 stores self-validating tagged entries straight into every peer's arena (pg.cu)
     bool p2p_enabled = false;
     unsigned char* arena = nullptr;               // local arena
     size_t arena_bytes = 0;
@@ -36,9 +36,8 @@ struct svmb200_ctx {
 };
 
 // arena layout
-constexpr size_t ARENA_FLAGS_OFF = 0;      // unsigned long long flag[SVM_MAX_RANKS]: last sequence number completed by rank r
-constexpr size_t ARENA_LOCAL_OFF = 256;    // unsigned rank_done ; unsigned fault
-constexpr size_t ARENA_DATA_OFF = 1024;    // two gathered buffers (double-buffered by sequence parity)
+constexpr size_t ARENA_LOCAL_OFF = 256;    // [+8] int fault: set by a reader whose bounded spin expired
+constexpr size_t ARENA_DATA_OFF = 1024;    // two gathered buffers of tagged 16-byte entries (double-buffered by sequence parity)
 
 void svmb200_set_error(const char* fmt, ...);
 
