@@ -255,7 +255,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    iters_total, mv_ms, mv_launches, pg_ms, comm_ms, vec_ms, step_s = 0, 0.0, 0, 0.0, 0.0, 0.0, []
+    iters_total, mv_ms, mv_launches, pg_ms, comm_ms, vec_ms, step_s, step_parts = 0, 0.0, 0, 0.0, 0.0, 0.0, [], []
     ctx.timer_start()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
@@ -269,6 +269,8 @@ def run_b200(args):
         pg_ms += m.optimizer.device_ms
         m.obj.release()
         step_s.append(round(time.perf_counter() - ts, 4))
+        step_parts.append({'gram_s': round(m.fit_times_['gram_s'], 4), 'solve_s': round(m.fit_times_['solve_s'], 4),
+                           'pg_device_s': round(m.optimizer.device_ms / 1e3, 4)})
     barrier()
     dev_ms = ctx.timer_stop_ms()
     wall_s = time.perf_counter() - t_wall
@@ -321,7 +323,7 @@ def run_b200(args):
         'hbm_gbps_pg_loop': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9,
         'frac_of_8TBps_nominal': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9 / world / 8000.0,
         'iters_per_step': iters_total / args.steps, 'status': status, 'f_x': fx, 'n_sv': nsv,
-        'wall_s_value_leg': wall_s, 'step_wall_s': step_s,
+        'wall_s_value_leg': wall_s, 'step_wall_s': step_s, 'step_parts': step_parts,
         'per_iteration_us': {'matvec': 1e3 * mv_ms / max(mv_launches, 1), 'allgather': 1e3 * comm_ms / max(mv_launches, 1),
                              'vector_phase': 1e3 * vec_ms / max(mv_launches, 1),
                              'pg_loop_total': 1e3 * pg_ms / max(mv_launches, 1)},
