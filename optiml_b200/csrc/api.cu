@@ -54,6 +54,17 @@ extern "C" int svmb200_ctx_create(int device, svmb200_ctx** out) {
     return SVMB200_OK;
 }
 
+int svm_scratch_reserve(svmb200_ctx* ctx, void** buf, size_t* have, size_t need) {
+    if (*have >= need) return SVMB200_OK;
+    SVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    SVM_CUDA(cudaMalloc(buf, need));
+    *have = need;
+    return SVMB200_OK;
+}
+
 extern "C" int svmb200_ctx_destroy(svmb200_ctx* ctx) {
     if (!ctx) return SVMB200_OK;
     cudaSetDevice(ctx->device);
@@ -61,6 +72,9 @@ extern "C" int svmb200_ctx_destroy(svmb200_ctx* ctx) {
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         svm_release_matvec_scratch(ctx);
+        svm_release_solver_cache(ctx);
+        if (ctx->norm_buf) cudaFree(ctx->norm_buf);
+        if (ctx->mp_buf) cudaFree(ctx->mp_buf);
         cudaStreamDestroy(ctx->stream);
     }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

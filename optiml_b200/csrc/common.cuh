@@ -33,7 +33,27 @@ struct svmb200_ctx {
     size_t arena_bytes = 0;
     unsigned char* peer_arena[SVM_MAX_RANKS] = {};  // peer_arena[r] = rank r's arena as mapped here (self: local)
     unsigned long long xseq = 0;                  // number of fused exchanges issued so far (same on all ranks)
+    // solver workspace recycled between solves (pg.cu): one device slab, one pinned state block, an event pool.
+    // cudaMalloc / cudaMallocHost / cudaEventCreate / cudaFree are slow and jittery (tens to hundreds of ms when
+    // the host is busy); a fit issues none of them after the first one of its size.
+    void* pg_slab = nullptr;
+    size_t pg_slab_bytes = 0;
+    bool pg_slab_busy = false;
+    void* pg_pinned = nullptr;
+    cudaEvent_t pg_ev0 = nullptr, pg_ev1 = nullptr;
+    std::vector<cudaEvent_t> event_pool;
+    size_t event_pool_used = 0;
+    // small per-call scratch, grown on demand and reused in stream order: row norms of K1, operands of K5
+    void* norm_buf = nullptr;
+    size_t norm_bytes = 0;
+    void* mp_buf = nullptr;
+    size_t mp_bytes = 0;
 };
+
+// grow-only device scratch; safe to reuse without a sync because every user runs on ctx->stream
+int svm_scratch_reserve(svmb200_ctx* ctx, void** buf, size_t* have, size_t need);
+
+void svm_release_solver_cache(svmb200_ctx* ctx);
 
 // arena layout
 constexpr size_t ARENA_LOCAL_OFF = 256;    // [+8] int fault: set by a reader whose bounded spin expired

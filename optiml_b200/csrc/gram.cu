@@ -577,18 +577,16 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
 
     double *norm_a = nullptr, *norm_b = nullptr;
     if (kernel == SVMB200_KERNEL_GAUSSIAN) {
-        SVM_CUDA(cudaMalloc(&norm_a, (size_t)na * sizeof(double)));
+        const bool shared_norms = (dB == dA && nb == na);
+        SVM_TRY(svm_scratch_reserve(ctx, &ctx->norm_buf, &ctx->norm_bytes, (size_t)(na + (shared_norms ? 0 : nb)) * sizeof(double)));
+        norm_a = static_cast<double*>(ctx->norm_buf);
         const int wpb = 8;
         row_sqnorm_kernel<<<(unsigned)((na + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(dA, na, lda, d, norm_a);
         ctx->launches++;
-        if (dB == dA && nb == na) {
+        if (shared_norms) {
             norm_b = norm_a;
         } else {
-            if (cudaMalloc(&norm_b, (size_t)nb * sizeof(double)) != cudaSuccess) {
-                cudaFree(norm_a);
-                svmb200_set_error("gram: out of device memory");
-                return SVMB200_ERR_CUDA;
-            }
+            norm_b = norm_a + na;
             row_sqnorm_kernel<<<(unsigned)((nb + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(dB, nb, ldb, d, norm_b);
             ctx->launches++;
         }
@@ -613,7 +611,7 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
         a.tiles_n = (int)((ldo + BN - 1) / BN);
         a.same = same;
         {
-            // hand-over only pays when there is an epilogue to hide (gaussian / poly); SVMB200_GRAM_EXCLUSIVE overrides
+            // phase lock-step when there is an epilogue (see kernel comment); SVMB200_GRAM_EXCLUSIVE=0/1/2 overrides
             const char* ev = getenv("SVMB200_GRAM_EXCLUSIVE");
             a.exclusive = ev ? atoi(ev) : (kernel != SVMB200_KERNEL_LINEAR ? 2 : 0);
         }
@@ -625,16 +623,6 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
         else if (kernel == SVMB200_KERNEL_POLY) rc = launch_gram<SVMB200_KERNEL_POLY>(ctx, ma, mb, a);
         else if (kernel == SVMB200_KERNEL_SIGMOID) rc = launch_gram<SVMB200_KERNEL_SIGMOID>(ctx, ma, mb, a);
         else rc = launch_gram<SVMB200_KERNEL_GAUSSIAN>(ctx, ma, mb, a);
-    }
-    if (norm_a || norm_b) {
-        // norms are consumed by the kernel just enqueued
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess && rc == SVMB200_OK) {
-            svmb200_set_error("gram kernel failed: %s", cudaGetErrorString(e));
-            rc = SVMB200_ERR_CUDA;
-        }
-        if (norm_b && norm_b != norm_a) cudaFree(norm_b);
-        if (norm_a) cudaFree(norm_a);
     }
     return rc;
 }

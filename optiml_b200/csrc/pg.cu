@@ -724,7 +724,9 @@ struct svmb200_pg {
     int64_t last_passes = 0;
     bool profile = false;
     std::vector<cudaEvent_t> mv_ev;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // own events: the context's pair belongs to svmb200_timer_*
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // the context's solver pair (svmb200_timer_* has its own)
+    void* slab = nullptr;        // all device buffers below live in this slab
+    bool slab_private = false;   // true: allocated for this solver only (the context's slab was busy)
 };
 
 static unsigned exchange_tag(unsigned long long seq) { return (unsigned)(seq % 0xfffffffful) + 1u; }  // never 0
@@ -775,14 +777,20 @@ static int launch_vec(svmb200_pg* pg, long long k) {
     return SVMB200_OK;
 }
 
+static cudaEvent_t pooled_event(svmb200_ctx* ctx);
+
 static int pg_product(svmb200_pg* pg, bool timed) {
     // w[row0 : row0+nrows] = Q_shard u, then all ranks exchange their shards (K4)
     svmb200_ctx* ctx = pg->ctx;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     if (timed && pg->profile) {
-        SVM_CUDA(cudaEventCreate(&e0));
-        SVM_CUDA(cudaEventCreate(&e1));
-        SVM_CUDA(cudaEventCreate(&e2));
+        e0 = pooled_event(ctx);
+        e1 = pooled_event(ctx);
+        e2 = pooled_event(ctx);
+        if (!e0 || !e1 || !e2) {
+            svmb200_set_error("cannot create profiling events");
+            return SVMB200_ERR_CUDA;
+        }
         SVM_CUDA(cudaEventRecord(e0, ctx->stream));
     }
     if (pg->p2p) {
@@ -817,17 +825,44 @@ static int pg_product(svmb200_pg* pg, bool timed) {
     return SVMB200_OK;
 }
 
+static cudaEvent_t pooled_event(svmb200_ctx* ctx) {
+    if (ctx->event_pool_used == ctx->event_pool.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->event_pool.push_back(e);
+    }
+    return ctx->event_pool[ctx->event_pool_used++];
+}
+
+void svm_release_solver_cache(svmb200_ctx* ctx) {
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    ctx->event_pool.clear();
+    ctx->event_pool_used = 0;
+    if (ctx->pg_ev0) cudaEventDestroy(ctx->pg_ev0);
+    if (ctx->pg_ev1) cudaEventDestroy(ctx->pg_ev1);
+    ctx->pg_ev0 = ctx->pg_ev1 = nullptr;
+    if (ctx->pg_slab) cudaFree(ctx->pg_slab);
+    ctx->pg_slab = nullptr;
+    ctx->pg_slab_bytes = 0;
+    if (ctx->pg_pinned) cudaFreeHost(ctx->pg_pinned);
+    ctx->pg_pinned = nullptr;
+}
+
 extern "C" int svmb200_pg_destroy(svmb200_pg* pg) {
     if (!pg) return SVMB200_OK;
-    if (pg->ctx) cudaSetDevice(pg->ctx->device);
-    for (cudaEvent_t e : pg->mv_ev) cudaEventDestroy(e);
-    if (pg->ev0) cudaEventDestroy(pg->ev0);
-    if (pg->ev1) cudaEventDestroy(pg->ev1);
-    double* bufs[] = {pg->x, pg->g, pg->d, pg->u, pg->w, pg->q, pg->lb, pg->ub, pg->part, pg->hist_f, pg->hist_ng};
-    for (double* b : bufs)
-        if (b) cudaFree(b);
-    if (pg->st) cudaFree(pg->st);
-    if (pg->st_host) cudaFreeHost(pg->st_host);
+    if (pg->ctx) {
+        cudaSetDevice(pg->ctx->device);
+        cudaStreamSynchronize(pg->ctx->stream);
+        if (pg->slab_private) {
+            if (pg->slab) cudaFree(pg->slab);
+            if (pg->st_host) cudaFreeHost(pg->st_host);
+            if (pg->ev0) cudaEventDestroy(pg->ev0);
+            if (pg->ev1) cudaEventDestroy(pg->ev1);
+        } else if (pg->slab) {
+            pg->ctx->pg_slab_busy = false;  // workspace, pinned block and events go back to the context
+            pg->ctx->event_pool_used = 0;
+        }
+    }
     delete pg;
     return SVMB200_OK;
 }
@@ -902,21 +937,55 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
             return fail(SVMB200_ERR_CUDA);                                                             \
         }                                                                                              \
     } while (0)
-    PG_CUDA(cudaMalloc(&pg->x, nv));
-    PG_CUDA(cudaMalloc(&pg->g, nv));
-    PG_CUDA(cudaMalloc(&pg->d, nv));
-    PG_CUDA(cudaMalloc(&pg->q, nv));
-    PG_CUDA(cudaMalloc(&pg->lb, nv));
-    PG_CUDA(cudaMalloc(&pg->ub, nv));
-    PG_CUDA(cudaMalloc(&pg->u, (size_t)ld * sizeof(double)));
-    PG_CUDA(cudaMalloc(&pg->w, (size_t)(pg->stride * P) * sizeof(double)));
-    PG_CUDA(cudaMalloc(&pg->part, 3 * VP_MAXC * sizeof(double)));
-    PG_CUDA(cudaMalloc(&pg->hist_f, (size_t)pg->hist_cap * sizeof(double)));
-    PG_CUDA(cudaMalloc(&pg->hist_ng, (size_t)pg->hist_cap * sizeof(double)));
-    PG_CUDA(cudaMalloc(&pg->st, sizeof(PGDeviceState)));
-    PG_CUDA(cudaMallocHost(&pg->st_host, sizeof(PGDeviceState)));
-    PG_CUDA(cudaEventCreate(&pg->ev0));
-    PG_CUDA(cudaEventCreate(&pg->ev1));
+    {
+        // one slab: x g d q lb ub (nvars each) | u (ld) | gathered (stride*P) | partials | two histories | state
+        auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+        const size_t sz_nv = up(nv), sz_u = up((size_t)ld * sizeof(double)), sz_w = up((size_t)(pg->stride * P) * sizeof(double));
+        const size_t sz_part = up(3 * VP_MAXC * sizeof(double)), sz_hist = up((size_t)pg->hist_cap * sizeof(double));
+        const size_t total = 6 * sz_nv + sz_u + sz_w + sz_part + 2 * sz_hist + up(sizeof(PGDeviceState));
+        unsigned char* base = nullptr;
+        if (!ctx->pg_slab_busy) {
+            if (ctx->pg_slab_bytes < total) {
+                PG_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (ctx->pg_slab) cudaFree(ctx->pg_slab);
+                ctx->pg_slab = nullptr;
+                ctx->pg_slab_bytes = 0;
+                PG_CUDA(cudaMalloc(&ctx->pg_slab, total));
+                ctx->pg_slab_bytes = total;
+            }
+            if (!ctx->pg_pinned) PG_CUDA(cudaMallocHost(&ctx->pg_pinned, 256));
+            if (!ctx->pg_ev0) PG_CUDA(cudaEventCreate(&ctx->pg_ev0));
+            if (!ctx->pg_ev1) PG_CUDA(cudaEventCreate(&ctx->pg_ev1));
+            ctx->pg_slab_busy = true;
+            ctx->event_pool_used = 0;
+            pg->slab = ctx->pg_slab;
+            pg->slab_private = false;
+            pg->st_host = static_cast<PGDeviceState*>(ctx->pg_pinned);
+            pg->ev0 = ctx->pg_ev0;
+            pg->ev1 = ctx->pg_ev1;
+        } else {
+            pg->slab_private = true;  // a second live solver on the same context: private workspace
+            PG_CUDA(cudaMalloc(&pg->slab, total));
+            PG_CUDA(cudaMallocHost(&pg->st_host, sizeof(PGDeviceState)));
+            PG_CUDA(cudaEventCreate(&pg->ev0));
+            PG_CUDA(cudaEventCreate(&pg->ev1));
+        }
+        base = static_cast<unsigned char*>(pg->slab);
+        size_t off = 0;
+        auto take = [&](size_t b) { unsigned char* q = base + off; off += b; return reinterpret_cast<double*>(q); };
+        pg->x = take(sz_nv);
+        pg->g = take(sz_nv);
+        pg->d = take(sz_nv);
+        pg->q = take(sz_nv);
+        pg->lb = take(sz_nv);
+        pg->ub = take(sz_nv);
+        pg->u = take(sz_u);
+        pg->w = take(sz_w);
+        pg->part = take(sz_part);
+        pg->hist_f = take(sz_hist);
+        pg->hist_ng = take(sz_hist);
+        pg->st = reinterpret_cast<PGDeviceState*>(take(up(sizeof(PGDeviceState))));
+    }
     cudaStream_t s = ctx->stream;
     PG_CUDA(cudaMemsetAsync(pg->st, 0, sizeof(PGDeviceState), s));
     PG_CUDA(cudaMemsetAsync(pg->u, 0, (size_t)ld * sizeof(double), s));
@@ -965,8 +1034,8 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
     SVM_CHECK_ARG(pg != nullptr, "null solver");
     svmb200_ctx* ctx = pg->ctx;
     SVM_TRY(svm_use(ctx));
-    for (cudaEvent_t e : pg->mv_ev) cudaEventDestroy(e);
-    pg->mv_ev.clear();
+    pg->mv_ev.clear();  // pooled events: reused, never destroyed per run
+    ctx->event_pool_used = 0;
     pg->last_passes = 0;
     pg->last_ms = pg->last_mv_ms = pg->last_comm_ms = pg->last_vec_ms = 0.f;
     SVM_CUDA(cudaEventRecord(pg->ev0, ctx->stream));
@@ -982,8 +1051,11 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
                 SVM_TRY(pg_product(pg, true));
                 SVM_TRY(launch_vec<VP_STEP>(pg, pg->k_next));
                 if (pg->profile) {
-                    cudaEvent_t e3 = nullptr;
-                    SVM_CUDA(cudaEventCreate(&e3));
+                    cudaEvent_t e3 = pooled_event(ctx);
+                    if (!e3) {
+                        svmb200_set_error("cannot create profiling events");
+                        return SVMB200_ERR_CUDA;
+                    }
                     SVM_CUDA(cudaEventRecord(e3, ctx->stream));
                     pg->mv_ev.push_back(e3);
                 }
@@ -1101,13 +1173,9 @@ extern "C" int svmb200_masked_product(svmb200_ctx* ctx, const double* dQ, int64_
         SVM_TRY(svmb200_shard_rows(n, ctx->rank, P, &exp_row0, &exp_rows));
         SVM_CHECK_ARG(row0 == exp_row0 && nrows == exp_rows, "row shard does not match svmb200_shard_rows");
     }
-    double *du = nullptr, *dw = nullptr;
-    SVM_CUDA(cudaMalloc(&du, (size_t)ld * sizeof(double)));
-    if (cudaMalloc(&dw, (size_t)(rpr * P) * sizeof(double)) != cudaSuccess) {
-        cudaFree(du);
-        svmb200_set_error("masked_product: out of device memory");
-        return SVMB200_ERR_CUDA;
-    }
+    SVM_TRY(svm_scratch_reserve(ctx, &ctx->mp_buf, &ctx->mp_bytes, (size_t)(ld + rpr * P) * sizeof(double)));
+    double* du = static_cast<double*>(ctx->mp_buf);
+    double* dw = du + ld;
     int rc = SVMB200_OK;
     cudaStream_t s = ctx->stream;
     cudaMemsetAsync(du, 0, (size_t)ld * sizeof(double), s);
@@ -1123,7 +1191,5 @@ extern "C" int svmb200_masked_product(svmb200_ctx* ctx, const double* dQ, int64_
             rc = SVMB200_ERR_CUDA;
         }
     }
-    cudaFree(du);
-    cudaFree(dw);
     return rc;
 }
