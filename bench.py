@@ -286,11 +286,13 @@ def run_b200(args):
         m.obj.release()
     barrier()
     t0 = time.perf_counter()
-    e2e_iters = 0
+    e2e_iters, e2e_steps = 0, []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         m = make_model().fit(X, y)
         e2e_iters += m.optimizer.iter
         m.obj.release()
+        e2e_steps.append(round(time.perf_counter() - ts, 4))
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     nvars = n
@@ -334,7 +336,7 @@ def run_b200(args):
                      'note': 'peak = measured copy bandwidth (read+write stream); a read-only stream can exceed it; '
                              'dram_theoretical = 2048 B/clk x 3.996 GHz as reported by ncu'},
         'e2e': {'value': e2e_iters / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'fit_s': e2e_s / args.steps, 'api': 'optiml_b200.ml.svm.DualSVC.fit(X_host_pinned, y_host)'},
+                'fit_s': e2e_s / args.steps, 'step_wall_s': e2e_steps, 'api': 'optiml_b200.ml.svm.DualSVC.fit(X_host_pinned, y_host)'},
         'gpu_launches': int(launches), 'clocks': clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

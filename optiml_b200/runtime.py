@@ -35,7 +35,8 @@ class Context:
         self._finalizer = weakref.finalize(self, N.load_library().svmb200_ctx_destroy, h)
 
     # ---------------------------------------------------------------- memory
-    POOL_MIN_BYTES = 64 << 20
+    POOL_MIN_BYTES = 1 << 20
+    POOL_MAX_BUFFERS = 4
 
     def malloc(self, nbytes):
         cached = self._pool.get(int(nbytes))
@@ -48,7 +49,7 @@ class Context:
     def free(self, dptr, nbytes=0):
         if not dptr:
             return
-        if nbytes >= self.POOL_MIN_BYTES and sum(len(v) for v in self._pool.values()) < 2:
+        if nbytes >= self.POOL_MIN_BYTES and sum(len(v) for v in self._pool.values()) < self.POOL_MAX_BUFFERS:
             self._pool.setdefault(int(nbytes), []).append(dptr)  # keep for the next fit
             return
         N.call('svmb200_free', self.handle, C.c_void_p(dptr))
