@@ -164,6 +164,39 @@ int svmb200_pg_stats_ex(svmb200_pg* pg, float* matvec_ms, float* comm_ms, float*
 int svmb200_pg_device_x(svmb200_pg* pg, double** dx); /* device pointer of the iterate (nvars)     */
 int svmb200_pg_destroy(svmb200_pg* pg);
 
+/* ---- widening: augmented-Lagrangian dual driven by a full-batch stochastic optimiser -----------
+ * Replaces  AugmentedLagrangianQuadratic.function_jacobian (opti/constrained/_base.py:395-407), the Lagrangian
+ * branches of Optimizer.callback / check_lagrangian_dual_optimality (opti/_base.py:94-149) and the loops of
+ * opti/unconstrained/stochastic/{adagrad,gradient_descent,rmsprop,adadelta,adam,amsgrad,adamax}.py, i.e. what
+ * SVC/SVR(dual=True, optimizer=AdaGrad, ...) runs for reg_intercept in {True, False} (ml/svm/_base.py:638-725,
+ * 1188-1270):   min x'Qx/2 + q'x  s.t.  a'x = b (optional),  lb <= x <= ub,   relaxed with multipliers
+ * (mu, lambda_lb, lambda_ub) and the penalty rho/2 |violations|^2; one optimiser step and one multiplier update per
+ * iteration.  Same resident matrix, same one streaming pass per iteration (K2) as the box-constrained solvers; the
+ * handle type and svmb200_pg_run / _state / _history / _stats / _destroy are shared.  With this solver
+ * svmb200_pg_history's second array holds the primal cost x'Qx/2 + q'x (ml/svm/_base.py:289-291 stores that) and
+ * svmb200_pg_state's `ng` the last one.
+ *   a_host      equality row (nvars) or NULL;  x0_host is required (the reference draws it with NumPy on the host)
+ *   step_sizes  `epochs` values (a constant learning rate repeated, or a schedule drawn in advance)
+ *   momenta     epochs + 1 values, ignored (may be NULL) when momentum_type is NONE
+ *   decay / beta1 / beta2 / offset: the rule's constants (ignored where the rule has none)                        */
+#define SVMB200_RULE_ADAGRAD 0
+#define SVMB200_RULE_SGD 1
+#define SVMB200_RULE_RMSPROP 2
+#define SVMB200_RULE_ADADELTA 3
+#define SVMB200_RULE_ADAM 4
+#define SVMB200_RULE_AMSGRAD 5
+#define SVMB200_RULE_ADAMAX 6
+#define SVMB200_MOMENTUM_NONE 0
+#define SVMB200_MOMENTUM_POLYAK 1
+#define SVMB200_MOMENTUM_NESTEROV 2
+int svmb200_al_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
+                      int hessian, const double* q_host, const double* lb_host, const double* ub_host,
+                      const double* x0_host, const double* a_host, double b, double rho, int rule, int momentum_type,
+                      const double* step_sizes, const double* momenta, double decay, double beta1, double beta2,
+                      double offset, double tol, int64_t epochs, svmb200_pg** out);
+/* multipliers after (or during) a run: mu of the equality row (0 without one), lambda of  -x <= -lb  and  x <= ub */
+int svmb200_al_multipliers(svmb200_pg* pg, double* mu, double* lam_lb_host, double* lam_ub_host);
+
 /* ---- K5: masked product for the intercept ---------------------------------------------------
  * Replaces the Python loop  ml/svm/_base.py:877-880 / :1433-1437:
  * v[i] = sum_m M[i][m] * beta[m] over the rank's rows (all-gathered when a communicator is attached),

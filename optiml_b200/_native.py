@@ -15,6 +15,8 @@ LIB_PATH = os.environ.get('SVMB200_LIB') or os.path.join(_HERE, '_lib', 'libsvmb
 KERNEL_LINEAR, KERNEL_POLY, KERNEL_GAUSSIAN, KERNEL_SIGMOID, KERNEL_LAPLACIAN = 0, 1, 2, 3, 4
 HESSIAN_PLAIN, HESSIAN_SVR = 0, 1
 STATUS = {0: 'unknown', 1: 'optimal', 2: 'stopped'}
+RULES = {'adagrad': 0, 'sgd': 1, 'rmsprop': 2, 'adadelta': 3, 'adam': 4, 'amsgrad': 5, 'adamax': 6}
+MOMENTUM = {'none': 0, 'polyak': 1, 'nesterov': 2}
 
 c_dp = C.POINTER(C.c_double)
 c_vp = C.c_void_p
@@ -54,6 +56,10 @@ PROTOTYPES = {
                           C.POINTER(c_vp)],
     'svmb200_fw_create': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, i64, C.c_double,
                           C.POINTER(c_vp)],
+    'svmb200_al_create': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_double,
+                          C.c_int, C.c_int, c_vp, c_vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64,
+                          C.POINTER(c_vp)],
+    'svmb200_al_multipliers': [c_vp, C.POINTER(C.c_double), c_vp, c_vp],
     'svmb200_pg_run': [c_vp, i64, C.POINTER(i64), C.POINTER(C.c_int)],
     'svmb200_pg_state': [c_vp, c_vp, c_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     'svmb200_pg_scalars': [c_vp, c_vp],

@@ -12,6 +12,7 @@
 // Every reduction has a fixed shape that depends on the problem size only -- never on the number of
 // GPUs, the grid or the arrival order -- so the iterate is bit-identical for 1, 2, 4 and 8 GPUs.
 #include "common.cuh"
+#include "al_math.cuh"
 #include <math.h>
 
 // ------------------------------------------------------------------------------------------ K2
@@ -336,6 +337,10 @@ struct PGDeviceState {
     int status;
     double f, ng, s, maxt, t, den;
     double best_lb;  // Frank-Wolfe: best lower bound so far
+    // augmented Lagrangian: launch index that raised `done` (a CTA of that same launch that starts late must not
+    // leave early: it still owes its slice of the gradient) and the multiplier of the equality row
+    long long done_k;
+    double mu;
 };
 
 struct VecArgs {
@@ -695,13 +700,235 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
     }
 }
 
+// ------------------------------------------------------------------------------------------ K3'' augmented Lagrangian
+// Vector phase of the reference's full-batch stochastic optimisers (stochastic/adagrad.py:84-125 and siblings) on
+// AugmentedLagrangianQuadratic (constrained/_base.py:224-410), SURVEY.md 8f-3.  One launch per iteration after the
+// streaming pass w = Q xe:  every CTA reduces the sums the previous launch left (ALSums) and the shares of xe'w,
+// updates the multiplier of the equality row, applies the optimality test of the PREVIOUS iteration
+// (opti/_base.py:129-149), evaluates L(xe) and the epoch limit, then takes the step on its slice: gradient, update
+// rule, box multipliers at the new point, next evaluation point, and its terms of the next ALSums.  The arithmetic
+// lives in al_math.cuh (shared with the host emulation of the CPU tests).  The second history array holds the
+// primal cost x'Qx/2 + q'x (what ml/svm/_base.py:289-291 stores for a Lagrangian dual).
+struct ALArgs {
+    ALParams p;
+    double *lam_lb, *lam_ub, *s1, *s2, *s3, *step, *xpre;
+    const double* A;                      // equality row (nvars), null without an equality constraint
+    const double *lr, *mom, *bc1, *bc2;   // per-iteration scalars, epochs + 1 entries each
+    double* part;                         // 2 x AL_NSUMS x VP_MAXC per-CTA sums, double-buffered by state parity
+    double* mu;                           // 2 entries, by state parity
+};
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_n(double (&v)[NV], double (*sm)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();  // protect sm from the previous use
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sm[wid][i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < VP_NT / 32; ++w) r = __dadd_rn(r, sm[w][i]);
+        v[i] = r;
+    }
+}
+
+__device__ __forceinline__ void al_sums_to_array(const ALSums& s, double (&v)[AL_NSUMS + 1]) {
+    v[0] = s.ax_pre; v[1] = s.ax_eval; v[2] = s.qx; v[3] = s.dx2; v[4] = s.dlam2; v[5] = s.c2; v[6] = s.cc2; v[7] = s.lamc;
+}
+__device__ __forceinline__ void al_array_to_sums(const double (&v)[AL_NSUMS + 1], ALSums& s) {
+    s.ax_pre = v[0]; s.ax_eval = v[1]; s.qx = v[2]; s.dx2 = v[3]; s.dlam2 = v[4]; s.c2 = v[5]; s.cc2 = v[6]; s.lamc = v[7];
+}
+
+__device__ __forceinline__ ALElem al_load(const VecArgs& a, const ALArgs& al, long long j) {
+    ALElem e;
+    e.x = a.x[j];
+    e.lam_lb = al.lam_lb[j];
+    e.lam_ub = al.lam_ub[j];
+    e.s1 = al.s1[j];
+    e.s2 = al.s2[j];
+    e.s3 = al.s3[j];
+    e.step = al.step[j];
+    return e;
+}
+__device__ __forceinline__ void al_store(const VecArgs& a, const ALArgs& al, long long j, const ALElem& e, double xpre) {
+    a.x[j] = e.x;
+    al.lam_lb[j] = e.lam_lb;
+    al.lam_ub[j] = e.lam_ub;
+    al.s1[j] = e.s1;
+    al.s2[j] = e.s2;
+    al.s3[j] = e.s3;
+    al.step[j] = e.step;
+    al.xpre[j] = xpre;
+}
+
+// INIT is launched with k = -1 (it prepares the sums of state 0)
+template <int MODE>
+__global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const ALArgs al, const long long k) {
+    __shared__ double sm[VP_NT / 32][AL_NSUMS + 1];
+    PGDeviceState* st = a.st;
+    if (*reinterpret_cast<volatile int*>(&st->done)) {
+        __threadfence();
+        if (*reinterpret_cast<volatile long long*>(&st->done_k) != k) return;
+    }
+    const int tid = threadIdx.x;
+    const long long n = a.n;
+    const long long chunk = (n + a.nctas - 1) / a.nctas;
+    const long long j0 = (long long)blockIdx.x * chunk;
+    const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
+    const unsigned rpr = (unsigned)a.rpr, gpr = rpr / MV_GROUP;
+    const ALParams& p = al.p;
+    double* part_w = al.part + (size_t)((k + 1) & 1) * AL_NSUMS * VP_MAXC;  // sums of state k+1
+    double v[AL_NSUMS + 1];
+
+    if (MODE == VP_INIT) {
+        ALSums acc = {};
+        for (long long j = j0 + tid; j < j1; j += VP_NT) {
+            const double x = a.x[j];
+            al_init_sums(x, a.q[j], al.A ? al.A[j] : 0.0, a.lb[j], a.ub[j], acc);
+            double uj = x;
+            if (a.svr) {
+                const long long i2 = j + n;
+                const double x2 = a.x[i2];
+                al_init_sums(x2, a.q[i2], al.A ? al.A[i2] : 0.0, a.lb[i2], a.ub[i2], acc);
+                uj = __dsub_rn(x, x2);
+            }
+            a.u[j] = uj;
+        }
+        al_sums_to_array(acc, v);
+        v[AL_NSUMS] = 0.0;
+        block_reduce_n<AL_NSUMS + 1>(v, sm);
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < AL_NSUMS; ++i) part_w[i * VP_MAXC + blockIdx.x] = v[i];
+        }
+        return;
+    }
+
+    // ---- sums over the whole problem, identical in every CTA
+    const double* part_r = al.part + (size_t)(k & 1) * AL_NSUMS * VP_MAXC;
+#pragma unroll
+    for (int i = 0; i < AL_NSUMS; ++i) v[i] = tid < a.nctas ? part_r[i * VP_MAXC + tid] : 0.0;
+    {
+        // xe'w: one share per 64-row group, thread-strided in global group order
+        double xw = 0.0;
+        const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
+        for (unsigned b0 = tid; b0 < ngrp; b0 += 4 * VP_NT) {
+            double sh[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned b = b0 + e * VP_NT;
+                const unsigned rk = b / gpr;
+                sh[e] = b < ngrp ? gathered_at(a, (size_t)rk * a.stride + rpr + (b - rk * gpr)) : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xw = __dadd_rn(xw, sh[e]);
+        }
+        v[AL_NSUMS] = xw;
+    }
+    block_reduce_n<AL_NSUMS + 1>(v, sm);
+    ALSums S;
+    al_array_to_sums(v, S);
+    const double mu_prev = k >= 1 ? al.mu[(k - 1) & 1] : 0.0;
+    double mu = 0.0, c_eq = 0.0, f = 0.0, pf = 0.0;
+    const int rc = al_scalar_phase(p, k, a.max_iter, S, v[AL_NSUMS], mu_prev, mu, c_eq, f, pf);
+    const bool lead = blockIdx.x == 0 && tid == 0;
+    if (rc == AL_OPTIMAL) {
+        // the previous iteration ended the run: x, the multipliers and iter = k - 1 stay, f and g are those of
+        // state k - 1 (the reference breaks out before re-evaluating them)
+        if (lead) {
+            al.mu[k & 1] = mu;
+            st->mu = mu;
+            st->status = SVMB200_STATUS_OPTIMAL;
+            st->done_k = k;
+            __threadfence();
+            st->done = 1;
+        }
+        return;
+    }
+    if (lead) {
+        if (k < a.hist_cap) {
+            a.hist_f[k] = f;
+            a.hist_ng[k] = pf;
+        }
+        st->f = f;
+        st->ng = pf;
+        st->iter = k;
+        st->mu = mu;
+        al.mu[k & 1] = mu;
+    }
+    ALScalars sc;
+    sc.mu = mu;
+    sc.ax = S.ax_eval;
+    sc.act_eq = c_eq != 0.0;
+    sc.lr = al.lr[k];
+    sc.mom = al.mom[k];
+    sc.mom_next = al.mom[k + 1];
+    sc.bc1 = al.bc1[k];
+    sc.bc2 = al.bc2[k];
+    const bool step = (rc == AL_CONTINUE) && (MODE == VP_STEP);
+
+    ALSums acc = {};
+    for (long long j = j0 + tid; j < j1; j += VP_NT) {
+        const unsigned rk = (unsigned)j / rpr;
+        const double wj = gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
+        const double Aj = al.A ? al.A[j] : 0.0, qj = a.q[j], lbj = a.lb[j], ubj = a.ub[j];
+        ALElem e = al_load(a, al, j);
+        const double g = al_gradient(p, sc, wj, qj, Aj, lbj, ubj, e);
+        a.g[j] = g;
+        double uj = e.x;
+        if (step) {
+            double xpre;
+            al_step(p, sc, g, qj, Aj, lbj, ubj, e, xpre, acc);
+            al_store(a, al, j, e, xpre);
+            uj = e.x;
+        }
+        if (a.svr) {
+            const long long i2 = j + n;
+            const double A2 = al.A ? al.A[i2] : 0.0, q2 = a.q[i2], lb2 = a.lb[i2], ub2 = a.ub[i2];
+            ALElem e2 = al_load(a, al, i2);
+            const double g2 = al_gradient(p, sc, -wj, q2, A2, lb2, ub2, e2);
+            a.g[i2] = g2;
+            if (step) {
+                double xpre2;
+                al_step(p, sc, g2, q2, A2, lb2, ub2, e2, xpre2, acc);
+                al_store(a, al, i2, e2, xpre2);
+            }
+            uj = __dsub_rn(uj, e2.x);
+        }
+        if (step) a.u[j] = uj;
+    }
+    if (!step) {
+        if (rc == AL_STOPPED && lead) {
+            st->status = SVMB200_STATUS_STOPPED;
+            st->done_k = k;
+            __threadfence();
+            st->done = 1;
+        }
+        return;
+    }
+    al_sums_to_array(acc, v);
+    v[AL_NSUMS] = 0.0;
+    block_reduce_n<AL_NSUMS + 1>(v, sm);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < AL_NSUMS; ++i) part_w[i * VP_MAXC + blockIdx.x] = v[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ driver
 struct svmb200_pg {
     svmb200_ctx* ctx = nullptr;
     const double* dQ = nullptr;
     int64_t n = 0, ld = 0, row0 = 0, nrows = 0, nvars = 0, rows_per_rank = 0;
     int svr = 0;
-    int solver = 0;      // 0: projected gradient, 1: Frank-Wolfe
+    int solver = 0;      // 0: projected gradient, 1: Frank-Wolfe, 2: augmented Lagrangian + stochastic rule
+    ALArgs al = {};      // solver 2 only
     double fw_t = 0.0;   // Frank-Wolfe stabilisation parameter
     double eps = 1e-6;
     int64_t max_iter = 1000;
@@ -770,7 +997,8 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
 template <int MODE>
 static int launch_vec(svmb200_pg* pg, long long k) {
     VecArgs a = make_vec_args(pg);
-    if (pg->solver == 1) fw_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
+    if (pg->solver == 2) al_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, pg->al, MODE == VP_INIT ? -1 : k);
+    else if (pg->solver == 1) fw_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
     else pg_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
     pg->ctx->launches++;
     SVM_CUDA(cudaGetLastError());
@@ -867,9 +1095,18 @@ extern "C" int svmb200_pg_destroy(svmb200_pg* pg) {
     return SVMB200_OK;
 }
 
+// host-side description of an augmented-Lagrangian solve (solver 2)
+struct ALSpec {
+    ALParams p;
+    const double* a_host;      // equality row or null
+    const double* lr_host;     // epochs step sizes
+    const double* mom_host;    // epochs + 1 momenta, or null (= 0)
+};
+
 static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows, int hessian,
                        const double* q_host, const double* lb_host, const double* ub_host, const double* x0_host,
-                       double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out);
+                       double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out,
+                       const ALSpec* al = nullptr);
 
 extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
                                  int hessian, const double* q_host, const double* lb_host, const double* ub_host,
@@ -886,7 +1123,7 @@ extern "C" int svmb200_fw_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
 
 static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows, int hessian,
                        const double* q_host, const double* lb_host, const double* ub_host, const double* x0_host,
-                       double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out) {
+                       double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out, const ALSpec* al) {
     SVM_TRY(svm_use(ctx));
     SVM_CHECK_ARG(out != nullptr, "out is null");
     *out = nullptr;
@@ -942,7 +1179,12 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
         auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
         const size_t sz_nv = up(nv), sz_u = up((size_t)ld * sizeof(double)), sz_w = up((size_t)(pg->stride * P) * sizeof(double));
         const size_t sz_part = up(3 * VP_MAXC * sizeof(double)), sz_hist = up((size_t)pg->hist_cap * sizeof(double));
-        const size_t total = 6 * sz_nv + sz_u + sz_w + sz_part + 2 * sz_hist + up(sizeof(PGDeviceState));
+        // augmented Lagrangian: + multipliers, rule state, previous step, pre-jump point, equality row (nvars each),
+        // four per-iteration scalar arrays (epochs + 1), double-buffered per-CTA sums, two slots of mu
+        const size_t sz_sched = up((size_t)(max_iter + 1) * sizeof(double));
+        const size_t sz_alpart = up(2 * AL_NSUMS * VP_MAXC * sizeof(double));
+        const size_t al_extra = solver == 2 ? 8 * sz_nv + 4 * sz_sched + sz_alpart + up(2 * sizeof(double)) : 0;
+        const size_t total = 6 * sz_nv + sz_u + sz_w + sz_part + 2 * sz_hist + up(sizeof(PGDeviceState)) + al_extra;
         unsigned char* base = nullptr;
         if (!ctx->pg_slab_busy) {
             if (ctx->pg_slab_bytes < total) {
@@ -985,6 +1227,26 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
         pg->hist_f = take(sz_hist);
         pg->hist_ng = take(sz_hist);
         pg->st = reinterpret_cast<PGDeviceState*>(take(up(sizeof(PGDeviceState))));
+        if (solver == 2) {
+            ALArgs& A = pg->al;
+            A.p = al->p;
+            A.lam_lb = take(sz_nv);
+            A.lam_ub = take(sz_nv);
+            A.s1 = take(sz_nv);
+            A.s2 = take(sz_nv);
+            A.s3 = take(sz_nv);
+            A.step = take(sz_nv);
+            A.xpre = take(sz_nv);
+            double* arow = take(sz_nv);
+            A.A = al->a_host ? arow : nullptr;
+            double* sched = take(4 * sz_sched);
+            A.lr = sched;
+            A.mom = sched + sz_sched / sizeof(double);
+            A.bc1 = sched + 2 * (sz_sched / sizeof(double));
+            A.bc2 = sched + 3 * (sz_sched / sizeof(double));
+            A.part = take(sz_alpart);
+            A.mu = take(up(2 * sizeof(double)));
+        }
     }
     cudaStream_t s = ctx->stream;
     PG_CUDA(cudaMemsetAsync(pg->st, 0, sizeof(PGDeviceState), s));
@@ -1003,12 +1265,44 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     PG_CUDA(cudaMemcpyAsync(pg->lb, lbv.data(), nv, cudaMemcpyHostToDevice, s));
     PG_CUDA(cudaMemcpyAsync(pg->x, x0v.data(), nv, cudaMemcpyHostToDevice, s));
     PG_CUDA(cudaMemcpyAsync(pg->u, u0.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    std::vector<double> sched;  // staging of the per-iteration scalars (augmented Lagrangian)
+    if (solver == 2) {
+        ALArgs& A = pg->al;
+        // multipliers, rule state, previous step: zero (rmsprop.py:93 starts its moving mean of g^2 at one)
+        PG_CUDA(cudaMemsetAsync(A.lam_lb, 0, 7 * (((nv + 255) & ~size_t(255))), s));
+        PG_CUDA(cudaMemsetAsync(A.part, 0, 2 * AL_NSUMS * VP_MAXC * sizeof(double), s));
+        PG_CUDA(cudaMemsetAsync(A.mu, 0, 2 * sizeof(double), s));
+        const size_t ne = (size_t)max_iter + 1;
+        sched.assign(4 * ne, 0.0);
+        for (size_t k = 0; k < ne; ++k) {
+            sched[k] = al->lr_host[k < (size_t)max_iter ? k : (size_t)max_iter - 1];
+            sched[ne + k] = al->mom_host ? al->mom_host[k] : 0.0;
+            // adam.py / adamax.py: 1 - beta ** t with t = iter + 1, evaluated with the C library's pow like Python does
+            sched[2 * ne + k] = 1.0 - pow(A.p.beta1, (double)(k + 1));
+            sched[3 * ne + k] = 1.0 - pow(A.p.beta2, (double)(k + 1));
+        }
+        PG_CUDA(cudaMemcpyAsync(const_cast<double*>(A.lr), sched.data(), ne * sizeof(double), cudaMemcpyHostToDevice, s));
+        PG_CUDA(cudaMemcpyAsync(const_cast<double*>(A.mom), sched.data() + ne, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+        PG_CUDA(cudaMemcpyAsync(const_cast<double*>(A.bc1), sched.data() + 2 * ne, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+        PG_CUDA(cudaMemcpyAsync(const_cast<double*>(A.bc2), sched.data() + 3 * ne, ne * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (al->a_host) PG_CUDA(cudaMemcpyAsync(const_cast<double*>(A.A), al->a_host, nv, cudaMemcpyHostToDevice, s));
+    }
     PG_CUDA(cudaStreamSynchronize(s));  // staging vectors go out of scope
+    if (solver == 2 && pg->al.p.rule == AL_RMSPROP) {
+        std::vector<double> ones((size_t)pg->nvars, 1.0);
+        PG_CUDA(cudaMemcpyAsync(pg->al.s1, ones.data(), nv, cudaMemcpyHostToDevice, s));
+        PG_CUDA(cudaStreamSynchronize(s));
+    }
 #undef PG_CUDA
-    // g0 = Q x0 + q, first direction and its partial reductions
     pg->last_passes = 0;
-    rc = pg_product(pg, false);
-    if (rc == SVMB200_OK) rc = launch_vec<VP_INIT>(pg, 0);
+    if (solver == 2) {
+        // sums of state 0 (no product needed: every launch of the loop is preceded by its own pass w = Q xe)
+        rc = launch_vec<VP_INIT>(pg, 0);
+    } else {
+        // g0 = Q x0 + q, first direction and its partial reductions
+        rc = pg_product(pg, false);
+        if (rc == SVMB200_OK) rc = launch_vec<VP_INIT>(pg, 0);
+    }
     if (rc != SVMB200_OK) return fail(rc);
     pg->k_next = 0;
     *out = pg;
@@ -1066,7 +1360,9 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
             if (pg->finished) pg->k_next = pg->st_host->iter;
         }
         if (!pg->finished) {
-            // make the state at callback point k_next visible (f, |d|, stopping tests)
+            // make the state at callback point k_next visible (f, |d|, stopping tests); the augmented Lagrangian
+            // needs w = Q xe for that (value and gradient at xe), the box-constrained solvers carry g along
+            if (pg->solver == 2) SVM_TRY(pg_product(pg, false));
             SVM_TRY(launch_vec<VP_FINALISE>(pg, pg->k_next));
             SVM_TRY(pg_poll(pg));
         }
@@ -1093,9 +1389,14 @@ extern "C" int svmb200_pg_state(svmb200_pg* pg, double* x_host, double* g_host, 
     SVM_TRY(svm_use(pg->ctx));
     cudaStream_t s = pg->ctx->stream;
     const size_t nv = (size_t)pg->nvars * sizeof(double);
-    if (x_host) SVM_CUDA(cudaMemcpyAsync(x_host, pg->x, nv, cudaMemcpyDeviceToHost, s));
-    if (g_host) SVM_CUDA(cudaMemcpyAsync(g_host, pg->g, nv, cudaMemcpyDeviceToHost, s));
     SVM_CUDA(cudaMemcpyAsync(pg->st_host, pg->st, sizeof(PGDeviceState), cudaMemcpyDeviceToHost, s));
+    SVM_CUDA(cudaStreamSynchronize(s));
+    // augmented Lagrangian with Nesterov momentum: the device iterate is the next evaluation point (jump included);
+    // when the optimality test ends the run the reference has not taken that jump yet
+    const bool pre_jump = pg->solver == 2 && pg->al.p.momentum_type == AL_MOM_NESTEROV && pg->st_host->done &&
+                          pg->st_host->status == SVMB200_STATUS_OPTIMAL;
+    if (x_host) SVM_CUDA(cudaMemcpyAsync(x_host, pre_jump ? pg->al.xpre : pg->x, nv, cudaMemcpyDeviceToHost, s));
+    if (g_host) SVM_CUDA(cudaMemcpyAsync(g_host, pg->g, nv, cudaMemcpyDeviceToHost, s));
     SVM_CUDA(cudaStreamSynchronize(s));
     if (f) *f = pg->st_host->f;
     if (ng) *ng = pg->st_host->ng;
@@ -1157,6 +1458,58 @@ extern "C" int svmb200_pg_set_profile(svmb200_pg* pg, int on) {
 extern "C" int svmb200_pg_device_x(svmb200_pg* pg, double** dx) {
     SVM_CHECK_ARG(pg != nullptr && dx != nullptr, "null argument");
     *dx = pg->x;
+    return SVMB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ augmented Lagrangian API
+extern "C" int svmb200_al_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
+                                 int hessian, const double* q_host, const double* lb_host, const double* ub_host,
+                                 const double* x0_host, const double* a_host, double b, double rho, int rule,
+                                 int momentum_type, const double* step_sizes, const double* momenta, double decay,
+                                 double beta1, double beta2, double offset, double tol, int64_t epochs, svmb200_pg** out) {
+    SVM_CHECK_ARG(x0_host != nullptr, "the start point is required (opti/_base.py:36-60 draws it on the host)");
+    SVM_CHECK_ARG(step_sizes != nullptr, "step_sizes is null");
+    SVM_CHECK_ARG(rho > 0.0, "rho must be must > 0");                       // constrained/_base.py:276-277
+    SVM_CHECK_ARG(rule >= AL_ADAGRAD && rule <= AL_ADAMAX, "unknown update rule");
+    SVM_CHECK_ARG(momentum_type >= AL_MOM_NONE && momentum_type <= AL_MOM_NESTEROV, "unknown momentum type");
+    SVM_CHECK_ARG(momentum_type == AL_MOM_NONE || (rule != AL_ADAGRAD && rule != AL_ADADELTA),
+                  "AdaGrad and AdaDelta take no momentum");
+    SVM_CHECK_ARG(momentum_type == AL_MOM_NONE || momenta != nullptr, "momenta is null");
+    SVM_CHECK_ARG(offset > 0.0, "offset must be > 0");                      // adagrad.py:80-81
+    SVM_CHECK_ARG(decay >= 0.0 && decay < 1.0, "decay has to lie in [0, 1)");
+    SVM_CHECK_ARG(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0, "beta has to lie in [0, 1)");
+    SVM_CHECK_ARG(epochs > 0 && epochs < (1ll << 24), "epochs must lie in [1, 2^24)");
+    ALSpec spec;
+    spec.p.rule = rule;
+    spec.p.momentum_type = momentum_type;
+    spec.p.has_eq = a_host != nullptr;
+    spec.p.b = b;
+    spec.p.rho = rho;
+    spec.p.offset = offset;
+    spec.p.tol = tol;
+    spec.p.decay = decay;
+    spec.p.om_decay = 1.0 - decay;
+    spec.p.beta1 = beta1;
+    spec.p.om_beta1 = 1.0 - beta1;
+    spec.p.beta2 = beta2;
+    spec.p.om_beta2 = 1.0 - beta2;
+    spec.a_host = a_host;
+    spec.lr_host = step_sizes;
+    spec.mom_host = momentum_type == AL_MOM_NONE ? nullptr : momenta;
+    return bcqp_create(ctx, dQ, n, ld, row0, nrows, hessian, q_host, lb_host, ub_host, x0_host, 0.0, epochs, 2, 0.0, out,
+                       &spec);
+}
+
+extern "C" int svmb200_al_multipliers(svmb200_pg* pg, double* mu, double* lam_lb_host, double* lam_ub_host) {
+    SVM_CHECK_ARG(pg != nullptr && pg->solver == 2, "not an augmented-Lagrangian solver");
+    SVM_TRY(svm_use(pg->ctx));
+    cudaStream_t s = pg->ctx->stream;
+    const size_t nv = (size_t)pg->nvars * sizeof(double);
+    SVM_CUDA(cudaMemcpyAsync(pg->st_host, pg->st, sizeof(PGDeviceState), cudaMemcpyDeviceToHost, s));
+    if (lam_lb_host) SVM_CUDA(cudaMemcpyAsync(lam_lb_host, pg->al.lam_lb, nv, cudaMemcpyDeviceToHost, s));
+    if (lam_ub_host) SVM_CUDA(cudaMemcpyAsync(lam_ub_host, pg->al.lam_ub, nv, cudaMemcpyDeviceToHost, s));
+    SVM_CUDA(cudaStreamSynchronize(s));
+    if (mu) *mu = pg->st_host->mu;
     return SVMB200_OK;
 }
 

@@ -11,9 +11,11 @@ Where the reference builds K, Q = K o yy' + yy' and three more n x n temporaries
 the fused Gram kernel, row-sharded over the GPUs of the job, and never visits the host.
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 from sklearn.base import BaseEstimator, ClassifierMixin, RegressorMixin
+from sklearn.exceptions import ConvergenceWarning
 from sklearn.preprocessing import LabelBinarizer
 
 from .kernels import gaussian, Kernel, LinearKernel, _dense_f64
@@ -21,11 +23,13 @@ from .losses import (squared_hinge, squared_epsilon_insensitive, Hinge, SquaredH
                      SquaredEpsilonInsensitive)
 from ... import _native as N
 from ...opti import Optimizer, Quadratic
-from ...opti.constrained import BoxConstrainedQuadraticOptimizer, ProjectedGradient
+from ...opti.constrained import AugmentedLagrangianQuadratic, BoxConstrainedQuadraticOptimizer, ProjectedGradient
+from ...opti.unconstrained.stochastic import StochasticOptimizer, StochasticMomentumOptimizer
 from ...runtime import DeviceHessian, default_context
 
-_SCOPE = ('optiml_b200 implements the dual formulation with reg_intercept=True solved by a '
-          'BoxConstrainedQuadraticOptimizer (ProjectedGradient); {} is outside that path')
+_SCOPE = ('optiml_b200 implements the dual formulation solved by a BoxConstrainedQuadraticOptimizer '
+          '(ProjectedGradient, FrankWolfe; reg_intercept=True) or, as its augmented-Lagrangian relaxation, by a '
+          'StochasticOptimizer (AdaGrad, ...); {} is outside that path')
 
 
 class SVM(BaseEstimator):
@@ -93,14 +97,17 @@ class SVM(BaseEstimator):
 
     # ------------------------------------------------------------------ shared pieces of fit
     def _bcqp_solver_class(self):
-        """The solver class to instantiate; mirrors the dispatch of ml/svm/_base.py:559-636."""
+        """The solver class to instantiate; mirrors the dispatch of ml/svm/_base.py:559-725.  A
+        ``StochasticOptimizer`` subclass selects the augmented-Lagrangian relaxation (:638-723)."""
         opt = self.optimizer
-        if isinstance(opt, BoxConstrainedQuadraticOptimizer):
+        if isinstance(opt, (BoxConstrainedQuadraticOptimizer, StochasticOptimizer)):
             opt = type(opt)  # refit of an estimator whose ``optimizer`` was replaced by the fitted instance
         if not self.dual:
             raise NotImplementedError(_SCOPE.format('dual=False (primal formulation)'))
         if isinstance(opt, str) or opt is None:
             raise NotImplementedError(_SCOPE.format(f'optimizer={opt!r}'))
+        if isinstance(opt, type) and issubclass(opt, StochasticOptimizer):
+            return opt
         if not (isinstance(opt, type) and issubclass(opt, BoxConstrainedQuadraticOptimizer)):
             raise NotImplementedError(_SCOPE.format(f'optimizer={opt}'))
         if not self.reg_intercept:
@@ -108,7 +115,39 @@ class SVM(BaseEstimator):
             raise NotImplementedError
         return opt
 
-    def _build_hessian(self, X, signs, layout, X_device=None):
+    def _solve_dual(self, solver_cls, hessian, q, ub, eq_row):
+        """Run the selected solver on  min x'Qx/2 + q'x : 0 <= x <= ub (, eq_row'x = 0 when the intercept is not
+        regularised)  and return the fitted instance; sets ``self.obj`` like ml/svm/_base.py:628-725."""
+        if issubclass(solver_cls, BoxConstrainedQuadraticOptimizer):
+            self.obj = Quadratic(hessian, q)
+            return self._solve(solver_cls, ub)
+        # augmented-Lagrangian relaxation of the box (and of the equality), ml/svm/_base.py:638-655, 1188-1205
+        lb = np.zeros_like(ub)
+        if self.reg_intercept:
+            self.obj = AugmentedLagrangianQuadratic(primal=Quadratic(hessian, q), lb=lb, ub=ub, rho=self.rho)
+        else:
+            self.obj = AugmentedLagrangianQuadratic(primal=Quadratic(hessian, q), A=eq_row, b=np.zeros(1), lb=lb,
+                                                    ub=ub, rho=self.rho)
+        kwargs = dict(f=self.obj, tol=self.tol, step_size=self.learning_rate, epochs=self.max_iter,
+                      random_state=self.random_state, callback=self._store_train_info, verbose=self.verbose)
+        if issubclass(solver_cls, StochasticMomentumOptimizer):
+            kwargs.update(momentum_type=self.momentum_type, momentum=self.momentum)
+        solver = solver_cls(**kwargs)
+        solver.profile = bool(getattr(self, 'profile_matvec', False))
+        import time
+        t0 = time.perf_counter()
+        solver.minimize()
+        self.fit_times_['solve_s'] = time.perf_counter() - t0
+        if solver.status == 'stopped':  # ml/svm/_base.py:715-717
+            warnings.warn('max_iter reached but the optimization has not converged yet', ConvergenceWarning)
+        return solver
+
+    def _bias(self):
+        """The Hessian carries the rank-one term yy' (SVC) / ee' (SVR) only when the intercept is regularised
+        (ml/svm/_base.py:628, 652 vs 644; 1178, 1202 vs 1194)."""
+        return 1.0 if self.reg_intercept else 0.0
+
+    def _build_hessian(self, X, signs, layout, X_device=None, bias=1.0):
         """K1: Gram matrix + bias (+ label signs) straight into this rank's row shard in HBM.
         ``X_device`` (a DeviceMatrix already holding X) skips the host->device copy of X."""
         import time
@@ -121,7 +160,7 @@ class SVM(BaseEstimator):
         H = DeviceHessian(ctx, n, layout)
         sp = C.c_void_p(dS.dptr) if dS is not None else None
         N.call('svmb200_gram', ctx.handle, C.c_void_p(dX.dptr), n, dX.ld, C.c_void_p(dX.dptr), n, dX.ld, d, 1, kid,
-               gamma, coef0, degree, sp, sp, 1.0, H.row0, H.nrows, C.c_void_p(H.matrix.dptr), H.ld)
+               gamma, coef0, degree, sp, sp, float(bias), H.row0, H.nrows, C.c_void_p(H.matrix.dptr), H.ld)
         ctx.sync()
         if X_device is None:
             dX.release()
@@ -170,7 +209,8 @@ class SVM(BaseEstimator):
         return out + self.intercept_
 
     def _store_train_info(self, opt):
-        self.train_loss_history.append(opt.f_x)
+        # ml/svm/_base.py:289-293
+        self.train_loss_history.append(opt.primal_f_x if opt.is_lagrangian_dual() else opt.f_x)
 
     _store_train_info._svmb200_history_only = True
 
@@ -210,10 +250,11 @@ class SVC(ClassifierMixin, SVM):
         n = len(y)
         ys = y.astype(np.float64)
 
-        # Q = K o yy' + yy'  (ml/svm/_base.py:552-554, 628), q = -1, 0 <= alpha <= C
-        self.obj = Quadratic(self._build_hessian(X, ys, 'plain', X_device), -np.ones(n))
+        # Q = K o yy' (+ yy' when the intercept is regularised)  (ml/svm/_base.py:552-554, 628), q = -1, 0 <= alpha <= C
+        bias = self._bias()
+        hessian = self._build_hessian(X, ys, 'plain', X_device, bias)
         ub = np.ones(n) * self.C
-        self.optimizer = self._solve(solver_cls, ub)
+        self.optimizer = self._solve_dual(solver_cls, hessian, -np.ones(n), ub, y)
         self.alphas_ = self.optimizer.x
 
         # support set, dual coefficients, intercept (ml/svm/_base.py:867-880)
@@ -224,9 +265,9 @@ class SVC(ClassifierMixin, SVM):
         if isinstance(self.kernel, LinearKernel):
             self.coef_ = np.dot(self.dual_coef_, self.support_vectors_)
         # K5: sum_m dual_coef_m K[n, m] for every n from ONE masked pass over the resident
-        # Q = s_n s_m (K + 1):  s_n (Q beta)_n = sum_m dual_coef_m K[n, m] + sum_m dual_coef_m
+        # Q = s_n s_m (K + bias):  s_n (Q beta)_n = sum_m dual_coef_m K[n, m] + bias sum_m dual_coef_m
         v = self.obj.device_hessian().product(np.where(sv, self.alphas_, 0.))
-        k_dot = ys[sv] * v[sv] - np.sum(self.dual_coef_)
+        k_dot = ys[sv] * v[sv] - bias * np.sum(self.dual_coef_)
         self.intercept_ = float(np.sum(sv_y - k_dot)) / len(alphas)
         return self
 
@@ -271,11 +312,13 @@ class SVR(RegressorMixin, SVM):
         y = y.astype(np.float64).ravel()
         n = len(y)
 
-        # Q = [[K, -K], [-K, K]] + ee', e = [1, -1]  (ml/svm/_base.py:1098-1100, 1126, 1178): only
-        # M = K + 1 (n x n) is resident, the solver applies the block signs
-        self.obj = Quadratic(self._build_hessian(X, None, 'svr', X_device), np.hstack((-y, y)) + self.epsilon)
+        # Q = [[K, -K], [-K, K]] (+ ee', e = [1, -1], when the intercept is regularised)  (ml/svm/_base.py:1098-1100,
+        # 1126, 1178): only M = K + bias (n x n) is resident, the solver applies the block signs
+        bias = self._bias()
+        hessian = self._build_hessian(X, None, 'svr', X_device, bias)
         ub = np.ones(2 * n) * self.C
-        self.optimizer = self._solve(solver_cls, ub)
+        e = np.hstack((np.ones(n), -np.ones(n)))
+        self.optimizer = self._solve_dual(solver_cls, hessian, np.hstack((-y, y)) + self.epsilon, ub, e)
         self.alphas_ = self.optimizer.x
         alphas_p, alphas_n = np.split(self.alphas_, 2)
 
@@ -287,8 +330,8 @@ class SVR(RegressorMixin, SVM):
         if isinstance(self.kernel, LinearKernel):
             self.coef_ = np.dot(self.dual_coef_, self.support_vectors_)
         beta = np.where(sv, alphas_p - alphas_n, 0.)
-        v = self.obj.device_hessian().product(np.concatenate((beta, np.zeros(n))))[:n]  # (K + 1) beta
-        k_dot = v[sv] - np.sum(self.dual_coef_)
+        v = self.obj.device_hessian().product(np.concatenate((beta, np.zeros(n))))[:n]  # (K + bias) beta
+        k_dot = v[sv] - bias * np.sum(self.dual_coef_)
         self.intercept_ = (float(np.sum(sv_y - k_dot)) - self.epsilon) / len(sv_y)
         return self
 

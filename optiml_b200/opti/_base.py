@@ -102,8 +102,9 @@ class Quadratic(OptimizationFunction):
 
 
 class Optimizer:
-    """State and callback protocol shared by the solvers (optiml/opti/_base.py:9-127, plain-function
-    branch only: no Lagrangian-dual objectives on this path)."""
+    """State and callback protocol shared by the solvers (optiml/opti/_base.py:9-172): plain objectives and the
+    augmented-Lagrangian dual (``f.primal`` and ``f.rho`` present).  The plain Lagrangian dual of the reference
+    (multipliers appended to x) is not on the path."""
 
     def __init__(self, f, x=None, eps=1e-6, tol=1e-8, max_iter=1000, callback=None, callback_args=(),
                  random_state=None, verbose=False):
@@ -114,6 +115,10 @@ class Optimizer:
             x = (np.random.uniform if random_state is None else np.random.RandomState(random_state).uniform)
         self.x = x(size=f.ndim) if callable(x) else np.asarray(x, dtype=float)
         self.f_x = np.nan
+        if self.is_lagrangian_dual():  # optiml/opti/_base.py:66-69
+            self.past_x = self.x.copy()
+            self.primal_f_x = np.nan
+            self.dgap = np.nan
         self.g_x = np.zeros(0)
         self.eps = eps
         self.tol = tol
@@ -122,7 +127,7 @@ class Optimizer:
         self.max_iter = max_iter
         self.iter = 0
         self.status = 'unknown'
-        if self.f.ndim <= 3:
+        if self.f.ndim <= 3 or (hasattr(self.f, 'primal') and self.f.primal.ndim <= 3):
             self.x0_history, self.x1_history, self.f_x_history = [], [], []
         self._callback = callback
         self.callback_args = callback_args
@@ -136,6 +141,21 @@ class Optimizer:
         return self.is_lagrangian_dual() and hasattr(self.f, 'rho')
 
     def callback(self, args=()):
+        if self.is_lagrangian_dual():
+            # optiml/opti/_base.py:96-117; primal_f_x (= primal.function(x)) is set by the device loop, which gets
+            # x'Qx from the same streaming pass that produced the gradient
+            self.dgap = abs((self.primal_f_x - self.f_x) / max(abs(self.primal_f_x), 1))
+            if self.is_verbose():
+                print('\tpcost: {: 1.4e}'.format(self.primal_f_x), end='')
+                print('\tdgap: {: 1.4e}'.format(self.dgap), end='')
+            if self.f.primal.ndim == 2:
+                self.x0_history.append(self.x[0])
+                self.x1_history.append(self.x[1])
+                self.f_x_history.append(self.primal_f_x)
+            if callable(self._callback):
+                self._callback(self, *args, *self.callback_args)
+            self.past_x = self.x.copy()
+            return
         if self.f.ndim <= 3:
             self.x0_history.append(self.x[0])
             self.x1_history.append(self.x[1])

@@ -1,5 +1,5 @@
-__all__ = ['BoxConstrainedQuadraticOptimizer', 'ProjectedGradient', 'FrankWolfe']
+__all__ = ['BoxConstrainedQuadraticOptimizer', 'AugmentedLagrangianQuadratic', 'ProjectedGradient', 'FrankWolfe']
 
-from ._base import BoxConstrainedQuadraticOptimizer
+from ._base import BoxConstrainedQuadraticOptimizer, AugmentedLagrangianQuadratic
 from .projected_gradient import ProjectedGradient
 from .frank_wolfe import FrankWolfe
