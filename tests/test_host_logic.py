@@ -143,3 +143,83 @@ def test_loss_tags_and_kernel_singletons():
         assert isinstance(k, kernels.Kernel)
     assert kernels.poly.get_params() == {'coef0': 0., 'degree': 3, 'gamma': 'scale'}
     assert kernels.sigmoid.gram_spec(np.ones((3, 2)) * [[1.], [2.], [4.]])[0] == 3
+
+
+def test_augmented_lagrangian_host_validation():
+    """argument checks of the augmented-Lagrangian mirror that run before any device call
+    (opti/constrained/_base.py:239-277; stochastic/_base.py:79-81, 196-201; adagrad.py:76-77; adam.py:92-103)"""
+    import warnings
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import AugmentedLagrangianQuadratic as ALQ
+    from optiml_b200.opti.unconstrained.stochastic import (AdaGrad, AdaDelta, Adam, AMSGrad, AdaMax, RMSProp,
+                                                           StochasticGradientDescent, StochasticOptimizer,
+                                                           StochasticMomentumOptimizer)
+    quad = Quadratic(np.eye(3), np.ones(3))
+    lb, ub = np.zeros(3), np.ones(3)
+    with pytest.raises(TypeError):
+        ALQ(primal=np.eye(3), lb=lb, ub=ub)
+    for kw in (dict(h=np.ones(1)), dict(G=np.eye(3)), dict(b=np.zeros(1)), dict(A=np.ones(3))):
+        with pytest.raises(ValueError, match='incomplete'):
+            ALQ(primal=quad, lb=lb, ub=ub, **kw)
+    with pytest.raises(ValueError, match='rho'):
+        ALQ(primal=quad, lb=lb, ub=ub, rho=0)
+    with pytest.raises(NotImplementedError):
+        ALQ(primal=quad, G=np.eye(3), h=np.ones(3), lb=lb, ub=ub)
+    with pytest.raises(NotImplementedError):
+        ALQ(primal=quad, ub=ub)
+    with pytest.raises(NotImplementedError):
+        ALQ(primal=quad, A=np.ones((2, 3)), b=np.zeros(2), lb=lb, ub=ub)
+    f = ALQ(primal=quad, A=np.array([1, -1, 1]), b=np.zeros(1), lb=lb, ub=ub, rho=2)
+    assert f.ndim == 3 and f.n_eq == 1 and f.dual_x.shape == (7,) and f.A.dtype == float and f.primal is quad
+    assert f.AG.shape == (7, 3) and np.array_equal(f.bh, [0, 0, 0, 0, 1, 1, 1])
+    x = np.array([0.5, -0.25, 2.])
+    assert np.array_equal(f.constraints(x), f.AG @ x - f.bh)  # the implicit identity blocks equal the dense form
+    g = ALQ(primal=quad, lb=lb, ub=ub)
+    assert g.n_eq == 0 and g.dual_x.shape == (6,) and np.array_equal(g.constraints(x), g.AG @ x - g.bh)
+
+    assert issubclass(AdaGrad, StochasticOptimizer) and not issubclass(AdaGrad, StochasticMomentumOptimizer)
+    assert all(issubclass(c, StochasticMomentumOptimizer) for c in (StochasticGradientDescent, Adam, AMSGrad, AdaMax, RMSProp))
+    opt = AdaGrad(f=f, random_state=3)
+    assert np.array_equal(opt.x, np.random.RandomState(3).uniform(size=3)) and opt.is_augmented_lagrangian_dual()
+    assert np.array_equal(opt.past_x, opt.x) and np.isnan(opt.primal_f_x) and opt.epochs == opt.max_iter == 1000
+    assert hasattr(opt, 'x0_history')  # primal.ndim <= 3
+    assert next(opt.step_size()) == 1. and opt.is_batch_end()
+    for cls, kw in ((AdaGrad, dict(step_size=0)), (AdaGrad, dict(offset=0)), (AdaGrad, dict(epochs=0)),
+                    (AdaDelta, dict(decay=1)), (RMSProp, dict(decay=-0.1)), (Adam, dict(beta1=1)), (AMSGrad, dict(beta2=1)),
+                    (AdaMax, dict(offset=0)), (StochasticGradientDescent, dict(momentum_type='heavy')),
+                    (StochasticGradientDescent, dict(momentum=1))):
+        with pytest.raises(ValueError):
+            cls(f=f, **kw)
+    with pytest.raises(NotImplementedError):
+        AdaGrad(f=f, batch_size=2)
+    with pytest.raises(TypeError):
+        AdaGrad(f=np.eye(3))
+    with pytest.warns(UserWarning, match='convergence analysis'):
+        Adam(f=f, beta1=0.99, beta2=0.9)
+    assert AdaMax(f=f).step_size().__next__() == 0.002 and Adam(f=f).beta2 == 0.999
+    # schedules: an iterable / a callable returning an iterator are drawn `epochs` values in advance
+    from optiml_b200.opti.unconstrained.stochastic.schedules import constant, decaying, linear_annealing, repeater
+    from itertools import islice
+    assert list(islice(decaying(10, .9), 3)) == [10.0, 9.0, 10 * .9 ** 2]
+    assert list(islice(linear_annealing(1, 0, 4), 6)) == [1.0, 0.75, 0.5, 0.25, 0.0, 0.0]
+    assert list(islice(repeater([1, 2, 3], 2), 6)) == [1, 1, 2, 2, 3, 3] and next(constant(3)) == 3
+    sched = AdaGrad(f=f, step_size=[0.5, 0.25, 0.125], epochs=3)
+    assert np.array_equal(sched._draw(sched.step_size(), 3), [0.5, 0.25, 0.125])
+    with pytest.raises(ValueError, match='schedule ended'):
+        sched._draw(sched.step_size(), 4)
+
+
+def test_estimators_dispatch_stochastic_optimizers_to_the_lagrangian_path():
+    """ml/svm/_base.py:619-725: a BCQP solver needs reg_intercept=True, a StochasticOptimizer takes either; clone works"""
+    from sklearn.base import clone
+    from optiml_b200.ml.svm import SVC, SVR
+    from optiml_b200.ml.svm.losses import hinge, epsilon_insensitive
+    from optiml_b200.opti.constrained import ProjectedGradient
+    from optiml_b200.opti.unconstrained.stochastic import AdaGrad, Adam
+    for ri in (True, False):
+        m = SVC(loss=hinge, dual=True, reg_intercept=ri, optimizer=AdaGrad, learning_rate=1., momentum=0.5)
+        assert m._bcqp_solver_class() is AdaGrad and m._bias() == (1.0 if ri else 0.0)
+        assert clone(m).get_params()['optimizer'] is AdaGrad
+    assert SVR(loss=epsilon_insensitive, dual=True, optimizer=Adam)._bcqp_solver_class() is Adam
+    with pytest.raises(NotImplementedError):
+        SVC(loss=hinge, dual=True, reg_intercept=False, optimizer=ProjectedGradient)._bcqp_solver_class()
