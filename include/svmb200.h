@@ -223,6 +223,14 @@ int svmb200_bcqp_pg_host(svmb200_ctx* ctx, const double* Q_host, const double* q
                          double* x_out, double* g_out, double* f_hist, double* ng_hist, int64_t* iter,
                          int* status);
 
+/* ---- host-side helpers of the fit path (no device involved; every rank of a sharded fit repeats them) ---------- */
+/* Population variance of `count` contiguous doubles, BIT-IDENTICAL to NumPy's x.var() (pairwise summation of
+ * numpy/_core/src/umath/loops_utils.h.src, two passes of numpy/_core/_methods.py _var), fused and spread over
+ * `threads` host threads.  Replaces the X.var() of kernels.py:93, 127 (gamma='scale').                          */
+int svmb200_host_variance(const double* x_host, int64_t count, int threads, double* var);
+/* out[i][:] = x[idx[i]][:] for rows of d doubles: support_vectors_ = X[sv] (ml/svm/_base.py:869, 1425)          */
+int svmb200_host_gather_rows(const double* x_host, int64_t d, const int64_t* idx, int64_t nidx, double* out, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,8 @@ PROTOTYPES = {
                          C.c_double, c_vp],
     'svmb200_kernel_matrix_host': [c_vp, c_vp, i64, c_vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_double,
                                    c_vp],
+    'svmb200_host_variance': [c_vp, i64, C.c_int, C.POINTER(C.c_double)],
+    'svmb200_host_gather_rows': [c_vp, i64, c_vp, i64, c_vp, C.c_int],
     'svmb200_bcqp_pg_host': [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i64, C.c_double, i64, c_vp, c_vp, c_vp, c_vp,
                              C.POINTER(i64), C.POINTER(C.c_int)],
 }

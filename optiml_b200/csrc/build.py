@@ -6,10 +6,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(os.path.dirname(HERE), '_lib')
 LIB = os.path.join(LIB_DIR, 'libsvmb200.so')
-SOURCES = ['api.cu', 'pg.cu', 'gram.cu', 'comm.cu']
+SOURCES = ['api.cu', 'pg.cu', 'gram.cu', 'comm.cu', 'hostmath.cu']
 HEADERS = ['common.cuh', 'al_math.cuh', os.path.join('..', '..', 'include', 'svmb200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall', '--fmad=true']
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall', '--fmad=true',
+              '-Xcompiler', '-ffp-contract=off']  # host arithmetic (start point, variance) rounds like NumPy
 
 
 def _stale(target, deps):
@@ -34,7 +35,7 @@ def build(verbose=False, force=False):
                 print(' '.join(cmd), flush=True)
             subprocess.run(cmd, check=True)
     if force or _stale(LIB, objs):
-        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-ldl']
+        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-ldl', '-lpthread']
         if verbose:
             print(' '.join(cmd), flush=True)
         subprocess.run(cmd, check=True)

@@ -223,3 +223,50 @@ def test_estimators_dispatch_stochastic_optimizers_to_the_lagrangian_path():
     assert SVR(loss=epsilon_insensitive, dual=True, optimizer=Adam)._bcqp_solver_class() is Adam
     with pytest.raises(NotImplementedError):
         SVC(loss=hinge, dual=True, reg_intercept=False, optimizer=ProjectedGradient)._bcqp_solver_class()
+
+
+def test_host_variance_is_bit_identical_to_numpy():
+    """gamma='scale' is 1 / (d * X.var()) (kernels.py:93, 127) and feeds every Gram entry: the threaded, fused
+    svmb200_host_variance must return NumPy's bits exactly, on ragged shapes and for every thread count"""
+    import ctypes as C
+    from optiml_b200 import _native as N
+    from optiml_b200.configs import make_config
+    from optiml_b200.ml.svm.kernels import variance, GaussianKernel
+
+    def native(X, threads):
+        v = C.c_double(0)
+        N.call('svmb200_host_variance', N.ptr(X), X.size, threads, C.byref(v))
+        return v.value
+
+    rng = np.random.default_rng(0)
+    for _ in range(120):
+        n, d = int(rng.integers(1, 2500)), int(rng.integers(1, 33))
+        X = rng.standard_normal((n, d)) * rng.uniform(0.1, 100) + rng.uniform(-50, 50)
+        assert all(native(X, t) == X.var() for t in (1, 3, 4))
+    for _ in range(8):
+        n, d = int(rng.integers(70000, 300000)), int(rng.integers(1, 7))
+        X = rng.standard_normal((n, d)) * 3 + 1
+        assert all(native(X, t) == X.var() for t in (1, 2, 3, 4, 5, 8, 16))
+    for cfg, n in (('C1', None), ('C2', None), ('C4', 9000)):
+        spec, X, y = make_config(cfg, n=n)
+        assert variance(X) == X.var()
+        assert GaussianKernel().gram_spec(X)[1] == 1. / (X.shape[1] * X.var())
+    Xf = np.asfortranarray(rng.standard_normal((400, 300)))  # not C-contiguous: NumPy's own var
+    assert variance(Xf) == Xf.var()
+
+
+def test_host_gather_rows_and_label_binarisation_shortcuts():
+    from sklearn.preprocessing import LabelBinarizer
+    from optiml_b200.ml.svm._base import _binarize
+    from optiml_b200.ml.svm.kernels import gather_rows
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((5000, 37))
+    for idx in (np.arange(5000)[rng.random(5000) < 0.9], np.array([4999, 0, 17]), np.zeros(0, dtype=np.int64)):
+        out = gather_rows(X, idx)
+        assert np.array_equal(out, X[idx]) and out.flags['C_CONTIGUOUS'] and out.flags['OWNDATA']
+    for y in (rng.integers(0, 2, 1000), np.where(rng.random(500) < .3, 'a', 'b'), rng.choice([-3., 2.], 300), [0, 1, 1, 0],
+              np.array([True, False, True]), np.zeros(10, int), rng.integers(0, 2, (50, 1)), rng.integers(5, 7, 100).astype(np.int32),
+              rng.integers(5, 7, 100).astype(np.uint16), rng.choice([-3., 2.], 300).astype(np.float32)):
+        lb = LabelBinarizer(neg_label=-1).fit(y)
+        a, b = _binarize(lb, y), lb.transform(y).ravel()
+        assert np.array_equal(a, b) and a.dtype == b.dtype
