@@ -348,7 +348,7 @@ struct VecArgs {
     const double *q, *lb, *ub;
     const double* gathered;  // per rank: [rpr results w | rpr/MV_GROUP shares of u'w]
     long long rpr, stride;
-    double* part;            // 3 x VP_MAXC : |d|^2, x'(g+q), max_t per CTA
+    double* part;            // 2 x 3 x VP_MAXC : |d|^2, x'(g+q), max_t per CTA, double-buffered by state parity
     double *hist_f, *hist_ng;
     long long hist_cap;
     PGDeviceState* st;
@@ -446,6 +446,10 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     const long long j0 = (long long)blockIdx.x * chunk;
     const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
     const unsigned rpr = (unsigned)a.rpr, gpr = rpr / MV_GROUP;  // rows / groups per rank (n < 2^31)
+    // per-CTA partials are double-buffered by state parity: this launch reads the sums of state k and leaves those of
+    // state k+1 (INIT: of state 0) in the other half, so a CTA that starts late never reads a half-updated set
+    const double* part_r = a.part + (size_t)(k & 1) * 3 * VP_MAXC;
+    double* part_w = a.part + (size_t)((MODE == VP_INIT ? k : k + 1) & 1) * 3 * VP_MAXC;
 
     double t = 0.0;
     if (MODE != VP_INIT) {
@@ -454,9 +458,9 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
         r.a = r.b = r.c = 0.0;
         r.m = INFINITY;
         if (tid < a.nctas) {
-            r.a = a.part[tid];
-            r.b = a.part[VP_MAXC + tid];
-            r.m = a.part[2 * VP_MAXC + tid];
+            r.a = part_r[tid];
+            r.b = part_r[VP_MAXC + tid];
+            r.m = part_r[2 * VP_MAXC + tid];
         }
         if (MODE == VP_STEP) {
             // u'w: one share per 64-row group, thread-strided in global group order
@@ -549,9 +553,9 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     }
     acc = block_reduce(acc, sm);
     if (tid == 0) {
-        a.part[blockIdx.x] = acc.a;
-        a.part[VP_MAXC + blockIdx.x] = acc.b;
-        a.part[2 * VP_MAXC + blockIdx.x] = acc.m;
+        part_w[blockIdx.x] = acc.a;
+        part_w[VP_MAXC + blockIdx.x] = acc.b;
+        part_w[2 * VP_MAXC + blockIdx.x] = acc.m;
     }
 }
 
@@ -582,6 +586,8 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
     const long long j0 = (long long)blockIdx.x * chunk;
     const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
     const unsigned rpr = (unsigned)a.rpr, gpr = rpr / MV_GROUP;
+    const double* part_r = a.part + (size_t)(k & 1) * 3 * VP_MAXC;  // double-buffered by state parity (see pg_vector_kernel)
+    double* part_w = a.part + (size_t)((MODE == VP_INIT ? k : k + 1) & 1) * 3 * VP_MAXC;
 
     double step = 0.0;
     if (MODE != VP_INIT) {
@@ -590,9 +596,9 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
         r.m = 0.0;  // used as a fourth SUM here (g'd), not a min
         double gd_part = 0.0;
         if (tid < a.nctas) {
-            r.a = a.part[tid];                 // x'(g+q)
-            r.b = a.part[VP_MAXC + tid];       // g'(y-x)
-            gd_part = a.part[2 * VP_MAXC + tid];  // g'd
+            r.a = part_r[tid];                 // x'(g+q)
+            r.b = part_r[VP_MAXC + tid];       // g'(y-x)
+            gd_part = part_r[2 * VP_MAXC + tid];  // g'd
         }
         if (MODE == VP_STEP) {
             const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
@@ -694,9 +700,9 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
     }
     acc = block_reduce(acc, sm);
     if (tid == 0) {
-        a.part[blockIdx.x] = acc.a;
-        a.part[VP_MAXC + blockIdx.x] = acc.b;
-        a.part[2 * VP_MAXC + blockIdx.x] = acc.c;
+        part_w[blockIdx.x] = acc.a;
+        part_w[VP_MAXC + blockIdx.x] = acc.b;
+        part_w[2 * VP_MAXC + blockIdx.x] = acc.c;
     }
 }
 
@@ -1178,7 +1184,7 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
         // one slab: x g d q lb ub (nvars each) | u (ld) | gathered (stride*P) | partials | two histories | state
         auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
         const size_t sz_nv = up(nv), sz_u = up((size_t)ld * sizeof(double)), sz_w = up((size_t)(pg->stride * P) * sizeof(double));
-        const size_t sz_part = up(3 * VP_MAXC * sizeof(double)), sz_hist = up((size_t)pg->hist_cap * sizeof(double));
+        const size_t sz_part = up(2 * 3 * VP_MAXC * sizeof(double)), sz_hist = up((size_t)pg->hist_cap * sizeof(double));
         // augmented Lagrangian: + multipliers, rule state, previous step, pre-jump point, equality row (nvars each),
         // four per-iteration scalar arrays (epochs + 1), double-buffered per-CTA sums, two slots of mu
         const size_t sz_sched = up((size_t)(max_iter + 1) * sizeof(double));
@@ -1252,7 +1258,7 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     PG_CUDA(cudaMemsetAsync(pg->st, 0, sizeof(PGDeviceState), s));
     PG_CUDA(cudaMemsetAsync(pg->u, 0, (size_t)ld * sizeof(double), s));
     PG_CUDA(cudaMemsetAsync(pg->w, 0, (size_t)(pg->stride * P) * sizeof(double), s));
-    PG_CUDA(cudaMemsetAsync(pg->part, 0, 3 * VP_MAXC * sizeof(double), s));
+    PG_CUDA(cudaMemsetAsync(pg->part, 0, 2 * 3 * VP_MAXC * sizeof(double), s));
     PG_CUDA(cudaMemsetAsync(pg->d, 0, nv, s));
     PG_CUDA(cudaMemsetAsync(pg->g, 0, nv, s));
     // bounds / start point: opti/constrained/_base.py:61-65 (lb = 0, x0 = (lb+ub)/2)

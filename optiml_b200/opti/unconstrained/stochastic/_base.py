@@ -73,6 +73,9 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
         n = H.nvars
         if self.x.size != n:
             raise ValueError('start point size does not match with Q')
+        if self.random_state is None:
+            # an unseeded start point (opti/_base.py:40-41) differs from rank to rank: all ranks take rank 0's
+            self.x = H.ctx.broadcast_array(self.x)
         q, lb, ub, x0 = (np.ascontiguousarray(v, dtype=np.float64) for v in (f.q, f.lb, f.ub, self.x))
         a = np.ascontiguousarray(f.A[0]) if f.n_eq else None
         b = float(f.b[0]) if f.n_eq else 0.

@@ -141,6 +141,16 @@ class Context:
         N.call('svmb200_comm_unique_id', C.cast(buf, C.c_void_p))
         return buf.raw
 
+    def broadcast_array(self, arr, src=0):
+        """Every rank gets rank ``src``'s copy of a host array (replicated solver inputs that were drawn at random
+        must be identical on all ranks: the vector phase runs redundantly on each of them)."""
+        if self.nranks == 1:
+            return arr
+        import torch.distributed as dist
+        box = [arr if self.rank == src else None]
+        dist.broadcast_object_list(box, src=src)
+        return box[0]
+
     def row_shard(self, n):
         """Rows [row0, row0+nrows) of an n-row matrix owned by this rank."""
         return shard_rows(n, self.rank, self.nranks)

@@ -26,8 +26,14 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     from optiml_b200 import runtime
     from optiml_b200.configs import make_config
-    from optiml_b200.ml.svm import DualSVC, DualSVR
+    import warnings
+    from sklearn.exceptions import ConvergenceWarning
+    from optiml_b200.ml.svm import DualSVC, DualSVR, SVC, SVR
     from optiml_b200.ml.svm.kernels import GaussianKernel, PolyKernel, LinearKernel
+    from optiml_b200.ml.svm.losses import hinge, epsilon_insensitive
+    from optiml_b200.opti.constrained import FrankWolfe
+    from optiml_b200.opti.unconstrained.stochastic import AdaGrad, Adam
+    warnings.simplefilter('ignore', ConvergenceWarning)
 
     ctx = runtime.default_context()
     assert ctx.nranks == world and ctx.rank == rank
@@ -38,12 +44,20 @@ def main():
         ('C4', 8192 + 37, lambda: DualSVC(kernel=GaussianKernel(), C=1, max_iter=200)),
         ('C2', 1003, lambda: DualSVR(kernel=PolyKernel(degree=3), epsilon=0.1, C=1, max_iter=150)),
         ('C3', 517, lambda: DualSVC(kernel=LinearKernel(), C=1, max_iter=100)),
+        # widening steps on the sharded matrix: Frank-Wolfe, and the augmented-Lagrangian dual (equality row, SVR blocks)
+        ('C1', 1500, lambda: DualSVC(kernel=GaussianKernel(), C=1, optimizer=FrankWolfe, max_iter=120)),
+        ('C1', None, lambda: SVC(loss=hinge, kernel=GaussianKernel(), C=1, reg_intercept=False, dual=True, optimizer=AdaGrad,
+                                 learning_rate=1., max_iter=120, random_state=5)),
+        ('C2', 777, lambda: SVR(loss=epsilon_insensitive, epsilon=0.1, kernel=PolyKernel(degree=3), C=1, reg_intercept=True,
+                                dual=True, optimizer=Adam, learning_rate=0.001, momentum_type='nesterov', momentum=0.5,
+                                max_iter=80, random_state=5)),
     ]
     ok = True
     for cfg, n, mk in cases:
         spec, X, y = make_config(cfg, n=n)
         m = mk().fit(X, y)
-        digest = hashlib.sha256(m.alphas_.tobytes() + np.float64(m.intercept_).tobytes()).hexdigest()
+        duals = getattr(m.obj, 'dual_x', np.zeros(0))  # multipliers of the augmented-Lagrangian runs
+        digest = hashlib.sha256(m.alphas_.tobytes() + np.float64(m.intercept_).tobytes() + duals.tobytes()).hexdigest()
         all_digests = [None] * world
         dist.all_gather_object(all_digests, digest)
         same_across_ranks = len(set(all_digests)) == 1
@@ -56,11 +70,12 @@ def main():
             try:
                 m1 = mk().fit(X, y)
                 single_ok = bool(np.array_equal(m1.alphas_, m.alphas_) and m1.intercept_ == m.intercept_
-                                 and np.array_equal(m1.decision_function(X[:64]), dec))
+                                 and np.array_equal(m1.decision_function(X[:64]), dec)
+                                 and np.array_equal(getattr(m1.obj, 'dual_x', np.zeros(0)), duals))
                 m1.obj.release()
             finally:
                 runtime.set_default_context(ctx)
-            if cfg == 'C1':
+            if cfg == 'C1' and n is None and isinstance(m, DualSVC):
                 g = np.load(os.path.join(ROOT, 'tests', 'golden', 'c1_svc_gaussian.npz'))
                 golden_ok = bool(np.abs(m.alphas_ - g['alphas']).max() <= 1e-8 and np.array_equal(m.support_, g['support']))
             print(f'[multigpu N={world}] {cfg} n={len(y)} iters={m.optimizer.iter} status={m.optimizer.status} '

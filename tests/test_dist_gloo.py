@@ -79,6 +79,19 @@ def _worker(rank, world, port, out_dir):
         others = [None] * world
         dist.all_gather_object(others, x.tobytes())
         assert len(set(others)) == 1  # identical iterate on every rank
+        # 4. augmented-Lagrangian dual on the sharded matrix: an unseeded start point is drawn per rank and must be
+        #    replaced by rank 0's (runtime.Context.broadcast_array); the replicated loop then agrees everywhere
+        from oracle import al_oracle as AL
+        ctx = runtime.Context.__new__(runtime.Context)  # no device needed for the host plumbing
+        ctx.rank, ctx.nranks = rank, world
+        x0 = ctx.broadcast_array(np.random.default_rng(100 + rank).uniform(size=n))
+        assert np.array_equal(x0, np.random.default_rng(100).uniform(size=n))
+        A = np.where(np.arange(n) % 3 == 0, 1., -1.)
+        al = AL.al_stochastic(product, q, lb, ub, x0, A=A, rho=1., rule='adagrad', step_size=1., tol=1e-9, epochs=40)
+        solo = AL.al_stochastic(lambda v: Q @ v, q, lb, ub, x0, A=A, rho=1., rule='adagrad', step_size=1., tol=1e-9, epochs=40)
+        assert al.iter == solo.iter and np.abs(al.x - solo.x).max() <= 1e-12 and np.abs(al.dual_x - solo.dual_x).max() <= 1e-11
+        dist.all_gather_object(others, al.x.tobytes() + al.dual_x.tobytes())
+        assert len(set(others)) == 1
         with open(os.path.join(out_dir, f'ok{rank}'), 'w') as fh:
             fh.write('ok')
     finally:
