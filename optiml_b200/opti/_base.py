@@ -86,6 +86,13 @@ class Quadratic(OptimizationFunction):
             self._device.release()
             self._device = None
 
+    def __getstate__(self):
+        """Pickling / deep-copying a fitted estimator (joblib.dump, sklearn meta-estimators with n_jobs) must not
+        drag device handles along: the copy keeps q and -- only if it was ever materialised -- the host Q."""
+        state = self.__dict__.copy()
+        state['_device'] = None
+        return state
+
     # -- values -------------------------------------------------------------------------------
     def _Qx(self, x):
         return self.device_hessian().product(np.asarray(x, dtype=float))

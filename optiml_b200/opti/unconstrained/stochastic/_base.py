@@ -19,6 +19,17 @@ from ...constrained._device_loop import DeviceLoopMixin
 from .... import _native as N
 
 
+class _StepSize:
+    """``step_size(*batch)`` -> iterator, the protocol of stochastic/_base.py:82-87 -- as a picklable object (the
+    reference wraps scalars and iterables in lambdas, which makes its fitted estimators unpicklable)."""
+
+    def __init__(self, value, is_iterable):
+        self.value, self.is_iterable = value, is_iterable
+
+    def __call__(self, *args):
+        return self.value if self.is_iterable else constant(self.value)
+
+
 class StochasticOptimizer(DeviceLoopMixin, Optimizer):
     _rule = None            # name of the update rule in _native.RULES
     _momentum_capable = False
@@ -31,11 +42,11 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
         if not callable(step_size) and not isinstance(step_size, Iterable) and not step_size > 0:
             raise ValueError('step_size must be > 0 or a callable or an iterator')
         if isinstance(step_size, Iterable):
-            self.step_size = lambda *args: step_size
+            self.step_size = _StepSize(step_size, True)
         elif callable(step_size):
             self.step_size = step_size
         else:
-            self.step_size = lambda *args: constant(step_size)
+            self.step_size = _StepSize(step_size, False)
         self.epochs = epochs
         self.epoch = 0
         self.shuffle = shuffle

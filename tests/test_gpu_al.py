@@ -222,3 +222,58 @@ def test_c_abi_argument_checks():
                       (dict(offset=0.), b'offset'), (dict(x0=None), b'start point')):
         assert lib.svmb200_al_create(*args(**bad)) == 1 and text in lib.svmb200_last_error()
     assert lib.svmb200_al_multipliers(None, None, None, None) == 1
+
+
+def test_reference_acceptance_recipe_ovr_adagrad():
+    """the reference's own test (ml/tests/test_svc.py:134-147): OneVsRest over iris, unseeded AdaGrad with
+    learning_rate=1., both intercept formulations, accuracy >= 0.97"""
+    import warnings
+    from sklearn.datasets import load_iris
+    from sklearn.model_selection import train_test_split
+    from sklearn.multiclass import OneVsRestClassifier as OVR
+    from sklearn.preprocessing import MinMaxScaler
+    from optiml_b200.ml.svm import SVC
+    from optiml_b200.ml.svm.kernels import gaussian
+    from optiml_b200.ml.svm.losses import hinge
+    from optiml_b200.opti.unconstrained.stochastic import AdaGrad
+    X, y = load_iris(return_X_y=True)
+    X_scaled = MinMaxScaler().fit_transform(X)
+    X_train, X_test, y_train, y_test = train_test_split(X_scaled, y, train_size=0.75, random_state=123456)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for ri in (True, False):
+            svc = OVR(SVC(loss=hinge, kernel=gaussian, reg_intercept=ri, dual=True, optimizer=AdaGrad, learning_rate=1.))
+            svc = svc.fit(X_train, y_train)
+            assert svc.score(X_test, y_test) >= 0.97
+
+
+def test_fitted_estimators_pickle_without_device_handles():
+    """joblib.dump / sklearn meta-estimators copy fitted models: the copy predicts identically and carries no device
+    state (the Hessian stays on the GPU of the original; asking the copy for Q says so)"""
+    import copy
+    import pickle
+    import warnings
+    from sklearn.multiclass import OneVsRestClassifier as OVR
+    from optiml_b200.ml.svm import DualSVC, SVC
+    from optiml_b200.ml.svm.kernels import gaussian
+    from optiml_b200.ml.svm.losses import hinge
+    from optiml_b200.opti.constrained import FrankWolfe
+    from optiml_b200.opti.unconstrained.stochastic import Adam
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((150, 4))
+    y = (X[:, 0] + 0.3 * X[:, 1] > 0).astype(int)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        models = [DualSVC(kernel=gaussian, max_iter=100).fit(X, y),
+                  SVC(loss=hinge, kernel=gaussian, dual=True, reg_intercept=False, optimizer=Adam, learning_rate=0.01,
+                      momentum_type='polyak', max_iter=60, random_state=0).fit(X, y),
+                  OVR(DualSVC(kernel=gaussian, optimizer=FrankWolfe, max_iter=80)).fit(X, rng.integers(0, 3, 150))]
+    for m in models:
+        for clone in (pickle.loads(pickle.dumps(m)), copy.deepcopy(m)):
+            assert np.array_equal(clone.predict(X[:40]), m.predict(X[:40]))
+    solo = pickle.loads(pickle.dumps(models[0]))
+    assert np.array_equal(solo.alphas_, models[0].alphas_) and solo.optimizer.status == models[0].optimizer.status
+    assert len(solo.train_loss_history) == len(models[0].train_loss_history)
+    with pytest.raises(RuntimeError, match='device copy of Q was released'):
+        solo.obj.Q
+    assert models[0].obj.Q.shape == (150, 150)  # the original still owns its device matrix

@@ -270,3 +270,21 @@ def test_host_gather_rows_and_label_binarisation_shortcuts():
         lb = LabelBinarizer(neg_label=-1).fit(y)
         a, b = _binarize(lb, y), lb.transform(y).ravel()
         assert np.array_equal(a, b) and a.dtype == b.dtype
+
+
+def test_objectives_and_solvers_pickle_on_the_host():
+    import copy
+    import pickle
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import AugmentedLagrangianQuadratic, ProjectedGradient
+    from optiml_b200.opti.unconstrained.stochastic import AdaGrad, Adam
+    q = Quadratic(np.eye(3), np.ones(3))
+    assert np.array_equal(pickle.loads(pickle.dumps(q)).Q, np.eye(3))
+    f = AugmentedLagrangianQuadratic(primal=q, A=np.ones(3), b=np.zeros(1), lb=np.zeros(3), ub=np.ones(3))
+    f2 = copy.deepcopy(f)
+    assert f2.primal is not q and np.array_equal(f2.Q, np.eye(3)) and np.array_equal(f2.A, f.A)
+    pg = pickle.loads(pickle.dumps(ProjectedGradient(quad=q, ub=np.ones(3))))
+    assert np.array_equal(pg.ub, np.ones(3)) and pg.status == 'unknown'
+    for opt in (AdaGrad(f=f, step_size=0.5, random_state=1), Adam(f=f, step_size=[0.1, 0.2], momentum_type='polyak', random_state=1)):
+        opt2 = pickle.loads(pickle.dumps(opt))
+        assert np.array_equal(opt2.x, opt.x) and next(iter(opt2.step_size())) == next(iter(opt.step_size()))
