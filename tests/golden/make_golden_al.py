@@ -62,5 +62,18 @@ for kname, name, ri in SVR_RUNS:
                 optimizer=REF_CLASS[rule], learning_rate=lr, max_iter=min(iters, 400), random_state=3, **kw).fit(Xd, yd)
     record(svr_key(kname, name, ri), m, out['svr_X_test'])
 
+# --- the reference's own unit test of AugmentedLagrangianQuadratic (opti/constrained/tests/test_lagrangian_quadratic.py:18-22):
+#     the 2-variable generator problem with the equality row A = [2, 7], b = 0 and 0 <= x <= ub; the optimum is x = 0
+from optiml.opti.constrained import AugmentedLagrangianQuadratic  # noqa: E402
+bc = dict(np.load(os.path.join(OUT, 'bcqp.npz')))
+for seed in (0, 1, 2):
+    ld = AugmentedLagrangianQuadratic(primal=ref.Quadratic(bc['p2_Q'], bc['p2_q']), A=[2, 7], b=np.zeros(1),
+                                      lb=np.zeros(2), ub=bc['p2_ub'], rho=1)
+    o = AdaGrad(ld, step_size=1, epochs=15000, random_state=seed).minimize()
+    out.update({f'alq2d_s{seed}_x': o.x, f'alq2d_s{seed}_iter': o.iter, f'alq2d_s{seed}_status': o.status,
+                f'alq2d_s{seed}_dual_x': ld.dual_x, f'alq2d_s{seed}_f_x': o.f_x, f'alq2d_s{seed}_g_x': o.g_x,
+                f'alq2d_s{seed}_pf_hist': np.array(o.f_x_history)})
+    print('alq2d', seed, o.x, o.iter, o.status)
+
 np.savez_compressed(os.path.join(OUT, 'al_stochastic.npz'), **out)
 print('wrote', len(out), 'arrays')

@@ -277,3 +277,24 @@ def test_fitted_estimators_pickle_without_device_handles():
     with pytest.raises(RuntimeError, match='device copy of Q was released'):
         solo.obj.Q
     assert models[0].obj.Q.shape == (150, 150)  # the original still owns its device matrix
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_reference_own_lagrangian_quadratic_test(golden, seed):
+    """opti/constrained/tests/test_lagrangian_quadratic.py:18-22 as written there (a general equality row, two
+    variables, so the step-wise loop with its histories; the run ends through the optimality test)"""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import AugmentedLagrangianQuadratic
+    from optiml_b200.opti.unconstrained.stochastic import AdaGrad
+    g, bc = golden('al_stochastic'), golden('bcqp')
+    Q, q, ub = bc['p2_Q'], bc['p2_q'], bc['p2_ub']
+    A, b, lb = [2, 7], np.zeros(1), np.zeros_like(q)
+    ld = AugmentedLagrangianQuadratic(primal=Quadratic(Q, q), A=A, b=b, lb=lb, ub=ub, rho=1)
+    opt = AdaGrad(ld, step_size=1, epochs=15000, random_state=seed).minimize()
+    assert np.allclose(opt.x, np.zeros(2))  # ld.x_star() of the reference's assertion: the origin
+    key = f'alq2d_s{seed}'
+    assert opt.iter == int(g[key + '_iter']) and opt.status == str(g[key + '_status']) == 'optimal'
+    assert np.abs(opt.x - g[key + '_x']).max() <= 1e-12 and np.abs(ld.dual_x - g[key + '_dual_x']).max() <= 1e-10
+    assert abs(opt.f_x - float(g[key + '_f_x'])) <= 1e-10 and np.abs(opt.g_x - g[key + '_g_x']).max() <= 1e-9
+    assert np.abs(np.array(opt.f_x_history) - g[key + '_pf_hist']).max() <= 1e-10 * np.abs(g[key + '_pf_hist']).max()
+    assert len(opt.x0_history) == opt.iter + 1 and opt.epoch == opt.iter + 1

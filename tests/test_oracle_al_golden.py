@@ -114,3 +114,21 @@ def test_emulated_vector_phase_svr_block_layout(golden, kernel, name, ri):
     e = al_emulate(M, np.hstack((-y, y)) + 0.1, np.zeros(2 * n), np.ones(2 * n), AL.start_point(2 * n, 3),
                    A=None if ri else e_row, rho=1., rule=rule, step_size=lr, tol=1e-4, epochs=min(iters, 400), svr=True, **kw)
     check_emulation(g, svr_key(kernel, name, ri), e)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_reference_own_lagrangian_quadratic_test(golden, seed):
+    """opti/constrained/tests/test_lagrangian_quadratic.py:18-22: a general equality row (A = [2, 7]) and the
+    optimality exit after ~200 iterations; oracle and emulated vector phase against the reference's run"""
+    from oracle.emulator import al_emulate
+    g, bc = golden('al_stochastic'), golden('bcqp')
+    Q, q, ub, A = bc['p2_Q'], bc['p2_q'], bc['p2_ub'], np.array([2., 7.])
+    key = f'alq2d_s{seed}'
+    kw = dict(A=A, b=0., rho=1., rule='adagrad', step_size=1., tol=1e-8, epochs=15000)
+    a = AL.al_stochastic(lambda v: Q @ v, q, np.zeros(2), ub, AL.start_point(2, seed), **kw)
+    e = al_emulate(Q, q, np.zeros(2), ub, AL.start_point(2, seed), finalise_every=1, **kw)
+    for r in (a, e):
+        assert r.iter == int(g[key + '_iter']) and r.status == str(g[key + '_status']) == 'optimal'
+        assert np.abs(r.x - g[key + '_x']).max() <= 1e-14 and np.abs(r.dual_x - g[key + '_dual_x']).max() <= 1e-12
+        assert np.abs(r.pf_hist - g[key + '_pf_hist']).max() <= 1e-10 * np.abs(g[key + '_pf_hist']).max()
+        assert np.allclose(r.x, np.zeros(2))  # the reference's assertion: x_star is the origin
