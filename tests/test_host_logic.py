@@ -288,3 +288,28 @@ def test_objectives_and_solvers_pickle_on_the_host():
     for opt in (AdaGrad(f=f, step_size=0.5, random_state=1), Adam(f=f, step_size=[0.1, 0.2], momentum_type='polyak', random_state=1)):
         opt2 = pickle.loads(pickle.dumps(opt))
         assert np.array_equal(opt2.x, opt.x) and next(iter(opt2.step_size())) == next(iter(opt.step_size()))
+
+
+def test_integration_doc_stubs_compile_and_name_real_symbols():
+    """INTEGRATION.md is the binding a maintainer of the reference would add: its Python stub must be valid Python and every
+    svmb200_* name it mentions must be declared in include/svmb200.h; every test named in DESIGN.md's coverage table must exist"""
+    import re
+    with open(os.path.join(ROOT, 'INTEGRATION.md')) as fh:
+        doc = fh.read()
+    blocks = re.findall(r'```python\n(.*?)```', doc, flags=re.S)
+    assert blocks
+    for b in blocks:
+        compile(b, 'INTEGRATION.md', 'exec')
+    with open(os.path.join(ROOT, 'include', 'svmb200.h')) as fh:
+        header = fh.read()
+    for name in set(re.findall(r'svmb200_[a-z0-9_]+', doc)):
+        if name.rstrip('_') in ('svmb200_pg', 'svmb200_comm', 'svmb200_al', 'svmb200'):
+            continue  # prefixes of families ("svmb200_pg_create/run/...")
+        assert re.search(r'\b' + name + r'\b', header), f'{name} is not declared in include/svmb200.h'
+    with open(os.path.join(ROOT, 'DESIGN.md')) as fh:
+        design = fh.read()
+    for fname, tname in re.findall(r'`(test_[a-z_]+\.py)::(test_[a-z0-9_]+)', design):
+        with open(os.path.join(ROOT, 'tests', fname)) as fh:
+            assert f'def {tname}' in fh.read(), f'{fname}::{tname} named in DESIGN.md does not exist'
+    for fname in set(re.findall(r'`(r1_[A-Za-z0-9_.]+\.(?:json|jsonl|txt|log|csv))`', design)):
+        assert os.path.exists(os.path.join(ROOT, 'profiles', fname)), f'profiles/{fname} named in DESIGN.md does not exist'
