@@ -197,6 +197,39 @@ int svmb200_al_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld,
 /* multipliers after (or during) a run: mu of the equality row (0 without one), lambda of  -x <= -lb  and  x <= ub */
 int svmb200_al_multipliers(svmb200_pg* pg, double* mu, double* lam_lb_host, double* lam_ub_host);
 
+/* ---- widening: problems that share one resident matrix -- one-vs-rest, multi-target -------------
+ * sklearn's OneVsRestClassifier(SVC(...)) (the pattern of ml/tests/test_svc.py:101-147) clones the estimator per class
+ * and every clone rebuilds the same Gram matrix and streams its own Q = (y_c y_c') o (K + 1) -- the classes differ in
+ * the label signs only.  Here M = K + bias is built ONCE without signs (svmb200_gram with NULL signs) and
+ *   - a `_signed` solver poses its problem on Q = (s s') o M for a host vector s of +-1 (hessian must be PLAIN;
+ *     sign_host NULL = the unsigned entry point): the vector kernels apply s to the operand and to the product,
+ *     both exact, so the iterates are BIT-IDENTICAL to a solve on a materialised Q;
+ *   - svmb200_pg_run_batch runs `count` fresh solvers of one kind (all PG, all FW or all AL, same max_iter) that
+ *     share the matrix, shard and layout to termination in lockstep: per iteration ceil(count/4) passes over M
+ *     (K2 with up to four vector operands per pass, per-vector results bit-identical to svmb200_matvec) and one
+ *     vector launch for all problems.  Each solver keeps its own state / history / stopping test and afterwards
+ *     answers svmb200_pg_state / _history / _scalars / _al_multipliers as after svmb200_pg_run.  Multi-GPU batches
+ *     exchange with ncclAllGather.  iters / statuses: `count` entries each (may be NULL).
+ * Also usable without signs (SVR layout included): several right-hand sides q against one matrix
+ * (sklearn MultiOutputRegressor(SVR(...))).                                                                         */
+int svmb200_pg_create_signed(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
+                             int hessian, const double* sign_host, const double* q_host, const double* lb_host,
+                             const double* ub_host, const double* x0_host, double eps, int64_t max_iter, svmb200_pg** out);
+int svmb200_fw_create_signed(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
+                             int hessian, const double* sign_host, const double* q_host, const double* lb_host,
+                             const double* ub_host, const double* x0_host, double eps, int64_t max_iter, double t,
+                             svmb200_pg** out);
+int svmb200_al_create_signed(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
+                             int hessian, const double* sign_host, const double* q_host, const double* lb_host,
+                             const double* ub_host, const double* x0_host, const double* a_host, double b, double rho,
+                             int rule, int momentum_type, const double* step_sizes, const double* momenta, double decay,
+                             double beta1, double beta2, double offset, double tol, int64_t epochs, svmb200_pg** out);
+int svmb200_pg_run_batch(svmb200_pg* const* pgs, int count, int64_t* iters, int* statuses);
+/* dw[b][i] = sum_j dQ[i][j] * du[b][j] for `count` device vectors against one pass (per four vectors) over dQ;
+ * every dw[b] is bit-identical to svmb200_matvec(dQ, du[b]).  du / dw: host arrays of device pointers.             */
+int svmb200_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* const* du,
+                         double* const* dw, int count);
+
 /* ---- K5: masked product for the intercept ---------------------------------------------------
  * Replaces the Python loop  ml/svm/_base.py:877-880 / :1433-1437:
  * v[i] = sum_m M[i][m] * beta[m] over the rank's rows (all-gathered when a communicator is attached),

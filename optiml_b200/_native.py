@@ -59,6 +59,15 @@ PROTOTYPES = {
     'svmb200_al_create': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_double,
                           C.c_int, C.c_int, c_vp, c_vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64,
                           C.POINTER(c_vp)],
+    'svmb200_pg_create_signed': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double, i64,
+                                 C.POINTER(c_vp)],
+    'svmb200_fw_create_signed': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double, i64,
+                                 C.c_double, C.POINTER(c_vp)],
+    'svmb200_al_create_signed': [c_vp, c_vp, i64, i64, i64, i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_double,
+                                 C.c_double, C.c_int, C.c_int, c_vp, c_vp, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, i64, C.POINTER(c_vp)],
+    'svmb200_pg_run_batch': [C.POINTER(c_vp), C.c_int, C.POINTER(i64), C.POINTER(C.c_int)],
+    'svmb200_matvec_multi': [c_vp, c_vp, i64, i64, C.POINTER(c_vp), C.POINTER(c_vp), C.c_int],
     'svmb200_al_multipliers': [c_vp, C.POINTER(C.c_double), c_vp, c_vp],
     'svmb200_pg_run': [c_vp, i64, C.POINTER(i64), C.POINTER(C.c_int)],
     'svmb200_pg_state': [c_vp, c_vp, c_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
@@ -102,17 +111,21 @@ def load_library():
         if not os.path.exists(LIB_PATH):
             raise NativeError(f'{LIB_PATH} not found: build it with `python -m optiml_b200.csrc.build` '
                               '(or __graft_entry__.build()); optiml_b200 has no CPU fallback')
-        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
-        for name, argtypes in PROTOTYPES.items():
-            fn = getattr(lib, name)
-            fn.argtypes = argtypes
-            fn.restype = C.c_int
-        for name, (argtypes, restype) in _NON_STATUS.items():
-            fn = getattr(lib, name)
-            fn.argtypes = argtypes
-            fn.restype = restype
-        _lib = lib
-        return lib
+        _lib = bind_prototypes(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
+        return _lib
+
+
+def bind_prototypes(lib):
+    """Declare the argument / result types of every entry point of include/svmb200.h on a loaded library."""
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    for name, (argtypes, restype) in _NON_STATUS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    return lib
 
 
 def exported_symbols():

@@ -75,6 +75,7 @@ extern "C" int svmb200_ctx_destroy(svmb200_ctx* ctx) {
         svm_release_solver_cache(ctx);
         if (ctx->norm_buf) cudaFree(ctx->norm_buf);
         if (ctx->mp_buf) cudaFree(ctx->mp_buf);
+        if (ctx->batch_buf) cudaFree(ctx->batch_buf);
         cudaStreamDestroy(ctx->stream);
     }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -48,6 +48,9 @@ struct svmb200_ctx {
     size_t norm_bytes = 0;
     void* mp_buf = nullptr;
     size_t mp_bytes = 0;
+    // argument blocks of a batched solve (one VecArgs / ALArgs per problem, read by the batch vector kernels)
+    void* batch_buf = nullptr;
+    size_t batch_bytes = 0;
 };
 
 // grow-only device scratch; safe to reuse without a sync because every user runs on ctx->stream

@@ -52,6 +52,7 @@ struct MatvecArgs {
     ulonglong2* peer_w[SVM_MAX_RANKS];           // this rank's slot in rank r's gathered buffer
 };
 
+#ifndef SVMB200_HOST_EMULATION
 __device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned tag) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t)
@@ -80,6 +81,20 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
 }
+#else
+// tests/cuda_emu compiles this file for the host (the kernels run thread by thread on fibers): same entry format and
+// loads, without the PTX
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+    p->x = (b & 0xffffffffull) | t;
+    p->y = (b >> 32) | t;
+}
+__device__ __forceinline__ double ll_load(const ulonglong2* p, unsigned tag, int* fault) {
+    if ((unsigned)(p->x >> 32) != tag || (unsigned)(p->y >> 32) != tag) *fault = 1;  // single rank: never waits
+    return __longlong_as_double((long long)((p->y << 32) | (p->x & 0xffffffffull)));
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) { return *p; }
+#endif
 
 __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const MatvecArgs a) {
     if (a.done != nullptr && *a.done) return;
@@ -209,10 +224,10 @@ struct MatvecScratch {
     size_t wpart_elems = 0, ticket_elems = 0;
 };
 
-static int matvec_scratch_reserve(svmb200_ctx* ctx, MatvecScratch& s, int64_t nrows, int64_t ld) {
+static int matvec_scratch_reserve(svmb200_ctx* ctx, MatvecScratch& s, int64_t nrows, int64_t ld, int nvec = 1) {
     const int nseg = (int)((ld + MV_SEG - 1) / MV_SEG);
     const size_t nrows_pad = (size_t)round_up64(nrows, 16);
-    const size_t need_w = (size_t)nseg * nrows_pad;
+    const size_t need_w = (size_t)nvec * nseg * nrows_pad;
     const size_t need_t = (size_t)((nrows + MV_GROUP - 1) / MV_GROUP);
     if (need_w > s.wpart_elems) {
         SVM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -308,6 +323,257 @@ extern "C" int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows,
     return svm_launch_matvec(ctx, dQ, nrows, ld, du, dw, nullptr);
 }
 
+// ------------------------------------------------------------------------------------------ K2 x NB
+// Several products against ONE pass over the matrix (the binary problems of a one-vs-rest fit, or the
+// targets of a multi-output regression, share the resident M): a work item streams its R x MV_SEG tile once and feeds
+// NB accumulator sets.  Per row and per thread the columns are visited in the order of matvec_seg_kernel (c, c + NT,
+// ... ; x then y), the warp / CTA / segment reductions are the same trees, so every w_b is BIT-IDENTICAL to the
+// single-vector kernel's -- a batched fit reproduces the sequential fits exactly.  The vector operands (NB x 64 KB per
+// item) come through L2: R rows amortise them, the ratio of L2 to HBM bytes is NB / R.
+constexpr int MV_MULTI_MAX = 4;  // vectors per launch; larger batches are split into balanced launches
+
+template <int NB>
+struct MultiCfg {
+    static constexpr int R = 4;                   // rows per work item
+    static constexpr int U = 2;                   // 128-bit loads in flight per row and thread
+    static constexpr int MINB = NB <= 2 ? 3 : 2;  // CTAs per SM the register budget is cut for
+};
+
+struct MatvecMultiArgs {
+    const double* Q;
+    long long ld, nrows, nrows_pad;
+    double* wpart;      // [NB][nseg][nrows_pad]
+    unsigned* tickets;
+    int nseg;
+    const double* u[MV_MULTI_MAX];       // ld entries each, zero beyond n
+    double* w[MV_MULTI_MAX];             // nrows results each
+    const double* u_rows[MV_MULTI_MAX];  // u at this shard's rows, or null
+    double* denpart[MV_MULTI_MAX];       // one share of u'w per 64-row group, or null
+    const int* done[MV_MULTI_MAX];       // problem b finished: its results are not stored (may be null)
+};
+
+template <int NB>
+__global__ void __launch_bounds__(MV_NT, MultiCfg<NB>::MINB) matvec_seg_multi_kernel(const MatvecMultiArgs a) {
+    constexpr int R = MultiCfg<NB>::R, NT = MV_NT, U = MultiCfg<NB>::U, BPG = MV_GROUP / R;
+    static_assert(NB >= 1 && NB <= MV_MULTI_MAX && NB * MV_GROUP <= NT && MV_GROUP % R == 0, "bad multi-vector shape");
+    bool live[NB];
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        live[b] = !(a.done[b] != nullptr && *a.done[b]);
+        any = any || live[b];
+    }
+    if (!any) return;
+    const unsigned items_per_group = (unsigned)(BPG * a.nseg);
+    const unsigned group = blockIdx.x / items_per_group;
+    const unsigned within = blockIdx.x - group * items_per_group;
+    const unsigned rb_in_group = within / (unsigned)a.nseg;
+    const int seg = (int)(within - rb_in_group * (unsigned)a.nseg);
+    const long long row_base = (long long)group * MV_GROUP + (long long)rb_in_group * R;
+    const size_t pstride = (size_t)a.nseg * a.nrows_pad;  // wpart elements per problem
+    __shared__ double red[NT / 32][NB][R];
+    __shared__ double red2[NB][2];
+    __shared__ unsigned is_last;
+
+    if (row_base < a.nrows) {
+        const long long c0 = (long long)seg * MV_SEG;
+        long long c1 = c0 + MV_SEG;
+        if (c1 > a.ld) c1 = a.ld;
+        const int nvec = (int)((c1 - c0) >> 1);
+        const double2* rows[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            long long rr = row_base + r;
+            if (rr >= a.nrows) rr = a.nrows - 1;  // clamp: read a valid row, result discarded below
+            rows[r] = reinterpret_cast<const double2*>(a.Q + rr * a.ld + c0);
+        }
+        double acc[NB][R];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[b][r] = 0.0;
+        }
+        int c = threadIdx.x;
+        for (; c + (U - 1) * NT < nvec; c += U * NT) {
+            double2 qv[U][R];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) qv[j][r] = ld_stream_f64x2(rows[r] + c + j * NT);
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const double2* __restrict__ u2 = reinterpret_cast<const double2*>(a.u[b] + c0);
+                double2 uv[U];
+#pragma unroll
+                for (int j = 0; j < U; ++j) uv[j] = __ldg(u2 + c + j * NT);
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[b][r] = fma(qv[j][r].x, uv[j].x, acc[b][r]);
+                        acc[b][r] = fma(qv[j][r].y, uv[j].y, acc[b][r]);
+                    }
+                }
+            }
+        }
+        for (; c < nvec; c += NT) {
+            double2 qv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) qv[r] = ld_stream_f64x2(rows[r] + c);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const double2 uv = __ldg(reinterpret_cast<const double2*>(a.u[b] + c0) + c);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    acc[b][r] = fma(qv[r].x, uv.x, acc[b][r]);
+                    acc[b][r] = fma(qv[r].y, uv.y, acc[b][r]);
+                }
+            }
+        }
+        // warp butterfly, then fixed-order sum over warps (the trees of matvec_seg_kernel)
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double v = acc[b][r];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[wid][b][r] = v;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < NB * R) {
+            const int b = threadIdx.x / R, r = threadIdx.x - b * R;
+            if (row_base + r < a.nrows) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < NT / 32; ++k) v += red[k][b][r];
+                a.wpart[(size_t)b * pstride + (size_t)seg * a.nrows_pad + row_base + r] = v;
+            }
+        }
+    }
+    // ---- one ticket per group; the last arriver combines the group for every problem
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicInc(&a.tickets[group], items_per_group - 1) == items_per_group - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // thread t handles row (t % 64) of problem (t / 64): whole warps share a problem
+    {
+        const int b = (int)(threadIdx.x / MV_GROUP);
+        const int t = (int)(threadIdx.x % MV_GROUP);
+        double dv = 0.0;
+        bool has_den = false;
+#pragma unroll
+        for (int bb = 0; bb < NB; ++bb) {  // static indexing of the per-problem pointer arrays
+            if (bb != b) continue;
+            has_den = a.denpart[bb] != nullptr;
+            const long long rr = (long long)group * MV_GROUP + t;
+            if (rr < a.nrows) {
+                double v = 0.0;
+                const double* wp = a.wpart + (size_t)bb * pstride + rr;
+                for (int s = 0; s < a.nseg; ++s) v += __ldcg(wp + (size_t)s * a.nrows_pad);
+                if (live[bb]) a.w[bb][rr] = v;
+                if (a.u_rows[bb] != nullptr) dv = __dmul_rn(a.u_rows[bb][rr], v);
+            }
+        }
+        if (b < NB && has_den) {
+            // fixed tree over the 64 rows: butterfly inside each warp, then the problem's two warps in order
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dv = __dadd_rn(dv, __shfl_xor_sync(0xffffffffu, dv, o));
+            if ((threadIdx.x & 31) == 0) red2[b][t >> 5] = dv;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NB) {
+#pragma unroll
+        for (int bb = 0; bb < NB; ++bb) {
+            if (bb == (int)threadIdx.x && a.denpart[bb] != nullptr && live[bb])
+                a.denpart[bb][group] = __dadd_rn(red2[bb][0], red2[bb][1]);
+        }
+    }
+}
+
+static int launch_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, int nb,
+                               const double* const* du, double* const* dw, const double* const* du_rows,
+                               double* const* ddenpart, const int* const* d_done) {
+    if (nrows <= 0) return SVMB200_OK;
+    if (nb < 1 || nb > MV_MULTI_MAX) {
+        svmb200_set_error("matvec_multi: between 1 and %d vectors per launch", MV_MULTI_MAX);
+        return SVMB200_ERR_ARG;
+    }
+    if (ld % 2 != 0 || ld <= 0) {
+        svmb200_set_error("matvec: ld must be a positive multiple of 2");
+        return SVMB200_ERR_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(dQ) & 15) {
+        svmb200_set_error("matvec: operands must be 16-byte aligned");
+        return SVMB200_ERR_ARG;
+    }
+    if (!ctx->matvec_scratch) ctx->matvec_scratch = new MatvecScratch();
+    MatvecScratch& s = *static_cast<MatvecScratch*>(ctx->matvec_scratch);
+    SVM_TRY(matvec_scratch_reserve(ctx, s, nrows, ld, nb));
+    MatvecMultiArgs a = {};
+    a.Q = dQ;
+    a.ld = ld;
+    a.nrows = nrows;
+    a.nrows_pad = round_up64(nrows, 16);
+    a.wpart = s.wpart;
+    a.tickets = s.tickets;
+    a.nseg = (int)((ld + MV_SEG - 1) / MV_SEG);
+    for (int b = 0; b < nb; ++b) {
+        if (reinterpret_cast<uintptr_t>(du[b]) & 15) {
+            svmb200_set_error("matvec: operands must be 16-byte aligned");
+            return SVMB200_ERR_ARG;
+        }
+        a.u[b] = du[b];
+        a.w[b] = dw[b];
+        a.u_rows[b] = du_rows ? du_rows[b] : nullptr;
+        a.denpart[b] = ddenpart ? ddenpart[b] : nullptr;
+        a.done[b] = d_done ? d_done[b] : nullptr;
+    }
+    const int64_t ngroups = (nrows + MV_GROUP - 1) / MV_GROUP;
+    int64_t nitems = 0;
+    switch (nb) {
+#define LAUNCH_MULTI(NB)                                                                                \
+    case NB:                                                                                            \
+        nitems = ngroups * (MV_GROUP / MultiCfg<NB>::R) * a.nseg;                                       \
+        if (nitems >= (1ll << 31)) break;                                                               \
+        matvec_seg_multi_kernel<NB><<<(unsigned)nitems, MV_NT, 0, ctx->stream>>>(a);                    \
+        break;
+        LAUNCH_MULTI(1)
+        LAUNCH_MULTI(2)
+        LAUNCH_MULTI(3)
+        LAUNCH_MULTI(4)
+#undef LAUNCH_MULTI
+    }
+    if (nitems >= (1ll << 31)) {
+        svmb200_set_error("matvec: grid too large");
+        return SVMB200_ERR_ARG;
+    }
+    ctx->launches++;
+    SVM_CUDA(cudaGetLastError());
+    return SVMB200_OK;
+}
+
+// dw[b][i] = sum_j dQ[i][j] du[b][j] for `count` vectors, ceil(count / 4) passes over the matrix
+extern "C" int svmb200_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld,
+                                    const double* const* du, double* const* dw, int count) {
+    SVM_TRY(svm_use(ctx));
+    SVM_CHECK_ARG(dQ != nullptr && du != nullptr && dw != nullptr && count >= 1, "bad argument");
+    for (int b = 0; b < count; ++b) SVM_CHECK_ARG(du[b] != nullptr && dw[b] != nullptr, "null vector");
+    const int nlaunch = (count + MV_MULTI_MAX - 1) / MV_MULTI_MAX;
+    for (int l = 0, b0 = 0; l < nlaunch; ++l) {
+        const int nb = (count - b0 + (nlaunch - l) - 1) / (nlaunch - l);  // balanced split
+        SVM_TRY(launch_matvec_multi(ctx, dQ, nrows, ld, nb, du + b0, dw + b0, nullptr, nullptr, nullptr));
+        b0 += nb;
+    }
+    return SVMB200_OK;
+}
+
 static int64_t rows_per_rank(int64_t n, int nranks) { return round_up64((n + nranks - 1) / nranks, ROW_ALIGN); }
 
 extern "C" int svmb200_shard_rows(int64_t n, int rank, int nranks, int64_t* row0, int64_t* nrows) {
@@ -362,10 +628,20 @@ struct VecArgs {
     const ulonglong2* gathered_ll;
     unsigned tag;
     int* fault;
+    // label signs (nvars entries of +-1, or null): the resident matrix is M and the problem is posed on
+    // Q = (s s') o M.  Q u = s o (M (s o u)) is exact for s = +-1, so the vector kernels sign w on the way in and
+    // u on the way out and K2 never sees the signs -- several such problems can share one pass over M (one-vs-rest)
+    const double* sgn;
 };
 
 __device__ __forceinline__ double gathered_at(const VecArgs& a, size_t idx) {
     return a.gathered_ll != nullptr ? ll_load(a.gathered_ll + idx, a.tag, a.fault) : a.gathered[idx];
+}
+
+// w = Q u for Q = (s s') o M:  the vector handed to K2 is s o u and the product that comes back is signed again
+// (multiplications by +-1 are exact; label signs never combine with the SVR block layout)
+__device__ __forceinline__ double apply_sign(const VecArgs& a, long long j, double v) {
+    return a.sgn != nullptr ? __dmul_rn(a.sgn[j], v) : v;
 }
 
 enum { VP_INIT = 0, VP_STEP = 1, VP_FINALISE = 2 };
@@ -434,7 +710,7 @@ __device__ __forceinline__ void tail_accumulate(Quad& a, double d, double x, dou
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const long long k) {
+__device__ __forceinline__ void pg_vector_body(const VecArgs& a, const long long k) {
     __shared__ double sm[VP_NT / 32][4];
     PGDeviceState* st = a.st;
     // `done` is raised inside the stop branch below, which every CTA of that launch takes anyway;
@@ -517,7 +793,7 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
     acc.m = INFINITY;
     for (long long j = j0 + tid; j < j1; j += VP_NT) {
         const unsigned rk = (unsigned)j / rpr;
-        const double wj = gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
+        const double wj = apply_sign(a, j, gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr)));
         double x = a.x[j], q = a.q[j], g;
         if (MODE == VP_INIT) {
             g = __dadd_rn(wj, q);  // g = Q x0 + q  (opti/_base.py:291)
@@ -549,7 +825,7 @@ __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const
             tail_accumulate(acc, dn2, x2, g2, q2, lb2, ub2);
             uj = __dsub_rn(dn, dn2);
         }
-        a.u[j] = uj;
+        a.u[j] = apply_sign(a, j, uj);
     }
     acc = block_reduce(acc, sm);
     if (tid == 0) {
@@ -576,7 +852,7 @@ __device__ __forceinline__ void fw_direction(double g, double x, double lb, doub
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const long long k) {
+__device__ __forceinline__ void fw_vector_body(const VecArgs& a, const long long k) {
     __shared__ double sm[VP_NT / 32][4];
     PGDeviceState* st = a.st;
     if (*reinterpret_cast<volatile int*>(&st->done)) return;
@@ -660,7 +936,7 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
     acc.m = INFINITY;
     for (long long j = j0 + tid; j < j1; j += VP_NT) {
         const unsigned rk = (unsigned)j / rpr;
-        const double wj = gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
+        const double wj = apply_sign(a, j, gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr)));
         double x = a.x[j], q = a.q[j], g;
         if (MODE == VP_INIT) {
             g = __dadd_rn(wj, q);
@@ -696,7 +972,7 @@ __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const
             acc.c = __dadd_rn(acc.c, __dmul_rn(g2, dn2));
             uj = __dsub_rn(dn, dn2);
         }
-        a.u[j] = uj;
+        a.u[j] = apply_sign(a, j, uj);
     }
     acc = block_reduce(acc, sm);
     if (tid == 0) {
@@ -775,7 +1051,7 @@ __device__ __forceinline__ void al_store(const VecArgs& a, const ALArgs& al, lon
 
 // INIT is launched with k = -1 (it prepares the sums of state 0)
 template <int MODE>
-__global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const ALArgs al, const long long k) {
+__device__ __forceinline__ void al_vector_body(const VecArgs& a, const ALArgs& al, const long long k) {
     __shared__ double sm[VP_NT / 32][AL_NSUMS + 1];
     PGDeviceState* st = a.st;
     if (*reinterpret_cast<volatile int*>(&st->done)) {
@@ -804,7 +1080,7 @@ __global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const
                 al_init_sums(x2, a.q[i2], al.A ? al.A[i2] : 0.0, a.lb[i2], a.ub[i2], acc);
                 uj = __dsub_rn(x, x2);
             }
-            a.u[j] = uj;
+            a.u[j] = apply_sign(a, j, uj);
         }
         al_sums_to_array(acc, v);
         v[AL_NSUMS] = 0.0;
@@ -882,7 +1158,7 @@ __global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const
     ALSums acc = {};
     for (long long j = j0 + tid; j < j1; j += VP_NT) {
         const unsigned rk = (unsigned)j / rpr;
-        const double wj = gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
+        const double wj = apply_sign(a, j, gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr)));
         const double Aj = al.A ? al.A[j] : 0.0, qj = a.q[j], lbj = a.lb[j], ubj = a.ub[j];
         ALElem e = al_load(a, al, j);
         const double g = al_gradient(p, sc, wj, qj, Aj, lbj, ubj, e);
@@ -907,7 +1183,7 @@ __global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const
             }
             uj = __dsub_rn(uj, e2.x);
         }
-        if (step) a.u[j] = uj;
+        if (step) a.u[j] = apply_sign(a, j, uj);
     }
     if (!step) {
         if (rc == AL_STOPPED && lead) {
@@ -925,6 +1201,40 @@ __global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const
 #pragma unroll
         for (int i = 0; i < AL_NSUMS; ++i) part_w[i * VP_MAXC + blockIdx.x] = v[i];
     }
+}
+
+// ------------------------------------------------------------------------------------------ kernel entry points
+// One problem per launch (argument block by value), or a batch of problems that share the resident matrix and
+// advance in lockstep (one-vs-rest / multi-target): blockIdx.y selects the problem, the argument
+// blocks live in device memory.  A problem that has finished ignores the launches that follow (its `done` flag).
+template <int MODE>
+__global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const long long k) {
+    pg_vector_body<MODE>(a, k);
+}
+template <int MODE>
+__global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const long long k) {
+    fw_vector_body<MODE>(a, k);
+}
+template <int MODE>
+__global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const ALArgs al, const long long k) {
+    al_vector_body<MODE>(a, al, k);
+}
+template <int MODE>
+__global__ void __launch_bounds__(VP_NT) pg_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k) {
+    const VecArgs a = args[blockIdx.y];
+    pg_vector_body<MODE>(a, k);
+}
+template <int MODE>
+__global__ void __launch_bounds__(VP_NT) fw_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k) {
+    const VecArgs a = args[blockIdx.y];
+    fw_vector_body<MODE>(a, k);
+}
+template <int MODE>
+__global__ void __launch_bounds__(VP_NT) al_vector_batch_kernel(const VecArgs* __restrict__ args,
+                                                                const ALArgs* __restrict__ als, const long long k) {
+    const VecArgs a = args[blockIdx.y];
+    const ALArgs al = als[blockIdx.y];
+    al_vector_body<MODE>(a, al, k);
 }
 
 // ------------------------------------------------------------------------------------------ driver
@@ -946,6 +1256,7 @@ struct svmb200_pg {
     unsigned long long cur_seq = 0;  // sequence number of the product the next vector kernel consumes
     int nctas = 1;
     double *q = nullptr, *lb = nullptr, *ub = nullptr;
+    double* sgn = nullptr;  // label signs (Q = (s s') o resident matrix), or null
     double *part = nullptr, *hist_f = nullptr, *hist_ng = nullptr;
     PGDeviceState* st = nullptr;
     PGDeviceState* st_host = nullptr;  // pinned
@@ -973,6 +1284,7 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
     a.q = pg->q;
     a.lb = pg->lb;
     a.ub = pg->ub;
+    a.sgn = pg->sgn;
     a.gathered = pg->w;
     a.gathered_ll = nullptr;
     a.tag = 0;
@@ -1112,7 +1424,7 @@ struct ALSpec {
 static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows, int hessian,
                        const double* q_host, const double* lb_host, const double* ub_host, const double* x0_host,
                        double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out,
-                       const ALSpec* al = nullptr);
+                       const ALSpec* al = nullptr, const double* sign_host = nullptr);
 
 extern "C" int svmb200_pg_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,
                                  int hessian, const double* q_host, const double* lb_host, const double* ub_host,
@@ -1127,9 +1439,27 @@ extern "C" int svmb200_fw_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
     return bcqp_create(ctx, dQ, n, ld, row0, nrows, hessian, q_host, lb_host, ub_host, x0_host, eps, max_iter, 1, t, out);
 }
 
+extern "C" int svmb200_pg_create_signed(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0,
+                                        int64_t nrows, int hessian, const double* sign_host, const double* q_host,
+                                        const double* lb_host, const double* ub_host, const double* x0_host, double eps,
+                                        int64_t max_iter, svmb200_pg** out) {
+    return bcqp_create(ctx, dQ, n, ld, row0, nrows, hessian, q_host, lb_host, ub_host, x0_host, eps, max_iter, 0, 0.0, out,
+                       nullptr, sign_host);
+}
+
+extern "C" int svmb200_fw_create_signed(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0,
+                                        int64_t nrows, int hessian, const double* sign_host, const double* q_host,
+                                        const double* lb_host, const double* ub_host, const double* x0_host, double eps,
+                                        int64_t max_iter, double t, svmb200_pg** out) {
+    SVM_CHECK_ARG(t >= 0.0 && t < 1.0, "t has to lie in [0, 1)");  // frank_wolfe.py:84-85
+    return bcqp_create(ctx, dQ, n, ld, row0, nrows, hessian, q_host, lb_host, ub_host, x0_host, eps, max_iter, 1, t, out,
+                       nullptr, sign_host);
+}
+
 static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows, int hessian,
                        const double* q_host, const double* lb_host, const double* ub_host, const double* x0_host,
-                       double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out, const ALSpec* al) {
+                       double eps, int64_t max_iter, int solver, double fw_t, svmb200_pg** out, const ALSpec* al,
+                       const double* sign_host) {
     SVM_TRY(svm_use(ctx));
     SVM_CHECK_ARG(out != nullptr, "out is null");
     *out = nullptr;
@@ -1138,6 +1468,10 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     SVM_CHECK_ARG(ld >= n && ld % 2 == 0, "ld must be >= n and even");
     SVM_CHECK_ARG(hessian == SVMB200_HESSIAN_PLAIN || hessian == SVMB200_HESSIAN_SVR, "bad hessian layout");
     SVM_CHECK_ARG(max_iter > 0, "max_iter must be > 0");  // opti/_base.py:73-74
+    SVM_CHECK_ARG(sign_host == nullptr || hessian == SVMB200_HESSIAN_PLAIN, "label signs need the plain layout");
+    if (sign_host != nullptr) {
+        for (int64_t i = 0; i < n; ++i) SVM_CHECK_ARG(sign_host[i] == 1.0 || sign_host[i] == -1.0, "signs must be +-1");
+    }
     const int P = ctx->nranks;
     const int64_t rpr = rows_per_rank(n, P);
     {
@@ -1190,7 +1524,7 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
         const size_t sz_sched = up((size_t)(max_iter + 1) * sizeof(double));
         const size_t sz_alpart = up(2 * AL_NSUMS * VP_MAXC * sizeof(double));
         const size_t al_extra = solver == 2 ? 8 * sz_nv + 4 * sz_sched + sz_alpart + up(2 * sizeof(double)) : 0;
-        const size_t total = 6 * sz_nv + sz_u + sz_w + sz_part + 2 * sz_hist + up(sizeof(PGDeviceState)) + al_extra;
+        const size_t total = 7 * sz_nv + sz_u + sz_w + sz_part + 2 * sz_hist + up(sizeof(PGDeviceState)) + al_extra;
         unsigned char* base = nullptr;
         if (!ctx->pg_slab_busy) {
             if (ctx->pg_slab_bytes < total) {
@@ -1227,6 +1561,10 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
         pg->q = take(sz_nv);
         pg->lb = take(sz_nv);
         pg->ub = take(sz_nv);
+        {
+            double* sg = take(sz_nv);
+            pg->sgn = sign_host ? sg : nullptr;
+        }
         pg->u = take(sz_u);
         pg->w = take(sz_w);
         pg->part = take(sz_part);
@@ -1265,12 +1603,13 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     std::vector<double> lbv((size_t)pg->nvars, 0.0), x0v((size_t)pg->nvars), u0((size_t)n);
     if (lb_host) memcpy(lbv.data(), lb_host, nv);
     for (int64_t i = 0; i < pg->nvars; ++i) x0v[i] = x0_host ? x0_host[i] : (lbv[i] + ub_host[i]) / 2;
-    for (int64_t j = 0; j < n; ++j) u0[j] = pg->svr ? x0v[j] - x0v[j + n] : x0v[j];
+    for (int64_t j = 0; j < n; ++j) u0[j] = pg->svr ? x0v[j] - x0v[j + n] : (sign_host ? sign_host[j] * x0v[j] : x0v[j]);
     PG_CUDA(cudaMemcpyAsync(pg->q, q_host, nv, cudaMemcpyHostToDevice, s));
     PG_CUDA(cudaMemcpyAsync(pg->ub, ub_host, nv, cudaMemcpyHostToDevice, s));
     PG_CUDA(cudaMemcpyAsync(pg->lb, lbv.data(), nv, cudaMemcpyHostToDevice, s));
     PG_CUDA(cudaMemcpyAsync(pg->x, x0v.data(), nv, cudaMemcpyHostToDevice, s));
     PG_CUDA(cudaMemcpyAsync(pg->u, u0.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (sign_host) PG_CUDA(cudaMemcpyAsync(pg->sgn, sign_host, nv, cudaMemcpyHostToDevice, s));
     std::vector<double> sched;  // staging of the per-iteration scalars (augmented Lagrangian)
     if (solver == 2) {
         ALArgs& A = pg->al;
@@ -1390,6 +1729,147 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
     return SVMB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------ batched driver
+// `count` solvers of one kind that share the resident matrix (same context, shard, layout and iteration limit) run
+// to termination in lockstep: per iteration ceil(count / MV_MULTI_MAX) passes over the matrix
+// instead of `count`, and one vector launch for all problems.  Every problem keeps its own state, histories and
+// stopping tests -- one that finishes early ignores the remaining launches -- and, because the multi-vector pass
+// reproduces the single-vector reductions bit for bit, ends exactly where its own svmb200_pg_run would have.
+// Multi-GPU: the product shards of every problem are exchanged with ncclAllGather (the fused peer exchange of the
+// single solves is not used here).
+static int batch_product(svmb200_ctx* ctx, svmb200_pg* const* pgs, int count) {
+    const int nlaunch = (count + MV_MULTI_MAX - 1) / MV_MULTI_MAX;
+    for (int l = 0, b0 = 0; l < nlaunch; ++l) {
+        const int nb = (count - b0 + (nlaunch - l) - 1) / (nlaunch - l);  // balanced split
+        const double* du[MV_MULTI_MAX];
+        double* dw[MV_MULTI_MAX];
+        const double* dur[MV_MULTI_MAX];
+        double* dden[MV_MULTI_MAX];
+        const int* ddone[MV_MULTI_MAX];
+        for (int i = 0; i < nb; ++i) {
+            svmb200_pg* pg = pgs[b0 + i];
+            double* wshard = pg->w + (size_t)ctx->rank * pg->stride;
+            du[i] = pg->u;
+            dw[i] = wshard;
+            dur[i] = pg->u + pg->row0;
+            dden[i] = wshard + pg->rows_per_rank;
+            ddone[i] = &pg->st->done;
+        }
+        SVM_TRY(launch_matvec_multi(ctx, pgs[0]->dQ, pgs[0]->nrows, pgs[0]->ld, nb, du, dw, dur, dden, ddone));
+        b0 += nb;
+    }
+    if (ctx->nranks > 1) {
+        for (int b = 0; b < count; ++b) SVM_TRY(svm_comm_allgather(ctx, pgs[b]->w, pgs[b]->stride));
+    }
+    for (int b = 0; b < count; ++b) pgs[b]->last_passes += nlaunch;
+    return SVMB200_OK;
+}
+
+template <int MODE>
+static int launch_vec_batch(svmb200_ctx* ctx, int solver, int nctas, int count, const VecArgs* dva, const ALArgs* dal,
+                            long long k) {
+    const dim3 grid((unsigned)nctas, (unsigned)count);
+    if (solver == 2) al_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, dal, k);
+    else if (solver == 1) fw_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, k);
+    else pg_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, k);
+    ctx->launches++;
+    SVM_CUDA(cudaGetLastError());
+    return SVMB200_OK;
+}
+
+// one copy per problem, one synchronisation; returns the number of problems still running
+static int batch_poll(svmb200_ctx* ctx, svmb200_pg* const* pgs, int count, int* running) {
+    for (int b = 0; b < count; ++b)
+        SVM_CUDA(cudaMemcpyAsync(pgs[b]->st_host, pgs[b]->st, sizeof(PGDeviceState), cudaMemcpyDeviceToHost, ctx->stream));
+    SVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    int r = 0;
+    for (int b = 0; b < count; ++b) {
+        if (pgs[b]->st_host->done) pgs[b]->finished = true;
+        else ++r;
+    }
+    *running = r;
+    return SVMB200_OK;
+}
+
+extern "C" int svmb200_pg_run_batch(svmb200_pg* const* pgs, int count, int64_t* iters, int* statuses) {
+    SVM_CHECK_ARG(pgs != nullptr && count >= 1 && count <= 65535, "bad argument");
+    svmb200_pg* p0 = pgs[0];
+    for (int b = 0; b < count; ++b) {
+        const svmb200_pg* p = pgs[b];
+        SVM_CHECK_ARG(p != nullptr, "null solver");
+        SVM_CHECK_ARG(p->ctx == p0->ctx && p->dQ == p0->dQ && p->n == p0->n && p->ld == p0->ld && p->row0 == p0->row0 &&
+                          p->nrows == p0->nrows && p->svr == p0->svr,
+                      "the solvers of a batch must share the resident matrix, its shard and its layout");
+        SVM_CHECK_ARG(p->solver == p0->solver && p->max_iter == p0->max_iter,
+                      "the solvers of a batch must be of one kind and share the iteration limit");
+        SVM_CHECK_ARG(p->k_next == 0 && !p->finished, "a batch takes solvers that have not run yet");
+        for (int c = 0; c < b; ++c) SVM_CHECK_ARG(pgs[c] != p, "a solver is listed twice");
+    }
+    svmb200_ctx* ctx = p0->ctx;
+    SVM_TRY(svm_use(ctx));
+    // per-problem slab pointers differ, so every problem needs its own pinned state block (the context owns one)
+    for (int b = 0; b < count; ++b) {
+        for (int c = 0; c < b; ++c) SVM_CHECK_ARG(pgs[c]->st_host != pgs[b]->st_host, "solvers share a state block");
+        pgs[b]->p2p = false;  // products go to the solver's own gathered buffer from here on
+        pgs[b]->mv_ev.clear();
+        pgs[b]->last_passes = 0;
+        pgs[b]->last_ms = pgs[b]->last_mv_ms = pgs[b]->last_comm_ms = pgs[b]->last_vec_ms = 0.f;
+    }
+    // argument blocks of the vector kernels (constant over the run: only k changes from launch to launch)
+    const int solver = p0->solver;
+    const size_t va_bytes = ((size_t)count * sizeof(VecArgs) + 255) & ~size_t(255);
+    const size_t al_bytes = solver == 2 ? (((size_t)count * sizeof(ALArgs) + 255) & ~size_t(255)) : 0;
+    SVM_TRY(svm_scratch_reserve(ctx, &ctx->batch_buf, &ctx->batch_bytes, va_bytes + al_bytes));
+    VecArgs* dva = static_cast<VecArgs*>(ctx->batch_buf);
+    ALArgs* dal = solver == 2 ? reinterpret_cast<ALArgs*>(static_cast<unsigned char*>(ctx->batch_buf) + va_bytes) : nullptr;
+    {
+        std::vector<VecArgs> hv((size_t)count);
+        for (int b = 0; b < count; ++b) hv[b] = make_vec_args(pgs[b]);
+        SVM_CUDA(cudaMemcpyAsync(dva, hv.data(), (size_t)count * sizeof(VecArgs), cudaMemcpyHostToDevice, ctx->stream));
+        if (solver == 2) {
+            std::vector<ALArgs> ha((size_t)count);
+            for (int b = 0; b < count; ++b) ha[b] = pgs[b]->al;
+            SVM_CUDA(cudaMemcpyAsync(dal, ha.data(), (size_t)count * sizeof(ALArgs), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        SVM_CUDA(cudaStreamSynchronize(ctx->stream));  // staging vectors go out of scope
+    }
+    SVM_CUDA(cudaEventRecord(p0->ev0, ctx->stream));
+    const int64_t max_iter = p0->max_iter;
+    int64_t k = 0;
+    int running = count;
+    const int64_t BATCH = 64;  // iterations enqueued between two looks at the done flags
+    while (k < max_iter && running > 0) {
+        const int64_t nb = max_iter - k < BATCH ? max_iter - k : BATCH;
+        for (int64_t i = 0; i < nb; ++i, ++k) {
+            SVM_TRY(batch_product(ctx, pgs, count));
+            SVM_TRY(launch_vec_batch<VP_STEP>(ctx, solver, p0->nctas, count, dva, dal, k));
+        }
+        SVM_TRY(batch_poll(ctx, pgs, count, &running));
+    }
+    if (running > 0) {
+        // state at callback point max_iter (see svmb200_pg_run): the epoch / iteration limit ends every problem left
+        if (solver == 2) SVM_TRY(batch_product(ctx, pgs, count));
+        SVM_TRY(launch_vec_batch<VP_FINALISE>(ctx, solver, p0->nctas, count, dva, dal, k));
+        SVM_TRY(batch_poll(ctx, pgs, count, &running));
+    }
+    SVM_CUDA(cudaEventRecord(p0->ev1, ctx->stream));
+    SVM_CUDA(cudaEventSynchronize(p0->ev1));
+    float ms = 0.f;
+    SVM_CUDA(cudaEventElapsedTime(&ms, p0->ev0, p0->ev1));
+    for (int b = 0; b < count; ++b) {
+        svmb200_pg* pg = pgs[b];
+        pg->last_ms = ms;  // device time of the whole batch
+        pg->k_next = pg->finished ? pg->st_host->iter : k;
+        if (iters) iters[b] = pg->st_host->iter;
+        if (statuses) statuses[b] = pg->st_host->done ? pg->st_host->status : SVMB200_STATUS_UNKNOWN;
+    }
+    if (running > 0) {
+        svmb200_set_error("batched solve: %d problem(s) did not reach a stopping test", running);
+        return SVMB200_ERR_STATE;
+    }
+    return SVMB200_OK;
+}
+
 extern "C" int svmb200_pg_state(svmb200_pg* pg, double* x_host, double* g_host, double* f, double* ng) {
     SVM_CHECK_ARG(pg != nullptr, "null solver");
     SVM_TRY(svm_use(pg->ctx));
@@ -1473,6 +1953,17 @@ extern "C" int svmb200_al_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
                                  const double* x0_host, const double* a_host, double b, double rho, int rule,
                                  int momentum_type, const double* step_sizes, const double* momenta, double decay,
                                  double beta1, double beta2, double offset, double tol, int64_t epochs, svmb200_pg** out) {
+    return svmb200_al_create_signed(ctx, dQ, n, ld, row0, nrows, hessian, nullptr, q_host, lb_host, ub_host, x0_host, a_host,
+                                    b, rho, rule, momentum_type, step_sizes, momenta, decay, beta1, beta2, offset, tol,
+                                    epochs, out);
+}
+
+extern "C" int svmb200_al_create_signed(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0,
+                                        int64_t nrows, int hessian, const double* sign_host, const double* q_host,
+                                        const double* lb_host, const double* ub_host, const double* x0_host,
+                                        const double* a_host, double b, double rho, int rule, int momentum_type,
+                                        const double* step_sizes, const double* momenta, double decay, double beta1,
+                                        double beta2, double offset, double tol, int64_t epochs, svmb200_pg** out) {
     SVM_CHECK_ARG(x0_host != nullptr, "the start point is required (opti/_base.py:36-60 draws it on the host)");
     SVM_CHECK_ARG(step_sizes != nullptr, "step_sizes is null");
     SVM_CHECK_ARG(rho > 0.0, "rho must be must > 0");                       // constrained/_base.py:276-277
@@ -1503,7 +1994,7 @@ extern "C" int svmb200_al_create(svmb200_ctx* ctx, const double* dQ, int64_t n, 
     spec.lr_host = step_sizes;
     spec.mom_host = momentum_type == AL_MOM_NONE ? nullptr : momenta;
     return bcqp_create(ctx, dQ, n, ld, row0, nrows, hessian, q_host, lb_host, ub_host, x0_host, 0.0, epochs, 2, 0.0, out,
-                       &spec);
+                       &spec, sign_host);
 }
 
 extern "C" int svmb200_al_multipliers(svmb200_pg* pg, double* mu, double* lam_lb_host, double* lam_ub_host) {

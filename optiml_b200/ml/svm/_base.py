@@ -127,12 +127,15 @@ class SVM(BaseEstimator):
             raise NotImplementedError
         return opt
 
-    def _solve_dual(self, solver_cls, hessian, q, ub, eq_row):
-        """Run the selected solver on  min x'Qx/2 + q'x : 0 <= x <= ub (, eq_row'x = 0 when the intercept is not
-        regularised)  and return the fitted instance; sets ``self.obj`` like ml/svm/_base.py:628-725."""
+    def _make_solver(self, solver_cls, hessian, q, ub, eq_row):
+        """The selected solver, ready to run, on  min x'Qx/2 + q'x : 0 <= x <= ub (, eq_row'x = 0 when the intercept
+        is not regularised); sets ``self.obj`` like ml/svm/_base.py:628-725."""
         if issubclass(solver_cls, BoxConstrainedQuadraticOptimizer):
             self.obj = Quadratic(hessian, q)
-            return self._solve(solver_cls, ub)
+            solver = solver_cls(quad=self.obj, ub=ub, tol=self.tol, max_iter=self.max_iter,
+                                callback=self._store_train_info, verbose=self.verbose)
+            solver.profile = bool(getattr(self, 'profile_matvec', False))  # CUDA events around every K2 launch
+            return solver
         # augmented-Lagrangian relaxation of the box (and of the equality), ml/svm/_base.py:638-655, 1188-1205
         lb = np.zeros_like(ub)
         if self.reg_intercept:
@@ -146,13 +149,11 @@ class SVM(BaseEstimator):
             kwargs.update(momentum_type=self.momentum_type, momentum=self.momentum)
         solver = solver_cls(**kwargs)
         solver.profile = bool(getattr(self, 'profile_matvec', False))
-        import time
-        t0 = time.perf_counter()
-        solver.minimize()
-        self.fit_times_['solve_s'] = time.perf_counter() - t0
-        if solver.status == 'stopped':  # ml/svm/_base.py:715-717
-            warnings.warn('max_iter reached but the optimization has not converged yet', ConvergenceWarning)
         return solver
+
+    def _after_solver(self, solver):
+        if isinstance(solver, StochasticOptimizer) and solver.status == 'stopped':  # ml/svm/_base.py:715-717
+            warnings.warn('max_iter reached but the optimization has not converged yet', ConvergenceWarning)
 
     def _bias(self):
         """The Hessian carries the rank-one term yy' (SVC) / ee' (SVR) only when the intercept is regularised
@@ -180,16 +181,6 @@ class SVM(BaseEstimator):
             dS.release()
         self.fit_times_ = {'gram_s': time.perf_counter() - t0}  # gamma + upload + Gram kernel (wall clock)
         return H
-
-    def _solve(self, solver_cls, ub):
-        solver = solver_cls(quad=self.obj, ub=ub, tol=self.tol, max_iter=self.max_iter,
-                            callback=self._store_train_info, verbose=self.verbose)
-        solver.profile = bool(getattr(self, 'profile_matvec', False))  # CUDA events around every K2 launch
-        import time
-        t0 = time.perf_counter()
-        solver.minimize()
-        self.fit_times_['solve_s'] = time.perf_counter() - t0
-        return solver
 
     def decision_function(self, X):
         """ml/svm/_base.py:284-287.  ``gamma='scale'`` is resolved from ``support_vectors_`` (the first
@@ -248,6 +239,17 @@ class SVC(ClassifierMixin, SVM):
         self.lb = LabelBinarizer(neg_label=-1)
 
     def fit(self, X, y, X_device=None):
+        import time
+        plan = self._plan_fit(X, y, X_device)
+        t0 = time.perf_counter()
+        plan['solver'].minimize()
+        self.fit_times_['solve_s'] = time.perf_counter() - t0
+        return self._finish_fit(plan)
+
+    def _plan_fit(self, X, y, X_device=None, shared=None):
+        """Everything ``fit`` does before the solver runs.  ``shared``: an unsigned resident ``M = K + bias`` that other
+        binary problems on the same X use too (one-vs-rest, ml/multiclass.py); the label signs are then applied by
+        the solver instead of being baked into a private copy of Q."""
         self.lb.fit(y)
         if len(self.lb.classes_) > 2:
             raise ValueError('use OneVsOneClassifier or OneVsRestClassifier from sklearn.multiclass '
@@ -264,9 +266,20 @@ class SVC(ClassifierMixin, SVM):
 
         # Q = K o yy' (+ yy' when the intercept is regularised)  (ml/svm/_base.py:552-554, 628), q = -1, 0 <= alpha <= C
         bias = self._bias()
-        hessian = self._build_hessian(X, ys, 'plain', X_device, bias)
+        if shared is not None:
+            hessian = shared.with_signs(ys)
+            self.fit_times_ = {}
+        else:
+            hessian = self._build_hessian(X, ys, 'plain', X_device, bias)
         ub = np.ones(n) * self.C
-        self.optimizer = self._solve_dual(solver_cls, hessian, -np.ones(n), ub, y)
+        solver = self._make_solver(solver_cls, hessian, -np.ones(n), ub, y)
+        return dict(X=X, y=y, ys=ys, n=n, bias=bias, solver=solver)
+
+    def _finish_fit(self, plan):
+        """Everything ``fit`` does after the solver has run (ml/svm/_base.py:725, 867-880)."""
+        X, y, ys, n, bias = plan['X'], plan['y'], plan['ys'], plan['n'], plan['bias']
+        self.optimizer = plan['solver']
+        self._after_solver(self.optimizer)
         self.alphas_ = self.optimizer.x
 
         # support set, dual coefficients, intercept (ml/svm/_base.py:867-880)
@@ -310,6 +323,16 @@ class SVR(RegressorMixin, SVM):
         self.epsilon = epsilon
 
     def fit(self, X, y, X_device=None):
+        import time
+        plan = self._plan_fit(X, y, X_device)
+        t0 = time.perf_counter()
+        plan['solver'].minimize()
+        self.fit_times_['solve_s'] = time.perf_counter() - t0
+        return self._finish_fit(plan)
+
+    def _plan_fit(self, X, y, X_device=None, shared=None):
+        """Everything ``fit`` does before the solver runs.  ``shared``: the resident ``M = K + bias`` of another
+        regression on the same X (multi-target fits, ml/multiclass.py) -- targets only change q."""
         y = np.asarray(y)
         targets = y.shape[1] if y.ndim > 1 else 1
         if targets > 1:
@@ -327,10 +350,21 @@ class SVR(RegressorMixin, SVM):
         # Q = [[K, -K], [-K, K]] (+ ee', e = [1, -1], when the intercept is regularised)  (ml/svm/_base.py:1098-1100,
         # 1126, 1178): only M = K + bias (n x n) is resident, the solver applies the block signs
         bias = self._bias()
-        hessian = self._build_hessian(X, None, 'svr', X_device, bias)
+        if shared is not None:
+            hessian = shared
+            self.fit_times_ = {}
+        else:
+            hessian = self._build_hessian(X, None, 'svr', X_device, bias)
         ub = np.ones(2 * n) * self.C
         e = np.hstack((np.ones(n), -np.ones(n)))
-        self.optimizer = self._solve_dual(solver_cls, hessian, np.hstack((-y, y)) + self.epsilon, ub, e)
+        solver = self._make_solver(solver_cls, hessian, np.hstack((-y, y)) + self.epsilon, ub, e)
+        return dict(X=X, y=y, n=n, bias=bias, solver=solver)
+
+    def _finish_fit(self, plan):
+        """Everything ``fit`` does after the solver has run (ml/svm/_base.py:1275-1277, 1423-1437)."""
+        X, y, n, bias = plan['X'], plan['y'], plan['n'], plan['bias']
+        self.optimizer = plan['solver']
+        self._after_solver(self.optimizer)
         self.alphas_ = self.optimizer.x
         alphas_p, alphas_n = np.split(self.alphas_, 2)
 

@@ -31,9 +31,16 @@ class DeviceLoopMixin:
             raise ValueError('bounds / start point size does not match with Q')
         q, lb, ub, x0 = (np.ascontiguousarray(v, dtype=np.float64) for v in (self.f.q, self.lb, self.ub, self.x))
         h = C.c_void_p()
-        N.call(self._create_symbol, H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows,
-               N.HESSIAN_SVR if H.layout == 'svr' else N.HESSIAN_PLAIN, N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0),
-               float(self.eps), int(self.max_iter), *self._extra_create_args(), C.byref(h))
+        layout = N.HESSIAN_SVR if H.layout == 'svr' else N.HESSIAN_PLAIN
+        if H.signs is not None:
+            # Q = (s s') o M on a shared, unsigned resident matrix (one-vs-rest)
+            N.call(self._create_symbol + '_signed', H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows,
+                   layout, N.ptr(H.signs), N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0), float(self.eps),
+                   int(self.max_iter), *self._extra_create_args(), C.byref(h))
+        else:
+            N.call(self._create_symbol, H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows, layout,
+                   N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0), float(self.eps), int(self.max_iter),
+                   *self._extra_create_args(), C.byref(h))
         if profile:
             N.call('svmb200_pg_set_profile', h, 1)
         return h, n
@@ -64,26 +71,40 @@ class DeviceLoopMixin:
         return cb is None or getattr(cb, '_svmb200_history_only', False) or \
             getattr(getattr(cb, '__func__', None), '_svmb200_history_only', False)
 
+    def _problem_ndim(self):
+        return self.f.ndim
+
+    def _resident_ok(self):
+        """The whole loop can stay on the device: nothing runs on the host between iterations."""
+        return self._history_only_callback() and not self.verbose and self._problem_ndim() > 3
+
     def minimize(self):
         if self.verbose:
             print(self._verbose_header, end='')
         profile = bool(getattr(self, 'profile', False))
         h, n = self._create(profile)
         try:
-            if self._history_only_callback() and not self.verbose and self.f.ndim > 3:
+            if self._resident_ok():
                 self._minimize_resident(h, n)
             else:
                 self._minimize_stepwise(h, n)
-            self._collect_stats(h)
+            self._after_run(h, n)
         finally:
             N.load_library().svmb200_pg_destroy(h)
         if self.verbose:
             print('\n')
         return self
 
+    def _after_run(self, h, n):
+        self._collect_stats(h)
+
     def _minimize_resident(self, h, n):
         # whole loop on the device; f at every callback point comes back in one copy
-        self.iter, self.status = self._run(h, -1)
+        self._finish_resident(h, n, *self._run(h, -1))
+
+    def _finish_resident(self, h, n, it, status):
+        """Collect the outcome of a device-resident run (also used by the batched driver, opti/batch.py)."""
+        self.iter, self.status = it, status
         self._pull_state(h, n)
         cnt = C.c_int64(0)
         f_hist, second = np.empty(self.iter + 1), np.empty(self.iter + 1)

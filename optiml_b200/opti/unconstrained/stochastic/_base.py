@@ -95,11 +95,15 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
         mom = self._draw(self.momentum, self.epochs + 1) if momentum_type != 'none' else None
         k = self._rule_constants()
         h = C.c_void_p()
-        N.call('svmb200_al_create', H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows,
-               N.HESSIAN_SVR if H.layout == 'svr' else N.HESSIAN_PLAIN, N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0),
-               N.ptr(a), b, float(f.rho), N.RULES[self._rule], N.MOMENTUM[momentum_type], N.ptr(lr), N.ptr(mom),
-               float(k['decay']), float(k['beta1']), float(k['beta2']), float(k['offset']), float(self.tol),
-               int(self.epochs), C.byref(h))
+        layout = N.HESSIAN_SVR if H.layout == 'svr' else N.HESSIAN_PLAIN
+        tail = (N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0), N.ptr(a), b, float(f.rho), N.RULES[self._rule],
+                N.MOMENTUM[momentum_type], N.ptr(lr), N.ptr(mom), float(k['decay']), float(k['beta1']), float(k['beta2']),
+                float(k['offset']), float(self.tol), int(self.epochs), C.byref(h))
+        if H.signs is not None:  # Q = (s s') o M on a shared, unsigned resident matrix
+            N.call('svmb200_al_create_signed', H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows, layout,
+                   N.ptr(H.signs), *tail)
+        else:
+            N.call('svmb200_al_create', H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows, layout, *tail)
         if profile:
             N.call('svmb200_pg_set_profile', h, 1)
         return h, n
@@ -123,26 +127,32 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
         if self.is_verbose():
             print('\n{:4d}\t{:4d}\t{: 1.4e}'.format(self.epoch, self.iter, self.f_x), end='')  # _base.py:128-130
 
+    def _problem_ndim(self):
+        return self.f.primal.ndim
+
     def minimize(self):
         self._print_header()
         h, n = self._create(bool(getattr(self, 'profile', False)))
         try:
-            if self._history_only_callback() and not self.verbose and self.f.primal.ndim > 3:
+            if self._resident_ok():
                 self._minimize_resident(h, n)
             else:
                 self._minimize_stepwise(h, n)
-            self._pull_multipliers(h, n)
-            self._collect_stats(h)
+            self._after_run(h, n)
         finally:
             N.load_library().svmb200_pg_destroy(h)
-        assert all(self.f.dual_x[self.f.n_eq:] >= 0)  # opti/_base.py:163-167
         if self.verbose:
             print('\n')
         return self
 
-    def _minimize_resident(self, h, n):
+    def _after_run(self, h, n):
+        self._pull_multipliers(h, n)
+        self._collect_stats(h)
+        assert all(self.f.dual_x[self.f.n_eq:] >= 0)  # opti/_base.py:163-167
+
+    def _finish_resident(self, h, n, it, status):
         # whole loop on the device; L and the primal cost at every callback point come back in one copy
-        self.iter, self.status = self._run(h, -1)
+        self.iter, self.status = it, status
         self._pull_state(h, n)
         self.epoch = self.iter + 1
         cnt = C.c_int64(0)

@@ -217,15 +217,36 @@ class DeviceHessian:
     ``layout='plain'``: the matrix is Q itself.  ``layout='svr'``: the matrix is M = K + 1 and the
     Hessian is [[M, -M], [-M, M]] (ml/svm/_base.py:1098-1099, 1178 of the reference) -- the 2n x 2n
     matrix is never materialised on the device.
+
+    ``signs`` (n values of +-1, plain layout only): the resident matrix is M and the Hessian is
+    Q = (s s') o M -- what ml/svm/_base.py:554, 628 build from the labels.  ``with_signs`` returns such a view
+    of an unsigned matrix without copying it, so the binary problems of a one-vs-rest fit share one M in HBM
+    (SURVEY.md 8f-4); the solvers apply s to their vectors, which is exact.
     """
 
-    def __init__(self, ctx, n, layout='plain', matrix=None, row0=None, nrows=None):
+    def __init__(self, ctx, n, layout='plain', matrix=None, row0=None, nrows=None, signs=None):
         self.ctx, self.n, self.layout = ctx, int(n), layout
         if row0 is None:
             row0, nrows = ctx.row_shard(n)
         self.row0, self.nrows = int(row0), int(nrows)
         self.ld = N.padded_ld(n)
+        self.owns_matrix = matrix is None
         self.matrix = matrix if matrix is not None else DeviceMatrix(ctx, self.nrows, self.n, self.ld)
+        self.signs = None
+        if signs is not None:
+            signs = np.ascontiguousarray(signs, dtype=np.float64).ravel()
+            if layout != 'plain':
+                raise ValueError('label signs apply to the plain layout only')
+            if signs.size != self.n or not np.all(np.abs(signs) == 1.0):
+                raise ValueError('signs must be n values of +-1')
+            self.signs = signs
+
+    def with_signs(self, signs):
+        """A view of the same resident matrix whose Hessian is (s s') o M (no copy; the view does not own M)."""
+        if self.signs is not None:
+            raise ValueError('the matrix already carries label signs')
+        return DeviceHessian(self.ctx, self.n, self.layout, matrix=self.matrix, row0=self.row0, nrows=self.nrows,
+                             signs=signs)
 
     @property
     def nvars(self):
@@ -257,6 +278,8 @@ class DeviceHessian:
             M = np.vstack(parts)
         if self.layout == 'svr':
             return np.vstack((np.hstack((M, -M)), np.hstack((-M, M))))
+        if self.signs is not None:
+            return self.signs[:, None] * M * self.signs[None, :]
         return M
 
     def product(self, v):
@@ -264,16 +287,21 @@ class DeviceHessian:
         v = np.asarray(v, dtype=np.float64).ravel()
         if self.layout == 'svr':
             beta = v[:self.n] - v[self.n:]
+        elif self.signs is not None:
+            beta = self.signs * v
         else:
             beta = v
         beta = np.ascontiguousarray(beta)
         out = np.empty(self.n)
         N.call('svmb200_masked_product', self.ctx.handle, C.c_void_p(self.matrix.dptr), self.n, self.ld, self.row0,
                self.nrows, N.ptr(beta), N.ptr(out))
+        if self.signs is not None:
+            out *= self.signs
         return np.concatenate((out, -out)) if self.layout == 'svr' else out
 
     def release(self):
-        self.matrix.release()
+        if self.owns_matrix:
+            self.matrix.release()
 
 
 def default_context():

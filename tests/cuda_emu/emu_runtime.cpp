@@ -1,0 +1,369 @@
+// tests/cuda_emu -- fiber runtime behind the host stand-in for the CUDA runtime  (TEST INFRASTRUCTURE ONLY).
+//
+// A launch runs its blocks one after the other; inside a block every CUDA thread is a fiber with its own stack.
+// A fiber runs until it reaches __syncthreads() or a warp shuffle (or returns); when no fiber of the block can run,
+// the scheduler releases the barriers that are complete:
+//   * __syncthreads(): all threads of the block that have not returned are waiting at it;
+//   * __shfl_xor_sync(full mask): all 32 lanes of the warp are waiting at it (a lane that has returned, or that waits
+//     at __syncthreads() instead, is an error -- on the GPU that is undefined behaviour with a full mask).
+// Anything else is a deadlock and fails the launch (sticky error, reported by cudaGetLastError / the next sync).
+// The order in which runnable fibers are resumed is selectable (forward, reverse, seeded shuffle): code that is
+// correctly synchronised gives the same bits under every order, a missing barrier usually does not.
+// "Device" memory is host memory, filled with 0xFF on allocation (NaNs: nothing may rely on zero-initialisation) and
+// fenced by canaries that cudaFree checks.
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace emu {
+
+thread_local uint3 threadIdx_ = {0, 0, 0}, blockIdx_ = {0, 0, 0};
+thread_local dim3 blockDim_(1, 1, 1), gridDim_(1, 1, 1);
+
+// ---------------------------------------------------------------------------------------------- context switch
+#if defined(__x86_64__)
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+#else
+#error "tests/cuda_emu needs x86-64 (hand-written fiber switch)"
+#endif
+
+enum State { READY, AT_SYNC, AT_SHFL, DONE };
+
+struct Fiber {
+    void* sp = nullptr;
+    State state = DONE;
+    double shfl_val = 0.0;
+    int shfl_mask = 0;
+};
+
+constexpr size_t STACK_BYTES = 64 * 1024;
+
+struct BlockRunner {
+    std::vector<Fiber> fibers;
+    char* stacks = nullptr;
+    std::vector<char*>* owner = nullptr;
+    ~BlockRunner() {
+        if (stacks && owner) owner->push_back(stacks);
+    }
+    void* sched_sp = nullptr;
+    int current = -1;
+    const std::function<void()>* body = nullptr;
+};
+
+static thread_local BlockRunner* g_run = nullptr;
+static thread_local int g_sticky_error = 0;
+static thread_local std::string g_sticky_text;
+static int g_order = 0;  // 0 forward, 1 reverse, 2 shuffle
+static unsigned g_seed = 1;
+
+static void fail(const std::string& what) {
+    if (!g_sticky_error) {
+        g_sticky_error = cudaErrorLaunchFailure;
+        g_sticky_text = what;
+        fprintf(stderr, "[cuda_emu] %s\n", what.c_str());
+    }
+}
+
+static void yield_to_scheduler() {
+    BlockRunner* r = g_run;
+    emu_switch(&r->fibers[r->current].sp, r->sched_sp);
+}
+
+extern "C" void emu_fiber_main() {
+    BlockRunner* r = g_run;
+    (*r->body)();
+    r->fibers[r->current].state = DONE;
+    yield_to_scheduler();
+    abort();  // a finished fiber is never resumed
+}
+
+void syncthreads() {
+    g_run->fibers[g_run->current].state = AT_SYNC;
+    yield_to_scheduler();
+}
+
+double shfl_xor(double v, int lane_mask) {
+    Fiber& f = g_run->fibers[g_run->current];
+    f.shfl_val = v;
+    f.shfl_mask = lane_mask;
+    f.state = AT_SHFL;
+    yield_to_scheduler();
+    return g_run->fibers[g_run->current].shfl_val;
+}
+
+static void prepare_fiber(BlockRunner& r, int t) {
+    char* top = r.stacks + (size_t)(t + 1) * STACK_BYTES;
+    top = reinterpret_cast<char*>(reinterpret_cast<uintptr_t>(top) & ~uintptr_t(15));
+    void** sp = reinterpret_cast<void**>(top);
+    *--sp = nullptr;                                    // keeps (rsp + 8) 16-byte aligned at entry
+    *--sp = reinterpret_cast<void*>(&emu_fiber_main);   // `ret` of the first switch lands here
+    for (int i = 0; i < 6; ++i) *--sp = nullptr;        // rbp rbx r12 r13 r14 r15
+    r.fibers[t].sp = sp;
+    r.fibers[t].state = READY;
+}
+
+static bool run_block(BlockRunner& r, int nt, std::mt19937& rng) {
+    for (int t = 0; t < nt; ++t) prepare_fiber(r, t);
+    std::vector<int> order(nt);
+    for (int t = 0; t < nt; ++t) order[t] = t;
+    int live = nt;
+    while (live > 0) {
+        if (g_order == 1) std::reverse(order.begin(), order.end());
+        else if (g_order == 2) std::shuffle(order.begin(), order.end(), rng);
+        for (int t : order) {
+            if (r.fibers[t].state != READY) continue;
+            r.current = t;
+            threadIdx_.x = (unsigned)t;
+            emu_switch(&r.sched_sp, r.fibers[t].sp);
+            if (r.fibers[t].state == DONE) --live;
+        }
+        if (live == 0) break;
+        // nothing can run: release the barriers that are complete
+        int at_sync = 0;
+        for (int t = 0; t < nt; ++t) at_sync += r.fibers[t].state == AT_SYNC;
+        if (at_sync == live) {
+            for (int t = 0; t < nt; ++t)
+                if (r.fibers[t].state == AT_SYNC) r.fibers[t].state = READY;
+            continue;
+        }
+        bool released = false;
+        for (int w0 = 0; w0 < nt; w0 += 32) {
+            const int w1 = std::min(w0 + 32, nt);
+            int at_shfl = 0;
+            for (int t = w0; t < w1; ++t) at_shfl += r.fibers[t].state == AT_SHFL;
+            if (at_shfl == 0) continue;
+            if (at_shfl != w1 - w0) {
+                fail("warp shuffle with a full mask reached by only part of the warp (block " +
+                     std::to_string(blockIdx_.x) + "," + std::to_string(blockIdx_.y) + ", warp " + std::to_string(w0 / 32) + ")");
+                return false;
+            }
+            double vals[32];
+            for (int t = w0; t < w1; ++t) vals[t - w0] = r.fibers[t].shfl_val;
+            for (int t = w0; t < w1; ++t) {
+                const int src = (t - w0) ^ r.fibers[t].shfl_mask;
+                r.fibers[t].shfl_val = (src >= 0 && src < w1 - w0) ? vals[src] : vals[t - w0];
+                r.fibers[t].state = READY;
+            }
+            released = true;
+        }
+        if (!released) {
+            fail("deadlock: __syncthreads() not reached by all live threads of block " + std::to_string(blockIdx_.x) + "," +
+                 std::to_string(blockIdx_.y));
+            return false;
+        }
+    }
+    return true;
+}
+
+static thread_local uint64_t g_launches = 0, g_blocks = 0;
+
+void launch(dim3 grid, dim3 block, const std::function<void()>& thread_body) {
+    if (g_sticky_error) return;
+    if (block.y != 1 || block.z != 1 || grid.z != 1 || block.x == 0 || block.x > 1024) {
+        fail("unsupported launch shape");
+        return;
+    }
+    const int nt = (int)block.x;
+    BlockRunner r;
+    r.fibers.resize(nt);
+    {
+        // fiber stacks are recycled between launches (zero-filling 16 MB per launch would dominate tiny kernels)
+        static thread_local std::vector<char*> pool;
+        r.stacks = pool.empty() ? static_cast<char*>(malloc((size_t)(1024 + 1) * STACK_BYTES)) : pool.back();
+        if (!pool.empty()) pool.pop_back();
+        if (!r.stacks) {
+            fail("out of memory for fiber stacks");
+            return;
+        }
+        r.owner = &pool;
+    }
+    r.body = &thread_body;
+    BlockRunner* outer = g_run;
+    g_run = &r;
+    std::mt19937 rng(g_seed + (unsigned)g_launches * 7919u);
+    blockDim_ = block;
+    gridDim_ = grid;
+    ++g_launches;
+    for (unsigned by = 0; by < grid.y && !g_sticky_error; ++by) {
+        for (unsigned bx = 0; bx < grid.x && !g_sticky_error; ++bx) {
+            blockIdx_ = {bx, by, 0};
+            ++g_blocks;
+            if (!run_block(r, nt, rng)) break;
+        }
+    }
+    g_run = outer;
+}
+
+// ---------------------------------------------------------------------------------------------- memory
+constexpr size_t GUARD = 256;
+constexpr unsigned char CANARY = 0xA5;
+struct Alloc {
+    size_t bytes;
+    bool pinned;
+};
+static std::mutex g_mem_mutex;
+static std::map<void*, Alloc> g_allocs;
+
+static cudaError_t alloc_fenced(void** p, size_t bytes, bool pinned) {
+    if (!p) return cudaErrorInvalidValue;
+    void* raw = nullptr;
+    if (posix_memalign(&raw, 256, bytes + 2 * GUARD) != 0) return cudaErrorMemoryAllocation;
+    unsigned char* base = static_cast<unsigned char*>(raw);
+    memset(base, CANARY, GUARD);
+    memset(base + GUARD, 0xFF, bytes);  // NaN doubles, -1 integers: nothing may rely on fresh memory being zero
+    memset(base + GUARD + bytes, CANARY, GUARD);
+    *p = base + GUARD;
+    std::lock_guard<std::mutex> lock(g_mem_mutex);
+    g_allocs[*p] = Alloc{bytes, pinned};
+    return cudaSuccess;
+}
+
+static cudaError_t free_fenced(void* p) {
+    if (!p) return cudaSuccess;
+    Alloc a;
+    {
+        std::lock_guard<std::mutex> lock(g_mem_mutex);
+        auto it = g_allocs.find(p);
+        if (it == g_allocs.end()) {
+            fail("free of a pointer that was not allocated (or double free)");
+            return cudaErrorInvalidValue;
+        }
+        a = it->second;
+        g_allocs.erase(it);
+    }
+    unsigned char* base = static_cast<unsigned char*>(p) - GUARD;
+    for (size_t i = 0; i < GUARD; ++i) {
+        if (base[i] != CANARY || base[GUARD + a.bytes + i] != CANARY) {
+            fail("out-of-bounds write detected around an allocation of " + std::to_string(a.bytes) + " bytes");
+            break;
+        }
+    }
+    free(base);
+    return cudaSuccess;
+}
+
+}  // namespace emu
+
+// ---------------------------------------------------------------------------------------------- runtime API subset
+cudaError_t cudaGetDeviceCount(int* count) {
+    *count = 1;
+    return cudaSuccess;
+}
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp* prop, int) {
+    prop->major = 10;
+    prop->minor = 0;
+    prop->multiProcessorCount = 148;
+    return cudaSuccess;
+}
+cudaError_t cudaMemGetInfo(size_t* free_bytes, size_t* total_bytes) {
+    *free_bytes = *total_bytes = (size_t)180 << 30;
+    return cudaSuccess;
+}
+cudaError_t cudaMalloc(void** p, size_t bytes) { return emu::alloc_fenced(p, bytes, false); }
+cudaError_t cudaFree(void* p) { return emu::free_fenced(p); }
+cudaError_t cudaMallocHost(void** p, size_t bytes) { return emu::alloc_fenced(p, bytes, true); }
+cudaError_t cudaFreeHost(void* p) { return emu::free_fenced(p); }
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) {
+    memmove(dst, src, bytes);
+    return emu::g_sticky_error;
+}
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) {
+    memmove(dst, src, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                              cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < height; ++r)
+        memmove(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+    return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) {
+    memset(p, value, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
+    *s = reinterpret_cast<cudaStream_t>(new int(0));
+    return cudaSuccess;
+}
+cudaError_t cudaStreamDestroy(cudaStream_t s) {
+    delete reinterpret_cast<int*>(s);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return emu::g_sticky_error; }
+struct emu_event {
+    std::chrono::steady_clock::time_point t;
+};
+cudaError_t cudaEventCreate(cudaEvent_t* e) {
+    *e = new emu_event();
+    return cudaSuccess;
+}
+cudaError_t cudaEventDestroy(cudaEvent_t e) {
+    delete e;
+    return cudaSuccess;
+}
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+    e->t = std::chrono::steady_clock::now();
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return emu::g_sticky_error; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
+cudaError_t cudaGetLastError() { return emu::g_sticky_error; }
+const char* cudaGetErrorString(cudaError_t e) {
+    if (e == cudaSuccess) return "no error";
+    return emu::g_sticky_text.empty() ? "emulated CUDA error" : emu::g_sticky_text.c_str();
+}
+
+// ---------------------------------------------------------------------------------------------- test hooks
+extern "C" {
+// 0: threads resumed in index order, 1: reversed after every barrier, 2: shuffled (seeded)
+void emu_set_schedule(int order, unsigned seed) {
+    emu::g_order = order;
+    emu::g_seed = seed;
+}
+int emu_live_allocations(void) {
+    std::lock_guard<std::mutex> lock(emu::g_mem_mutex);
+    return (int)emu::g_allocs.size();
+}
+int emu_sticky_error(void) { return emu::g_sticky_error; }
+void emu_clear_error(void) {
+    emu::g_sticky_error = 0;
+    emu::g_sticky_text.clear();
+}
+uint64_t emu_launches(void) { return emu::g_launches; }
+uint64_t emu_blocks(void) { return emu::g_blocks; }
+}

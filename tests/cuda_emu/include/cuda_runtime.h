@@ -1,0 +1,102 @@
+// tests/cuda_emu -- host stand-in for <cuda_runtime.h>  (TEST INFRASTRUCTURE ONLY, never part of the product).
+//
+// Lets the CPU test-suite compile optiml_b200/csrc/pg.cu and api.cu with g++ and run the REAL kernel source thread by
+// thread: every CUDA thread of a block is a fiber, __syncthreads() and the warp shuffles are fiber barriers
+// (emu_runtime.cpp), blocks run one after the other, "device" memory is host memory with canaries.  What this
+// checks: indexing, barrier placement, launch sequences, double-buffering, arithmetic order -- not timing, not memory
+// ordering between CTAs (blocks are serial), not PTX.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+// ---- language extensions
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static thread_local
+#define __grid_constant__
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct alignas(16) double2 { double x, y; };
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+
+namespace emu {
+extern thread_local uint3 threadIdx_, blockIdx_;
+extern thread_local dim3 blockDim_, gridDim_;
+void syncthreads();
+double shfl_xor(double v, int lane_mask);
+}  // namespace emu
+#define threadIdx (emu::threadIdx_)
+#define blockIdx (emu::blockIdx_)
+#define blockDim (emu::blockDim_)
+#define gridDim (emu::gridDim_)
+
+// ---- device intrinsics used by the kernels
+static inline void __syncthreads() { emu::syncthreads(); }
+static inline void __threadfence() {}
+static inline double __shfl_xor_sync(unsigned, double v, int lane_mask) { return emu::shfl_xor(v, lane_mask); }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
+static inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
+static inline unsigned atomicInc(unsigned* addr, unsigned val) {
+    const unsigned old = *addr;
+    *addr = old >= val ? 0u : old + 1u;
+    return old;
+}
+
+// ---- runtime API subset
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorLaunchFailure = 719 };
+typedef struct emu_stream* cudaStream_t;
+typedef struct emu_event* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1 };
+struct cudaDeviceProp {
+    int major, minor, multiProcessorCount;
+};
+
+cudaError_t cudaGetDeviceCount(int* count);
+cudaError_t cudaSetDevice(int device);
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp* prop, int device);
+cudaError_t cudaMemGetInfo(size_t* free_bytes, size_t* total_bytes);
+cudaError_t cudaMalloc(void** p, size_t bytes);
+template <typename T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc((void**)p, bytes); }
+cudaError_t cudaFree(void* p);
+cudaError_t cudaMallocHost(void** p, size_t bytes);
+template <typename T> static inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return cudaMallocHost((void**)p, bytes); }
+cudaError_t cudaFreeHost(void* p);
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s);
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                              cudaMemcpyKind kind, cudaStream_t s);
+cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t s);
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
+cudaError_t cudaStreamDestroy(cudaStream_t s);
+cudaError_t cudaStreamSynchronize(cudaStream_t s);
+cudaError_t cudaEventCreate(cudaEvent_t* e);
+cudaError_t cudaEventDestroy(cudaEvent_t e);
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
+cudaError_t cudaEventSynchronize(cudaEvent_t e);
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
+cudaError_t cudaGetLastError();
+const char* cudaGetErrorString(cudaError_t e);
+
+// ---- kernel launches: `k<<<grid, block, smem, stream>>>(args)` is rewritten by tests/cuda_emu/build.py into
+// emu::launch(grid, block, [=]() { k(args); })
+#include <functional>
+namespace emu {
+void launch(dim3 grid, dim3 block, const std::function<void()>& thread_body);
+}
