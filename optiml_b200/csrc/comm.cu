@@ -20,6 +20,28 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
+#ifdef SVMB200_HOST_EMULATION
+// tests/cuda_emu: ranks are threads of one process and the six NCCL entry points are in-process stand-ins
+extern "C" {
+ncclResult_t emu_ncclGetUniqueId(ncclUniqueId*);
+ncclResult_t emu_ncclCommInitRank(ncclComm_t*, int, ncclUniqueId, int);
+ncclResult_t emu_ncclCommDestroy(ncclComm_t);
+ncclResult_t emu_ncclAllGather(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+const char* emu_ncclGetErrorString(ncclResult_t);
+ncclResult_t emu_ncclGetVersion(int*);
+}
+static int nccl_load() {
+    static int bound = 0;
+    g_nccl.lib = &bound;
+    g_nccl.GetUniqueId = emu_ncclGetUniqueId;
+    g_nccl.CommInitRank = emu_ncclCommInitRank;
+    g_nccl.CommDestroy = emu_ncclCommDestroy;
+    g_nccl.AllGather = emu_ncclAllGather;
+    g_nccl.GetErrorString = emu_ncclGetErrorString;
+    g_nccl.GetVersion = emu_ncclGetVersion;
+    return SVMB200_OK;
+}
+#else
 static int nccl_load() {
     if (g_nccl.lib) return SVMB200_OK;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -48,6 +70,7 @@ static int nccl_load() {
     g_nccl.lib = h;
     return SVMB200_OK;
 }
+#endif
 
 #define SVM_NCCL(call)                                                                        \
     do {                                                                                      \

@@ -82,16 +82,25 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
     return r;
 }
 #else
-// tests/cuda_emu compiles this file for the host (the kernels run thread by thread on fibers): same entry format and
-// loads, without the PTX
+// tests/cuda_emu compiles this file for the host (the kernels run thread by thread on fibers, ranks are host threads):
+// same entry format, same wait-until-both-tags-match protocol, without the PTX
 __device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned tag) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
-    p->x = (b & 0xffffffffull) | t;
-    p->y = (b >> 32) | t;
+    __atomic_store_n(&p->x, (b & 0xffffffffull) | t, __ATOMIC_RELEASE);
+    __atomic_store_n(&p->y, (b >> 32) | t, __ATOMIC_RELEASE);
 }
 __device__ __forceinline__ double ll_load(const ulonglong2* p, unsigned tag, int* fault) {
-    if ((unsigned)(p->x >> 32) != tag || (unsigned)(p->y >> 32) != tag) *fault = 1;  // single rank: never waits
-    return __longlong_as_double((long long)((p->y << 32) | (p->x & 0xffffffffull)));
+    unsigned long long w0, w1;
+    for (unsigned long long spins = 0;; ++spins) {
+        w0 = __atomic_load_n(&p->x, __ATOMIC_ACQUIRE);
+        w1 = __atomic_load_n(&p->y, __ATOMIC_ACQUIRE);
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+        if (emu::spin_wait(spins)) {  // yields the host thread; true after 20 s
+            *fault = 1;
+            break;
+        }
+    }
+    return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
 }
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) { return *p; }
 #endif

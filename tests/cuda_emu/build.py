@@ -1,9 +1,10 @@
 """Build the host emulation of libsvmb200 for the CPU test-suite  --  TEST INFRASTRUCTURE ONLY.
 
-``pg.cu`` (all solver kernels and their drivers), ``api.cu`` and ``hostmath.cu`` are compiled FROM THE PRODUCT SOURCES
+``pg.cu`` (all solver kernels and their drivers), ``api.cu``, ``comm.cu`` and ``hostmath.cu`` are compiled FROM THE PRODUCT SOURCES
 with g++ against the stand-in ``include/cuda_runtime.h``; the only source transformation is the launch syntax,
 ``k<<<grid, block, smem, stream>>>(args)`` -> ``emu::launch(grid, block, [=]() { k(args); })``, applied to a scratch
-copy under ``_build/`` (git-ignored).  ``gram.cu`` / ``comm.cu`` are replaced by ``emu_standins.cpp``.  Nothing under
+copy under ``_build/`` (git-ignored).  ``gram.cu`` is replaced by ``emu_standins.cpp``; NCCL and CUDA IPC by in-process
+stand-ins (ranks are threads).  Nothing under
 ``optiml_b200/`` knows about this library; tests load it explicitly.
 """
 import os
@@ -15,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'optiml_b200', 'csrc')
 BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(BUILD, 'libsvmb200_emu.so')
-PRODUCT_SOURCES = ['pg.cu', 'api.cu', 'hostmath.cu']
+PRODUCT_SOURCES = ['pg.cu', 'api.cu', 'comm.cu', 'hostmath.cu']
 HARNESS_SOURCES = ['emu_runtime.cpp', 'emu_standins.cpp']
 CXXFLAGS = ['-O1', '-g', '-std=c++17', '-fPIC', '-ffp-contract=off', '-fno-omit-frame-pointer', '-DSVMB200_HOST_EMULATION',
             '-Wall', '-Wno-unknown-pragmas', '-Wno-unused-function', '-Wno-unused-variable']

@@ -13,12 +13,15 @@
 // fenced by canaries that cudaFree checks.
 #include <cuda_runtime.h>
 
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <random>
 #include <string>
@@ -120,6 +123,16 @@ double shfl_xor(double v, int lane_mask) {
     f.state = AT_SHFL;
     yield_to_scheduler();
     return g_run->fibers[g_run->current].shfl_val;
+}
+
+bool spin_wait(unsigned long long spins) {
+    static thread_local std::chrono::steady_clock::time_point t0;
+    if (spins == 0) t0 = std::chrono::steady_clock::now();
+    if ((spins & 63) == 63) {
+        sched_yield();
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) return true;
+    }
+    return false;
 }
 
 static void prepare_fiber(BlockRunner& r, int t) {
@@ -313,6 +326,20 @@ cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) {
     memset(p, value, bytes);
     return cudaSuccess;
 }
+cudaError_t cudaMemset(void* p, int value, size_t bytes) {
+    memset(p, value, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+    memset(h, 0, sizeof(*h));
+    memcpy(h->reserved, &p, sizeof(p));
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+    memcpy(p, h.reserved, sizeof(*p));
+    return *p ? cudaSuccess : cudaErrorInvalidValue;
+}
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
     *s = reinterpret_cast<cudaStream_t>(new int(0));
     return cudaSuccess;
@@ -366,4 +393,93 @@ void emu_clear_error(void) {
 }
 uint64_t emu_launches(void) { return emu::g_launches; }
 uint64_t emu_blocks(void) { return emu::g_blocks; }
+}
+
+// ---------------------------------------------------------------------------------------------- NCCL stand-in
+// Ranks are THREADS of the test process (one svmb200 context each).  A communicator is a slot in a "world" keyed by
+// the unique id; ncclCommInitRank blocks until every rank has joined (like NCCL), ncclAllGather is a barrier, a copy
+// of every peer's slice out of the peer's own buffer, and a second barrier.  comm.cu binds these instead of
+// dlopen("libnccl.so.2") when it is compiled for the emulation.
+namespace emu {
+struct World {
+    int nranks = 0;
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0;
+    uint64_t generation = 0;
+    std::vector<void*> bufs;
+    bool wait(double seconds = 60.0) {  // all ranks arrive, or time out (a rank died): false
+        std::unique_lock<std::mutex> lock(m);
+        const uint64_t gen = generation;
+        if (++arrived == nranks) {
+            arrived = 0;
+            ++generation;
+            cv.notify_all();
+            return true;
+        }
+        return cv.wait_for(lock, std::chrono::duration<double>(seconds), [&] { return generation != gen; });
+    }
+};
+struct Comm {
+    std::shared_ptr<World> world;
+    int rank;
+};
+static std::mutex g_world_mutex;
+static std::map<uint64_t, std::shared_ptr<World>> g_worlds;
+static uint64_t g_next_id = 1;
+}  // namespace emu
+
+struct ncclUniqueIdEmu {
+    char internal[128];
+};
+extern "C" {
+int emu_ncclGetUniqueId(ncclUniqueIdEmu* id) {
+    std::lock_guard<std::mutex> lock(emu::g_world_mutex);
+    memset(id, 0, sizeof(*id));
+    const uint64_t v = emu::g_next_id++;
+    memcpy(id->internal, &v, sizeof(v));
+    return 0;
+}
+int emu_ncclCommInitRank(void** comm, int nranks, ncclUniqueIdEmu id, int rank) {
+    uint64_t key = 0;
+    memcpy(&key, id.internal, sizeof(key));
+    std::shared_ptr<emu::World> w;
+    {
+        std::lock_guard<std::mutex> lock(emu::g_world_mutex);
+        auto& slot = emu::g_worlds[key];
+        if (!slot) {
+            slot = std::make_shared<emu::World>();
+            slot->nranks = nranks;
+            slot->bufs.assign((size_t)nranks, nullptr);
+        }
+        w = slot;
+    }
+    if (w->nranks != nranks || rank < 0 || rank >= nranks) return 4;
+    if (!w->wait()) return 6;
+    *comm = new emu::Comm{w, rank};
+    return 0;
+}
+int emu_ncclCommDestroy(void* comm) {
+    delete static_cast<emu::Comm*>(comm);
+    return 0;
+}
+int emu_ncclAllGather(const void*, void* recv, size_t count, int dtype, void* comm, cudaStream_t) {
+    emu::Comm* c = static_cast<emu::Comm*>(comm);
+    if (dtype != 8) return 4;  // ncclFloat64
+    emu::World& w = *c->world;
+    w.bufs[(size_t)c->rank] = recv;
+    if (!w.wait()) return 6;
+    for (int r = 0; r < w.nranks; ++r) {
+        if (r == c->rank) continue;
+        memcpy(static_cast<double*>(recv) + (size_t)r * count, static_cast<const double*>(w.bufs[(size_t)r]) + (size_t)r * count,
+               count * sizeof(double));
+    }
+    if (!w.wait()) return 6;
+    return 0;
+}
+const char* emu_ncclGetErrorString(int code) { return code == 6 ? "emulated NCCL: a rank did not arrive" : "emulated NCCL error"; }
+int emu_ncclGetVersion(int* v) {
+    *v = 22809;
+    return 0;
+}
 }

@@ -1,9 +1,9 @@
 // tests/cuda_emu -- stand-ins for the parts of the library that cannot be emulated  (TEST INFRASTRUCTURE ONLY).
 //
-// gram.cu (TMA + DMMA tensor-core kernel) and comm.cu (NCCL, CUDA IPC) are NOT compiled into the emulated library.
-// svmb200_gram below is a plain host loop with the same contract (include/svmb200.h) so that whole fits can run
-// through the emulated solver kernels; it says nothing about K1 itself, which is checked on the GPU.  The
-// communicator entry points fail: the emulation is single-rank.
+// gram.cu (TMA + DMMA tensor-core kernel) is NOT compiled into the emulated library.  svmb200_gram below is a plain
+// host loop with the same contract (include/svmb200.h) so that whole fits can run through the emulated solver
+// kernels; it says nothing about K1 itself, which is checked on the GPU.  (comm.cu IS compiled: CUDA IPC and the six
+// NCCL entry points it binds have in-process stand-ins in emu_runtime.cpp, ranks being threads.)
 #include "common.cuh"
 
 extern "C" int64_t svmb200_padded_ld(int64_t ncols) { return round_up64(ncols < 1 ? 1 : ncols, 16); }
@@ -50,23 +50,4 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
     }
     ctx->launches++;
     return SVMB200_OK;
-}
-
-static int single_rank_only(const char* what) {
-    svmb200_set_error("%s: the host emulation is single-rank", what);
-    return SVMB200_ERR_NCCL;
-}
-extern "C" int svmb200_comm_unique_id(void*) { return single_rank_only("svmb200_comm_unique_id"); }
-extern "C" int svmb200_comm_init(svmb200_ctx*, const void*, int, int) { return single_rank_only("svmb200_comm_init"); }
-extern "C" int svmb200_comm_destroy(svmb200_ctx*) { return SVMB200_OK; }
-extern "C" int svmb200_comm_p2p_export(svmb200_ctx*, size_t, void*) { return single_rank_only("svmb200_comm_p2p_export"); }
-extern "C" int svmb200_comm_p2p_attach(svmb200_ctx*, const void*, int) { return single_rank_only("svmb200_comm_p2p_attach"); }
-extern "C" int svmb200_comm_p2p_disable(svmb200_ctx*) { return SVMB200_OK; }
-extern "C" int svmb200_comm_p2p_enabled(svmb200_ctx*, int* enabled) {
-    if (enabled) *enabled = 0;
-    return SVMB200_OK;
-}
-int svm_comm_allgather(svmb200_ctx* ctx, double*, int64_t) {
-    if (ctx->nranks <= 1) return SVMB200_OK;
-    return single_rank_only("svm_comm_allgather");
 }

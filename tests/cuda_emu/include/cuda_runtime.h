@@ -33,6 +33,7 @@ extern thread_local uint3 threadIdx_, blockIdx_;
 extern thread_local dim3 blockDim_, gridDim_;
 void syncthreads();
 double shfl_xor(double v, int lane_mask);
+bool spin_wait(unsigned long long spins);  // called from a wait loop on peer memory: yield; true once 20 s have passed
 }  // namespace emu
 #define threadIdx (emu::threadIdx_)
 #define blockIdx (emu::blockIdx_)
@@ -91,6 +92,15 @@ cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
+cudaError_t cudaMemset(void* p, int value, size_t bytes);
+// CUDA IPC between "ranks" that are threads of this process: the handle carries the pointer
+struct cudaIpcMemHandle_t {
+    char reserved[64];
+};
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void* p);
 cudaError_t cudaGetLastError();
 const char* cudaGetErrorString(cudaError_t e);
 

@@ -1,0 +1,138 @@
+"""SURVEY.md 8(e) on the host emulation: row-sharded solves with ranks as THREADS of the test process.
+
+Each thread owns a context (= one emulated GPU), joins the communicator through the product's own comm.cu (NCCL and
+CUDA IPC replaced by in-process stand-ins, tests/cuda_emu/emu_runtime.cpp) and runs the real solver kernels on its
+row shard.  Both exchange paths are driven: the all-gather, and the fused peer-memory exchange (K2 stores tagged
+entries straight into every rank's arena, K3 waits on them).  The property asserted is the one the GPU runs showed at
+2 and 8 GPUs: the iterate is BIT-IDENTICAL to the single-rank solve for every rank count, including ragged and empty
+shards.  What the emulation cannot show: memory ordering over NVLink, timing.
+"""
+import ctypes as C
+import threading
+import warnings
+
+import numpy as np
+import pytest
+
+import shared_gram_checks as S
+from emu import emulated_device
+from optiml_b200 import _native as N
+
+
+def run_ranks(nranks, exchange, body):
+    """body(ctx) on `nranks` threads, each with its own context attached to one communicator; returns the results in
+    rank order.  exchange: 'nccl' (all-gather) or 'p2p' (fused peer-memory exchange)."""
+    from optiml_b200.runtime import Context
+    uid = Context.new_unique_id()
+    gate = threading.Barrier(nranks)
+    handles, results, errors = [None] * nranks, [None] * nranks, []
+
+    def main(rank):
+        try:
+            ctx = Context(device=0)
+            ctx.attach_communicator(rank, nranks, uid)
+            if exchange == 'p2p':
+                buf = C.create_string_buffer(64)
+                N.call('svmb200_comm_p2p_export', ctx.handle, 1 << 20, C.cast(buf, C.c_void_p))
+                handles[rank] = buf.raw
+                gate.wait(timeout=60)
+                blob = C.create_string_buffer(b''.join(handles), 64 * nranks)
+                N.call('svmb200_comm_p2p_attach', ctx.handle, C.cast(blob, C.c_void_p), nranks)
+                gate.wait(timeout=60)
+                assert ctx.exchange == 'p2p'
+            else:
+                assert ctx.exchange == ('nccl' if nranks > 1 else 'none')
+            results[rank] = body(ctx)
+            assert N.load_library().emu_sticky_error() == 0
+            gate.wait(timeout=120)   # nobody tears its arena down while a peer may still store into it
+            ctx._finalizer()
+        except BaseException as exc:  # noqa: surfaced in the main thread below
+            errors.append((rank, exc))
+            gate.abort()
+
+    threads = [threading.Thread(target=main, args=(r,)) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    if errors:
+        raise errors[0][1]
+    assert not any(t.is_alive() for t in threads), 'a rank is stuck'
+    return results
+
+
+def shard_hessian(ctx, M, layout='plain'):
+    from optiml_b200.runtime import DeviceHessian
+    n = M.shape[0]
+    H = DeviceHessian(ctx, n, layout)
+    block = np.zeros((max(H.nrows, 1), H.ld))
+    block[:H.nrows, :n] = M[H.row0:H.row0 + H.nrows]
+    ctx.h2d(H.matrix.dptr, block)
+    return H
+
+
+def solve(kind, H, q, ub, max_iter):
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import AugmentedLagrangianQuadratic, FrankWolfe, ProjectedGradient
+    from optiml_b200.opti.unconstrained.stochastic import Adam
+    quad = Quadratic(H, q)
+    if kind == 'pg':
+        s = ProjectedGradient(quad=quad, ub=ub, max_iter=max_iter)
+    elif kind == 'fw':
+        s = FrankWolfe(quad=quad, ub=ub, max_iter=max_iter, t=0.1)
+    else:
+        f = AugmentedLagrangianQuadratic(primal=quad, lb=np.zeros_like(ub), ub=ub, rho=1.)
+        s = Adam(f=f, step_size=0.05, epochs=max_iter, random_state=3, tol=1e-6, momentum_type='polyak', momentum=0.3)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        s.minimize()
+    return S.solver_state(s)
+
+
+@pytest.mark.parametrize('kind,layout,n,nranks,exchange', [
+    ('pg', 'plain', 200, 2, 'nccl'), ('pg', 'plain', 200, 2, 'p2p'), ('pg', 'plain', 200, 3, 'p2p'),
+    ('pg', 'plain', 70, 4, 'p2p'),       # 64-row shards: ranks 2 and 3 own nothing
+    ('pg', 'svr', 150, 2, 'p2p'), ('fw', 'plain', 130, 3, 'nccl'), ('fw', 'plain', 130, 2, 'p2p'),
+    ('adam', 'plain', 130, 2, 'p2p'), ('adam', 'svr', 100, 2, 'nccl'),
+])
+def test_sharded_solve_is_bit_identical_to_one_rank(kind, layout, n, nranks, exchange):
+    rng = np.random.default_rng(n + nranks)
+    M = S.psd(rng, n)
+    nv = 2 * n if layout == 'svr' else n
+    q, ub = rng.standard_normal(nv), np.full(nv, 1.5)
+    max_iter = 10
+    with emulated_device():
+        one = run_ranks(1, 'nccl', lambda ctx: solve(kind, shard_hessian(ctx, M, layout), q, ub, max_iter))[0]
+        many = run_ranks(nranks, exchange, lambda ctx: solve(kind, shard_hessian(ctx, M, layout), q, ub, max_iter))
+    for rank_state in many:
+        for a, b in zip(one, rank_state):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('kind,count,nranks', [('pg', 3, 2), ('fw', 5, 2), ('adagrad', 2, 3)])
+def test_sharded_lockstep_batch_is_bit_identical_to_one_rank(kind, count, nranks):
+    """the batched (one-vs-rest) driver on row shards: all-gather per problem"""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.batch import minimize_batch
+    rng = np.random.default_rng(count + nranks)
+    n = 150
+    M = S.psd(rng, n, shift=0.0) + 1.0
+    signs = [np.where(rng.random(n) < 0.4, 1.0, -1.0) for _ in range(count)]
+    q, ub = -np.ones(n), np.ones(n)
+
+    def body(ctx):
+        shared = shard_hessian(ctx, M)
+        solvers = S.make_solvers(kind, lambda c: Quadratic(shared.with_signs(signs[c]), q), signs, ub, 8, [1e-6])
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            minimize_batch(solvers)
+        assert all(s.batch_size_ == count for s in solvers)
+        return [S.solver_state(s) for s in solvers]
+
+    with emulated_device():
+        one = run_ranks(1, 'nccl', body)[0]
+        for exchange in ('nccl', 'p2p'):
+            for rank_states in run_ranks(nranks, exchange, body):
+                for sa, sb in zip(one, rank_states):
+                    for a, b in zip(sa, sb):
+                        assert np.array_equal(a, b)
