@@ -208,8 +208,9 @@ int svmb200_al_multipliers(svmb200_pg* pg, double* mu, double* lam_lb_host, doub
  *     share the matrix, shard and layout to termination in lockstep: per iteration ceil(count/4) passes over M
  *     (K2 with up to four vector operands per pass, per-vector results bit-identical to svmb200_matvec) and one
  *     vector launch for all problems.  Each solver keeps its own state / history / stopping test and afterwards
- *     answers svmb200_pg_state / _history / _scalars / _al_multipliers as after svmb200_pg_run.  Multi-GPU batches
- *     exchange with ncclAllGather.  iters / statuses: `count` entries each (may be NULL).
+ *     answers svmb200_pg_state / _history / _scalars / _al_multipliers as after svmb200_pg_run.  Multi-GPU batches use
+ *     the fused peer exchange (own arena region, one tag per iteration for all problems) when it is enabled and the
+ *     region fits the arena, ncclAllGather per problem otherwise.  iters / statuses: `count` entries each (may be NULL).
  * Also usable without signs (SVR layout included): several right-hand sides q against one matrix
  * (sklearn MultiOutputRegressor(SVR(...))).                                                                         */
 int svmb200_pg_create_signed(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t row0, int64_t nrows,

@@ -359,6 +359,12 @@ struct MatvecMultiArgs {
     const double* u_rows[MV_MULTI_MAX];  // u at this shard's rows, or null
     double* denpart[MV_MULTI_MAX];       // one share of u'w per 64-row group, or null
     const int* done[MV_MULTI_MAX];       // problem b finished: its results are not stored (may be null)
+    // fused exchange (nranks_x > 0), as in MatvecArgs: results of problem b go to peer_w[p] + b * xstride (+ row for
+    // w, + share_off + group for the u'w share) in every rank's arena as tagged entries
+    int nranks_x;
+    unsigned tag;
+    long long xstride, share_off;
+    ulonglong2* peer_w[SVM_MAX_RANKS];
 };
 
 template <int NB>
@@ -485,7 +491,13 @@ __global__ void __launch_bounds__(MV_NT, MultiCfg<NB>::MINB) matvec_seg_multi_ke
                 double v = 0.0;
                 const double* wp = a.wpart + (size_t)bb * pstride + rr;
                 for (int s = 0; s < a.nseg; ++s) v += __ldcg(wp + (size_t)s * a.nrows_pad);
-                if (live[bb]) a.w[bb][rr] = v;
+                if (live[bb]) {
+                    if (a.nranks_x > 0) {
+                        for (int p = 0; p < a.nranks_x; ++p) ll_store(a.peer_w[p] + bb * a.xstride + rr, v, a.tag);
+                    } else {
+                        a.w[bb][rr] = v;
+                    }
+                }
                 if (a.u_rows[bb] != nullptr) dv = __dmul_rn(a.u_rows[bb][rr], v);
             }
         }
@@ -500,15 +512,23 @@ __global__ void __launch_bounds__(MV_NT, MultiCfg<NB>::MINB) matvec_seg_multi_ke
     if (threadIdx.x < NB) {
 #pragma unroll
         for (int bb = 0; bb < NB; ++bb) {
-            if (bb == (int)threadIdx.x && a.denpart[bb] != nullptr && live[bb])
-                a.denpart[bb][group] = __dadd_rn(red2[bb][0], red2[bb][1]);
+            if (bb == (int)threadIdx.x && a.denpart[bb] != nullptr && live[bb]) {
+                const double tot = __dadd_rn(red2[bb][0], red2[bb][1]);
+                if (a.nranks_x > 0) {
+                    for (int p = 0; p < a.nranks_x; ++p)
+                        ll_store(a.peer_w[p] + bb * a.xstride + a.share_off + group, tot, a.tag);
+                } else {
+                    a.denpart[bb][group] = tot;
+                }
+            }
         }
     }
 }
 
 static int launch_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, int nb,
                                const double* const* du, double* const* dw, const double* const* du_rows,
-                               double* const* ddenpart, const int* const* d_done) {
+                               double* const* ddenpart, const int* const* d_done, const ExchangeTargets* xt = nullptr,
+                               long long xstride = 0, long long share_off = 0) {
     if (nrows <= 0) return SVMB200_OK;
     if (nb < 1 || nb > MV_MULTI_MAX) {
         svmb200_set_error("matvec_multi: between 1 and %d vectors per launch", MV_MULTI_MAX);
@@ -543,6 +563,13 @@ static int launch_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows
         a.u_rows[b] = du_rows ? du_rows[b] : nullptr;
         a.denpart[b] = ddenpart ? ddenpart[b] : nullptr;
         a.done[b] = d_done ? d_done[b] : nullptr;
+    }
+    if (xt != nullptr) {
+        a.nranks_x = xt->nranks;
+        a.tag = xt->tag;
+        a.xstride = xstride;
+        a.share_off = share_off;
+        for (int r = 0; r < xt->nranks; ++r) a.peer_w[r] = xt->peer_w[r];
     }
     const int64_t ngroups = (nrows + MV_GROUP - 1) / MV_GROUP;
     int64_t nitems = 0;
@@ -637,6 +664,7 @@ struct VecArgs {
     const ulonglong2* gathered_ll;
     unsigned tag;
     int* fault;
+    long long ll_pstride;  // batched solves: entries between the two parity copies of this problem's gathered buffer
     // label signs (nvars entries of +-1, or null): the resident matrix is M and the problem is posed on
     // Q = (s s') o M.  Q u = s o (M (s o u)) is exact for s = +-1, so the vector kernels sign w on the way in and
     // u on the way out and K2 never sees the signs -- several such problems can share one pass over M (one-vs-rest)
@@ -1228,20 +1256,33 @@ template <int MODE>
 __global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const ALArgs al, const long long k) {
     al_vector_body<MODE>(a, al, k);
 }
+// The argument blocks are constant over a run except for the fused exchange: the tag and the parity of the gathered
+// buffer change with every product and come as launch parameters.
+__device__ __forceinline__ VecArgs batch_args(const VecArgs* __restrict__ args, unsigned tag, int parity) {
+    VecArgs a = args[blockIdx.y];
+    if (a.gathered_ll != nullptr) {
+        a.gathered_ll += (size_t)parity * a.ll_pstride;
+        a.tag = tag;
+    }
+    return a;
+}
 template <int MODE>
-__global__ void __launch_bounds__(VP_NT) pg_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k) {
-    const VecArgs a = args[blockIdx.y];
+__global__ void __launch_bounds__(VP_NT) pg_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k,
+                                                                const unsigned tag, const int parity) {
+    const VecArgs a = batch_args(args, tag, parity);
     pg_vector_body<MODE>(a, k);
 }
 template <int MODE>
-__global__ void __launch_bounds__(VP_NT) fw_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k) {
-    const VecArgs a = args[blockIdx.y];
+__global__ void __launch_bounds__(VP_NT) fw_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k,
+                                                                const unsigned tag, const int parity) {
+    const VecArgs a = batch_args(args, tag, parity);
     fw_vector_body<MODE>(a, k);
 }
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) al_vector_batch_kernel(const VecArgs* __restrict__ args,
-                                                                const ALArgs* __restrict__ als, const long long k) {
-    const VecArgs a = args[blockIdx.y];
+                                                                const ALArgs* __restrict__ als, const long long k,
+                                                                const unsigned tag, const int parity) {
+    const VecArgs a = batch_args(args, tag, parity);
     const ALArgs al = als[blockIdx.y];
     al_vector_body<MODE>(a, al, k);
 }
@@ -1298,6 +1339,7 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
     a.gathered_ll = nullptr;
     a.tag = 0;
     a.fault = nullptr;
+    a.ll_pstride = 0;
     if (pg->p2p) {
         svmb200_ctx* ctx = pg->ctx;
         const size_t bufbytes = (size_t)pg->stride * ctx->nranks * sizeof(ulonglong2);
@@ -1744,10 +1786,22 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
 // instead of `count`, and one vector launch for all problems.  Every problem keeps its own state, histories and
 // stopping tests -- one that finishes early ignores the remaining launches -- and, because the multi-vector pass
 // reproduces the single-vector reductions bit for bit, ends exactly where its own svmb200_pg_run would have.
-// Multi-GPU: the product shards of every problem are exchanged with ncclAllGather (the fused peer exchange of the
-// single solves is not used here).
-static int batch_product(svmb200_ctx* ctx, svmb200_pg* const* pgs, int count) {
+// Multi-GPU: the fused peer exchange of the single solves carries over -- K2 x NB stores every problem's shard into
+// every rank's arena as tagged entries, the vector launch waits on the entries it reads; one sequence number (tag,
+// buffer parity) per iteration for the whole batch.  The batch has its own arena region behind the two buffers of
+// the single-solver layout (whose last reader, a member's INIT launch, may still be running on a slower rank when
+// the first batched product of a faster rank arrives).  Without peer access: one ncclAllGather per problem.
+struct BatchExchange {
+    bool p2p = false;
+    size_t base = 0;        // arena offset of the batch region
+    size_t bufbytes = 0;    // one problem's gathered buffer (stride * nranks tagged entries)
+    unsigned long long seq = 0;
+};
+
+static int batch_product(svmb200_ctx* ctx, svmb200_pg* const* pgs, int count, BatchExchange& bx) {
     const int nlaunch = (count + MV_MULTI_MAX - 1) / MV_MULTI_MAX;
+    svmb200_pg* p0 = pgs[0];
+    if (bx.p2p) bx.seq = ++ctx->xseq;
     for (int l = 0, b0 = 0; l < nlaunch; ++l) {
         const int nb = (count - b0 + (nlaunch - l) - 1) / (nlaunch - l);  // balanced split
         const double* du[MV_MULTI_MAX];
@@ -1764,10 +1818,22 @@ static int batch_product(svmb200_ctx* ctx, svmb200_pg* const* pgs, int count) {
             dden[i] = wshard + pg->rows_per_rank;
             ddone[i] = &pg->st->done;
         }
-        SVM_TRY(launch_matvec_multi(ctx, pgs[0]->dQ, pgs[0]->nrows, pgs[0]->ld, nb, du, dw, dur, dden, ddone));
+        if (bx.p2p) {
+            ExchangeTargets xt;
+            xt.nranks = ctx->nranks;
+            xt.tag = exchange_tag(bx.seq);
+            // this rank's slot of problem b0 in the parity copy of the batch region, in every rank's arena
+            const size_t slot = bx.base + (bx.seq & 1) * (size_t)count * bx.bufbytes + (size_t)b0 * bx.bufbytes +
+                                (size_t)ctx->rank * p0->stride * sizeof(ulonglong2);
+            for (int r = 0; r < ctx->nranks; ++r) xt.peer_w[r] = reinterpret_cast<ulonglong2*>(ctx->peer_arena[r] + slot);
+            SVM_TRY(launch_matvec_multi(ctx, p0->dQ, p0->nrows, p0->ld, nb, du, dw, dur, dden, ddone, &xt,
+                                        (long long)(bx.bufbytes / sizeof(ulonglong2)), (long long)p0->rows_per_rank));
+        } else {
+            SVM_TRY(launch_matvec_multi(ctx, p0->dQ, p0->nrows, p0->ld, nb, du, dw, dur, dden, ddone));
+        }
         b0 += nb;
     }
-    if (ctx->nranks > 1) {
+    if (!bx.p2p && ctx->nranks > 1) {
         for (int b = 0; b < count; ++b) SVM_TRY(svm_comm_allgather(ctx, pgs[b]->w, pgs[b]->stride));
     }
     for (int b = 0; b < count; ++b) pgs[b]->last_passes += nlaunch;
@@ -1776,21 +1842,31 @@ static int batch_product(svmb200_ctx* ctx, svmb200_pg* const* pgs, int count) {
 
 template <int MODE>
 static int launch_vec_batch(svmb200_ctx* ctx, int solver, int nctas, int count, const VecArgs* dva, const ALArgs* dal,
-                            long long k) {
+                            long long k, const BatchExchange& bx) {
     const dim3 grid((unsigned)nctas, (unsigned)count);
-    if (solver == 2) al_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, dal, k);
-    else if (solver == 1) fw_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, k);
-    else pg_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, k);
+    const unsigned tag = bx.p2p ? exchange_tag(bx.seq) : 0u;
+    const int parity = bx.p2p ? (int)(bx.seq & 1) : 0;
+    if (solver == 2) al_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, dal, k, tag, parity);
+    else if (solver == 1) fw_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, k, tag, parity);
+    else pg_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, k, tag, parity);
     ctx->launches++;
     SVM_CUDA(cudaGetLastError());
     return SVMB200_OK;
 }
 
 // one copy per problem, one synchronisation; returns the number of problems still running
-static int batch_poll(svmb200_ctx* ctx, svmb200_pg* const* pgs, int count, int* running) {
+static int batch_poll(svmb200_ctx* ctx, svmb200_pg* const* pgs, int count, int* running, const BatchExchange& bx) {
     for (int b = 0; b < count; ++b)
         SVM_CUDA(cudaMemcpyAsync(pgs[b]->st_host, pgs[b]->st, sizeof(PGDeviceState), cudaMemcpyDeviceToHost, ctx->stream));
     SVM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bx.p2p) {
+        int fault = 0;
+        SVM_CUDA(cudaMemcpy(&fault, ctx->arena + ARENA_LOCAL_OFF + 8, sizeof(int), cudaMemcpyDeviceToHost));
+        if (fault) {
+            svmb200_set_error("peer exchange timed out: a rank stopped publishing its product shards");
+            return SVMB200_ERR_STATE;
+        }
+    }
     int r = 0;
     for (int b = 0; b < count; ++b) {
         if (pgs[b]->st_host->done) pgs[b]->finished = true;
@@ -1816,10 +1892,17 @@ extern "C" int svmb200_pg_run_batch(svmb200_pg* const* pgs, int count, int64_t* 
     }
     svmb200_ctx* ctx = p0->ctx;
     SVM_TRY(svm_use(ctx));
+    // fused peer exchange when every member was created with it and the batch region fits the arena (the same
+    // decision on every rank: it depends on sizes only)
+    BatchExchange bx;
+    bx.bufbytes = (size_t)p0->stride * ctx->nranks * sizeof(ulonglong2);
+    bx.base = ARENA_DATA_OFF + 2 * bx.bufbytes;
+    bx.p2p = ctx->p2p_enabled && ctx->nranks > 1 && bx.base + 2 * (size_t)count * bx.bufbytes <= ctx->arena_bytes;
+    for (int b = 0; b < count; ++b) bx.p2p = bx.p2p && pgs[b]->p2p;
     // per-problem slab pointers differ, so every problem needs its own pinned state block (the context owns one)
     for (int b = 0; b < count; ++b) {
+        pgs[b]->p2p = false;  // the members' own (single-solver) exchange path is not used from here on
         for (int c = 0; c < b; ++c) SVM_CHECK_ARG(pgs[c]->st_host != pgs[b]->st_host, "solvers share a state block");
-        pgs[b]->p2p = false;  // products go to the solver's own gathered buffer from here on
         pgs[b]->mv_ev.clear();
         pgs[b]->last_passes = 0;
         pgs[b]->last_ms = pgs[b]->last_mv_ms = pgs[b]->last_comm_ms = pgs[b]->last_vec_ms = 0.f;
@@ -1833,7 +1916,14 @@ extern "C" int svmb200_pg_run_batch(svmb200_pg* const* pgs, int count, int64_t* 
     ALArgs* dal = solver == 2 ? reinterpret_cast<ALArgs*>(static_cast<unsigned char*>(ctx->batch_buf) + va_bytes) : nullptr;
     {
         std::vector<VecArgs> hv((size_t)count);
-        for (int b = 0; b < count; ++b) hv[b] = make_vec_args(pgs[b]);
+        for (int b = 0; b < count; ++b) {
+            hv[b] = make_vec_args(pgs[b]);
+            if (bx.p2p) {
+                hv[b].gathered_ll = reinterpret_cast<const ulonglong2*>(ctx->arena + bx.base + (size_t)b * bx.bufbytes);
+                hv[b].ll_pstride = (long long)((size_t)count * bx.bufbytes / sizeof(ulonglong2));
+                hv[b].fault = reinterpret_cast<int*>(ctx->arena + ARENA_LOCAL_OFF + 8);
+            }
+        }
         SVM_CUDA(cudaMemcpyAsync(dva, hv.data(), (size_t)count * sizeof(VecArgs), cudaMemcpyHostToDevice, ctx->stream));
         if (solver == 2) {
             std::vector<ALArgs> ha((size_t)count);
@@ -1850,16 +1940,16 @@ extern "C" int svmb200_pg_run_batch(svmb200_pg* const* pgs, int count, int64_t* 
     while (k < max_iter && running > 0) {
         const int64_t nb = max_iter - k < BATCH ? max_iter - k : BATCH;
         for (int64_t i = 0; i < nb; ++i, ++k) {
-            SVM_TRY(batch_product(ctx, pgs, count));
-            SVM_TRY(launch_vec_batch<VP_STEP>(ctx, solver, p0->nctas, count, dva, dal, k));
+            SVM_TRY(batch_product(ctx, pgs, count, bx));
+            SVM_TRY(launch_vec_batch<VP_STEP>(ctx, solver, p0->nctas, count, dva, dal, k, bx));
         }
-        SVM_TRY(batch_poll(ctx, pgs, count, &running));
+        SVM_TRY(batch_poll(ctx, pgs, count, &running, bx));
     }
     if (running > 0) {
         // state at callback point max_iter (see svmb200_pg_run): the epoch / iteration limit ends every problem left
-        if (solver == 2) SVM_TRY(batch_product(ctx, pgs, count));
-        SVM_TRY(launch_vec_batch<VP_FINALISE>(ctx, solver, p0->nctas, count, dva, dal, k));
-        SVM_TRY(batch_poll(ctx, pgs, count, &running));
+        if (solver == 2) SVM_TRY(batch_product(ctx, pgs, count, bx));
+        SVM_TRY(launch_vec_batch<VP_FINALISE>(ctx, solver, p0->nctas, count, dva, dal, k, bx));
+        SVM_TRY(batch_poll(ctx, pgs, count, &running, bx));
     }
     SVM_CUDA(cudaEventRecord(p0->ev1, ctx->stream));
     SVM_CUDA(cudaEventSynchronize(p0->ev1));

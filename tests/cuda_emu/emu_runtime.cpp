@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <map>
@@ -463,8 +464,11 @@ int emu_ncclCommDestroy(void* comm) {
     delete static_cast<emu::Comm*>(comm);
     return 0;
 }
+static std::atomic<uint64_t> g_allgathers{0};
+uint64_t emu_allgather_calls(void) { return g_allgathers.load(); }
 int emu_ncclAllGather(const void*, void* recv, size_t count, int dtype, void* comm, cudaStream_t) {
     emu::Comm* c = static_cast<emu::Comm*>(comm);
+    ++g_allgathers;
     if (dtype != 8) return 4;  // ncclFloat64
     emu::World& w = *c->world;
     w.bufs[(size_t)c->rank] = recv;

@@ -31,6 +31,7 @@ def load():
         lib.emu_set_schedule.restype = None
         lib.emu_launches.restype = C.c_uint64
         lib.emu_blocks.restype = C.c_uint64
+        lib.emu_allgather_calls.restype = C.c_uint64
         _cached = lib
     return _cached
 

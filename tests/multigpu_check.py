@@ -82,12 +82,56 @@ def main():
                   f'ranks_identical={same_across_ranks} bitwise_equal_to_1gpu={single_ok} golden={golden_ok}', flush=True)
             ok = ok and same_across_ranks and single_ok and (golden_ok is not False)
         dist.barrier()
+    if os.environ.get('SVMB200_CHECK_SHARED_GRAM', '0') == '1':
+        ok = shared_gram_cases(dist, runtime, ctx, rank, world, local_rank) and ok
     flag = torch.tensor([1 if ok else 0], device='cuda')
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
     if rank == 0:
         print('MULTIGPU_CHECK', 'PASS' if ok else 'FAIL', flush=True)
     sys.exit(0 if int(flag.item()) else 1)
+
+
+def shared_gram_cases(dist, runtime, ctx, rank, world, local_rank):
+    """Widening 8f-4 on row shards (opt-in: SVMB200_CHECK_SHARED_GRAM=1): the one-vs-rest fit on one shared Gram
+    matrix -- lockstep solvers, fused peer exchange for the whole batch -- must be bit-identical on all ranks and to
+    the same fit on one GPU."""
+    from sklearn.datasets import make_classification
+    from optiml_b200.ml.multiclass import OneVsRestClassifier
+    from optiml_b200.ml.svm import SVC
+    from optiml_b200.ml.svm.kernels import GaussianKernel
+    from optiml_b200.ml.svm.losses import hinge
+    from optiml_b200.opti.constrained import FrankWolfe, ProjectedGradient
+    from optiml_b200.opti.unconstrained.stochastic import AdaGrad
+    ok = True
+    X, y = make_classification(n_samples=3000 + 37, n_features=24, n_informative=8, n_classes=5, random_state=0)
+    for name, opt, kw in (('pg', ProjectedGradient, {}), ('fw', FrankWolfe, {}),
+                          ('adagrad', AdaGrad, dict(learning_rate=1., random_state=2))):
+        def fit():
+            est = SVC(loss=hinge, kernel=GaussianKernel(), C=1, reg_intercept=True, dual=True, optimizer=opt, max_iter=150, **kw)
+            model = OneVsRestClassifier(est).fit(X, y)
+            blob = b''.join(e.alphas_.tobytes() + np.float64(e.intercept_).tobytes() for e in model.estimators_)
+            sizes = [e.fit_times_['batch'] for e in model.estimators_]
+            for e in model.estimators_:
+                e.obj.release()
+            return hashlib.sha256(blob).hexdigest(), sizes
+        digest, sizes = fit()
+        all_digests = [None] * world
+        dist.all_gather_object(all_digests, digest)
+        same = len(set(all_digests)) == 1 and sizes == [5] * 5
+        single = None
+        if rank == 0:
+            solo = runtime.Context(device=local_rank)
+            runtime.set_default_context(solo)
+            try:
+                single = fit()[0] == digest
+            finally:
+                runtime.set_default_context(ctx)
+            print(f'[multigpu N={world}] shared-Gram one-vs-rest ({name}, 5 classes, n={len(y)}) ranks_identical={same} '
+                  f'bitwise_equal_to_1gpu={single}', flush=True)
+            ok = ok and same and single
+        dist.barrier()
+    return ok
 
 
 if __name__ == '__main__':

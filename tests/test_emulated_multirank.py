@@ -101,9 +101,12 @@ def test_sharded_solve_is_bit_identical_to_one_rank(kind, layout, n, nranks, exc
     nv = 2 * n if layout == 'svr' else n
     q, ub = rng.standard_normal(nv), np.full(nv, 1.5)
     max_iter = 10
-    with emulated_device():
+    with emulated_device() as lib:
         one = run_ranks(1, 'nccl', lambda ctx: solve(kind, shard_hessian(ctx, M, layout), q, ub, max_iter))[0]
+        gathers = lib.emu_allgather_calls()
         many = run_ranks(nranks, exchange, lambda ctx: solve(kind, shard_hessian(ctx, M, layout), q, ub, max_iter))
+        gathers = lib.emu_allgather_calls() - gathers
+        assert gathers == 0 if exchange == 'p2p' else gathers >= nranks * max_iter
     for rank_state in many:
         for a, b in zip(one, rank_state):
             assert np.array_equal(a, b)
@@ -111,7 +114,8 @@ def test_sharded_solve_is_bit_identical_to_one_rank(kind, layout, n, nranks, exc
 
 @pytest.mark.parametrize('kind,count,nranks', [('pg', 3, 2), ('fw', 5, 2), ('adagrad', 2, 3)])
 def test_sharded_lockstep_batch_is_bit_identical_to_one_rank(kind, count, nranks):
-    """the batched (one-vs-rest) driver on row shards: all-gather per problem"""
+    """the batched (one-vs-rest) driver on row shards, with the all-gather per problem and with the fused peer exchange
+    for the whole batch (own arena region, one tag per iteration)"""
     from optiml_b200.opti import Quadratic
     from optiml_b200.opti.batch import minimize_batch
     rng = np.random.default_rng(count + nranks)
@@ -129,10 +133,15 @@ def test_sharded_lockstep_batch_is_bit_identical_to_one_rank(kind, count, nranks
         assert all(s.batch_size_ == count for s in solvers)
         return [S.solver_state(s) for s in solvers]
 
-    with emulated_device():
+    with emulated_device() as lib:
         one = run_ranks(1, 'nccl', body)[0]
         for exchange in ('nccl', 'p2p'):
-            for rank_states in run_ranks(nranks, exchange, body):
+            gathers = lib.emu_allgather_calls()
+            states = run_ranks(nranks, exchange, body)
+            gathers = lib.emu_allgather_calls() - gathers
+            # the fused exchange needs no collective at all; the fallback gathers every problem's shard every pass
+            assert gathers == 0 if exchange == 'p2p' else gathers >= nranks * count * 8
+            for rank_states in states:
                 for sa, sb in zip(one, rank_states):
                     for a, b in zip(sa, sb):
                         assert np.array_equal(a, b)

@@ -88,3 +88,20 @@ def test_one_vs_rest_c1_sized_four_classes():
 
 def test_multi_output_regressor_shares_the_gram_matrix():
     S.check_multi_output(S.real_device, n=1200, max_iter=200)
+
+
+def test_sharded_one_vs_rest_is_bitwise_equal_to_single_gpu():
+    """row shards + lockstep batch + fused peer exchange for the whole batch (tests/multigpu_check.py, opt-in section)"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip('needs >= 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={2 if n < 4 else 4}',
+           '--master-addr', '127.0.0.1', '--master-port', '29519', os.path.join(root, 'tests', 'multigpu_check.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SVMB200_CHECK_SHARED_GRAM='1'))
+    assert out.returncode == 0 and 'MULTIGPU_CHECK PASS' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count('shared-Gram one-vs-rest') == 3
