@@ -20,26 +20,30 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose=False, force=False):
-    os.makedirs(LIB_DIR, exist_ok=True)
+def build(verbose=False, force=False, defines=(), lib_dir=None):
+    """``defines`` / ``lib_dir``: a variant of the library (``-DNAME=VALUE`` flags) built into its own directory --
+    used by the tuning sweeps in scripts/, loaded through the SVMB200_LIB environment variable."""
+    lib_dir = lib_dir or LIB_DIR
+    lib = os.path.join(lib_dir, 'libsvmb200.so')
+    os.makedirs(lib_dir, exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
     objs = []
     for src in SOURCES:
         s = os.path.join(HERE, src)
-        o = os.path.join(LIB_DIR, src.replace('.cu', '.o'))
+        o = os.path.join(lib_dir, src.replace('.cu', '.o'))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
+            cmd = [nvcc] + NVCC_FLAGS + [f'-D{d}' for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
             if verbose:
                 print(' '.join(cmd), flush=True)
             subprocess.run(cmd, check=True)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-ldl', '-lpthread']
+    if force or _stale(lib, objs):
+        cmd = [nvcc, '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-ldl', '-lpthread']
         if verbose:
             print(' '.join(cmd), flush=True)
         subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':

@@ -341,11 +341,23 @@ extern "C" int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows,
 // item) come through L2: R rows amortise them, the ratio of L2 to HBM bytes is NB / R.
 constexpr int MV_MULTI_MAX = 4;  // vectors per launch; larger batches are split into balanced launches
 
+// shape knobs, overridable at build time (scripts/sweep_multi.py): any R that divides 64 and any U keep the results
+// bit-identical, they only move the register budget and the L2 : HBM traffic ratio (NB / R)
+#ifndef SVMB200_MULTI_R
+#define SVMB200_MULTI_R 4
+#endif
+#ifndef SVMB200_MULTI_U
+#define SVMB200_MULTI_U 2
+#endif
+#ifndef SVMB200_MULTI_MINB
+#define SVMB200_MULTI_MINB 0
+#endif
 template <int NB>
 struct MultiCfg {
-    static constexpr int R = 4;                   // rows per work item
-    static constexpr int U = 2;                   // 128-bit loads in flight per row and thread
-    static constexpr int MINB = NB <= 2 ? 3 : 2;  // CTAs per SM the register budget is cut for
+    static constexpr int R = SVMB200_MULTI_R;  // rows per work item
+    static constexpr int U = SVMB200_MULTI_U;  // 128-bit loads in flight per row and thread
+    // CTAs per SM the register budget is cut for
+    static constexpr int MINB = SVMB200_MULTI_MINB > 0 ? SVMB200_MULTI_MINB : (NB <= 2 ? 3 : 2);
 };
 
 struct MatvecMultiArgs {
