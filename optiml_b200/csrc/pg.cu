@@ -352,12 +352,18 @@ constexpr int MV_MULTI_MAX = 4;  // vectors per launch; larger batches are split
 #ifndef SVMB200_MULTI_MINB
 #define SVMB200_MULTI_MINB 0
 #endif
+#ifndef SVMB200_MULTI_H
+#define SVMB200_MULTI_H 1
+#endif
 template <int NB>
 struct MultiCfg {
     static constexpr int R = SVMB200_MULTI_R;  // rows per work item
     static constexpr int U = SVMB200_MULTI_U;  // 128-bit loads in flight per row and thread
     // CTAs per SM the register budget is cut for
     static constexpr int MINB = SVMB200_MULTI_MINB > 0 ? SVMB200_MULTI_MINB : (NB <= 2 ? 3 : 2);
+    // H groups of 256 threads per CTA, each with its own R rows of the same column segment: the vector operands the
+    // groups read at about the same time are served once from L2 and H - 1 times from L1 (same results bit for bit)
+    static constexpr int H = SVMB200_MULTI_H;
 };
 
 struct MatvecMultiArgs {
@@ -380,9 +386,10 @@ struct MatvecMultiArgs {
 };
 
 template <int NB>
-__global__ void __launch_bounds__(MV_NT, MultiCfg<NB>::MINB) matvec_seg_multi_kernel(const MatvecMultiArgs a) {
-    constexpr int R = MultiCfg<NB>::R, NT = MV_NT, U = MultiCfg<NB>::U, BPG = MV_GROUP / R;
-    static_assert(NB >= 1 && NB <= MV_MULTI_MAX && NB * MV_GROUP <= NT && MV_GROUP % R == 0, "bad multi-vector shape");
+__global__ void __launch_bounds__(MV_NT * MultiCfg<NB>::H, MultiCfg<NB>::MINB) matvec_seg_multi_kernel(const MatvecMultiArgs a) {
+    constexpr int R = MultiCfg<NB>::R, NT = MV_NT, U = MultiCfg<NB>::U, H = MultiCfg<NB>::H, BPG = MV_GROUP / (R * H);
+    static_assert(NB >= 1 && NB <= MV_MULTI_MAX && NB * MV_GROUP <= NT * H && MV_GROUP % (R * H) == 0 && NT * H <= 1024,
+                  "bad multi-vector shape");
     bool live[NB];
     bool any = false;
 #pragma unroll
@@ -391,18 +398,21 @@ __global__ void __launch_bounds__(MV_NT, MultiCfg<NB>::MINB) matvec_seg_multi_ke
         any = any || live[b];
     }
     if (!any) return;
+    const int half = (int)threadIdx.x / NT;         // which group of 256 threads (whole warps)
+    const int tid = (int)threadIdx.x - half * NT;   // the thread's index inside its group: the column it starts at
     const unsigned items_per_group = (unsigned)(BPG * a.nseg);
     const unsigned group = blockIdx.x / items_per_group;
     const unsigned within = blockIdx.x - group * items_per_group;
     const unsigned rb_in_group = within / (unsigned)a.nseg;
     const int seg = (int)(within - rb_in_group * (unsigned)a.nseg);
-    const long long row_base = (long long)group * MV_GROUP + (long long)rb_in_group * R;
+    const long long row_base = (long long)group * MV_GROUP + (long long)rb_in_group * (R * H) + (long long)half * R;
     const size_t pstride = (size_t)a.nseg * a.nrows_pad;  // wpart elements per problem
-    __shared__ double red[NT / 32][NB][R];
+    __shared__ double red[H][NT / 32][NB][R];
     __shared__ double red2[NB][2];
     __shared__ unsigned is_last;
+    const bool active = row_base < a.nrows;  // uniform inside a group of 256 threads
 
-    if (row_base < a.nrows) {
+    if (active) {
         const long long c0 = (long long)seg * MV_SEG;
         long long c1 = c0 + MV_SEG;
         if (c1 > a.ld) c1 = a.ld;
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(MV_NT, MultiCfg<NB>::MINB) matvec_seg_multi_ke
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[b][r] = 0.0;
         }
-        int c = threadIdx.x;
+        int c = tid;
         for (; c + (U - 1) * NT < nvec; c += U * NT) {
             double2 qv[U][R];
 #pragma unroll
@@ -458,8 +468,8 @@ __global__ void __launch_bounds__(MV_NT, MultiCfg<NB>::MINB) matvec_seg_multi_ke
                 }
             }
         }
-        // warp butterfly, then fixed-order sum over warps (the trees of matvec_seg_kernel)
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        // warp butterfly, then fixed-order sum over the group's warps (the trees of matvec_seg_kernel)
+        const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
 #pragma unroll
@@ -467,18 +477,18 @@ __global__ void __launch_bounds__(MV_NT, MultiCfg<NB>::MINB) matvec_seg_multi_ke
                 double v = acc[b][r];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) red[wid][b][r] = v;
+                if (lane == 0) red[half][wid][b][r] = v;
             }
         }
-        __syncthreads();
-        if (threadIdx.x < NB * R) {
-            const int b = threadIdx.x / R, r = threadIdx.x - b * R;
-            if (row_base + r < a.nrows) {
-                double v = 0.0;
+    }
+    __syncthreads();
+    if (active && tid < NB * R) {
+        const int b = tid / R, r = tid - b * R;
+        if (row_base + r < a.nrows) {
+            double v = 0.0;
 #pragma unroll
-                for (int k = 0; k < NT / 32; ++k) v += red[k][b][r];
-                a.wpart[(size_t)b * pstride + (size_t)seg * a.nrows_pad + row_base + r] = v;
-            }
+            for (int k = 0; k < NT / 32; ++k) v += red[half][k][b][r];
+            a.wpart[(size_t)b * pstride + (size_t)seg * a.nrows_pad + row_base + r] = v;
         }
     }
     // ---- one ticket per group; the last arriver combines the group for every problem
@@ -588,9 +598,9 @@ static int launch_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows
     switch (nb) {
 #define LAUNCH_MULTI(NB)                                                                                \
     case NB:                                                                                            \
-        nitems = ngroups * (MV_GROUP / MultiCfg<NB>::R) * a.nseg;                                       \
+        nitems = ngroups * (MV_GROUP / (MultiCfg<NB>::R * MultiCfg<NB>::H)) * a.nseg;                   \
         if (nitems >= (1ll << 31)) break;                                                               \
-        matvec_seg_multi_kernel<NB><<<(unsigned)nitems, MV_NT, 0, ctx->stream>>>(a);                    \
+        matvec_seg_multi_kernel<NB><<<(unsigned)nitems, MV_NT * MultiCfg<NB>::H, 0, ctx->stream>>>(a);  \
         break;
         LAUNCH_MULTI(1)
         LAUNCH_MULTI(2)

@@ -15,6 +15,23 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+def pytest_addoption(parser):
+    parser.addoption('--emulate', action='store_true', default=False,
+                     help='development aid: run the selected tests (e.g. -m gpu ones) on the host emulation of the solver '
+                          'kernels (tests/cuda_emu) -- slow, and the Gram kernel is a host stand-in')
+
+
+@pytest.fixture(autouse=True)
+def _emulated_device_if_requested(request):
+    if not request.config.getoption('--emulate'):
+        yield
+        return
+    from emu import emulated_device
+    with emulated_device() as lib:
+        yield
+        assert lib.emu_sticky_error() == 0
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False) as z:
         return {k: z[k] for k in z.files}

@@ -18,7 +18,10 @@ BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(BUILD, 'libsvmb200_emu.so')
 PRODUCT_SOURCES = ['pg.cu', 'api.cu', 'comm.cu', 'hostmath.cu']
 HARNESS_SOURCES = ['emu_runtime.cpp', 'emu_standins.cpp']
+# -fno-gnu-unique / -Bsymbolic: several variants of the library can live in one process (shape sweeps); the statics of
+# template kernels ("__shared__" arrays whose size depends on the shape) must not be merged across them
 CXXFLAGS = ['-O1', '-g', '-std=c++17', '-fPIC', '-ffp-contract=off', '-fno-omit-frame-pointer', '-DSVMB200_HOST_EMULATION',
+            '-fno-gnu-unique',
             '-Wall', '-Wno-unknown-pragmas', '-Wno-unused-function', '-Wno-unused-variable']
 
 _LAUNCH = re.compile(r'([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\)\s*;', re.S)
@@ -48,26 +51,47 @@ def rewrite_launches(source):
     return _LAUNCH.subn(sub, source)
 
 
-def build(force=False):
+def _stale(target, deps):
+    return not os.path.exists(target) or os.path.getmtime(target) < max(os.path.getmtime(d) for d in deps)
+
+
+def build(force=False, defines=()):
+    """The emulated library; ``defines``: a variant (the shape knobs of the multi-vector pass, which only pg.cu reads)
+    under its own name -- the other objects are compiled once and shared."""
     os.makedirs(BUILD, exist_ok=True)
-    deps = [os.path.join(CSRC, f) for f in PRODUCT_SOURCES + ['common.cuh', 'al_math.cuh']] + \
-           [os.path.join(HERE, f) for f in HARNESS_SOURCES + ['build.py', os.path.join('include', 'cuda_runtime.h')]] + \
-           [os.path.join(ROOT, 'include', 'svmb200.h')]
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
-        return LIB
-    units = []
+    defines = tuple(defines)
+    suffix = ''.join('_' + d.replace('SVMB200_', '').replace('=', '') for d in defines)
+    lib = os.path.join(BUILD, f'libsvmb200_emu{suffix}.so')
+    common = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'al_math.cuh'), os.path.join(ROOT, 'include', 'svmb200.h'),
+              os.path.join(HERE, 'include', 'cuda_runtime.h'), os.path.abspath(__file__)]
+    include = ['-I', os.path.join(HERE, 'include'), '-I', CSRC]
+    jobs, objects = [], []
     for name in PRODUCT_SOURCES:
-        text, count = rewrite_launches(open(os.path.join(CSRC, name)).read())
-        if name == 'pg.cu' and count < 8:
-            raise RuntimeError(f'only {count} kernel launches recognised in pg.cu')
-        out = os.path.join(BUILD, name.replace('.cu', '_emu.cpp'))
-        with open(out, 'w') as fh:
-            fh.write(f'#line 1 "{os.path.join(CSRC, name)}"\n' + text)
-        units.append(out)
-    units += [os.path.join(HERE, f) for f in HARNESS_SOURCES]
-    cmd = ['g++'] + CXXFLAGS + ['-I', os.path.join(HERE, 'include'), '-I', CSRC, '-shared', '-o', LIB] + units + ['-lpthread']
-    subprocess.run(cmd, check=True)
-    return LIB
+        src = os.path.join(CSRC, name)
+        variant = suffix if name == 'pg.cu' else ''
+        obj = os.path.join(BUILD, name.replace('.cu', f'_emu{variant}.o'))
+        objects.append(obj)
+        if force or _stale(obj, [src] + common):
+            text, count = rewrite_launches(open(src).read())
+            if name == 'pg.cu' and count < 8:
+                raise RuntimeError(f'only {count} kernel launches recognised in pg.cu')
+            cpp = obj[:-2] + '.cpp'
+            with open(cpp, 'w') as fh:
+                fh.write(f'#line 1 "{src}"\n' + text)
+            flags = [f'-D{d}' for d in defines] if name == 'pg.cu' else []
+            jobs.append(['g++'] + CXXFLAGS + flags + include + ['-c', cpp, '-o', obj])
+    for name in HARNESS_SOURCES:
+        src = os.path.join(HERE, name)
+        obj = os.path.join(BUILD, name.replace('.cpp', '.o'))
+        objects.append(obj)
+        if force or _stale(obj, [src] + common):
+            jobs.append(['g++'] + CXXFLAGS + include + ['-c', src, '-o', obj])
+    procs = [subprocess.Popen(cmd) for cmd in jobs]   # a handful of translation units: compile them side by side
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError('tests/cuda_emu: compilation failed')
+    if force or jobs or _stale(lib, objects):
+        subprocess.run(['g++', '-shared', '-fno-gnu-unique', '-Wl,-Bsymbolic', '-o', lib] + objects + ['-lpthread'], check=True)
+    return lib
 
 
 if __name__ == '__main__':

@@ -7,8 +7,10 @@
 //   * __shfl_xor_sync(full mask): all 32 lanes of the warp are waiting at it (a lane that has returned, or that waits
 //     at __syncthreads() instead, is an error -- on the GPU that is undefined behaviour with a full mask).
 // Anything else is a deadlock and fails the launch (sticky error, reported by cudaGetLastError / the next sync).
-// The order in which runnable fibers are resumed is selectable (forward, reverse, seeded shuffle): code that is
-// correctly synchronised gives the same bits under every order, a missing barrier usually does not.
+// The order in which runnable fibers are resumed -- and the order in which the blocks of a launch run -- is selectable
+// (forward, reverse, seeded shuffle): code that is correctly synchronised and whose reductions have a fixed shape
+// gives the same bits under every order; a missing barrier, or a result that depends on which CTA arrives last at a
+// ticket, usually does not.
 // "Device" memory is host memory, filled with 0xFF on allocation (NaNs: nothing may rely on zero-initialisation) and
 // fenced by canaries that cudaFree checks.
 #include <cuda_runtime.h>
@@ -229,12 +231,17 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& thread_body) {
     blockDim_ = block;
     gridDim_ = grid;
     ++g_launches;
-    for (unsigned by = 0; by < grid.y && !g_sticky_error; ++by) {
-        for (unsigned bx = 0; bx < grid.x && !g_sticky_error; ++bx) {
-            blockIdx_ = {bx, by, 0};
-            ++g_blocks;
-            if (!run_block(r, nt, rng)) break;
-        }
+    // blocks run one after the other -- in index order, or (order 2) in a seeded shuffle: which CTA arrives last at a
+    // ticket must not change a bit of the result
+    std::vector<uint64_t> blocks((size_t)grid.x * grid.y);
+    for (size_t i = 0; i < blocks.size(); ++i) blocks[i] = i;
+    if (g_order == 2) std::shuffle(blocks.begin(), blocks.end(), rng);
+    else if (g_order == 1) std::reverse(blocks.begin(), blocks.end());
+    for (uint64_t id : blocks) {
+        if (g_sticky_error) break;
+        blockIdx_ = {(unsigned)(id % grid.x), (unsigned)(id / grid.x), 0};
+        ++g_blocks;
+        if (!run_block(r, nt, rng)) break;
     }
     g_run = outer;
 }

@@ -13,10 +13,17 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
                             const double* dsign_a, const double* dsign_b, double bias, int64_t row0, int64_t nrows,
                             double* dout, int64_t ldo) {
     SVM_TRY(svm_use(ctx));
+    // the argument contract of csrc/gram.cu, message for message
     SVM_CHECK_ARG(dA && dB && dout, "null matrix");
     SVM_CHECK_ARG(na > 0 && nb > 0 && d > 0, "empty operand");
-    SVM_CHECK_ARG(row0 >= 0 && nrows >= 0 && row0 + nrows <= na && ldo >= nb && ldo % 2 == 0, "bad shape");
-    SVM_CHECK_ARG(kernel >= SVMB200_KERNEL_LINEAR && kernel <= SVMB200_KERNEL_LAPLACIAN, "unknown kernel");
+    SVM_CHECK_ARG(lda >= d && ldb >= d && lda % 2 == 0 && ldb % 2 == 0, "lda/ldb must be even and >= d (16-byte row stride for TMA)");
+    SVM_CHECK_ARG((reinterpret_cast<uintptr_t>(dA) & 15) == 0 && (reinterpret_cast<uintptr_t>(dB) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dout) & 15) == 0, "matrices must be 16-byte aligned");
+    SVM_CHECK_ARG(ldo >= nb && ldo % 2 == 0, "ldo must be even and >= nb");
+    SVM_CHECK_ARG(row0 >= 0 && nrows >= 0 && row0 + nrows <= na, "row range outside A");
+    SVM_CHECK_ARG(kernel >= SVMB200_KERNEL_LINEAR && kernel <= SVMB200_KERNEL_LAPLACIAN, "unknown kernel id");
+    SVM_CHECK_ARG((kernel != SVMB200_KERNEL_GAUSSIAN && kernel != SVMB200_KERNEL_LAPLACIAN) || gamma >= 0.0,
+                  "gamma must be >= 0 for the gaussian / laplacian kernels");
     for (int64_t i = row0; i < row0 + nrows; ++i) {
         const double* a = dA + i * lda;
         double* out = dout + (i - row0) * ldo;

@@ -18,30 +18,32 @@ def _builder():
     return mod
 
 
-_cached = None
+_cached = {}
 
 
-def load():
-    """The emulated library with the prototypes of include/svmb200.h bound (built on first use)."""
-    global _cached
-    if _cached is None:
+def load(defines=()):
+    """The emulated library with the prototypes of include/svmb200.h bound (built on first use).  ``defines``: a
+    variant built with other shape knobs (-DSVMB200_MULTI_R=... etc.)."""
+    key = tuple(defines)
+    if key not in _cached:
         from optiml_b200 import _native as N
-        lib = N.bind_prototypes(C.CDLL(_builder().build()))
+        lib = N.bind_prototypes(C.CDLL(_builder().build(defines=key)))
         lib.emu_set_schedule.argtypes = [C.c_int, C.c_uint]
         lib.emu_set_schedule.restype = None
         lib.emu_launches.restype = C.c_uint64
         lib.emu_blocks.restype = C.c_uint64
         lib.emu_allgather_calls.restype = C.c_uint64
-        _cached = lib
-    return _cached
+        _cached[key] = lib
+    return _cached[key]
 
 
 @contextlib.contextmanager
-def emulated_device(order=0, seed=1):
+def emulated_device(order=0, seed=1, defines=()):
     """Inside the block every call of the host mirror lands in the emulated library.  ``order``: how the emulated
-    threads of a block are resumed between barriers (0 index order, 1 alternating reversed, 2 seeded shuffle)."""
+    threads of a block are resumed between barriers and in which order the blocks of a launch run (0 index order,
+    1 reversed, 2 seeded shuffle)."""
     from optiml_b200 import _native as N, runtime
-    lib = load()
+    lib = load(defines)
     lib.emu_clear_error()
     lib.emu_set_schedule(int(order), int(seed))
     saved_lib, saved_ctx = N._lib, runtime._default_ctx

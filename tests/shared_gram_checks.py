@@ -203,6 +203,17 @@ def check_batch_argument_checks(device, **dev_kw):
         finally:
             for h, _ in created:
                 N.load_library().svmb200_pg_destroy(h)
+        # a batch of one is a plain solve
+        solo = ProjectedGradient(quad=a, ub=ub, max_iter=7).minimize()
+        single = ProjectedGradient(quad=a, ub=ub, max_iter=7)
+        h, nvars = single._create(False)
+        try:
+            it, st = (C.c_int64 * 1)(), (C.c_int * 1)()
+            N.call('svmb200_pg_run_batch', (C.c_void_p * 1)(h.value), 1, it, st)
+            single._finish_resident(h, nvars, int(it[0]), N.STATUS[int(st[0])])
+        finally:
+            N.load_library().svmb200_pg_destroy(h)
+        assert np.array_equal(single.x, solo.x) and single.iter == solo.iter and np.array_equal(single.f_hist, solo.f_hist)
         with pytest.raises(N.NativeError, match=r'\+-1'):
             H = a.device_hessian()
             bad = DeviceHessian(default_context(), n, 'plain', matrix=H.matrix, row0=H.row0, nrows=H.nrows)

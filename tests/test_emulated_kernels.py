@@ -42,8 +42,9 @@ def test_frank_wolfe_reference_goldens(golden, key, p, t):
 
 @pytest.mark.parametrize('order', [1, 2])
 def test_thread_schedule_does_not_change_a_bit(order):
-    """Resuming the threads of a block in reversed / shuffled order between barriers must not change the result: a
-    missing __syncthreads() or a read of a half-written partial would."""
+    """Resuming the threads of a block in reversed / shuffled order between barriers, and running the blocks of a
+    launch in reversed / shuffled order, must not change the result: a missing __syncthreads(), a read of a
+    half-written partial, or a reduction whose shape follows the arrival order at a ticket would."""
     from optiml_b200.opti import Quadratic
     from optiml_b200.opti.constrained import ProjectedGradient, FrankWolfe
     rng = np.random.default_rng(3)
@@ -91,8 +92,8 @@ def test_svr_block_layout_vs_oracle():
 # --------------------------------------------------------------------------------------------- shared-Gram path
 # (the same checks run on the B200 in tests/test_gpu_shared_gram.py)
 @contextlib.contextmanager
-def emu_probe(order=0, seed=1):
-    with emulated_device(order=order, seed=seed) as lib:
+def emu_probe(order=0, seed=1, defines=()):
+    with emulated_device(order=order, seed=seed, defines=defines) as lib:
         class Probe:
             def launches(self):
                 return lib.emu_launches()
@@ -111,6 +112,16 @@ def test_multi_vector_pass_is_bit_identical_to_single(n, count):
 @pytest.mark.parametrize('kind,count', [('pg', 3), ('pg', 5), ('fw', 2), ('adagrad', 3), ('adam', 2)])
 def test_signed_views_and_lockstep_batches_are_bit_identical(kind, count):
     S.check_signed_views_and_batches(emu_probe, kind, count, n=96, max_iter=14, order=2, seed=count)
+
+
+@pytest.mark.parametrize('defines', [('SVMB200_MULTI_R=2', 'SVMB200_MULTI_U=4'), ('SVMB200_MULTI_H=2',),
+                                     ('SVMB200_MULTI_H=2', 'SVMB200_MULTI_R=8', 'SVMB200_MULTI_U=1')])
+def test_every_shape_of_the_multi_vector_pass_gives_the_same_bits(defines):
+    """rows per work item (R), loads in flight (U) and thread groups per CTA (H) are tuning knobs (scripts/sweep_multi.py):
+    none of them may change a bit"""
+    S.check_multi_vector_pass(emu_probe, 131, 4, order=2, seed=5, defines=defines)
+    S.check_multi_vector_pass(emu_probe, 200, 3, order=1, defines=defines)
+    S.check_signed_views_and_batches(emu_probe, 'pg', 4, n=70, max_iter=6, defines=defines)
 
 
 def test_batch_argument_checks():
