@@ -13,220 +13,11 @@
 // GPUs, the grid or the arrival order -- so the iterate is bit-identical for 1, 2, 4 and 8 GPUs.
 #include "common.cuh"
 #include "al_math.cuh"
+#include "k2_matvec.cuh"   // K2, K2 x NB (device code)
+#include "k3_vector.cuh"   // K3 vector phases and kernel entry points (device code)
 #include <math.h>
 
-// ------------------------------------------------------------------------------------------ K2
-// Work item = MV_R consecutive rows x one column segment of MV_SEG doubles.  Every thread keeps
-// MV_R*MV_U independent 128-bit streaming loads in flight (L1 no-allocate: Q is touched once per
-// pass); the vector operand comes through L1/L2.  Rows are grouped by MV_GROUP (64): the CTA that
-// finishes a group last (one atomic ticket per group) adds the segment partials of its 64 rows in
-// segment order, stores w and the group's share of u'w.  Segmenting keeps the grid at >= 20 waves
-// even for a 1/8 row shard (tail effect) and every work item at 256 KB.
-constexpr int MV_R = 4;
-constexpr int MV_NT = 256;
-constexpr int MV_U = 4;
-constexpr int MV_SEG = 8192;
-constexpr int MV_MINB = 3;
-constexpr int MV_GROUP = 64;            // rows per group (one u'w share per group)
-constexpr int ROW_ALIGN = MV_GROUP;     // row shards start on multiples of this, see svmb200_shard_rows
-constexpr int MV_BPG = MV_GROUP / MV_R;  // row blocks per group
-
-struct MatvecArgs {
-    const double* Q;        // nrows x ld shard
-    long long ld, nrows;
-    const double* u;        // ld entries, zero beyond n
-    double* w;              // nrows results
-    double* wpart;          // nseg x nrows_pad segment partials
-    long long nrows_pad;
-    unsigned* tickets;      // one per group, zero on entry, zero again on exit
-    const double* u_rows;   // u at this shard's rows (u + row0), or null
-    double* denpart;        // one per group: sum over the group's rows of u_rows[r] * w[r], or null
-    int nseg;
-    const int* done;
-    // fused exchange (nranks_x > 0): the group combiner stores w / u'w shares straight into every rank's
-    // gathered buffer as self-validating 16-byte entries {lo32 | tag, hi32 | tag} (two single-copy-atomic
-    // 8-byte words, tag = sequence number of the product): no fence, no flag, no counter -- the reader
-    // spins on the entry it needs until both tags match (the "LL" idea of NCCL, widened to FP64)
-    int nranks_x;
-    unsigned tag;
-    ulonglong2* peer_w[SVM_MAX_RANKS];           // this rank's slot in rank r's gathered buffer
-};
-
-#ifndef SVMB200_HOST_EMULATION
-__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned tag) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
-    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t)
-                 : "memory");
-}
-// bounded spin (20 s: a peer died) -> fault flag; the host turns it into an error
-__device__ __forceinline__ double ll_load(const ulonglong2* p, unsigned tag, int* fault) {
-    unsigned long long w0, w1, t0 = 0, now = 0;
-    for (unsigned spins = 0;; ++spins) {
-        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
-        if ((spins & 1023u) == 1023u) {
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 20000000000ull) {
-                *fault = 1;
-                break;
-            }
-        }
-    }
-    return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
-}
-
-__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
-    double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
-}
-#else
-// tests/cuda_emu compiles this file for the host (the kernels run thread by thread on fibers, ranks are host threads):
-// same entry format, same wait-until-both-tags-match protocol, without the PTX
-__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned tag) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
-    __atomic_store_n(&p->x, (b & 0xffffffffull) | t, __ATOMIC_RELEASE);
-    __atomic_store_n(&p->y, (b >> 32) | t, __ATOMIC_RELEASE);
-}
-__device__ __forceinline__ double ll_load(const ulonglong2* p, unsigned tag, int* fault) {
-    unsigned long long w0, w1;
-    for (unsigned long long spins = 0;; ++spins) {
-        w0 = __atomic_load_n(&p->x, __ATOMIC_ACQUIRE);
-        w1 = __atomic_load_n(&p->y, __ATOMIC_ACQUIRE);
-        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
-        if (emu::spin_wait(spins)) {  // yields the host thread; true after 20 s
-            *fault = 1;
-            break;
-        }
-    }
-    return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
-}
-__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) { return *p; }
-#endif
-
-__global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const MatvecArgs a) {
-    if (a.done != nullptr && *a.done) return;
-    constexpr int R = MV_R, NT = MV_NT, U = MV_U;
-    const unsigned items_per_group = (unsigned)(MV_BPG * a.nseg);
-    const unsigned group = blockIdx.x / items_per_group;
-    const unsigned within = blockIdx.x - group * items_per_group;
-    const unsigned rb_in_group = within / (unsigned)a.nseg;
-    const int seg = (int)(within - rb_in_group * (unsigned)a.nseg);
-    const long long row_base = (long long)group * MV_GROUP + (long long)rb_in_group * R;
-    __shared__ double red[NT / 32][R];
-    __shared__ unsigned is_last;
-
-    if (row_base < a.nrows) {
-        const long long c0 = (long long)seg * MV_SEG;
-        long long c1 = c0 + MV_SEG;
-        if (c1 > a.ld) c1 = a.ld;
-        const int nvec = (int)((c1 - c0) >> 1);
-        const double2* __restrict__ u2 = reinterpret_cast<const double2*>(a.u + c0);
-        const double2* rows[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            long long rr = row_base + r;
-            if (rr >= a.nrows) rr = a.nrows - 1;  // clamp: read a valid row, result discarded below
-            rows[r] = reinterpret_cast<const double2*>(a.Q + rr * a.ld + c0);
-        }
-        double acc[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.0;
-
-        int c = threadIdx.x;
-        for (; c + (U - 1) * NT < nvec; c += U * NT) {
-            double2 qv[U][R];
-            double2 uv[U];
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) qv[j][r] = ld_stream_f64x2(rows[r] + c + j * NT);
-            }
-#pragma unroll
-            for (int j = 0; j < U; ++j) uv[j] = __ldg(u2 + c + j * NT);
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    acc[r] = fma(qv[j][r].x, uv[j].x, acc[r]);
-                    acc[r] = fma(qv[j][r].y, uv[j].y, acc[r]);
-                }
-            }
-        }
-        for (; c < nvec; c += NT) {
-            double2 qv[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) qv[r] = ld_stream_f64x2(rows[r] + c);
-            const double2 uv = __ldg(u2 + c);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                acc[r] = fma(qv[r].x, uv.x, acc[r]);
-                acc[r] = fma(qv[r].y, uv.y, acc[r]);
-            }
-        }
-        // warp butterfly, then fixed-order sum over warps
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double v = acc[r];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            acc[r] = v;
-        }
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) red[wid][r] = acc[r];
-        }
-        __syncthreads();
-        if (threadIdx.x < R && row_base + threadIdx.x < a.nrows) {
-            double v = 0.0;
-#pragma unroll
-            for (int k = 0; k < NT / 32; ++k) v += red[k][threadIdx.x];
-            a.wpart[(size_t)seg * a.nrows_pad + row_base + threadIdx.x] = v;
-        }
-    }
-    // ---- one ticket per group; the last arriver combines the group
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicInc(&a.tickets[group], items_per_group - 1) == items_per_group - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (threadIdx.x < MV_GROUP) {
-        const long long rr = (long long)group * MV_GROUP + threadIdx.x;
-        double dv = 0.0;
-        if (rr < a.nrows) {
-            double v = 0.0;
-            for (int s = 0; s < a.nseg; ++s) v += __ldcg(&a.wpart[(size_t)s * a.nrows_pad + rr]);
-            if (a.nranks_x > 0) {
-                for (int p = 0; p < a.nranks_x; ++p) ll_store(a.peer_w[p] + rr, v, a.tag);  // NVLink stores (one is local)
-            } else {
-                a.w[rr] = v;
-            }
-            if (a.u_rows != nullptr) dv = __dmul_rn(a.u_rows[rr], v);
-        }
-        if (a.denpart != nullptr) {
-            // fixed tree over the 64 rows: butterfly inside each warp, then warp 0 + warp 1
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dv = __dadd_rn(dv, __shfl_xor_sync(0xffffffffu, dv, o));
-            if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = dv;
-        }
-    }
-    if (a.denpart != nullptr) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const double tot = __dadd_rn(red[0][0], red[0][1]);
-            if (a.nranks_x > 0) {
-                const size_t off = (size_t)(a.denpart - a.w) + group;  // share slot relative to the w slot
-                for (int p = 0; p < a.nranks_x; ++p) ll_store(a.peer_w[p] + off, tot, a.tag);
-            } else {
-                a.denpart[group] = tot;
-            }
-        }
-    }
-}
-
+// ------------------------------------------------------------------------------------------ K2 launchers
 struct MatvecScratch {
     double* wpart = nullptr;
     unsigned* tickets = nullptr;
@@ -332,221 +123,6 @@ extern "C" int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows,
     return svm_launch_matvec(ctx, dQ, nrows, ld, du, dw, nullptr);
 }
 
-// ------------------------------------------------------------------------------------------ K2 x NB
-// Several products against ONE pass over the matrix (the binary problems of a one-vs-rest fit, or the
-// targets of a multi-output regression, share the resident M): a work item streams its R x MV_SEG tile once and feeds
-// NB accumulator sets.  Per row and per thread the columns are visited in the order of matvec_seg_kernel (c, c + NT,
-// ... ; x then y), the warp / CTA / segment reductions are the same trees, so every w_b is BIT-IDENTICAL to the
-// single-vector kernel's -- a batched fit reproduces the sequential fits exactly.  The vector operands (NB x 64 KB per
-// item) come through L2: R rows amortise them, the ratio of L2 to HBM bytes is NB / R.
-constexpr int MV_MULTI_MAX = 4;  // vectors per launch; larger batches are split into balanced launches
-
-// shape knobs, overridable at build time (scripts/sweep_multi.py): any R that divides 64 and any U keep the results
-// bit-identical, they only move the register budget and the L2 : HBM traffic ratio (NB / R)
-#ifndef SVMB200_MULTI_R
-#define SVMB200_MULTI_R 4
-#endif
-#ifndef SVMB200_MULTI_U
-#define SVMB200_MULTI_U 2
-#endif
-#ifndef SVMB200_MULTI_MINB
-#define SVMB200_MULTI_MINB 0
-#endif
-#ifndef SVMB200_MULTI_H
-#define SVMB200_MULTI_H 1
-#endif
-template <int NB>
-struct MultiCfg {
-    static constexpr int R = SVMB200_MULTI_R;  // rows per work item
-    static constexpr int U = SVMB200_MULTI_U;  // 128-bit loads in flight per row and thread
-    // CTAs per SM the register budget is cut for
-    static constexpr int MINB = SVMB200_MULTI_MINB > 0 ? SVMB200_MULTI_MINB : (NB <= 2 ? 3 : 2);
-    // H groups of 256 threads per CTA, each with its own R rows of the same column segment: the vector operands the
-    // groups read at about the same time are served once from L2 and H - 1 times from L1 (same results bit for bit)
-    static constexpr int H = SVMB200_MULTI_H;
-};
-
-struct MatvecMultiArgs {
-    const double* Q;
-    long long ld, nrows, nrows_pad;
-    double* wpart;      // [NB][nseg][nrows_pad]
-    unsigned* tickets;
-    int nseg;
-    const double* u[MV_MULTI_MAX];       // ld entries each, zero beyond n
-    double* w[MV_MULTI_MAX];             // nrows results each
-    const double* u_rows[MV_MULTI_MAX];  // u at this shard's rows, or null
-    double* denpart[MV_MULTI_MAX];       // one share of u'w per 64-row group, or null
-    const int* done[MV_MULTI_MAX];       // problem b finished: its results are not stored (may be null)
-    // fused exchange (nranks_x > 0), as in MatvecArgs: results of problem b go to peer_w[p] + b * xstride (+ row for
-    // w, + share_off + group for the u'w share) in every rank's arena as tagged entries
-    int nranks_x;
-    unsigned tag;
-    long long xstride, share_off;
-    ulonglong2* peer_w[SVM_MAX_RANKS];
-};
-
-template <int NB>
-__global__ void __launch_bounds__(MV_NT * MultiCfg<NB>::H, MultiCfg<NB>::MINB) matvec_seg_multi_kernel(const MatvecMultiArgs a) {
-    constexpr int R = MultiCfg<NB>::R, NT = MV_NT, U = MultiCfg<NB>::U, H = MultiCfg<NB>::H, BPG = MV_GROUP / (R * H);
-    static_assert(NB >= 1 && NB <= MV_MULTI_MAX && NB * MV_GROUP <= NT * H && MV_GROUP % (R * H) == 0 && NT * H <= 1024,
-                  "bad multi-vector shape");
-    bool live[NB];
-    bool any = false;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        live[b] = !(a.done[b] != nullptr && *a.done[b]);
-        any = any || live[b];
-    }
-    if (!any) return;
-    const int half = (int)threadIdx.x / NT;         // which group of 256 threads (whole warps)
-    const int tid = (int)threadIdx.x - half * NT;   // the thread's index inside its group: the column it starts at
-    const unsigned items_per_group = (unsigned)(BPG * a.nseg);
-    const unsigned group = blockIdx.x / items_per_group;
-    const unsigned within = blockIdx.x - group * items_per_group;
-    const unsigned rb_in_group = within / (unsigned)a.nseg;
-    const int seg = (int)(within - rb_in_group * (unsigned)a.nseg);
-    const long long row_base = (long long)group * MV_GROUP + (long long)rb_in_group * (R * H) + (long long)half * R;
-    const size_t pstride = (size_t)a.nseg * a.nrows_pad;  // wpart elements per problem
-    __shared__ double red[H][NT / 32][NB][R];
-    __shared__ double red2[NB][2];
-    __shared__ unsigned is_last;
-    const bool active = row_base < a.nrows;  // uniform inside a group of 256 threads
-
-    if (active) {
-        const long long c0 = (long long)seg * MV_SEG;
-        long long c1 = c0 + MV_SEG;
-        if (c1 > a.ld) c1 = a.ld;
-        const int nvec = (int)((c1 - c0) >> 1);
-        const double2* rows[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            long long rr = row_base + r;
-            if (rr >= a.nrows) rr = a.nrows - 1;  // clamp: read a valid row, result discarded below
-            rows[r] = reinterpret_cast<const double2*>(a.Q + rr * a.ld + c0);
-        }
-        double acc[NB][R];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[b][r] = 0.0;
-        }
-        int c = tid;
-        for (; c + (U - 1) * NT < nvec; c += U * NT) {
-            double2 qv[U][R];
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) qv[j][r] = ld_stream_f64x2(rows[r] + c + j * NT);
-            }
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const double2* __restrict__ u2 = reinterpret_cast<const double2*>(a.u[b] + c0);
-                double2 uv[U];
-#pragma unroll
-                for (int j = 0; j < U; ++j) uv[j] = __ldg(u2 + c + j * NT);
-#pragma unroll
-                for (int j = 0; j < U; ++j) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        acc[b][r] = fma(qv[j][r].x, uv[j].x, acc[b][r]);
-                        acc[b][r] = fma(qv[j][r].y, uv[j].y, acc[b][r]);
-                    }
-                }
-            }
-        }
-        for (; c < nvec; c += NT) {
-            double2 qv[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) qv[r] = ld_stream_f64x2(rows[r] + c);
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const double2 uv = __ldg(reinterpret_cast<const double2*>(a.u[b] + c0) + c);
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    acc[b][r] = fma(qv[r].x, uv.x, acc[b][r]);
-                    acc[b][r] = fma(qv[r].y, uv.y, acc[b][r]);
-                }
-            }
-        }
-        // warp butterfly, then fixed-order sum over the group's warps (the trees of matvec_seg_kernel)
-        const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                double v = acc[b][r];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) red[half][wid][b][r] = v;
-            }
-        }
-    }
-    __syncthreads();
-    if (active && tid < NB * R) {
-        const int b = tid / R, r = tid - b * R;
-        if (row_base + r < a.nrows) {
-            double v = 0.0;
-#pragma unroll
-            for (int k = 0; k < NT / 32; ++k) v += red[half][k][b][r];
-            a.wpart[(size_t)b * pstride + (size_t)seg * a.nrows_pad + row_base + r] = v;
-        }
-    }
-    // ---- one ticket per group; the last arriver combines the group for every problem
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicInc(&a.tickets[group], items_per_group - 1) == items_per_group - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // thread t handles row (t % 64) of problem (t / 64): whole warps share a problem
-    {
-        const int b = (int)(threadIdx.x / MV_GROUP);
-        const int t = (int)(threadIdx.x % MV_GROUP);
-        double dv = 0.0;
-        bool has_den = false;
-#pragma unroll
-        for (int bb = 0; bb < NB; ++bb) {  // static indexing of the per-problem pointer arrays
-            if (bb != b) continue;
-            has_den = a.denpart[bb] != nullptr;
-            const long long rr = (long long)group * MV_GROUP + t;
-            if (rr < a.nrows) {
-                double v = 0.0;
-                const double* wp = a.wpart + (size_t)bb * pstride + rr;
-                for (int s = 0; s < a.nseg; ++s) v += __ldcg(wp + (size_t)s * a.nrows_pad);
-                if (live[bb]) {
-                    if (a.nranks_x > 0) {
-                        for (int p = 0; p < a.nranks_x; ++p) ll_store(a.peer_w[p] + bb * a.xstride + rr, v, a.tag);
-                    } else {
-                        a.w[bb][rr] = v;
-                    }
-                }
-                if (a.u_rows[bb] != nullptr) dv = __dmul_rn(a.u_rows[bb][rr], v);
-            }
-        }
-        if (b < NB && has_den) {
-            // fixed tree over the 64 rows: butterfly inside each warp, then the problem's two warps in order
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dv = __dadd_rn(dv, __shfl_xor_sync(0xffffffffu, dv, o));
-            if ((threadIdx.x & 31) == 0) red2[b][t >> 5] = dv;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < NB) {
-#pragma unroll
-        for (int bb = 0; bb < NB; ++bb) {
-            if (bb == (int)threadIdx.x && a.denpart[bb] != nullptr && live[bb]) {
-                const double tot = __dadd_rn(red2[bb][0], red2[bb][1]);
-                if (a.nranks_x > 0) {
-                    for (int p = 0; p < a.nranks_x; ++p)
-                        ll_store(a.peer_w[p] + bb * a.xstride + a.share_off + group, tot, a.tag);
-                } else {
-                    a.denpart[bb][group] = tot;
-                }
-            }
-        }
-    }
-}
-
 static int launch_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, int nb,
                                const double* const* du, double* const* dw, const double* const* du_rows,
                                double* const* ddenpart, const int* const* d_done, const ExchangeTargets* xt = nullptr,
@@ -644,669 +220,6 @@ extern "C" int svmb200_shard_rows(int64_t n, int rank, int nranks, int64_t* row0
     *row0 = r0;
     *nrows = nr;
     return SVMB200_OK;
-}
-
-// ------------------------------------------------------------------------------------------ K3
-// Grid-wide vector phase, no inter-CTA synchronisation: a CTA first reduces (redundantly, in a fixed
-// order) the per-row-block shares of u'w written by K2 and the per-CTA partials of |d|^2, x'(g+q) and
-// max_t written by the previous K3 launch, takes the step on its slice, and leaves its own partials
-// for the next launch.
-constexpr int VP_NT = 256;
-constexpr int VP_MAXC = 128;   // at most this many CTAs (fixed: the reduction shape must not follow the GPU)
-constexpr int VP_ELEMS = 512;  // target elements per CTA
-
-struct PGDeviceState {
-    long long iter;  // index of the state whose f/ng are stored below
-    int done;
-    int status;
-    double f, ng, s, maxt, t, den;
-    double best_lb;  // Frank-Wolfe: best lower bound so far
-    // augmented Lagrangian: launch index that raised `done` (a CTA of that same launch that starts late must not
-    // leave early: it still owes its slice of the gradient) and the multiplier of the equality row
-    long long done_k;
-    double mu;
-};
-
-struct VecArgs {
-    double *x, *g, *d, *u;
-    const double *q, *lb, *ub;
-    const double* gathered;  // per rank: [rpr results w | rpr/MV_GROUP shares of u'w]
-    long long rpr, stride;
-    double* part;            // 2 x 3 x VP_MAXC : |d|^2, x'(g+q), max_t per CTA, double-buffered by state parity
-    double *hist_f, *hist_ng;
-    long long hist_cap;
-    PGDeviceState* st;
-    long long n;   // matrix dimension
-    int svr;       // 0: nvars = n ; 1: nvars = 2n, Q = [[M,-M],[-M,M]]
-    int nctas;
-    double eps;
-    long long max_iter;
-    double fw_t;  // Frank-Wolfe stabilisation parameter t in [0, 1)
-    // fused exchange: `gathered_ll` (tagged 16-byte entries, see ll_store) replaces `gathered`
-    const ulonglong2* gathered_ll;
-    unsigned tag;
-    int* fault;
-    long long ll_pstride;  // batched solves: entries between the two parity copies of this problem's gathered buffer
-    // label signs (nvars entries of +-1, or null): the resident matrix is M and the problem is posed on
-    // Q = (s s') o M.  Q u = s o (M (s o u)) is exact for s = +-1, so the vector kernels sign w on the way in and
-    // u on the way out and K2 never sees the signs -- several such problems can share one pass over M (one-vs-rest)
-    const double* sgn;
-};
-
-__device__ __forceinline__ double gathered_at(const VecArgs& a, size_t idx) {
-    return a.gathered_ll != nullptr ? ll_load(a.gathered_ll + idx, a.tag, a.fault) : a.gathered[idx];
-}
-
-// w = Q u for Q = (s s') o M:  the vector handed to K2 is s o u and the product that comes back is signed again
-// (multiplications by +-1 are exact; label signs never combine with the SVR block layout)
-__device__ __forceinline__ double apply_sign(const VecArgs& a, long long j, double v) {
-    return a.sgn != nullptr ? __dmul_rn(a.sgn[j], v) : v;
-}
-
-enum { VP_INIT = 0, VP_STEP = 1, VP_FINALISE = 2 };
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-struct Quad {
-    double a, b, c, m;  // three sums and one min
-};
-
-// all threads receive the block-wide result; fixed tree: lanes (butterfly), then warps in order
-__device__ __forceinline__ Quad block_reduce(Quad v, double (*sm)[4]) {
-    v.a = warp_sum(v.a);
-    v.b = warp_sum(v.b);
-    v.c = warp_sum(v.c);
-    v.m = warp_min(v.m);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __syncthreads();  // protect sm from the previous use
-    if (lane == 0) {
-        sm[wid][0] = v.a;
-        sm[wid][1] = v.b;
-        sm[wid][2] = v.c;
-        sm[wid][3] = v.m;
-    }
-    __syncthreads();
-    Quad r;
-    r.a = r.b = r.c = 0.0;
-    r.m = INFINITY;
-#pragma unroll
-    for (int i = 0; i < VP_NT / 32; ++i) {
-        r.a = __dadd_rn(r.a, sm[i][0]);
-        r.b = __dadd_rn(r.b, sm[i][1]);
-        r.c = __dadd_rn(r.c, sm[i][2]);
-        r.m = fmin(r.m, sm[i][3]);
-    }
-    return r;
-}
-
-// element-wise pieces, written with explicit round-to-nearest intrinsics so that nvcc cannot
-// contract them into FMAs: NumPy rounds t*d and x + (t*d) separately (projected_gradient.py:129).
-__device__ __forceinline__ double axpy_rn(double a, double x, double y) { return __dadd_rn(y, __dmul_rn(a, x)); }
-
-__device__ __forceinline__ double project_dir(double g, double x, double lb, double ub) {
-    // projected_gradient.py:83-87
-    double d = -g;
-    if ((__dsub_rn(ub, x) <= 1e-12) && (d > 0.0)) d = 0.0;
-    if ((__dsub_rn(x, lb) <= 1e-12) && (d < 0.0)) d = 0.0;
-    return d;
-}
-
-__device__ __forceinline__ void tail_accumulate(Quad& a, double d, double x, double g, double q, double lb, double ub) {
-    a.a = __dadd_rn(a.a, __dmul_rn(d, d));
-    a.b = __dadd_rn(a.b, __dmul_rn(x, __dadd_rn(g, q)));
-    // projected_gradient.py:111-114 (correctly rounded IEEE division, exact min)
-    if (d > 0.0) a.m = fmin(a.m, __ddiv_rn(__dsub_rn(ub, x), d));
-    else if (d < 0.0) a.m = fmin(a.m, __ddiv_rn(__dsub_rn(lb, x), d));
-}
-
-template <int MODE>
-__device__ __forceinline__ void pg_vector_body(const VecArgs& a, const long long k) {
-    __shared__ double sm[VP_NT / 32][4];
-    PGDeviceState* st = a.st;
-    // `done` is raised inside the stop branch below, which every CTA of that launch takes anyway;
-    // a CTA that starts late and already sees the flag returns here instead -- same outcome.
-    if (*reinterpret_cast<volatile int*>(&st->done)) return;
-    const int tid = threadIdx.x;
-    const long long n = a.n;
-    const long long chunk = (n + a.nctas - 1) / a.nctas;
-    const long long j0 = (long long)blockIdx.x * chunk;
-    const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
-    const unsigned rpr = (unsigned)a.rpr, gpr = rpr / MV_GROUP;  // rows / groups per rank (n < 2^31)
-    // per-CTA partials are double-buffered by state parity: this launch reads the sums of state k and leaves those of
-    // state k+1 (INIT: of state 0) in the other half, so a CTA that starts late never reads a half-updated set
-    const double* part_r = a.part + (size_t)(k & 1) * 3 * VP_MAXC;
-    double* part_w = a.part + (size_t)((MODE == VP_INIT ? k : k + 1) & 1) * 3 * VP_MAXC;
-
-    double t = 0.0;
-    if (MODE != VP_INIT) {
-        // ---- reductions over the whole problem, identical in every CTA
-        Quad r;
-        r.a = r.b = r.c = 0.0;
-        r.m = INFINITY;
-        if (tid < a.nctas) {
-            r.a = part_r[tid];
-            r.b = part_r[VP_MAXC + tid];
-            r.m = part_r[2 * VP_MAXC + tid];
-        }
-        if (MODE == VP_STEP) {
-            // u'w: one share per 64-row group, thread-strided in global group order
-            const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
-            for (unsigned b0 = tid; b0 < ngrp; b0 += 4 * VP_NT) {
-                double v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const unsigned b = b0 + e * VP_NT;
-                    const unsigned rk = b / gpr;
-                    v[e] = b < ngrp ? gathered_at(a, (size_t)rk * a.stride + rpr + (b - rk * gpr)) : 0.0;
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) r.c = __dadd_rn(r.c, v[e]);
-            }
-        }
-        r = block_reduce(r, sm);
-        const double s = r.a, f = 0.5 * r.b, mt = r.m, den = r.c;
-        const double ng = sqrt(s);
-        if (blockIdx.x == 0 && tid == 0) {
-            if (k < a.hist_cap) {
-                a.hist_f[k] = f;
-                a.hist_ng[k] = ng;
-            }
-            st->f = f;
-            st->ng = ng;
-            st->s = s;
-            st->maxt = mt;
-            st->iter = k;
-        }
-        int stop = 0;
-        if (ng <= a.eps) stop = SVMB200_STATUS_OPTIMAL;          // projected_gradient.py:100-102
-        else if (k >= a.max_iter) stop = SVMB200_STATUS_STOPPED;  // projected_gradient.py:104-106
-        if (stop) {
-            if (blockIdx.x == 0 && tid == 0) {
-                st->status = stop;
-                __threadfence();
-                st->done = 1;
-            }
-            return;
-        }
-        if (MODE == VP_FINALISE) return;
-        // projected_gradient.py:121-127 ; -g'd equals d'd term by term, so the numerator is s
-        t = (den <= 1e-16) ? mt : fmin(__ddiv_rn(s, den), mt);
-        if (blockIdx.x == 0 && tid == 0) {
-            st->t = t;
-            st->den = den;
-        }
-    }
-
-    // ---- x += t d ; g += t w ; new direction, partial reductions for the next state
-    Quad acc;
-    acc.a = acc.b = acc.c = 0.0;
-    acc.m = INFINITY;
-    for (long long j = j0 + tid; j < j1; j += VP_NT) {
-        const unsigned rk = (unsigned)j / rpr;
-        const double wj = apply_sign(a, j, gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr)));
-        double x = a.x[j], q = a.q[j], g;
-        if (MODE == VP_INIT) {
-            g = __dadd_rn(wj, q);  // g = Q x0 + q  (opti/_base.py:291)
-        } else {
-            x = axpy_rn(t, a.d[j], x);
-            g = axpy_rn(t, wj, a.g[j]);
-            a.x[j] = x;
-        }
-        a.g[j] = g;
-        const double lb = a.lb[j], ub = a.ub[j];
-        const double dn = project_dir(g, x, lb, ub);
-        a.d[j] = dn;
-        tail_accumulate(acc, dn, x, g, q, lb, ub);
-        double uj = dn;
-        if (a.svr) {
-            const long long i2 = j + n;
-            double x2 = a.x[i2], q2 = a.q[i2], g2;
-            if (MODE == VP_INIT) {
-                g2 = __dadd_rn(-wj, q2);
-            } else {
-                x2 = axpy_rn(t, a.d[i2], x2);
-                g2 = axpy_rn(t, -wj, a.g[i2]);
-                a.x[i2] = x2;
-            }
-            a.g[i2] = g2;
-            const double lb2 = a.lb[i2], ub2 = a.ub[i2];
-            const double dn2 = project_dir(g2, x2, lb2, ub2);
-            a.d[i2] = dn2;
-            tail_accumulate(acc, dn2, x2, g2, q2, lb2, ub2);
-            uj = __dsub_rn(dn, dn2);
-        }
-        a.u[j] = apply_sign(a, j, uj);
-    }
-    acc = block_reduce(acc, sm);
-    if (tid == 0) {
-        part_w[blockIdx.x] = acc.a;
-        part_w[VP_MAXC + blockIdx.x] = acc.b;
-        part_w[2 * VP_MAXC + blockIdx.x] = acc.m;
-    }
-}
-
-// ------------------------------------------------------------------------------------------ K3' Frank-Wolfe
-// Vector phase of the reference's FrankWolfe.minimize (optiml/opti/constrained/frank_wolfe.py:88-165), same
-// structure as pg_vector_kernel: y = ub where g < 0 else lb; lower bound f + g'(y-x); relative gap against the
-// best bound; d = y - x (y clipped to x +- t(ub-lb) when stabilised); a = den<=1e-16 ? 1 : min(-g'd/den, 1).
-// Partials per CTA: x'(g+q), g'(y-x) with the UNclipped y, g'd.  History slot 2 holds the gap.
-__device__ __forceinline__ void fw_direction(double g, double x, double lb, double ub, double t, double& d, double& gy) {
-    const double y = (g < 0.0) ? ub : lb;                       // frank_wolfe.py:100
-    gy = __dmul_rn(g, __dsub_rn(y, x));                          // term of g'(y - x), frank_wolfe.py:104
-    double yc = y;
-    if (t > 0.0) {                                               // frank_wolfe.py:128-130
-        const double radius = __dmul_rn(t, __dsub_rn(ub, lb));
-        yc = fmin(fmax(y, __dsub_rn(x, radius)), __dadd_rn(x, radius));
-    }
-    d = __dsub_rn(yc, x);                                        // frank_wolfe.py:135
-}
-
-template <int MODE>
-__device__ __forceinline__ void fw_vector_body(const VecArgs& a, const long long k) {
-    __shared__ double sm[VP_NT / 32][4];
-    PGDeviceState* st = a.st;
-    if (*reinterpret_cast<volatile int*>(&st->done)) return;
-    const int tid = threadIdx.x;
-    const long long n = a.n;
-    const long long chunk = (n + a.nctas - 1) / a.nctas;
-    const long long j0 = (long long)blockIdx.x * chunk;
-    const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
-    const unsigned rpr = (unsigned)a.rpr, gpr = rpr / MV_GROUP;
-    const double* part_r = a.part + (size_t)(k & 1) * 3 * VP_MAXC;  // double-buffered by state parity (see pg_vector_kernel)
-    double* part_w = a.part + (size_t)((MODE == VP_INIT ? k : k + 1) & 1) * 3 * VP_MAXC;
-
-    double step = 0.0;
-    if (MODE != VP_INIT) {
-        Quad r;
-        r.a = r.b = r.c = 0.0;
-        r.m = 0.0;  // used as a fourth SUM here (g'd), not a min
-        double gd_part = 0.0;
-        if (tid < a.nctas) {
-            r.a = part_r[tid];                 // x'(g+q)
-            r.b = part_r[VP_MAXC + tid];       // g'(y-x)
-            gd_part = part_r[2 * VP_MAXC + tid];  // g'd
-        }
-        if (MODE == VP_STEP) {
-            const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
-            for (unsigned b0 = tid; b0 < ngrp; b0 += 4 * VP_NT) {
-                double v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const unsigned b = b0 + e * VP_NT;
-                    const unsigned rk = b / gpr;
-                    v[e] = b < ngrp ? gathered_at(a, (size_t)rk * a.stride + rpr + (b - rk * gpr)) : 0.0;
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) r.c = __dadd_rn(r.c, v[e]);
-            }
-        }
-        // reduce g'd through the sum slot of a second Quad (block_reduce's fourth slot is a min)
-        Quad r2;
-        r2.a = gd_part;
-        r2.b = r2.c = 0.0;
-        r2.m = INFINITY;
-        r = block_reduce(r, sm);
-        r2 = block_reduce(r2, sm);
-        const double f = 0.5 * r.a, gy = r.b, den = r.c, gd = r2.a;
-        const double lbv = __dadd_rn(f, gy);
-        const double prev_best = (k == 0) ? -INFINITY : st->best_lb;  // written by the previous launch
-        const double best = lbv > prev_best ? lbv : prev_best;        // frank_wolfe.py:105-106
-        const double gap = __ddiv_rn(__dsub_rn(f, best), fmax(fabs(f), 1.0));  // frank_wolfe.py:109
-        if (blockIdx.x == 0 && tid == 0) {
-            if (k < a.hist_cap) {
-                a.hist_f[k] = f;
-                a.hist_ng[k] = gap;
-            }
-            st->f = f;
-            st->ng = gap;
-            st->s = best;
-            st->best_lb = best;  // idempotent (max): a CTA that starts late and reads the new value computes the same
-            st->iter = k;
-        }
-        int stop = 0;
-        if (gap <= a.eps) stop = SVMB200_STATUS_OPTIMAL;          // frank_wolfe.py:120-122
-        else if (k >= a.max_iter) stop = SVMB200_STATUS_STOPPED;  // frank_wolfe.py:124-126
-        if (stop) {
-            if (blockIdx.x == 0 && tid == 0) {
-                st->status = stop;
-                __threadfence();
-                st->done = 1;
-            }
-            return;
-        }
-        if (MODE == VP_FINALISE) return;  // best_lb is committed by the STEP launch of the same k
-        step = (den <= 1e-16) ? 1.0 : fmin(__ddiv_rn(-gd, den), 1.0);  // frank_wolfe.py:145-149
-        if (blockIdx.x == 0 && tid == 0) {
-            st->t = step;
-            st->den = den;
-        }
-    }
-    Quad acc;
-    acc.a = acc.b = acc.c = 0.0;
-    acc.m = INFINITY;
-    for (long long j = j0 + tid; j < j1; j += VP_NT) {
-        const unsigned rk = (unsigned)j / rpr;
-        const double wj = apply_sign(a, j, gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr)));
-        double x = a.x[j], q = a.q[j], g;
-        if (MODE == VP_INIT) {
-            g = __dadd_rn(wj, q);
-        } else {
-            x = axpy_rn(step, a.d[j], x);
-            g = axpy_rn(step, wj, a.g[j]);
-            a.x[j] = x;
-        }
-        a.g[j] = g;
-        double dn, gyj;
-        fw_direction(g, x, a.lb[j], a.ub[j], a.fw_t, dn, gyj);
-        a.d[j] = dn;
-        acc.a = __dadd_rn(acc.a, __dmul_rn(x, __dadd_rn(g, q)));
-        acc.b = __dadd_rn(acc.b, gyj);
-        acc.c = __dadd_rn(acc.c, __dmul_rn(g, dn));
-        double uj = dn;
-        if (a.svr) {
-            const long long i2 = j + n;
-            double x2 = a.x[i2], q2 = a.q[i2], g2;
-            if (MODE == VP_INIT) {
-                g2 = __dadd_rn(-wj, q2);
-            } else {
-                x2 = axpy_rn(step, a.d[i2], x2);
-                g2 = axpy_rn(step, -wj, a.g[i2]);
-                a.x[i2] = x2;
-            }
-            a.g[i2] = g2;
-            double dn2, gy2;
-            fw_direction(g2, x2, a.lb[i2], a.ub[i2], a.fw_t, dn2, gy2);
-            a.d[i2] = dn2;
-            acc.a = __dadd_rn(acc.a, __dmul_rn(x2, __dadd_rn(g2, q2)));
-            acc.b = __dadd_rn(acc.b, gy2);
-            acc.c = __dadd_rn(acc.c, __dmul_rn(g2, dn2));
-            uj = __dsub_rn(dn, dn2);
-        }
-        a.u[j] = apply_sign(a, j, uj);
-    }
-    acc = block_reduce(acc, sm);
-    if (tid == 0) {
-        part_w[blockIdx.x] = acc.a;
-        part_w[VP_MAXC + blockIdx.x] = acc.b;
-        part_w[2 * VP_MAXC + blockIdx.x] = acc.c;
-    }
-}
-
-// ------------------------------------------------------------------------------------------ K3'' augmented Lagrangian
-// Vector phase of the reference's full-batch stochastic optimisers (stochastic/adagrad.py:84-125 and siblings) on
-// AugmentedLagrangianQuadratic (constrained/_base.py:224-410), SURVEY.md 8f-3.  One launch per iteration after the
-// streaming pass w = Q xe:  every CTA reduces the sums the previous launch left (ALSums) and the shares of xe'w,
-// updates the multiplier of the equality row, applies the optimality test of the PREVIOUS iteration
-// (opti/_base.py:129-149), evaluates L(xe) and the epoch limit, then takes the step on its slice: gradient, update
-// rule, box multipliers at the new point, next evaluation point, and its terms of the next ALSums.  The arithmetic
-// lives in al_math.cuh (shared with the host emulation of the CPU tests).  The second history array holds the
-// primal cost x'Qx/2 + q'x (what ml/svm/_base.py:289-291 stores for a Lagrangian dual).
-struct ALArgs {
-    ALParams p;
-    double *lam_lb, *lam_ub, *s1, *s2, *s3, *step, *xpre;
-    const double* A;                      // equality row (nvars), null without an equality constraint
-    const double *lr, *mom, *bc1, *bc2;   // per-iteration scalars, epochs + 1 entries each
-    double* part;                         // 2 x AL_NSUMS x VP_MAXC per-CTA sums, double-buffered by state parity
-    double* mu;                           // 2 entries, by state parity
-};
-
-template <int NV>
-__device__ __forceinline__ void block_reduce_n(double (&v)[NV], double (*sm)[NV]) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __syncthreads();  // protect sm from the previous use
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) sm[wid][i] = v[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double r = 0.0;
-#pragma unroll
-        for (int w = 0; w < VP_NT / 32; ++w) r = __dadd_rn(r, sm[w][i]);
-        v[i] = r;
-    }
-}
-
-__device__ __forceinline__ void al_sums_to_array(const ALSums& s, double (&v)[AL_NSUMS + 1]) {
-    v[0] = s.ax_pre; v[1] = s.ax_eval; v[2] = s.qx; v[3] = s.dx2; v[4] = s.dlam2; v[5] = s.c2; v[6] = s.cc2; v[7] = s.lamc;
-}
-__device__ __forceinline__ void al_array_to_sums(const double (&v)[AL_NSUMS + 1], ALSums& s) {
-    s.ax_pre = v[0]; s.ax_eval = v[1]; s.qx = v[2]; s.dx2 = v[3]; s.dlam2 = v[4]; s.c2 = v[5]; s.cc2 = v[6]; s.lamc = v[7];
-}
-
-__device__ __forceinline__ ALElem al_load(const VecArgs& a, const ALArgs& al, long long j) {
-    ALElem e;
-    e.x = a.x[j];
-    e.lam_lb = al.lam_lb[j];
-    e.lam_ub = al.lam_ub[j];
-    e.s1 = al.s1[j];
-    e.s2 = al.s2[j];
-    e.s3 = al.s3[j];
-    e.step = al.step[j];
-    return e;
-}
-__device__ __forceinline__ void al_store(const VecArgs& a, const ALArgs& al, long long j, const ALElem& e, double xpre) {
-    a.x[j] = e.x;
-    al.lam_lb[j] = e.lam_lb;
-    al.lam_ub[j] = e.lam_ub;
-    al.s1[j] = e.s1;
-    al.s2[j] = e.s2;
-    al.s3[j] = e.s3;
-    al.step[j] = e.step;
-    al.xpre[j] = xpre;
-}
-
-// INIT is launched with k = -1 (it prepares the sums of state 0)
-template <int MODE>
-__device__ __forceinline__ void al_vector_body(const VecArgs& a, const ALArgs& al, const long long k) {
-    __shared__ double sm[VP_NT / 32][AL_NSUMS + 1];
-    PGDeviceState* st = a.st;
-    if (*reinterpret_cast<volatile int*>(&st->done)) {
-        __threadfence();
-        if (*reinterpret_cast<volatile long long*>(&st->done_k) != k) return;
-    }
-    const int tid = threadIdx.x;
-    const long long n = a.n;
-    const long long chunk = (n + a.nctas - 1) / a.nctas;
-    const long long j0 = (long long)blockIdx.x * chunk;
-    const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
-    const unsigned rpr = (unsigned)a.rpr, gpr = rpr / MV_GROUP;
-    const ALParams& p = al.p;
-    double* part_w = al.part + (size_t)((k + 1) & 1) * AL_NSUMS * VP_MAXC;  // sums of state k+1
-    double v[AL_NSUMS + 1];
-
-    if (MODE == VP_INIT) {
-        ALSums acc = {};
-        for (long long j = j0 + tid; j < j1; j += VP_NT) {
-            const double x = a.x[j];
-            al_init_sums(x, a.q[j], al.A ? al.A[j] : 0.0, a.lb[j], a.ub[j], acc);
-            double uj = x;
-            if (a.svr) {
-                const long long i2 = j + n;
-                const double x2 = a.x[i2];
-                al_init_sums(x2, a.q[i2], al.A ? al.A[i2] : 0.0, a.lb[i2], a.ub[i2], acc);
-                uj = __dsub_rn(x, x2);
-            }
-            a.u[j] = apply_sign(a, j, uj);
-        }
-        al_sums_to_array(acc, v);
-        v[AL_NSUMS] = 0.0;
-        block_reduce_n<AL_NSUMS + 1>(v, sm);
-        if (tid == 0) {
-#pragma unroll
-            for (int i = 0; i < AL_NSUMS; ++i) part_w[i * VP_MAXC + blockIdx.x] = v[i];
-        }
-        return;
-    }
-
-    // ---- sums over the whole problem, identical in every CTA
-    const double* part_r = al.part + (size_t)(k & 1) * AL_NSUMS * VP_MAXC;
-#pragma unroll
-    for (int i = 0; i < AL_NSUMS; ++i) v[i] = tid < a.nctas ? part_r[i * VP_MAXC + tid] : 0.0;
-    {
-        // xe'w: one share per 64-row group, thread-strided in global group order
-        double xw = 0.0;
-        const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
-        for (unsigned b0 = tid; b0 < ngrp; b0 += 4 * VP_NT) {
-            double sh[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const unsigned b = b0 + e * VP_NT;
-                const unsigned rk = b / gpr;
-                sh[e] = b < ngrp ? gathered_at(a, (size_t)rk * a.stride + rpr + (b - rk * gpr)) : 0.0;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) xw = __dadd_rn(xw, sh[e]);
-        }
-        v[AL_NSUMS] = xw;
-    }
-    block_reduce_n<AL_NSUMS + 1>(v, sm);
-    ALSums S;
-    al_array_to_sums(v, S);
-    const double mu_prev = k >= 1 ? al.mu[(k - 1) & 1] : 0.0;
-    double mu = 0.0, c_eq = 0.0, f = 0.0, pf = 0.0;
-    const int rc = al_scalar_phase(p, k, a.max_iter, S, v[AL_NSUMS], mu_prev, mu, c_eq, f, pf);
-    const bool lead = blockIdx.x == 0 && tid == 0;
-    if (rc == AL_OPTIMAL) {
-        // the previous iteration ended the run: x, the multipliers and iter = k - 1 stay, f and g are those of
-        // state k - 1 (the reference breaks out before re-evaluating them)
-        if (lead) {
-            al.mu[k & 1] = mu;
-            st->mu = mu;
-            st->status = SVMB200_STATUS_OPTIMAL;
-            st->done_k = k;
-            __threadfence();
-            st->done = 1;
-        }
-        return;
-    }
-    if (lead) {
-        if (k < a.hist_cap) {
-            a.hist_f[k] = f;
-            a.hist_ng[k] = pf;
-        }
-        st->f = f;
-        st->ng = pf;
-        st->iter = k;
-        st->mu = mu;
-        al.mu[k & 1] = mu;
-    }
-    ALScalars sc;
-    sc.mu = mu;
-    sc.ax = S.ax_eval;
-    sc.act_eq = c_eq != 0.0;
-    sc.lr = al.lr[k];
-    sc.mom = al.mom[k];
-    sc.mom_next = al.mom[k + 1];
-    sc.bc1 = al.bc1[k];
-    sc.bc2 = al.bc2[k];
-    const bool step = (rc == AL_CONTINUE) && (MODE == VP_STEP);
-
-    ALSums acc = {};
-    for (long long j = j0 + tid; j < j1; j += VP_NT) {
-        const unsigned rk = (unsigned)j / rpr;
-        const double wj = apply_sign(a, j, gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr)));
-        const double Aj = al.A ? al.A[j] : 0.0, qj = a.q[j], lbj = a.lb[j], ubj = a.ub[j];
-        ALElem e = al_load(a, al, j);
-        const double g = al_gradient(p, sc, wj, qj, Aj, lbj, ubj, e);
-        a.g[j] = g;
-        double uj = e.x;
-        if (step) {
-            double xpre;
-            al_step(p, sc, g, qj, Aj, lbj, ubj, e, xpre, acc);
-            al_store(a, al, j, e, xpre);
-            uj = e.x;
-        }
-        if (a.svr) {
-            const long long i2 = j + n;
-            const double A2 = al.A ? al.A[i2] : 0.0, q2 = a.q[i2], lb2 = a.lb[i2], ub2 = a.ub[i2];
-            ALElem e2 = al_load(a, al, i2);
-            const double g2 = al_gradient(p, sc, -wj, q2, A2, lb2, ub2, e2);
-            a.g[i2] = g2;
-            if (step) {
-                double xpre2;
-                al_step(p, sc, g2, q2, A2, lb2, ub2, e2, xpre2, acc);
-                al_store(a, al, i2, e2, xpre2);
-            }
-            uj = __dsub_rn(uj, e2.x);
-        }
-        if (step) a.u[j] = apply_sign(a, j, uj);
-    }
-    if (!step) {
-        if (rc == AL_STOPPED && lead) {
-            st->status = SVMB200_STATUS_STOPPED;
-            st->done_k = k;
-            __threadfence();
-            st->done = 1;
-        }
-        return;
-    }
-    al_sums_to_array(acc, v);
-    v[AL_NSUMS] = 0.0;
-    block_reduce_n<AL_NSUMS + 1>(v, sm);
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < AL_NSUMS; ++i) part_w[i * VP_MAXC + blockIdx.x] = v[i];
-    }
-}
-
-// ------------------------------------------------------------------------------------------ kernel entry points
-// One problem per launch (argument block by value), or a batch of problems that share the resident matrix and
-// advance in lockstep (one-vs-rest / multi-target): blockIdx.y selects the problem, the argument
-// blocks live in device memory.  A problem that has finished ignores the launches that follow (its `done` flag).
-template <int MODE>
-__global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const long long k) {
-    pg_vector_body<MODE>(a, k);
-}
-template <int MODE>
-__global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const long long k) {
-    fw_vector_body<MODE>(a, k);
-}
-template <int MODE>
-__global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const ALArgs al, const long long k) {
-    al_vector_body<MODE>(a, al, k);
-}
-// The argument blocks are constant over a run except for the fused exchange: the tag and the parity of the gathered
-// buffer change with every product and come as launch parameters.
-__device__ __forceinline__ VecArgs batch_args(const VecArgs* __restrict__ args, unsigned tag, int parity) {
-    VecArgs a = args[blockIdx.y];
-    if (a.gathered_ll != nullptr) {
-        a.gathered_ll += (size_t)parity * a.ll_pstride;
-        a.tag = tag;
-    }
-    return a;
-}
-template <int MODE>
-__global__ void __launch_bounds__(VP_NT) pg_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k,
-                                                                const unsigned tag, const int parity) {
-    const VecArgs a = batch_args(args, tag, parity);
-    pg_vector_body<MODE>(a, k);
-}
-template <int MODE>
-__global__ void __launch_bounds__(VP_NT) fw_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k,
-                                                                const unsigned tag, const int parity) {
-    const VecArgs a = batch_args(args, tag, parity);
-    fw_vector_body<MODE>(a, k);
-}
-template <int MODE>
-__global__ void __launch_bounds__(VP_NT) al_vector_batch_kernel(const VecArgs* __restrict__ args,
-                                                                const ALArgs* __restrict__ als, const long long k,
-                                                                const unsigned tag, const int parity) {
-    const VecArgs a = batch_args(args, tag, parity);
-    const ALArgs al = als[blockIdx.y];
-    al_vector_body<MODE>(a, al, k);
 }
 
 // ------------------------------------------------------------------------------------------ driver

@@ -2,7 +2,7 @@
 
 Host mirror of optiml/opti/constrained/frank_wolfe.py:30-165 -- the first widening step after the projected
 gradient: identical solver protocol, and on the device the identical streaming pass over Q
-per iteration; only the O(n) vector phase differs (``fw_vector_kernel`` in csrc/pg.cu)."""
+per iteration; only the O(n) vector phase differs (``fw_vector_kernel`` in csrc/k3_vector.cuh)."""
 from . import BoxConstrainedQuadraticOptimizer
 from ._device_loop import DeviceLoopMixin
 

@@ -4,7 +4,7 @@ Host mirror of optiml/opti/unconstrained/stochastic/_base.py:13-140 (constructor
 output) for the one use the SVM dual path makes of them (ml/svm/_base.py:638-725, 1188-1270): ``f`` is an
 ``AugmentedLagrangianQuadratic`` and every iteration sees the whole problem (``batch_size=None``).  The loop --
 value and gradient of the Lagrangian, update rule, multiplier update, optimality test -- is ``svmb200_al_*``
-(csrc/pg.cu, csrc/al_math.cuh): one streaming pass over Q and one vector kernel per iteration.
+(csrc/pg.cu, csrc/k3_vector.cuh, csrc/al_math.cuh): one streaming pass over Q and one vector kernel per iteration.
 """
 import ctypes as C
 import itertools

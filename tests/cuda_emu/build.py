@@ -62,7 +62,8 @@ def build(force=False, defines=()):
     defines = tuple(defines)
     suffix = ''.join('_' + d.replace('SVMB200_', '').replace('=', '') for d in defines)
     lib = os.path.join(BUILD, f'libsvmb200_emu{suffix}.so')
-    common = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'al_math.cuh'), os.path.join(ROOT, 'include', 'svmb200.h'),
+    common = [os.path.join(CSRC, h) for h in ('common.cuh', 'al_math.cuh', 'k2_matvec.cuh', 'k3_vector.cuh')] + \
+             [os.path.join(ROOT, 'include', 'svmb200.h'),
               os.path.join(HERE, 'include', 'cuda_runtime.h'), os.path.abspath(__file__)]
     include = ['-I', os.path.join(HERE, 'include'), '-I', CSRC]
     jobs, objects = [], []
