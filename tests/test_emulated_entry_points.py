@@ -1,0 +1,45 @@
+"""The driver's entry points on the host emulation of the kernels: `__graft_entry__.smoke()` as is, and `bench.py`
+on a shrunken workload -- the JSON line must carry every key of the measurement contract (numbers are meaningless
+here: the "device" is a CPU).  Catches a refactor that breaks the round-end run before a GPU is involved."""
+import json
+import sys
+
+import pytest
+
+from emu import emulated_device
+
+
+def test_smoke_entry_point_passes_on_the_emulation(capsys):
+    import __graft_entry__ as entry
+    with emulated_device() as lib:
+        entry.smoke()   # one small DualSVC fit checked against the oracle: alphas, support set, decision values
+        assert lib.emu_sticky_error() == 0
+    assert 'smoke: n=512' in capsys.readouterr().out
+
+
+def test_bench_line_carries_the_whole_contract(capsys, monkeypatch):
+    import bench
+    monkeypatch.setattr(sys, 'argv', ['bench.py', '--n', '192', '--max-iter', '8', '--steps', '2', '--warmup', '1',
+                                      '--no-cpu-baseline'])
+    with emulated_device() as lib:
+        bench.main()
+        assert lib.emu_sticky_error() == 0
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1                                   # ONE JSON line
+    out = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'e2e', 'gpu_launches', 'clocks'):
+        assert key in out, key
+    assert out['n_gpus'] == 1 and out['steps'] == 2 and out['warmup'] == 1 and out['dtype'] == 'f64'
+    assert out['data'] == 'synthetic' and out['higher_is_better'] is True and out['vs_baseline'] is None
+    assert 'workload' in out['config'] and 'model' not in out['config']
+    roof = out['roofline']
+    assert roof['bound'] == 'hbm' and roof['unit'] == 'GB/s' and roof['peak'] > 0
+    assert roof['frac'] == pytest.approx(roof['achieved'] / roof['peak'])
+    assert roof['bytes_per_launch'] == 8.0 * 192 * 192        # algorithmic bytes: one pass over the n x n matrix
+    e2e = out['e2e']
+    assert e2e['unit'] == out['unit'] and e2e['h2d_bytes_per_step'] > 0 and e2e['d2h_bytes_per_step'] > 0
+    assert e2e['value'] != out['value']                       # measured separately, through the public API
+    # 8 iterations: 1 + 8 passes and 1 + 8 (+ final state) vector launches per fit, plus Gram / norms / K5
+    assert out['gpu_launches'] >= 2 * 8
+    assert set(out['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
