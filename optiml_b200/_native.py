@@ -111,7 +111,12 @@ def load_library():
         if not os.path.exists(LIB_PATH):
             raise NativeError(f'{LIB_PATH} not found: build it with `python -m optiml_b200.csrc.build` '
                               '(or __graft_entry__.build()); optiml_b200 has no CPU fallback')
-        _lib = bind_prototypes(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
+        lib = bind_prototypes(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
+        version = lib.svmb200_version().decode()
+        if 'sm_100a' not in version:
+            # e.g. SVMB200_LIB pointing at the host emulation the test-suite builds: not a compute path
+            raise NativeError(f'{LIB_PATH} is not the sm_100a build ({version!r}); optiml_b200 has no CPU fallback')
+        _lib = lib
         return _lib
 
 

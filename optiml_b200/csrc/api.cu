@@ -12,7 +12,12 @@ void svmb200_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* svmb200_last_error(void) { return g_err; }
+#ifndef SVMB200_HOST_EMULATION
 extern "C" const char* svmb200_version(void) { return "svmb200 0.1 (sm_100a)"; }
+#else
+// tests/cuda_emu: the host mirror refuses to load a library that identifies itself like this (_native.load_library)
+extern "C" const char* svmb200_version(void) { return "svmb200 0.1 (HOST EMULATION, test infrastructure only)"; }
+#endif
 
 extern "C" int svmb200_device_count(int* count) {
     SVM_CHECK_ARG(count != nullptr, "null argument");

@@ -43,3 +43,18 @@ def test_bench_line_carries_the_whole_contract(capsys, monkeypatch):
     # 8 iterations: 1 + 8 passes and 1 + 8 (+ final state) vector launches per fit, plus Gram / norms / K5
     assert out['gpu_launches'] >= 2 * 8
     assert set(out['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
+
+
+def test_product_refuses_to_load_the_emulated_library():
+    """SVMB200_LIB selects a build variant (tuning sweeps); pointing it at the emulation must not give a CPU path"""
+    import os
+    import subprocess
+    import emu
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = emu._builder().build()
+    code = ('from optiml_b200 import _native as N\n'
+            'try:\n    N.load_library()\n    print("LOADED")\n'
+            'except N.NativeError as e:\n    print("REFUSED", e)\n')
+    out = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, SVMB200_LIB=lib),
+                         capture_output=True, text=True, timeout=120)
+    assert 'REFUSED' in out.stdout and 'no CPU fallback' in out.stdout, out.stdout + out.stderr
