@@ -167,7 +167,7 @@ def check_signed_views_and_batches(device, kind, count, n, max_iter, **dev_kw):
             assert np.array_equal(vb, vc), 'lockstep batch differs from the sequential solves'
     iters = [s.iter for s in lock]
     if kind in ('pg', 'fw'):
-        assert min(iters) < max(iters) == max_iter   # one problem met its stopping test early, the others ran on
+        assert iters[1] <= max_iter // 2 and iters[1] < max(iters)   # problem 1 met its stopping test early, others ran on
     # ceil(count / 4) passes over M per iteration + one vector launch for all problems (+ set-up and the final state)
     per_iter = (count + 3) // 4 + 1
     assert launches <= count * 2 + (max_iter + 2) * per_iter
