@@ -290,3 +290,39 @@ def check_multi_output(device, n, max_iter, **dev_kw):
         one = MultiOutputRegressor(est).fit(X, Y[:, :1])
         assert np.array_equal(one.estimators_[0].alphas_, shared.estimators_[0].alphas_)
         probe.assert_clean()
+
+
+# --------------------------------------------------------------------------------------------- reference goldens
+def check_against_reference_meta_estimators(device, g, max_iter, **dev_kw):
+    """tests/golden/shared_gram.npz: the REAL reference wrapped in sklearn's OneVsRestClassifier / MultiOutputRegressor
+    (FrankWolfe, 400 iterations).  With max_iter = 400 everything is compared; with fewer iterations the loss
+    histories (Frank-Wolfe iterates do not depend on the iteration limit)."""
+    from optiml_b200.ml.multiclass import MultiOutputRegressor, OneVsRestClassifier
+    from optiml_b200.ml.svm import SVC, SVR
+    from optiml_b200.ml.svm.kernels import GaussianKernel
+    from optiml_b200.ml.svm.losses import epsilon_insensitive, hinge
+    from optiml_b200.opti.constrained import FrankWolfe
+    full = max_iter == 400
+    with device(**dev_kw) as probe, warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ovr = OneVsRestClassifier(SVC(loss=hinge, kernel=GaussianKernel(), C=1, reg_intercept=True, dual=True,
+                                      optimizer=FrankWolfe, max_iter=max_iter)).fit(g['ovr_X_train'], g['ovr_y_train'])
+        mor = MultiOutputRegressor(SVR(loss=epsilon_insensitive, epsilon=0.1, kernel=GaussianKernel(), C=1, reg_intercept=True,
+                                       dual=True, optimizer=FrankWolfe, max_iter=max_iter)).fit(g['mor_X_train'], g['mor_Y_train'])
+        for prefix, model in (('ovr_c', ovr), ('mor_t', mor)):
+            for i, e in enumerate(model.estimators_):
+                p = f'{prefix}{i}_'
+                assert e.fit_times_['batch'] == len(model.estimators_)
+                want = g[p + 'f_hist'][:max_iter + 1]
+                assert np.abs(np.array(e.train_loss_history) - want).max() <= 1e-9 * max(1., np.abs(want).max())
+                if full:
+                    assert e.optimizer.iter == int(g[p + 'iter']) and e.optimizer.status == str(g[p + 'status'])
+                    assert np.abs(e.alphas_ - g[p + 'alphas']).max() <= 1e-8
+                    assert np.array_equal(e.support_, g[p + 'support'])
+                    assert abs(e.intercept_ - float(g[p + 'intercept'])) <= 1e-8
+        if full:
+            assert np.array_equal(ovr.predict(g['ovr_X_test']), g['ovr_predict'])
+            assert np.abs(ovr.decision_function(g['ovr_X_test']) - g['ovr_decision']).max() <= 1e-8
+            assert np.abs(mor.predict(g['mor_X_test']) - g['mor_predict']).max() <= 1e-8
+            assert abs(ovr.score(g['ovr_X_test'], g['ovr_y_test']) - float(g['ovr_score'])) <= 1e-12
+        probe.assert_clean()

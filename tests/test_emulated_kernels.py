@@ -149,6 +149,11 @@ def test_one_vs_rest_augmented_lagrangian_batch(golden):
     S.check_one_vs_rest(emu_probe, iris['X_train'][:80], iris['y_train'][:80], iris['X_test'], AdaGrad, max_iter=12)
 
 
+def test_meta_estimators_follow_the_reference_wrapped_in_sklearn(golden):
+    """the first 30 Frank-Wolfe iterations of every class / target against the real reference's loss histories"""
+    S.check_against_reference_meta_estimators(emu_probe, golden('shared_gram'), max_iter=30)
+
+
 def test_multi_output_regressor_shares_the_gram_matrix():
     S.check_multi_output(emu_probe, n=60, max_iter=25)
 

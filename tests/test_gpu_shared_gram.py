@@ -74,6 +74,12 @@ def test_one_vs_rest_frank_wolfe_and_adagrad_recipes(golden):
     assert ovr.test_score_ >= 0.97
 
 
+def test_meta_estimators_against_the_reference_wrapped_in_sklearn(golden):
+    """tests/golden/shared_gram.npz: OneVsRestClassifier / MultiOutputRegressor over the REAL reference's SVC / SVR
+    (FrankWolfe, 400 iterations): alphas to 1e-8, support sets, intercepts, predictions, decision values"""
+    S.check_against_reference_meta_estimators(S.real_device, golden('shared_gram'), max_iter=400)
+
+
 def test_one_vs_rest_c1_sized_four_classes():
     """C1-sized inputs (n = 2000, d = 20) with four classes: four binary problems, one pass over M per iteration"""
     from sklearn.datasets import make_classification
