@@ -58,3 +58,34 @@ def test_product_refuses_to_load_the_emulated_library():
     out = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, SVMB200_LIB=lib),
                          capture_output=True, text=True, timeout=120)
     assert 'REFUSED' in out.stdout and 'no CPU fallback' in out.stdout, out.stdout + out.stderr
+
+
+def test_integration_md_stubs_run_against_the_emulated_library():
+    """INTEGRATION.md's ctypes stubs, executed: the host-pointer kernel / solver entry points and the device-resident
+    one-vs-rest recipe, against the oracle (the `-m "not gpu"` doc test only compiles them)."""
+    import os
+    import re
+    import numpy as np
+    import emu
+    from oracle import svm_oracle as O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, 'INTEGRATION.md')) as fh:
+        blocks = re.findall(r'```python\n(.*?)```', fh.read(), flags=re.S)
+    assert len(blocks) >= 2
+    ns = {}
+    exec(compile('\n'.join(blocks).replace("'libsvmb200.so'", repr(emu._builder().build())), 'INTEGRATION.md', 'exec'), ns)
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((90, 6))
+    gamma = 1.0 / (6 * X.var())
+    K = ns['kernel_matrix'](X, None, 2, gamma)
+    assert np.abs(K - O.gaussian_kernel(X)).max() <= 1e-12
+    labels = rng.integers(0, 3, 90)
+    signs = [np.where(labels == c, 1.0, -1.0) for c in range(3)]
+    alphas, iters, statuses = ns['one_vs_rest_alphas'](X, signs, gamma, max_iter=25)
+    for c in range(3):
+        want = O.svc_dual_fit(X, (labels == c).astype(int), kind='gaussian', max_iter=25)
+        assert iters[c] == want.pg.iter and np.abs(alphas[c] - want.alphas_).max() <= 1e-10
+    Q = O.svc_dual_fit(X, (labels == 0).astype(int), kind='gaussian', max_iter=1).Q
+    x, g, hist, it, status = ns['projected_gradient'](Q, -np.ones(90), np.ones(90), max_iter=25)
+    want = O.projected_gradient(Q, -np.ones(90), np.ones(90), max_iter=25)
+    assert it == want.iter and status == want.status and np.abs(x - want.x).max() <= 1e-10
