@@ -145,3 +145,55 @@ def test_sharded_lockstep_batch_is_bit_identical_to_one_rank(kind, count, nranks
                 for sa, sb in zip(one, rank_states):
                     for a, b in zip(sa, sb):
                         assert np.array_equal(a, b)
+
+
+def _fuzz_case(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([2, 3, 5, 17, 63, 64, 65, 100, 129, 200]))
+    case = dict(n=n, kind=str(rng.choice(['pg', 'fw'])), layout=str(rng.choice(['plain', 'svr'])),
+                nranks=int(rng.choice([1, 2, 3, 4])), exchange=str(rng.choice(['nccl', 'p2p'])),
+                matrix=str(rng.choice(['low rank', 'full rank', 'zero'])))
+    if case['matrix'] == 'zero':
+        M = np.zeros((n, n))
+    else:
+        G = rng.standard_normal((n, max(1, n // 3) if case['matrix'] == 'low rank' else n + 2))
+        M = G @ G.T / G.shape[1]
+    nv = 2 * n if case['layout'] == 'svr' else n
+    lb = np.where(rng.random(nv) < 0.5, 0.0, -rng.random(nv))
+    ub = lb + rng.uniform(0.1, 2.0, nv)
+    case.update(M=M, q=rng.standard_normal(nv), lb=lb, ub=ub,
+                x0=lb + rng.random(nv) * (ub - lb) if rng.random() < 0.5 else None, iters=int(rng.choice([1, 2, 6, 15])))
+    return case
+
+
+@pytest.mark.parametrize('block', range(4))
+def test_random_problems_shards_exchanges_and_schedules(block):
+    """Seeded fuzz: sizes from 2 to 200 (below, at and above the 64-row group), 1-4 ranks with both exchanges, plain
+    and SVR layouts, zero / low-rank / full-rank matrices, lower bounds != 0, given or default start points, 1-15
+    iterations, shuffled thread and block schedules.  Every case: sharded == one rank bitwise, and == the oracle."""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import FrankWolfe, ProjectedGradient
+    from oracle import svm_oracle as O
+
+    def run(ctx, c):
+        H = shard_hessian(ctx, c['M'], c['layout'])
+        cls, kw = (ProjectedGradient, {}) if c['kind'] == 'pg' else (FrankWolfe, dict(t=0.25))
+        s = cls(quad=Quadratic(H, c['q']), ub=c['ub'], lb=c['lb'], x=None if c['x0'] is None else c['x0'].copy(),
+                max_iter=c['iters'], **kw).minimize()
+        hist = np.asarray(getattr(s, 'f_hist', getattr(s, 'f_x_history', [])))   # ndim <= 3 takes the step-wise path
+        return [np.asarray(s.x), np.asarray(s.g_x), np.array([s.iter, s.f_x]), np.array([s.status == 'optimal']), hist]
+
+    for seed in range(15 * block, 15 * block + 15):
+        c = _fuzz_case(seed)
+        label = {k: v for k, v in c.items() if not isinstance(v, np.ndarray)}
+        with emulated_device(order=2, seed=seed):
+            one = run_ranks(1, 'nccl', lambda ctx: run(ctx, c))[0]
+            many = run_ranks(c['nranks'], c['exchange'], lambda ctx: run(ctx, c)) if c['nranks'] > 1 else []
+        for state in many:
+            assert all(np.array_equal(a, b) for a, b in zip(one, state)), label
+        M = c['M']
+        Q = M if c['layout'] == 'plain' else np.vstack((np.hstack((M, -M)), np.hstack((-M, M))))
+        solver, kw = (O.projected_gradient, {}) if c['kind'] == 'pg' else (O.frank_wolfe, dict(t=0.25))
+        want = solver(Q, c['q'], c['ub'], lb=c['lb'], x0=c['x0'], max_iter=c['iters'], **kw)
+        assert int(one[2][0]) == want.iter, label
+        assert np.abs(one[0] - want.x).max() <= 1e-9 * max(1., np.abs(want.x).max()), label
