@@ -215,7 +215,12 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& thread_body) {
     r.fibers.resize(nt);
     {
         // fiber stacks are recycled between launches (zero-filling 16 MB per launch would dominate tiny kernels)
-        static thread_local std::vector<char*> pool;
+        struct StackPool : std::vector<char*> {
+            ~StackPool() {  // a rank thread of the multi-rank tests ends: give its stacks back
+                for (char* p : *this) free(p);
+            }
+        };
+        static thread_local StackPool pool;
         r.stacks = pool.empty() ? static_cast<char*>(malloc((size_t)(1024 + 1) * STACK_BYTES)) : pool.back();
         if (!pool.empty()) pool.pop_back();
         if (!r.stacks) {

@@ -9,6 +9,7 @@ shards.  What the emulation cannot show: memory ordering over NVLink, timing.
 """
 import ctypes as C
 import threading
+import time
 import warnings
 
 import numpy as np
@@ -21,7 +22,7 @@ from optiml_b200 import _native as N
 
 def run_ranks(nranks, exchange, body):
     """body(ctx) on `nranks` threads, each with its own context attached to one communicator; returns the results in
-    rank order.  exchange: 'nccl' (all-gather) or 'p2p' (fused peer-memory exchange)."""
+    rank order.  exchange: 'nccl' (all-gather) or 'p2p' (fused peer-memory exchange; one rank has nothing to exchange)."""
     from optiml_b200.runtime import Context
     uid = Context.new_unique_id()
     gate = threading.Barrier(nranks)
@@ -31,7 +32,7 @@ def run_ranks(nranks, exchange, body):
         try:
             ctx = Context(device=0)
             ctx.attach_communicator(rank, nranks, uid)
-            if exchange == 'p2p':
+            if exchange == 'p2p' and nranks > 1:
                 buf = C.create_string_buffer(64)
                 N.call('svmb200_comm_p2p_export', ctx.handle, 1 << 20, C.cast(buf, C.c_void_p))
                 handles[rank] = buf.raw
@@ -50,11 +51,13 @@ def run_ranks(nranks, exchange, body):
             errors.append((rank, exc))
             gate.abort()
 
-    threads = [threading.Thread(target=main, args=(r,)) for r in range(nranks)]
+    # daemon threads: a rank that is stuck (a protocol bug would show up like that) fails the test, it cannot hang the run
+    threads = [threading.Thread(target=main, args=(r,), daemon=True) for r in range(nranks)]
     for t in threads:
         t.start()
+    deadline = time.monotonic() + 240
     for t in threads:
-        t.join(timeout=300)
+        t.join(timeout=max(0.1, deadline - time.monotonic()))
     if errors:
         raise errors[0][1]
     assert not any(t.is_alive() for t in threads), 'a rank is stuck'
@@ -197,3 +200,69 @@ def test_random_problems_shards_exchanges_and_schedules(block):
         want = solver(Q, c['q'], c['ub'], lb=c['lb'], x0=c['x0'], max_iter=c['iters'], **kw)
         assert int(one[2][0]) == want.iter, label
         assert np.abs(one[0] - want.x).max() <= 1e-9 * max(1., np.abs(want.x).max()), label
+
+
+def _batch_case(seed):
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.choice([4, 17, 64, 65, 100, 130]))
+    c = dict(n=n, kind=str(rng.choice(['pg', 'fw', 'adagrad', 'adam'])), layout=str(rng.choice(['plain', 'plain', 'svr'])),
+             count=int(rng.choice([2, 3, 4, 5, 7, 9])), nranks=int(rng.choice([1, 2, 3])),
+             exchange=str(rng.choice(['nccl', 'p2p'])), iters=int(rng.choice([1, 2, 7, 12])))
+    G = rng.standard_normal((n, n // 2 + 2))
+    nv = 2 * n if c['layout'] == 'svr' else n
+    signed = c['layout'] == 'plain' and rng.random() < 0.8
+    c.update(M=G @ G.T / G.shape[1] + 1.0, signed=signed,
+             signs=[np.where(rng.random(n) < 0.5, 1.0, -1.0) for _ in range(c['count'])] if signed else None,
+             qs=[rng.standard_normal(nv) for _ in range(c['count'])], ubs=[rng.uniform(0.3, 2.0, nv) for _ in range(c['count'])],
+             eps=[float(rng.choice([1e-6, 0.3, 5.0])) for _ in range(c['count'])])
+    return c
+
+
+@pytest.mark.parametrize('block', range(3))
+def test_random_lockstep_batches(block):
+    """Seeded fuzz of the batched driver: 2-9 problems (one to three multi-vector launches per iteration), with and
+    without label signs, SVR blocks, per-problem right-hand sides, bounds and stopping thresholds (some problems stop
+    at once, some never), PG / FW / AdaGrad / Adam-Nesterov with and without an equality row, 1-3 ranks with both
+    exchanges.  Every case: lockstep batch (sharded) == the solvers one after the other on one rank, bitwise."""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.batch import batchable, minimize_batch
+    from optiml_b200.opti.constrained import AugmentedLagrangianQuadratic, FrankWolfe, ProjectedGradient
+    from optiml_b200.opti.unconstrained.stochastic import AdaGrad, Adam
+
+    def run(ctx, c, batch):
+        H = shard_hessian(ctx, c['M'], c['layout'])
+        solvers = []
+        for i in range(c['count']):
+            quad, ub = Quadratic(H.with_signs(c['signs'][i]) if c['signed'] else H, c['qs'][i]), c['ubs'][i]
+            if c['kind'] == 'pg':
+                solvers.append(ProjectedGradient(quad=quad, ub=ub, max_iter=c['iters'], eps=c['eps'][i]))
+            elif c['kind'] == 'fw':
+                solvers.append(FrankWolfe(quad=quad, ub=ub, max_iter=c['iters'], eps=c['eps'][i], t=0.1))
+            else:
+                A = np.where(np.arange(len(ub)) % 2 == 0, 1.0, -1.0) if i % 2 == 0 else None
+                f = AugmentedLagrangianQuadratic(primal=quad, A=A, b=None if A is None else np.zeros(1), lb=np.zeros(len(ub)),
+                                                 ub=ub, rho=1.5)
+                solvers.append(AdaGrad(f=f, step_size=0.5, epochs=c['iters'], tol=1e-3 if i == 1 else 1e-12, random_state=i)
+                               if c['kind'] == 'adagrad' else
+                               Adam(f=f, step_size=0.02, epochs=c['iters'], tol=1e-12, random_state=i, momentum_type='nesterov',
+                                    momentum=0.4))
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            if batch:
+                assert batchable(solvers)
+                minimize_batch(solvers)
+                assert all(s.batch_size_ == c['count'] for s in solvers)
+            else:
+                for s in solvers:
+                    s.minimize()
+        return [S.solver_state(s) for s in solvers]
+
+    for seed in range(8 * block, 8 * block + 8):
+        c = _batch_case(seed)
+        label = {k: v for k, v in c.items() if not isinstance(v, (np.ndarray, list))}
+        with emulated_device(order=2, seed=seed):
+            sequential = run_ranks(1, 'nccl', lambda ctx: run(ctx, c, False))[0]
+            batched = run_ranks(c['nranks'], c['exchange'], lambda ctx: run(ctx, c, True))
+        for rank_states in batched:
+            for sa, sb in zip(sequential, rank_states):
+                assert all(np.array_equal(a, b) for a, b in zip(sa, sb)), label
