@@ -10,6 +10,7 @@ Prints one JSON line per arm (fit seconds, problem-iterations/s, passes over the
 problem-iteration) and whether the two arms agree bitwise.
 
     python scripts/bench_ovr.py [--n N] [--classes K] [--iters I] [--solver pg|fw]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/bench_ovr.py   (row-sharded M)
 """
 import argparse
 import json
@@ -41,6 +42,14 @@ def main():
     from optiml_b200.opti.constrained import FrankWolfe, ProjectedGradient
     from optiml_b200.runtime import default_context
     warnings.simplefilter('ignore')
+    rank, world = 0, int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:   # under torchrun: one rank per GPU, M row-sharded, fused peer exchange for the whole batch
+        import torch
+        import torch.distributed as dist
+        local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend='nccl', device_id=torch.device('cuda', local_rank))
+        rank = dist.get_rank()
     spec, X, y2 = make_config('C4', n=args.n)
     n = len(y2)
     # synthetic multi-class labels on C4's inputs: quantiles of a fixed random projection
@@ -71,19 +80,23 @@ def main():
         else:
             loop_ms, passes = sum(e.optimizer.device_ms for e in ests), sum(e.optimizer.q_passes for e in ests)
         fitted[arm] = [e.alphas_.copy() for e in ests]
-        print(json.dumps(dict(arm=arm, case=f'C4 inputs n={n}, {args.classes} classes, {args.solver}, max_iter={args.iters}',
+        if rank == 0:
+            print(json.dumps(dict(arm=arm, n_gpus=world, exchange=ctx.exchange,
+                              case=f'C4 inputs n={n}, {args.classes} classes, {args.solver}, max_iter={args.iters}',
                               fit_s=round(fit_s, 4), loop_ms=round(loop_ms, 2), problem_iterations=int(iters),
                               problem_its_per_s=round(iters / (loop_ms / 1e3), 1), passes_over_matrix=int(passes),
                               us_per_pass=round(1e3 * loop_ms / max(passes, 1), 1),
-                              hbm_gbps=round(8.0 * n * n * passes / (loop_ms / 1e3) / 1e9, 1),
+                              hbm_gbps_all_gpus=round(8.0 * n * n * passes / (loop_ms / 1e3) / 1e9, 1),
                               gb_per_problem_iteration=round(8.0 * n * n * passes / max(iters, 1) / 1e9, 2),
                               kernel_launches=int(launches), n_sv=[int(len(e.support_)) for e in ests])), flush=True)
         for e in ests:
             e.obj.release()
         del model, ests
-    if len(fitted) == 2:
+    if len(fitted) == 2 and rank == 0:
         same = all(np.array_equal(a, b) for a, b in zip(fitted['shared'], fitted['cloned']))
         print(json.dumps(dict(bitwise_equal_shared_vs_cloned=bool(same))), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
