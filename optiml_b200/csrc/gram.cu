@@ -55,6 +55,7 @@ struct GramArgs {
     double gamma, coef0, degree, bias;
 };
 
+#ifndef SVMB200_HOST_EMULATION
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -90,6 +91,22 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+#define SVM_PTX(...) asm volatile(__VA_ARGS__)
+#else
+// tests/cuda_emu compiles this file for the host: the PTX wrappers map onto the emulation's shared-memory offsets,
+// mbarriers (arrival count + transaction bytes + phase), tiled copies with the 128-byte swizzle, and a warp-collective
+// m8n8k4 product; fences, register re-allocation and prefetches have no counterpart there
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return emu::smem_offset(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { emu::mbar_arrive(bar, bytes); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { emu::mbar_arrive(bar, 0); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    emu::tma_load_2d(dst, map, bar, c0, c1);
+}
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) { emu::dmma_m8n8k4(c0, c1, a, b); }
+#define SVM_PTX(...) ((void)0)
+#endif
 
 // pow() stays out of line (the poly epilogue is unrolled 64x per thread and pow is ~300 instructions).
 __device__ __noinline__ double pow_outofline(double x, double y) { return pow(x, y); }
@@ -129,6 +146,7 @@ __device__ __forceinline__ void exp8(const double (&x)[8], double (&out)[8]) {
         out[e] = __hiloint2double(__double2hiint(p[e]) + ((k[e] + 1000) << 20), __double2loint(p[e])) * TWO_M1000;
 }
 
+#ifndef SVMB200_HOST_EMULATION
 __device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -138,11 +156,20 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+#else
+__device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src) { *smem_dst = *gmem_src; }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { emu::named_barrier(id, nthreads, true); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { emu::named_barrier(id, nthreads, false); }
+#endif
 
 template <int KERNEL>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GramArgs p) {
+#ifndef SVMB200_HOST_EMULATION
     extern __shared__ unsigned char smem_raw[];
+#else
+    unsigned char* smem_raw = emu::dynamic_smem();
+#endif
     // 1024-byte alignment required by the 128B swizzle pattern
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * RING_BYTES);  // [group][full x STAGES | empty x STAGES]
@@ -154,8 +181,8 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_init(smem_u32(bars + gq * 2 * STAGES + s), 1);
                 mbar_init(smem_u32(bars + gq * 2 * STAGES + STAGES + s), GROUP_WARPS);
             }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        SVM_PTX("fence.mbarrier_init.release.cluster;" ::: "memory");
+        SVM_PTX("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
@@ -163,11 +190,11 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     if (warp >= 2 * GROUP_WARPS) {
         // ===================== TMA producers: warp 8 -> ring 0, warp 9 -> ring 1 =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        SVM_PTX("setmaxnreg.dec.sync.aligned.u32 40;");
         const int grp = warp - 2 * GROUP_WARPS;
         if (grp < 2 && lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+            SVM_PTX("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            SVM_PTX("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
             const uint32_t ring = smem_u32(smem) + grp * RING_BYTES;
             const uint32_t full0 = smem_u32(bars + grp * 2 * STAGES), empty0 = full0 + 8 * STAGES;
             int stage = 0;
@@ -194,7 +221,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
 
     // ===================== consumer groups (ping-pong) =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    SVM_PTX("setmaxnreg.inc.sync.aligned.u32 232;");
     const int grp = warp / GROUP_WARPS;           // 0 or 1
     const int wg = warp % GROUP_WARPS;
     const int wm = wg >> 1, wn = wg & 1;          // 2 x 2 warps -> 64 x 32 per warp
@@ -248,7 +275,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 if (p.sign_b != nullptr && cok) cp_async_8(sm_sb + gt, p.sign_b + c);
                 else sm_sb[gt] = 1.0;
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            SVM_PTX("cp.async.commit_group;" ::: "memory");
         }
         // wait for the tensor pipe (the other group has finished its contraction)
         if (pingpong) named_bar_sync(BAR_GROUP0 + grp, 2 * GROUP_WARPS * 32);
@@ -286,7 +313,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
         // ---- fused epilogue: kernel function, bias, label signs, 128-bit stores
         const long long col_base = (long long)tn * BN + wn * 32 + 2 * t;
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        SVM_PTX("cp.async.wait_all;" ::: "memory");
         named_bar_sync(BAR_LOCAL0 + grp, GROUP_WARPS * 32);  // every thread's staged operands are visible
         double nbv[4][2];
         unsigned sbh[4][2];  // sign bit of s_b

@@ -18,7 +18,7 @@ def pytest_configure(config):
 def pytest_addoption(parser):
     parser.addoption('--emulate', action='store_true', default=False,
                      help='development aid: run the selected tests (e.g. -m gpu ones) on the host emulation of the solver '
-                          'kernels (tests/cuda_emu) -- slow, and the Gram kernel is a host stand-in')
+                          'kernels (tests/cuda_emu) -- slow')
 
 
 @pytest.fixture(autouse=True)

@@ -1,10 +1,11 @@
 """Build the host emulation of libsvmb200 for the CPU test-suite  --  TEST INFRASTRUCTURE ONLY.
 
-``pg.cu`` (all solver kernels and their drivers), ``api.cu``, ``comm.cu`` and ``hostmath.cu`` are compiled FROM THE PRODUCT SOURCES
+``pg.cu`` (all solver kernels and their drivers), ``gram.cu``, ``api.cu``, ``comm.cu`` and ``hostmath.cu`` are compiled FROM THE PRODUCT SOURCES
 with g++ against the stand-in ``include/cuda_runtime.h``; the only source transformation is the launch syntax,
 ``k<<<grid, block, smem, stream>>>(args)`` -> ``emu::launch(grid, block, [=]() { k(args); })``, applied to a scratch
-copy under ``_build/`` (git-ignored).  ``gram.cu`` is replaced by ``emu_standins.cpp``; NCCL and CUDA IPC by in-process
-stand-ins (ranks are threads).  Nothing under
+copy under ``_build/`` (git-ignored).  ``gram.cu`` (K1) is compiled too: its PTX wrappers have emulation twins (mbarriers,
+tiled copies with the 128-byte swizzle, the m8n8k4 FP64 tensor-core product as a warp collective, named barriers).  NCCL
+and CUDA IPC are in-process stand-ins (ranks are threads).  Nothing under
 ``optiml_b200/`` knows about this library; tests load it explicitly.
 """
 import os
@@ -16,8 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'optiml_b200', 'csrc')
 BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(BUILD, 'libsvmb200_emu.so')
-PRODUCT_SOURCES = ['pg.cu', 'api.cu', 'comm.cu', 'hostmath.cu']
-HARNESS_SOURCES = ['emu_runtime.cpp', 'emu_standins.cpp']
+PRODUCT_SOURCES = ['pg.cu', 'gram.cu', 'api.cu', 'comm.cu', 'hostmath.cu']
+HARNESS_SOURCES = ['emu_runtime.cpp']
 # -fno-gnu-unique / -Bsymbolic: several variants of the library can live in one process (shape sweeps); the statics of
 # template kernels ("__shared__" arrays whose size depends on the shape) must not be merged across them
 CXXFLAGS = ['-O1', '-g', '-std=c++17', '-fPIC', '-ffp-contract=off', '-fno-omit-frame-pointer', '-DSVMB200_HOST_EMULATION',
@@ -47,8 +48,10 @@ def rewrite_launches(source):
     """CUDA launch syntax -> emu::launch; returns (text, number of launches rewritten)."""
     def sub(m):
         kernel, config, args = m.group(1), _split_top_level(m.group(2)), m.group(3)
-        return f'emu::launch(dim3({config[0]}), dim3({config[1]}), [=]() {{ {kernel}({args}); }});'
-    return _LAUNCH.subn(sub, source)
+        smem = config[2] if len(config) > 2 else '0'
+        return f'emu::launch(dim3({config[0]}), dim3({config[1]}), (size_t)({smem}), [=]() {{ {kernel}({args}); }});'
+    text, count = _LAUNCH.subn(sub, source)
+    return text.replace('__noinline__', 'EMU_NOINLINE'), count
 
 
 def _stale(target, deps):
@@ -64,7 +67,8 @@ def build(force=False, defines=()):
     lib = os.path.join(BUILD, f'libsvmb200_emu{suffix}.so')
     common = [os.path.join(CSRC, h) for h in ('common.cuh', 'al_math.cuh', 'k2_matvec.cuh', 'k3_vector.cuh')] + \
              [os.path.join(ROOT, 'include', 'svmb200.h'),
-              os.path.join(HERE, 'include', 'cuda_runtime.h'), os.path.abspath(__file__)]
+              os.path.join(HERE, 'include', 'cuda_runtime.h'), os.path.join(HERE, 'include', 'cudaTypedefs.h'),
+              os.path.abspath(__file__)]
     include = ['-I', os.path.join(HERE, 'include'), '-I', CSRC]
     jobs, objects = [], []
     for name in PRODUCT_SOURCES:

@@ -14,6 +14,7 @@
 // "Device" memory is host memory, filled with 0xFF on allocation (NaNs: nothing may rely on zero-initialisation) and
 // fenced by canaries that cudaFree checks.
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 
 #include <sched.h>
 #include <stdio.h>
@@ -64,13 +65,21 @@ emu_switch:
 #error "tests/cuda_emu needs x86-64 (hand-written fiber switch)"
 #endif
 
-enum State { READY, AT_SYNC, AT_SHFL, DONE };
+enum State { READY, AT_SYNC, AT_SHFL, AT_MMA, DONE };
 
 struct Fiber {
     void* sp = nullptr;
     State state = DONE;
     double shfl_val = 0.0;
     int shfl_mask = 0;
+    double mma[4] = {0, 0, 0, 0};  // a, b, c0, c1 of a pending m8n8k4 product
+    bool progressed = false;       // made progress since it was last resumed (a polling loop that only yields has not)
+};
+
+// mbarrier of the emulated block: arrivals still expected in the current phase, transaction bytes still in flight
+struct MBar {
+    uint32_t init_count = 0, pending = 0, phase = 0;
+    long long tx = 0;
 };
 
 constexpr size_t STACK_BYTES = 64 * 1024;
@@ -85,6 +94,12 @@ struct BlockRunner {
     void* sched_sp = nullptr;
     int current = -1;
     const std::function<void()>* body = nullptr;
+    // K1 support: dynamic shared memory (1024-byte aligned), mbarriers by shared offset, named barriers
+    unsigned char* smem = nullptr;
+    size_t smem_bytes = 0;
+    std::map<uint32_t, MBar> mbars;
+    int named_count[16] = {};
+    unsigned named_gen[16] = {};
 };
 
 static thread_local BlockRunner* g_run = nullptr;
@@ -128,6 +143,125 @@ double shfl_xor(double v, int lane_mask) {
     return g_run->fibers[g_run->current].shfl_val;
 }
 
+// a polling loop inside a kernel (mbarrier wait, named barrier): let the other threads of the block run
+static void yield_polling() {
+    Fiber& f = g_run->fibers[g_run->current];
+    f.progressed = false;
+    yield_to_scheduler();   // state stays READY: resumed in the next round
+}
+
+unsigned char* dynamic_smem() { return g_run->smem; }
+
+uint32_t smem_offset(const void* p) {
+    const unsigned char* q = static_cast<const unsigned char*>(p);
+    if (q < g_run->smem || q >= g_run->smem + g_run->smem_bytes) {
+        fail("shared-window address of a pointer outside the dynamic shared memory");
+        return 0;
+    }
+    return (uint32_t)(q - g_run->smem) + 1024u;  // never 0
+}
+static unsigned char* smem_ptr(uint32_t off) { return g_run->smem + (off - 1024u); }
+
+static void mbar_complete_if_done(MBar& b) {
+    if (b.pending == 0 && b.tx == 0) {
+        b.phase ^= 1u;
+        b.pending = b.init_count;
+    }
+}
+void mbar_init(uint32_t bar, uint32_t count) {
+    MBar& b = g_run->mbars[bar];
+    b.init_count = b.pending = count;
+    b.phase = 0;
+    b.tx = 0;
+}
+void mbar_arrive(uint32_t bar, uint32_t expect_tx_bytes) {
+    auto it = g_run->mbars.find(bar);
+    if (it == g_run->mbars.end() || it->second.pending == 0) {
+        fail("arrival at an mbarrier that was not initialised or expects no more arrivals in this phase");
+        return;
+    }
+    it->second.tx += expect_tx_bytes;
+    it->second.pending -= 1;
+    mbar_complete_if_done(it->second);
+}
+void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        auto it = g_run->mbars.find(bar);
+        if (it == g_run->mbars.end()) {
+            fail("wait on an mbarrier that was not initialised");
+            return;
+        }
+        if (it->second.phase != (parity & 1u)) return;  // the phase of that parity has completed
+        if (g_sticky_error) return;
+        yield_polling();
+    }
+}
+
+void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    // box of map->box[1] rows x map->box[0] elements starting at (inner c0, outer c1); out-of-bounds elements are
+    // zero; rows are 128 bytes apart in shared memory and, with the 128-byte swizzle, the 16-byte chunk j of a row
+    // whose shared address has bits [7:9] = r lands at chunk j ^ r
+    const size_t row_bytes = (size_t)map->box[0] * map->elem_bytes;
+    unsigned char* base = smem_ptr(dst);
+    if (map->swizzle != CU_TENSOR_MAP_SWIZZLE_128B || row_bytes != 128 || (reinterpret_cast<uintptr_t>(base) & 1023u) != 0) {
+        fail("emulated TMA: only 128-byte rows with the 128-byte swizzle into 1024-byte aligned tiles are modelled");
+        return;
+    }
+    if (base + (size_t)map->box[1] * row_bytes > g_run->smem + g_run->smem_bytes) {
+        fail("emulated TMA: destination tile exceeds the dynamic shared memory");
+        return;
+    }
+    for (uint32_t r = 0; r < map->box[1]; ++r) {
+        const long long gr = (long long)c1 + r;
+        for (uint32_t e = 0; e < map->box[0]; ++e) {
+            const long long gc = (long long)c0 + e;
+            double v = 0.0;
+            if (gr >= 0 && gr < (long long)map->dim[1] && gc >= 0 && gc < (long long)map->dim[0])
+                memcpy(&v, map->base + (size_t)gr * map->row_stride + (size_t)gc * map->elem_bytes, sizeof(v));
+            const uint32_t byte = e * map->elem_bytes, chunk = byte >> 4, within = byte & 15u;
+            memcpy(base + (size_t)r * 128 + (((chunk ^ (r & 7u)) << 4) | within), &v, sizeof(v));
+        }
+    }
+    auto it = g_run->mbars.find(bar);
+    if (it == g_run->mbars.end()) {
+        fail("emulated TMA: completion mbarrier was not initialised");
+        return;
+    }
+    it->second.tx -= (long long)map->box[1] * (long long)row_bytes;
+    mbar_complete_if_done(it->second);
+}
+
+void named_barrier(int id, int nthreads, bool wait) {
+    BlockRunner* r = g_run;
+    if (id < 0 || id >= 16) {
+        fail("named barrier id out of range");
+        return;
+    }
+    const unsigned gen = r->named_gen[id];
+    if (++r->named_count[id] >= nthreads) {
+        r->named_count[id] = 0;
+        ++r->named_gen[id];
+        return;
+    }
+    if (!wait) return;  // bar.arrive
+    while (r->named_gen[id] == gen && !g_sticky_error) yield_polling();
+}
+
+void syncwarp() { (void)shfl_xor(0.0, 0); }
+
+void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    Fiber& f = g_run->fibers[g_run->current];
+    f.mma[0] = a;
+    f.mma[1] = b;
+    f.mma[2] = c0;
+    f.mma[3] = c1;
+    f.state = AT_MMA;
+    yield_to_scheduler();
+    const Fiber& g = g_run->fibers[g_run->current];
+    c0 = g.mma[2];
+    c1 = g.mma[3];
+}
+
 bool spin_wait(unsigned long long spins) {
     static thread_local std::chrono::steady_clock::time_point t0;
     if (spins == 0) t0 = std::chrono::steady_clock::now();
@@ -151,51 +285,91 @@ static void prepare_fiber(BlockRunner& r, int t) {
 
 static bool run_block(BlockRunner& r, int nt, std::mt19937& rng) {
     for (int t = 0; t < nt; ++t) prepare_fiber(r, t);
+    r.mbars.clear();
+    for (int i = 0; i < 16; ++i) r.named_count[i] = 0, r.named_gen[i] = 0;
     std::vector<int> order(nt);
     for (int t = 0; t < nt; ++t) order[t] = t;
     int live = nt;
+    unsigned long long idle_rounds = 0;
     while (live > 0) {
         if (g_order == 1) std::reverse(order.begin(), order.end());
         else if (g_order == 2) std::shuffle(order.begin(), order.end(), rng);
+        bool progress = false;
         for (int t : order) {
             if (r.fibers[t].state != READY) continue;
             r.current = t;
             threadIdx_.x = (unsigned)t;
+            r.fibers[t].progressed = true;   // a polling loop that only yields clears it again
             emu_switch(&r.sched_sp, r.fibers[t].sp);
             if (r.fibers[t].state == DONE) --live;
+            progress = progress || r.fibers[t].progressed;
         }
         if (live == 0) break;
-        // nothing can run: release the barriers that are complete
-        int at_sync = 0;
-        for (int t = 0; t < nt; ++t) at_sync += r.fibers[t].state == AT_SYNC;
+        // release the barriers that are complete
+        int at_sync = 0, ready = 0;
+        for (int t = 0; t < nt; ++t) {
+            at_sync += r.fibers[t].state == AT_SYNC;
+            ready += r.fibers[t].state == READY;
+        }
+        bool released = false;
         if (at_sync == live) {
             for (int t = 0; t < nt; ++t)
                 if (r.fibers[t].state == AT_SYNC) r.fibers[t].state = READY;
-            continue;
+            released = true;
         }
-        bool released = false;
-        for (int w0 = 0; w0 < nt; w0 += 32) {
+        for (int w0 = 0; w0 < nt && !released; w0 += 32) {
             const int w1 = std::min(w0 + 32, nt);
-            int at_shfl = 0;
-            for (int t = w0; t < w1; ++t) at_shfl += r.fibers[t].state == AT_SHFL;
-            if (at_shfl == 0) continue;
-            if (at_shfl != w1 - w0) {
-                fail("warp shuffle with a full mask reached by only part of the warp (block " +
+            int at_shfl = 0, at_mma = 0;
+            for (int t = w0; t < w1; ++t) {
+                at_shfl += r.fibers[t].state == AT_SHFL;
+                at_mma += r.fibers[t].state == AT_MMA;
+            }
+            if (at_shfl == w1 - w0) {
+                double vals[32];
+                for (int t = w0; t < w1; ++t) vals[t - w0] = r.fibers[t].shfl_val;
+                for (int t = w0; t < w1; ++t) {
+                    const int src = (t - w0) ^ r.fibers[t].shfl_mask;
+                    r.fibers[t].shfl_val = (src >= 0 && src < w1 - w0) ? vals[src] : vals[t - w0];
+                    r.fibers[t].state = READY;
+                }
+                released = true;
+            } else if (at_mma == 32) {
+                // mma.sync.m8n8k4 f64: lane l holds A[l/4][l%4], B[l%4][l/4] and C[l/4][2(l%4) + {0,1}]
+                double A[8][4], B[4][8];
+                for (int l = 0; l < 32; ++l) {
+                    A[l >> 2][l & 3] = r.fibers[w0 + l].mma[0];
+                    B[l & 3][l >> 2] = r.fibers[w0 + l].mma[1];
+                }
+                for (int l = 0; l < 32; ++l) {
+                    const int i = l >> 2;
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 2 * (l & 3) + e;
+                        double c = r.fibers[w0 + l].mma[2 + e];
+                        for (int k = 0; k < 4; ++k) c = fma(A[i][k], B[k][j], c);
+                        r.fibers[w0 + l].mma[2 + e] = c;
+                    }
+                    r.fibers[w0 + l].state = READY;
+                }
+                released = true;
+            } else if ((at_shfl > 0 || at_mma > 0) && ready == 0 && at_sync + at_shfl + at_mma == live) {
+                // everybody is blocked and this warp can never complete its collective
+                fail("warp collective (shuffle / mma with a full mask) reached by only part of the warp (block " +
                      std::to_string(blockIdx_.x) + "," + std::to_string(blockIdx_.y) + ", warp " + std::to_string(w0 / 32) + ")");
                 return false;
             }
-            double vals[32];
-            for (int t = w0; t < w1; ++t) vals[t - w0] = r.fibers[t].shfl_val;
-            for (int t = w0; t < w1; ++t) {
-                const int src = (t - w0) ^ r.fibers[t].shfl_mask;
-                r.fibers[t].shfl_val = (src >= 0 && src < w1 - w0) ? vals[src] : vals[t - w0];
-                r.fibers[t].state = READY;
-            }
-            released = true;
         }
-        if (!released) {
+        if (released || progress) {
+            idle_rounds = 0;
+            continue;
+        }
+        if (ready == 0) {
             fail("deadlock: __syncthreads() not reached by all live threads of block " + std::to_string(blockIdx_.x) + "," +
                  std::to_string(blockIdx_.y));
+            return false;
+        }
+        if (++idle_rounds > 100000) {  // only polling loops are running and nothing they poll ever changes
+            fail("deadlock: threads of block " + std::to_string(blockIdx_.x) + "," + std::to_string(blockIdx_.y) +
+                 " poll an mbarrier / named barrier that nobody completes");
             return false;
         }
     }
@@ -204,7 +378,7 @@ static bool run_block(BlockRunner& r, int nt, std::mt19937& rng) {
 
 static thread_local uint64_t g_launches = 0, g_blocks = 0;
 
-void launch(dim3 grid, dim3 block, const std::function<void()>& thread_body) {
+void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()>& thread_body) {
     if (g_sticky_error) return;
     if (block.y != 1 || block.z != 1 || grid.z != 1 || block.x == 0 || block.x > 1024) {
         fail("unsupported launch shape");
@@ -230,6 +404,14 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& thread_body) {
         r.owner = &pool;
     }
     r.body = &thread_body;
+    std::vector<unsigned char> smem_storage;
+    if (dynamic_smem_bytes > 0) {
+        // handed out at an address that is NOT 1024-byte aligned (kernels that need the alignment round up themselves)
+        smem_storage.assign(dynamic_smem_bytes + 2048, 0xFF);
+        unsigned char* aligned = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_storage.data()) + 1023) & ~uintptr_t(1023));
+        r.smem = aligned + 16;
+        r.smem_bytes = dynamic_smem_bytes;
+    }
     BlockRunner* outer = g_run;
     g_run = &r;
     std::mt19937 rng(g_seed + (unsigned)g_launches * 7919u);
@@ -380,6 +562,36 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return emu::g_sticky_error; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
     *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
+static CUresult emu_encode_tiled(CUtensorMap* map, CUtensorMapDataType type, cuuint32_t rank, void* base, const cuuint64_t* gdim,
+                                 const cuuint64_t* gstride, const cuuint32_t* box, const cuuint32_t* estride,
+                                 CUtensorMapInterleave interleave, CUtensorMapSwizzle swizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill) {
+    // the constraints of the real encoder that this code base can run into
+    if (type != CU_TENSOR_MAP_DATA_TYPE_FLOAT64 || rank != 2 || interleave != CU_TENSOR_MAP_INTERLEAVE_NONE) return CUDA_ERROR_INVALID_VALUE;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (gstride[0] & 15) != 0) return CUDA_ERROR_INVALID_VALUE;
+    if (box[0] == 0 || box[1] == 0 || box[0] > 256 || box[1] > 256 || estride[0] != 1 || estride[1] != 1) return CUDA_ERROR_INVALID_VALUE;
+    if (swizzle == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * 8 > 128) return CUDA_ERROR_INVALID_VALUE;
+    memset(map, 0, sizeof(*map));
+    map->base = static_cast<const unsigned char*>(base);
+    map->dim[0] = gdim[0];
+    map->dim[1] = gdim[1];
+    map->row_stride = gstride[0];
+    map->box[0] = box[0];
+    map->box[1] = box[1];
+    map->swizzle = (uint32_t)swizzle;
+    map->elem_bytes = 8;
+    return CUDA_SUCCESS;
+}
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* res) {
+    if (strcmp(symbol, "cuTensorMapEncodeTiled") == 0) {
+        *fn = reinterpret_cast<void*>(&emu_encode_tiled);
+        *res = cudaDriverEntryPointSuccess;
+    } else {
+        *fn = nullptr;
+        *res = cudaDriverEntryPointSymbolNotFound;
+    }
     return cudaSuccess;
 }
 cudaError_t cudaGetLastError() { return emu::g_sticky_error; }

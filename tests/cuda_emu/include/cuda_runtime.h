@@ -1,10 +1,11 @@
 // tests/cuda_emu -- host stand-in for <cuda_runtime.h>  (TEST INFRASTRUCTURE ONLY, never part of the product).
 //
-// Lets the CPU test-suite compile optiml_b200/csrc/pg.cu and api.cu with g++ and run the REAL kernel source thread by
-// thread: every CUDA thread of a block is a fiber, __syncthreads() and the warp shuffles are fiber barriers
-// (emu_runtime.cpp), blocks run one after the other, "device" memory is host memory with canaries.  What this
-// checks: indexing, barrier placement, launch sequences, double-buffering, arithmetic order -- not timing, not memory
-// ordering between CTAs (blocks are serial), not PTX.
+// Lets the CPU test-suite compile optiml_b200/csrc/*.cu with g++ and run the REAL kernel source thread by thread: every
+// CUDA thread of a block is a fiber, __syncthreads(), the warp shuffles and the m8n8k4 tensor-core product are fiber
+// barriers / warp collectives, mbarriers, tiled (TMA) copies and named barriers are modelled (emu_runtime.cpp), blocks
+// run one after the other, "device" memory is host memory with canaries.  What this checks: indexing, barrier
+// placement, producer / consumer protocols, launch sequences, double-buffering, arithmetic order -- not timing, not
+// memory ordering between CTAs (blocks are serial), not PTX.
 #pragma once
 #include <math.h>
 #include <stddef.h>
@@ -19,6 +20,8 @@
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
 #define __grid_constant__
+#define EMU_NOINLINE __attribute__((noinline))   // build.py rewrites __noinline__ (libstdc++ uses that token itself)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
@@ -34,6 +37,19 @@ extern thread_local dim3 blockDim_, gridDim_;
 void syncthreads();
 double shfl_xor(double v, int lane_mask);
 bool spin_wait(unsigned long long spins);  // called from a wait loop on peer memory: yield; true once 20 s have passed
+// K1 (csrc/gram.cu): dynamic shared memory, mbarriers, tiled (TMA) copies, the FP64 tensor-core product, named barriers
+unsigned char* dynamic_smem();
+uint32_t smem_offset(const void* p);                            // stand-in for the 32-bit shared-window address
+void mbar_init(uint32_t bar, uint32_t count);
+void mbar_arrive(uint32_t bar, uint32_t expect_tx_bytes);       // arrive (+ expect_tx)
+void mbar_wait(uint32_t bar, uint32_t parity);                  // until the phase of that parity has completed
+void named_barrier(int id, int nthreads, bool wait);            // bar.sync / bar.arrive
+void syncwarp();
+void dmma_m8n8k4(double& c0, double& c1, double a, double b);   // D = A(8x4, row) * B(4x8, col) + C, one warp
+}  // namespace emu
+struct CUtensorMap;
+namespace emu {
+void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1);  // box copy, zero fill, swizzle, complete_tx
 }  // namespace emu
 #define threadIdx (emu::threadIdx_)
 #define blockIdx (emu::blockIdx_)
@@ -43,6 +59,13 @@ bool spin_wait(unsigned long long spins);  // called from a wait loop on peer me
 // ---- device intrinsics used by the kernels
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __threadfence() {}
+static inline void __syncwarp() { emu::syncwarp(); }
+static inline int __double2loint(double v) { long long r; memcpy(&r, &v, 8); return (int)(unsigned)(r & 0xffffffffll); }
+static inline int __double2hiint(double v) { long long r; memcpy(&r, &v, 8); return (int)(unsigned)((unsigned long long)r >> 32); }
+static inline double __hiloint2double(int hi, int lo) {
+    const unsigned long long r = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+    double v; memcpy(&v, &r, 8); return v;
+}
 static inline double __shfl_xor_sync(unsigned, double v, int lane_mask) { return emu::shfl_xor(v, lane_mask); }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
@@ -104,9 +127,15 @@ cudaError_t cudaIpcCloseMemHandle(void* p);
 cudaError_t cudaGetLastError();
 const char* cudaGetErrorString(cudaError_t e);
 
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+enum { cudaEnableDefault = 0 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long flags, cudaDriverEntryPointQueryResult* res);
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+
 // ---- kernel launches: `k<<<grid, block, smem, stream>>>(args)` is rewritten by tests/cuda_emu/build.py into
-// emu::launch(grid, block, [=]() { k(args); })
+// emu::launch(grid, block, smem, [=]() { k(args); })
 #include <functional>
 namespace emu {
-void launch(dim3 grid, dim3 block, const std::function<void()>& thread_body);
+void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()>& thread_body);
 }

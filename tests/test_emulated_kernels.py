@@ -1,7 +1,7 @@
-"""The solver kernels of csrc/pg.cu executed on the CPU, thread by thread (tests/cuda_emu), in the `not gpu` suite.
+"""The kernels of csrc/gram.cu and csrc/pg.cu executed on the CPU, thread by thread (tests/cuda_emu), in the `not gpu` suite.
 
 The emulated library is compiled from the PRODUCT sources (only the launch syntax is rewritten), so these tests run the
-real K2 / K3 code -- indexing, barriers, launch sequences, double-buffering, reduction order -- against the reference's
+real K1 / K2 / K3 code -- indexing, barriers, launch sequences, double-buffering, reduction order -- against the reference's
 golden vectors and the oracle without a GPU, and pin the properties the batched one-vs-rest path
 rests on:  the multi-vector pass is bit-identical to the single-vector pass;  a solver on the signed view
 (s s') o M is bit-identical to a solver on the materialised Q;  a lockstep batch is bit-identical to the solvers run
@@ -9,6 +9,7 @@ one after the other.  Timing, PTX and inter-CTA memory ordering are out of the e
 remain the parity tests proper.
 """
 import contextlib
+import ctypes as C
 
 import numpy as np
 import pytest
@@ -87,6 +88,69 @@ def test_svr_block_layout_vs_oracle():
     assert got.iter == want.iter and got.status == want.status
     assert np.abs(got.x - want.x).max() <= 1e-11
     assert np.abs(got.f_hist - want.f_hist).max() <= 1e-10 * np.abs(want.f_hist).max()
+
+
+# --------------------------------------------------------------------------------------------- K1 (csrc/gram.cu)
+# The Gram kernel itself -- TMA producers, mbarrier rings, the m8n8k4 FP64 tensor-core contraction, the fused
+# epilogues -- runs on the emulation from the product source (its PTX wrappers have emulation twins).
+@pytest.mark.parametrize('name', ['linear', 'poly_d3_scale', 'poly_d4_g05_c05', 'gauss_scale', 'gauss_g03'])
+def test_gram_kernel_reference_goldens(golden, name):
+    """kernels.py:49-51, 91-95, 125-129 of the REAL reference (tests/golden/kernels.npz): 1e-12 relative"""
+    import test_gpu_kernels as T
+    with emulated_device() as lib:
+        T.test_kernel_golden(golden, name)
+        assert lib.emu_sticky_error() == 0
+
+
+@pytest.mark.parametrize('name', ['lap_scale', 'sig_g01_c05'])
+def test_extra_kernels_reference_goldens(golden, name):
+    import test_gpu_kernels as T
+    with emulated_device() as lib:
+        T.test_extra_kernel_golden(golden, name)
+        assert lib.emu_sticky_error() == 0
+
+
+@pytest.mark.parametrize('shape', [(1, 1, 1), (2, 3, 1), (129, 127, 17), (257, 1, 33), (128, 128, 15)])
+def test_gram_kernel_ragged_shapes_vs_oracle(shape):
+    import test_gpu_kernels as T
+    with emulated_device(order=2, seed=shape[0]) as lib:
+        for name in ('linear', 'poly_d3_scale', 'gauss_scale'):
+            T.test_kernel_ragged_shapes_vs_oracle(shape, name)
+        T.test_kernel_input_validation()
+        assert lib.emu_sticky_error() == 0
+
+
+def test_gram_kernel_schedules_and_sharding_give_the_same_bits(monkeypatch):
+    """The Hessian Q = s_i s_j (k(x_i, x_j) + 1) built (a) with the two consumer groups in lockstep, ping-pong and
+    free-running (SVMB200_GRAM_EXCLUSIVE = 2 / 1 / 0), (b) under shuffled thread and block schedules, (c) in row shards:
+    always the same bits, and the oracle's values."""
+    from optiml_b200.ml.svm.kernels import GaussianKernel
+    from optiml_b200.runtime import DeviceHessian, default_context
+    rng = np.random.default_rng(8)
+    n, d = 200, 37
+    X = rng.standard_normal((n, d))
+    signs = np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    kid, gamma, coef0, degree = GaussianKernel().gram_spec(X)
+
+    def build(row0, nrows, order):
+        with emulated_device(order=order, seed=3) as lib:
+            ctx = default_context()
+            dX, dS = ctx.upload_matrix(X), ctx.upload_vector(signs)
+            H = DeviceHessian(ctx, n, 'plain', row0=row0, nrows=nrows)
+            N.call('svmb200_gram', ctx.handle, C.c_void_p(dX.dptr), n, dX.ld, C.c_void_p(dX.dptr), n, dX.ld, d, 1, kid, gamma,
+                   coef0, degree, C.c_void_p(dS.dptr), C.c_void_p(dS.dptr), 1.0, row0, nrows, C.c_void_p(H.matrix.dptr), H.ld)
+            out = H.shard_to_host()
+            assert lib.emu_sticky_error() == 0
+        return out
+
+    full = build(0, n, 0)
+    want = signs[:, None] * (O.gaussian_kernel(X) + 1.0) * signs[None, :]
+    assert np.abs(full - want).max() <= 1e-12
+    for mode, order in (('2', 2), ('1', 0), ('1', 2), ('0', 1)):
+        monkeypatch.setenv('SVMB200_GRAM_EXCLUSIVE', mode)
+        assert np.array_equal(build(0, n, order), full), (mode, order)
+    monkeypatch.delenv('SVMB200_GRAM_EXCLUSIVE')
+    assert np.array_equal(np.vstack((build(0, 64, 2), build(64, 128, 0), build(192, 8, 1))), full)
 
 
 # --------------------------------------------------------------------------------------------- shared-Gram path
