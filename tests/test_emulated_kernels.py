@@ -153,6 +153,60 @@ def test_gram_kernel_schedules_and_sharding_give_the_same_bits(monkeypatch):
     assert np.array_equal(np.vstack((build(0, 64, 2), build(64, 128, 0), build(192, 8, 1))), full)
 
 
+def test_gram_kernel_random_shapes_signs_shards_and_modes(monkeypatch):
+    """Seeded fuzz of svmb200_gram on the emulation: sizes around the 128 x 64 tile and the 16-wide k chunk, all five
+    kernels, label signs on either side, bias, self / cross Gram, arbitrary row ranges (empty ones too), the three
+    consumer-group modes, shuffled schedules.  Against the oracle to 1e-12; pad columns must be exact zeros."""
+    from optiml_b200.runtime import default_context
+    kinds = {0: 'linear', 1: 'poly', 2: 'gaussian', 3: 'sigmoid', 4: 'laplacian'}
+    for seed in range(80):
+        rng = np.random.default_rng(9000 + seed)
+        na = int(rng.choice([1, 2, 7, 63, 64, 65, 127, 128, 129, 200, 260]))
+        same = bool(rng.random() < 0.5)
+        nb = na if same else int(rng.choice([1, 3, 31, 64, 65, 130]))
+        d = int(rng.choice([1, 2, 3, 15, 16, 17, 32, 33, 50]))
+        kid = int(rng.integers(0, 5))
+        gamma, coef0 = float(rng.uniform(0.01, 0.5)), float(rng.choice([0., 0.5, 1.]))
+        degree, bias = float(rng.choice([1, 2, 3, 4])), float(rng.choice([0., 1.]))
+        use_sa, use_sb = bool(rng.random() < 0.5), bool(rng.random() < 0.5)
+        row0 = int(rng.integers(0, na))
+        nrows = int(rng.integers(0, na - row0 + 1))
+        monkeypatch.setenv('SVMB200_GRAM_EXCLUSIVE', str(rng.choice(['0', '1', '2'])))
+        A = rng.standard_normal((na, d))
+        B = A if same else rng.standard_normal((nb, d))
+        sa = np.where(rng.random(na) < 0.5, 1., -1.)
+        sb = sa if same else np.where(rng.random(nb) < 0.5, 1., -1.)
+        label = dict(seed=seed, na=na, nb=nb, d=d, kind=kinds[kid], same=same, row0=row0, nrows=nrows)
+        with emulated_device(order=2, seed=seed) as lib:
+            ctx = default_context()
+            dA = ctx.upload_matrix(A)
+            dB = dA if same else ctx.upload_matrix(B)
+            dsa = ctx.upload_vector(sa) if use_sa else None
+            dsb = ctx.upload_vector(sb) if use_sb else None
+            ldo = N.padded_ld(nb)
+            nbytes = 8 * max(nrows, 1) * ldo
+            dout = ctx.malloc(nbytes)
+            ctx.memset(dout, 0xFF, nbytes)
+            N.call('svmb200_gram', ctx.handle, C.c_void_p(dA.dptr), na, dA.ld, C.c_void_p(dB.dptr), nb, dB.ld, d, int(same), kid,
+                   gamma, coef0, degree, C.c_void_p(dsa.dptr) if dsa else None, C.c_void_p(dsb.dptr) if dsb else None, bias,
+                   row0, nrows, C.c_void_p(dout), ldo)
+            out = np.empty((max(nrows, 1), ldo))
+            ctx.d2h(out, dout)
+            ctx.free(dout)
+            assert lib.emu_sticky_error() == 0, label
+        if nrows == 0:
+            continue
+        kw = {} if kid == 0 else dict(gamma=gamma)
+        if kid in (1, 3):
+            kw['coef0'] = coef0
+        if kid == 1:
+            kw['degree'] = degree
+        K = O.kernel_matrix(kinds[kid], A, None if same else B, **kw)
+        want = (K + bias) * (sa[:, None] if use_sa else 1.0) * (sb[None, :] if use_sb else 1.0)
+        assert np.abs(out[:nrows, :nb] - want[row0:row0 + nrows]).max() <= 1e-12 * max(1., np.abs(want).max()), label
+        assert np.all(out[:nrows, nb:] == 0.0), label
+
+
 # --------------------------------------------------------------------------------------------- shared-Gram path
 # (the same checks run on the B200 in tests/test_gpu_shared_gram.py)
 @contextlib.contextmanager
