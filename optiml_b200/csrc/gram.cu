@@ -52,6 +52,7 @@ struct GramArgs {
     int tiles_m, tiles_n;
     int same;
     int exclusive;  // 0: groups run free; 1: ping-pong on the tensor pipe; 2: lockstep phases (see kernel)
+    int backoff;    // 1: the producers sleep between polls of a full ring (default); 0: they spin (A/B: SVMB200_GRAM_BACKOFF)
     double gamma, coef0, degree, bias;
 };
 
@@ -80,6 +81,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Producer-side wait: a producer whose ring is full has nothing to do until a consumer frees a stage (one k chunk of
+// contraction, ~1 us; never during an epilogue phase).  Spinning on try_wait it issued 3.7e9 of the kernel's 9.5e9
+// warp-instructions (profiles/r1_gram_kernel_sass_stalls.txt) in the two schedulers it shares with consumer warps,
+// whose epilogue is issue-bound -- so it sleeps between polls (the ring is four stages deep: ~3 us of slack).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(128);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -101,6 +122,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { emu::m
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { emu::mbar_arrive(bar, bytes); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { emu::mbar_arrive(bar, 0); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     emu::tma_load_2d(dst, map, bar, c0, c1);
 }
@@ -209,7 +231,8 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 const int arow = (int)p.row0 + tm * BM;
                 const int brow = tn * BN;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    if (p.backoff) mbar_wait_backoff(empty0 + 8 * stage, phase ^ 1);
+                    else mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t fb = full0 + 8 * stage;
                     mbar_expect_tx(fb, STAGE_BYTES);
                     const uint32_t dst = ring + stage * STAGE_BYTES;
@@ -658,6 +681,8 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
             // phase lock-step when there is an epilogue (see kernel comment); SVMB200_GRAM_EXCLUSIVE=0/1/2 overrides
             const char* ev = getenv("SVMB200_GRAM_EXCLUSIVE");
             a.exclusive = ev ? atoi(ev) : (kernel != SVMB200_KERNEL_LINEAR ? 2 : 0);
+            const char* bo = getenv("SVMB200_GRAM_BACKOFF");
+            a.backoff = bo ? atoi(bo) : 1;
         }
         a.gamma = gamma;
         a.coef0 = coef0;

@@ -12,6 +12,9 @@ timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.er
 timeout 900 python scripts/bench_ovr.py --classes 4 --iters 300 > gpurun_out/bench_ovr_c4.jsonl 2> gpurun_out/bench_ovr_c4.err; echo "bench_ovr rc=$?"; cat gpurun_out/bench_ovr_c4.jsonl; tail -3 gpurun_out/bench_ovr_c4.err
 # 4. shape sweep of K2 x NB
 timeout 900 python scripts/sweep_multi.py > gpurun_out/sweep_multi.jsonl 2> gpurun_out/sweep_multi.err; echo "sweep rc=$?"; cat gpurun_out/sweep_multi.jsonl; tail -3 gpurun_out/sweep_multi.err
+# 4b. Gram kernel: interior-tile epilogue (new) and producer back-off A/B (round-1 reference: C4 Gaussian 26.6 ms)
+timeout 600 python scripts/bench_gram.py > gpurun_out/bench_gram_backoff1.log 2>&1; echo "bench_gram rc=$?"; cat gpurun_out/bench_gram_backoff1.log
+SVMB200_GRAM_BACKOFF=0 timeout 600 python scripts/bench_gram.py > gpurun_out/bench_gram_backoff0.log 2>&1; echo "bench_gram (spin) rc=$?"; cat gpurun_out/bench_gram_backoff0.log
 # 5. ncu: launch list of a short one-vs-rest fit, full capture of the multi-vector pass
 PROF="python scripts/bench_ovr.py --classes 4 --iters 20 --skip-cloned"
 timeout 300 $PROF > gpurun_out/plain_ovr.log 2>&1 && \
