@@ -21,6 +21,14 @@ def pytest_addoption(parser):
                           'kernels (tests/cuda_emu) -- slow')
 
 
+@pytest.fixture(scope='session', autouse=True)
+def _library_is_built():
+    """A fresh checkout has no optiml_b200/_lib/libsvmb200.so (build artefacts are not in the history): build it once per
+    session (nvcc cross-compiles without a GPU; a no-op when it is up to date) so that no test depends on test order."""
+    from optiml_b200.csrc.build import build
+    build()
+
+
 @pytest.fixture(autouse=True)
 def _emulated_device_if_requested(request):
     if not request.config.getoption('--emulate'):
