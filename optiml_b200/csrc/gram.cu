@@ -197,8 +197,10 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #else
     unsigned char* smem_raw = emu::dynamic_smem();
 #endif
-    // 1024-byte alignment required by the 128B swizzle pattern
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment required by the 128B swizzle pattern -- as an OFFSET from the shared array, so that the compiler
+    // keeps the address space and the fragment / operand loads below are LDS (an integer round-up of the generic address
+    // turned all of them into generic LD: profiles/r1_gram_kernel_sass_stalls.txt)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * RING_BYTES);  // [group][full x STAGES | empty x STAGES]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 

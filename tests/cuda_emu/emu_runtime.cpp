@@ -152,15 +152,20 @@ static void yield_polling() {
 
 unsigned char* dynamic_smem() { return g_run->smem; }
 
+// The dynamic shared memory of a block starts 16 bytes past a 1024-byte boundary -- in the host address AND in the
+// emulated shared-window offsets -- so a kernel that needs an aligned tile has to round up itself, whether it does so
+// on the generic address or on the window offset.
+constexpr uint32_t SMEM_WINDOW_SKEW = 16;
+
 uint32_t smem_offset(const void* p) {
     const unsigned char* q = static_cast<const unsigned char*>(p);
     if (q < g_run->smem || q >= g_run->smem + g_run->smem_bytes) {
         fail("shared-window address of a pointer outside the dynamic shared memory");
         return 0;
     }
-    return (uint32_t)(q - g_run->smem) + 1024u;  // never 0
+    return (uint32_t)(q - g_run->smem) + SMEM_WINDOW_SKEW;
 }
-static unsigned char* smem_ptr(uint32_t off) { return g_run->smem + (off - 1024u); }
+static unsigned char* smem_ptr(uint32_t off) { return g_run->smem + (off - SMEM_WINDOW_SKEW); }
 
 static void mbar_complete_if_done(MBar& b) {
     if (b.pending == 0 && b.tx == 0) {
@@ -406,10 +411,10 @@ void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::functio
     r.body = &thread_body;
     std::vector<unsigned char> smem_storage;
     if (dynamic_smem_bytes > 0) {
-        // handed out at an address that is NOT 1024-byte aligned (kernels that need the alignment round up themselves)
+        // handed out at an address that is NOT 1024-byte aligned (see SMEM_WINDOW_SKEW)
         smem_storage.assign(dynamic_smem_bytes + 2048, 0xFF);
         unsigned char* aligned = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_storage.data()) + 1023) & ~uintptr_t(1023));
-        r.smem = aligned + 16;
+        r.smem = aligned + SMEM_WINDOW_SKEW;
         r.smem_bytes = dynamic_smem_bytes;
     }
     BlockRunner* outer = g_run;
