@@ -148,7 +148,9 @@ __device__ __forceinline__ void exp8(const double (&x)[8], double (&out)[8]) {
     int k[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const double xe = fmax(x[e], -800.0);  // exp(-800) == 0 in FP64; keeps k in range
+        // exp(-800) == 0 in FP64; keeps k in range.  A compare + select, not fmax(): fmax's NaN rule costs DSETP + 2 SEL +
+        // LOP3 + moves (7 instructions), the select 3, and the results agree for every non-NaN argument
+        const double xe = x[e] < -800.0 ? -800.0 : x[e];
         double t = fma(xe, L2E, MAGIC);
         k[e] = __double2loint(t);
         t -= MAGIC;
@@ -382,7 +384,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             double dist = __dadd_rn(fma(-2.0, acc[mi][ni][e], na), nbv[ni][e]);  // -2<a,b> is exact
-                            dist = fmax(dist, 0.0);
+                            dist = dist < 0.0 ? 0.0 : dist;  // np.maximum(D, 0); select instead of fmax(), see exp8
                             if (EDGE && p.same && (i == col_base + ni * 8 + e)) dist = 0.0;
                             x[ni * 2 + e] = __dmul_rn(-p.gamma, dist);
                         }
