@@ -22,3 +22,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
 echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:matvec_seg_multi -s 10 -c 3 -o gpurun_out/prof_matvec_multi $PROF > gpurun_out/ncu_ovr2.log 2>&1
 echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gram_kernel -s 2 -c 1 -o gpurun_out/prof_gram_r2 python scripts/bench_gram.py > gpurun_out/ncu_gram_r2.log 2>&1
+echo "ncu gram rc=$?"
