@@ -1,12 +1,12 @@
 """Shape sweep of the multi-vector streaming pass K2 x NB (widening 8f-4) at the headline size.
 
-For every (R, U, MINB) variant: rebuild the library with -DSVMB200_MULTI_R/U/MINB into its own directory (nvcc is on
+For every (R, U, MINB[, H]) variant: rebuild the library with -DSVMB200_MULTI_R/U/MINB/H into its own directory (nvcc is on
 the GPU box), then, in a subprocess that loads that variant, time svmb200_matvec_multi with NB = 1..4 vectors against a
 resident n x n matrix with CUDA events (inputs larger than L2: 20 GB at n = 50 000) and check every result bitwise
 against svmb200_matvec.  One JSON line per (variant, NB): ms per pass, HBM GB/s of the pass (8 n^2 bytes), and the
 per-problem rate NB x that.
 
-    python scripts/sweep_multi.py [--n 50000] [--reps 20] [--variants R:U:MINB,...]
+    python scripts/sweep_multi.py [--n 50000] [--reps 20] [--variants R:U:MINB[:H],...]
     python scripts/sweep_multi.py --child ...   (internal)
 """
 import argparse
@@ -75,23 +75,25 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--n', type=int, default=50000)
     ap.add_argument('--reps', type=int, default=20)
-    ap.add_argument('--variants', default='4:2:0,8:1:2,8:1:1,8:2:2,2:4:3,16:1:1')
+    ap.add_argument('--variants', default='4:2:0,8:1:2,8:1:1,2:4:3,16:1:1,4:2:1:2,2:4:1:2')
     ap.add_argument('--child', default=None)
     args = ap.parse_args()
     if args.child is not None:
         return child(args.n, args.reps, args.child)
     from optiml_b200.csrc import build
     for v in args.variants.split(','):
-        r, u, minb = (int(t) for t in v.split(':'))
-        lib_dir = os.path.join(ROOT, 'optiml_b200', '_lib_sweep', f'R{r}_U{u}_B{minb}')
+        fields = [int(t) for t in v.split(':')]
+        r, u, minb = fields[:3]
+        h = fields[3] if len(fields) > 3 else 1   # thread groups per CTA (L1 reuse of the vector operands)
+        lib_dir = os.path.join(ROOT, 'optiml_b200', '_lib_sweep', f'R{r}_U{u}_B{minb}_H{h}')
         try:
-            lib = build.build(defines=(f'SVMB200_MULTI_R={r}', f'SVMB200_MULTI_U={u}', f'SVMB200_MULTI_MINB={minb}'),
-                              lib_dir=lib_dir)
+            lib = build.build(defines=(f'SVMB200_MULTI_R={r}', f'SVMB200_MULTI_U={u}', f'SVMB200_MULTI_MINB={minb}',
+                                       f'SVMB200_MULTI_H={h}'), lib_dir=lib_dir)
         except subprocess.CalledProcessError as exc:
             print(json.dumps(dict(variant=v, error=f'build failed: {exc}')), flush=True)
             continue
         env = dict(os.environ, SVMB200_LIB=lib)
-        subprocess.run([sys.executable, os.path.abspath(__file__), '--child', f'R{r}_U{u}_B{minb}', '--n', str(args.n),
+        subprocess.run([sys.executable, os.path.abspath(__file__), '--child', f'R{r}_U{u}_B{minb}_H{h}', '--n', str(args.n),
                         '--reps', str(args.reps)], env=env, check=False)
 
 
