@@ -290,3 +290,45 @@ def test_emulated_device_leaves_no_allocation_behind():
         gc.collect()
     assert lib.emu_live_allocations() <= base   # context, workspace, scratch, matrices: all returned, canaries intact
     assert lib.emu_sticky_error() == 0
+
+
+def test_one_vs_rest_host_contract_labels_clone_pickle():
+    """sklearn's contract around the shared-Gram fit: string labels, a multilabel indicator target, two classes (a single
+    binary problem: sklearn's own path), clone / get_params, pickling the fitted meta-estimator without device handles"""
+    import pickle
+    from sklearn.base import clone
+    from optiml_b200.ml.multiclass import OneVsRestClassifier
+    from optiml_b200.ml.svm import SVC
+    from optiml_b200.ml.svm.kernels import GaussianKernel
+    from optiml_b200.ml.svm.losses import hinge
+    from optiml_b200.opti.constrained import FrankWolfe
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((90, 4))
+    centres = rng.standard_normal((3, 4)) * 2
+    idx = rng.integers(0, 3, 90)
+    X += centres[idx]
+    names = np.array(['setosa', 'versicolor', 'virginica'])[idx]
+    est = SVC(loss=hinge, kernel=GaussianKernel(gamma=0.5), reg_intercept=True, dual=True, optimizer=FrankWolfe, max_iter=15)
+    with emulated_device() as lib:
+        ovr = OneVsRestClassifier(est).fit(X, names)
+        assert list(ovr.classes_) == ['setosa', 'versicolor', 'virginica'] and len(ovr.estimators_) == 3
+        assert [e.fit_times_['batch'] for e in ovr.estimators_] == [3, 3, 3]
+        pred = ovr.predict(X)
+        assert pred.dtype.kind == 'U' and (pred == names).mean() > 0.8
+        # multilabel indicator: one binary problem per column, same lockstep fit
+        Y = np.stack((idx == 0, idx != 1, idx == 2), axis=1).astype(int)
+        multi = OneVsRestClassifier(est).fit(X, Y)
+        assert multi.multilabel_ and multi.predict(X).shape == Y.shape
+        assert np.array_equal(multi.estimators_[0].alphas_, ovr.estimators_[0].alphas_)   # same column, same problem
+        # two classes: sklearn fits ONE estimator through its own path (nothing to share)
+        two = OneVsRestClassifier(est).fit(X, (idx == 0).astype(int))
+        assert len(two.estimators_) == 1 and 'batch' not in two.estimators_[0].fit_times_
+        assert np.array_equal(two.estimators_[0].alphas_, ovr.estimators_[0].alphas_)
+        # clone / params / pickle
+        again = clone(ovr)
+        assert again.get_params()['estimator__max_iter'] == 15 and not hasattr(again, 'estimators_')
+        blob = pickle.dumps(ovr)
+        assert len(blob) < 200_000   # no n x n matrix, no device handle
+        back = pickle.loads(blob)
+        assert np.array_equal(back.predict(X), pred)
+        assert lib.emu_sticky_error() == 0
