@@ -41,6 +41,22 @@ def test_frank_wolfe_reference_goldens(golden, key, p, t):
         assert lib.emu_sticky_error() == 0
 
 
+@pytest.mark.filterwarnings('ignore::sklearn.exceptions.ConvergenceWarning')
+@pytest.mark.parametrize('which', ['svc_adam_nesterov_equality_row', 'svr_adadelta_blocks', 'optimality_exit'])
+def test_augmented_lagrangian_reference_goldens(golden, which):
+    """Whole estimator fits through the real kernels (K1 + K2 + al_vector_kernel) against the REAL reference's runs
+    (tests/golden/al_stochastic.npz): alphas, multipliers, histories, support set, intercept, decision values to 1e-8"""
+    import test_gpu_al as T
+    with emulated_device() as lib:
+        if which == 'svc_adam_nesterov_equality_row':
+            T.test_svc_matches_reference(golden, 'adam_nesterov', False, 1)   # reg_intercept=False: y'alpha = 0 relaxed
+        elif which == 'svr_adadelta_blocks':
+            T.test_svr_matches_reference(golden, 'gaussian', 'adadelta', True)
+        else:
+            T.test_optimality_exit_matches_reference(golden, 'sgd_nesterov', 0.1)
+        assert lib.emu_sticky_error() == 0
+
+
 @pytest.mark.parametrize('order', [1, 2])
 def test_thread_schedule_does_not_change_a_bit(order):
     """Resuming the threads of a block in reversed / shuffled order between barriers, and running the blocks of a
