@@ -89,7 +89,8 @@ int svmb200_comm_destroy(svmb200_ctx* ctx);
  * the handles of all ranks, concatenated in rank order, are passed to svmb200_comm_p2p_attach.  The
  * matvec kernel then stores its results directly into every peer's arena as self-validating tagged
  * 16-byte entries (no fence, no flag); the vector kernel spins on the entries it reads.  Without it
- * (or if IPC mapping fails) NCCL is used. */
+ * (or if IPC mapping fails, or for a problem so small that the 64-row shard granularity leaves a rank
+ * without rows) NCCL is used. */
 int svmb200_comm_p2p_export(svmb200_ctx* ctx, size_t arena_bytes, void* handle64);
 int svmb200_comm_p2p_attach(svmb200_ctx* ctx, const void* handles, int nranks);
 int svmb200_comm_p2p_enabled(svmb200_ctx* ctx, int* enabled);

@@ -476,7 +476,13 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     pg->nvars = pg->svr ? 2 * n : n;
     pg->rows_per_rank = rpr;
     pg->stride = rpr + rpr / MV_GROUP;
-    pg->p2p = ctx->p2p_enabled && P > 1 &&
+    // The fused exchange double-buffers by sequence parity; that is safe because a rank's vector launch of product
+    // s + 1 waits for EVERY peer's shard of s + 1, which a peer only publishes after its own vector launch of s -- so
+    // nobody can overwrite a buffer that is still being read.  A rank with an EMPTY shard (the 64-row granularity leaves
+    // the last ranks without rows when (P - 1) rows_per_rank >= n: small problems) publishes nothing, nobody waits for it, and it could be lapped and lose entries (found by the
+    // multi-rank fuzz on the host emulation).  Such problems use the all-gather, which synchronises all ranks.
+    const bool every_rank_owns_rows = (int64_t)(P - 1) * rpr < n;
+    pg->p2p = ctx->p2p_enabled && P > 1 && every_rank_owns_rows &&
               ARENA_DATA_OFF + 2 * (size_t)pg->stride * P * sizeof(ulonglong2) <= ctx->arena_bytes;
     pg->nctas = (int)((n + VP_ELEMS - 1) / VP_ELEMS);
     if (pg->nctas > VP_MAXC) pg->nctas = VP_MAXC;

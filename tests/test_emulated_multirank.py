@@ -109,7 +109,11 @@ def test_sharded_solve_is_bit_identical_to_one_rank(kind, layout, n, nranks, exc
         gathers = lib.emu_allgather_calls()
         many = run_ranks(nranks, exchange, lambda ctx: solve(kind, shard_hessian(ctx, M, layout), q, ub, max_iter))
         gathers = lib.emu_allgather_calls() - gathers
-        assert gathers == 0 if exchange == 'p2p' else gathers >= nranks * max_iter
+        # the fused exchange needs no collective; a problem that leaves a rank without rows falls back to the all-gather
+        # (an empty rank publishes nothing, nobody would wait for it, and it could be lapped: csrc/pg.cu, bcqp_create)
+        rows_per_rank = -(-(-(-n // nranks)) // 64) * 64     # ceil(n / P) rounded up to the 64-row group
+        fused = exchange == 'p2p' and (nranks - 1) * rows_per_rank < n
+        assert gathers == 0 if fused else gathers >= nranks * max_iter
     for rank_state in many:
         for a, b in zip(one, rank_state):
             assert np.array_equal(a, b)
@@ -266,3 +270,33 @@ def test_random_lockstep_batches(block):
         for rank_states in batched:
             for sa, sb in zip(sequential, rank_states):
                 assert all(np.array_equal(a, b) for a, b in zip(sa, sb)), label
+
+
+def test_rank_without_rows_cannot_be_lapped():
+    """Regression for a hazard the fuzz found: with n <= 64 (P - 1) some ranks own no rows; under the fused exchange
+    nobody waited for them, so a rank with rows could run two products ahead and overwrite tagged entries an empty
+    rank had not read yet (intermittent: the empty rank then spun until its 20 s time-out).  Such problems now take
+    the all-gather; many short solves with a deliberately slow empty rank must all agree with one rank."""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import ProjectedGradient
+    rng = np.random.default_rng(428)
+    n = 5
+    G = rng.standard_normal((n, n + 2))
+    M, q, ub = G @ G.T / (n + 2), rng.standard_normal(n), np.full(n, 2.0)
+
+    def body(ctx):
+        out = []
+        for rep in range(12):
+            if ctx.rank == ctx.nranks - 1:
+                time.sleep(0.002 * (rep % 3))       # the empty rank dawdles
+            s = ProjectedGradient(quad=Quadratic(shard_hessian(ctx, M), q), ub=ub, max_iter=40).minimize()
+            out.append(np.concatenate((s.x, [s.iter])))
+        return np.array(out)
+
+    with emulated_device() as lib:
+        one = run_ranks(1, 'nccl', body)[0]
+        gathers = lib.emu_allgather_calls()
+        many = run_ranks(3, 'p2p', body)
+        assert lib.emu_allgather_calls() - gathers > 0          # fell back to the all-gather
+    for state in many:
+        assert np.array_equal(state, one)
