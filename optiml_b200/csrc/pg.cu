@@ -16,6 +16,7 @@
 #include "k2_matvec.cuh"   // K2, K2 x NB (device code)
 #include "k3_vector.cuh"   // K3 vector phases and kernel entry points (device code)
 #include <math.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------ K2 launchers
 struct MatvecScratch {
@@ -632,6 +633,16 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     }
 #undef PG_CUDA
     pg->last_passes = 0;
+    if (pg->p2p) {
+        // Optional (SVMB200_P2P_CREATE_BARRIER=1, off by default until it has been timed on hardware): a one-double
+        // all-gather before the first fused product of this solver.  Every rank's previous solve has then left the
+        // arena, which turns the inter-solve margin of the fused exchange into a guarantee.
+        const char* ev = getenv("SVMB200_P2P_CREATE_BARRIER");
+        if (ev != nullptr && atoi(ev) != 0) {
+            rc = svm_comm_allgather(ctx, pg->w, 1);
+            if (rc != SVMB200_OK) return fail(rc);
+        }
+    }
     if (solver == 2) {
         // sums of state 0 (no product needed: every launch of the loop is preceded by its own pass w = Q xe)
         rc = launch_vec<VP_INIT>(pg, 0);

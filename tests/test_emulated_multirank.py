@@ -300,3 +300,25 @@ def test_rank_without_rows_cannot_be_lapped():
         assert lib.emu_allgather_calls() - gathers > 0          # fell back to the all-gather
     for state in many:
         assert np.array_equal(state, one)
+
+
+def test_optional_barrier_before_the_first_fused_product(monkeypatch):
+    """SVMB200_P2P_CREATE_BARRIER=1: one tiny all-gather per solver creation, then the fused exchange as before --
+    same bits, and exactly `ranks x solves` collectives"""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import ProjectedGradient
+    rng = np.random.default_rng(6)
+    sizes = (200, 150, 260, 130)     # solves of different size back to back: the layouts of the arena change
+    problems = [(S.psd(rng, n), rng.standard_normal(n), np.full(n, 1.5)) for n in sizes]
+
+    def body(ctx):
+        return [ProjectedGradient(quad=Quadratic(shard_hessian(ctx, M), q), ub=ub, max_iter=6).minimize().x for M, q, ub in problems]
+
+    with emulated_device() as lib:
+        one = run_ranks(1, 'nccl', body)[0]
+        monkeypatch.setenv('SVMB200_P2P_CREATE_BARRIER', '1')
+        gathers = lib.emu_allgather_calls()
+        many = run_ranks(2, 'p2p', body)
+        assert lib.emu_allgather_calls() - gathers == 2 * len(sizes)
+    for state in many:
+        assert all(np.array_equal(a, b) for a, b in zip(one, state))
