@@ -95,7 +95,7 @@ _NON_STATUS = {
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()   # re-entrant: see load_library
 
 
 class NativeError(RuntimeError):
@@ -105,6 +105,12 @@ class NativeError(RuntimeError):
 def load_library():
     """Load libsvmb200.so (once).  Raises if it has not been built -- there is no CPU path."""
     global _lib
+    # Fast path without the lock: finalizers of device objects (runtime._free_quiet) call this from the garbage
+    # collector, which can run at ANY allocation -- also while this very function holds the lock on the same thread.
+    # With a plain Lock taken on every call that self-deadlocked (seen once in the CPU suite, as a 120 s stall).
+    lib = _lib
+    if lib is not None:
+        return lib
     with _lock:
         if _lib is not None:
             return _lib

@@ -356,3 +356,21 @@ def test_sass_carries_the_instructions_the_design_claims():
         if 'matvec_seg' in name:
             assert any(o.startswith('LDG.E.NA.128') or o.startswith('LDG.E.128') for o in ops), name
             assert sum(o == 'DFMA' for o in ops) >= 32, name
+
+
+def test_load_library_cannot_deadlock_on_a_finalizer():
+    """Finalizers of device objects free their buffers through _native.call -> load_library(); the garbage collector can
+    run them at any allocation, including while load_library() itself holds its lock on the same thread.  The fast path
+    takes no lock and the lock is re-entrant (a plain Lock taken on every call self-deadlocked: a 120 s stall in the suite)."""
+    import threading
+    from optiml_b200 import _native as N
+    lib = N.load_library()
+    done = []
+
+    def reenter():
+        with N._lock:                       # the collector fires inside load_library() ...
+            done.append(N.load_library())   # ... and a finalizer calls it again on the same thread
+    t = threading.Thread(target=reenter, daemon=True)
+    t.start()
+    t.join(timeout=10)
+    assert not t.is_alive() and done == [lib]
