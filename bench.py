@@ -15,8 +15,15 @@ iteration ends with one NCCL all-gather, total work fixed (strong scaling).
             history and the intercept product are inside the timed region.
 ``roofline`` the streaming matvec (one launch per iteration): 8 n^2 / N bytes per launch / mean
             launch duration from CUDA events around every launch, vs the measured HBM copy peak.
-``cpu_baseline`` / ``--impl reference``: the NumPy oracle (the reference's algorithm, 3 passes over Q
-            per iteration) on the host cores, on a bounded sample of the same workload.
+``parity``  the last timed fit against the golden vectors of the REAL reference's run of the same config
+            (tests/golden/c4_full_svc_gaussian.npz): max |delta alpha|, support set, objective, intercept.
+``cpu_baseline`` / ``--impl reference``: the UNMODIFIED reference (pip-installed into the git-ignored
+            ``baseline/_ref``) on the host cores, on the FULL problem (same n, d, kernel, C) for a
+            bounded number of iterations: one ``SVC.fit(max_iter=m)`` with a time-stamping callback gives the
+            set-up time (Gram, Q, first evaluation), the time per PG iteration (iteration-independent: three
+            passes over Q) and the post-processing time; the reported it/s is max_iter / (set-up +
+            max_iter * per-iteration + post), the whole-fit figure the GPU arm reports.  Falls back to the
+            NumPy oracle port on a row sample when the reference copy or the host memory (~90 GB) is missing.
 """
 import argparse
 import json
@@ -113,9 +120,19 @@ class ClockSampler:
                 'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------- CPU arms (oracle)
+# ----------------------------------------------------------------------------- CPU arms
+def workload_name(config, n, d, max_iter):
+    return f'{config} DualSVC GaussianKernel C=1 n={n} d={d} max_iter={max_iter} (make_classification random_state=0)'
+
+
+def bench_config(config, n, d, max_iter, world):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm."""
+    return {'workload': workload_name(config, n, d, max_iter), 'parallelism': f'row-block x{world}',
+            'l2': f'inputs larger than L2: Q shard = {8.0 * n * n / world / 1e9:.2f} GB per GPU, streamed once per iteration'}
+
+
 def oracle_sample(config, n_full, n_sample, iters, max_iter):
-    """Time the oracle (reference algorithm, NumPy FP64, 3 products with Q per iteration) on the first
+    """Fallback: time the oracle (reference algorithm, NumPy FP64, 3 products with Q per iteration) on the first
     n_sample rows of the workload for `iters` PG iterations; scale it/s to n_full by (n_sample/n_full)^2
     (every iteration is 3 passes over the n x n matrix: cost is proportional to n^2)."""
     from oracle import svm_oracle as O
@@ -158,33 +175,135 @@ def use_all_host_threads():
         pass
 
 
+def available_host_bytes():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 0
+
+
+class ReferenceRun:
+    """The unmodified reference (baseline/_ref) on the full problem.  `fit_sample(m)` runs the reference's own
+    ``SVC(loss=hinge, kernel=GaussianKernel(), C=1, dual=True, reg_intercept=True, optimizer=ProjectedGradient,
+    max_iter=m).fit(X, y)`` with a time-stamping wrapper around its per-iteration callback; `loop_sample(m)` re-runs the
+    reference's ``ProjectedGradient(quad, ub, max_iter=m).minimize()`` on the Hessian that fit left in ``model.obj``."""
+
+    # K, the int64 outer(y, y), Q = K * yy and the copy Quadratic takes are alive together (ml/svm/_base.py:552-554, 628;
+    # opti/_base.py:243): ~4 n^2 doubles at the peak, plus NumPy temporaries
+    @staticmethod
+    def bytes_needed(n):
+        return int(4.6 * 8 * n * n)
+
+    def __init__(self, config, n):
+        from oracle.ref_shim import load_reference, REFERENCE_ROOT
+        from optiml_b200.configs import make_config
+        self.ref = load_reference()
+        self.root = REFERENCE_ROOT
+        self.spec, self.X, self.y = make_config(config, n=n)
+        self.n = len(self.y)
+        self.model = None
+
+    def fit_sample(self, m):
+        ref = self.ref
+        model = ref.SVC(loss=ref.hinge, kernel=ref.GaussianKernel(), C=1, reg_intercept=True, dual=True,
+                        optimizer=ref.ProjectedGradient, max_iter=m)
+        stamps = []
+        inner = model._store_train_info  # the callback SVC.fit hands to the solver (ml/svm/_base.py:631-636)
+
+        def stamped(opt):
+            inner(opt)
+            stamps.append(time.perf_counter())
+
+        model._store_train_info = stamped
+        t0 = time.perf_counter()
+        model.fit(self.X, self.y)
+        t1 = time.perf_counter()
+        self.model = model
+        iters = len(stamps) - 1
+        return dict(setup_s=stamps[0] - t0, iter_s=(stamps[-1] - stamps[0]) / max(iters, 1), post_s=t1 - stamps[-1],
+                    iters=iters, fit_s=t1 - t0, n_sv=len(model.support_), f_x=float(model.optimizer.f_x))
+
+    def loop_sample(self, m):
+        ref, quad = self.ref, self.model.obj
+        stamps = []
+        opt = ref.ProjectedGradient(quad=quad, ub=np.ones(self.n), max_iter=m, callback=lambda o: stamps.append(time.perf_counter()))
+        opt.minimize()
+        iters = len(stamps) - 1
+        return (stamps[-1] - stamps[0]) / max(iters, 1), iters
+
+
+def reference_measure(config, n_full, max_iter, steps=0, warmup=0, fit_iters=8):
+    """One reference fit on the full problem (+ `warmup + steps` solver-only samples).  Returns the dict both
+    `cpu_baseline` and the `--impl reference` line are built from; falls back to the oracle port on a row sample."""
+    from optiml_b200.configs import CONFIGS
+    use_all_host_threads()
+    d = CONFIGS[config]['d']
+    why = None
+    try:
+        from oracle.ref_shim import reference_available
+        if not reference_available():
+            why = 'no reference copy under baseline/_ref'
+    except Exception as e:  # pragma: no cover
+        why = f'reference not importable: {e}'
+    need, have = ReferenceRun.bytes_needed(n_full), available_host_bytes()
+    if why is None and have < need:
+        why = f'host memory: {have / 1e9:.0f} GB available, the reference needs ~{need / 1e9:.0f} GB at n={n_full}'
+    if why is None:
+        try:
+            run = ReferenceRun(config, n_full)
+            first = run.fit_sample(fit_iters)
+            iter_s = [first['iter_s']]
+            # per-step samples: the reference's own solver on the Hessian its fit built, sized for ~3 s each
+            m = int(min(max(3, round(3.0 / first['iter_s'])), 50))
+            extra = []
+            for i in range(warmup + steps):
+                t, _ = run.loop_sample(m)
+                if i >= warmup:
+                    extra.append(t)
+            if extra:
+                iter_s = extra
+            it = float(np.mean(iter_s))
+            fit_full_s = first['setup_s'] + max_iter * it + first['post_s']
+            sample = (f'UNMODIFIED reference (optiml 1.8 from {os.path.relpath(run.root, ROOT)}) on the FULL workload n={n_full} d={d}: '
+                      f'SVC(hinge, GaussianKernel, C=1, dual, reg_intercept, ProjectedGradient).fit with max_iter={first["iters"]}: '
+                      f'set-up (Gram, Q, first evaluation) {first["setup_s"]:.1f} s, {first["iter_s"] * 1e3:.0f} ms per PG iteration '
+                      f'(3 passes over Q), support set + intercept {first["post_s"]:.1f} s'
+                      + (f'; then {len(extra)} timed samples of ProjectedGradient.minimize(max_iter={m}) on the same Hessian: '
+                         f'{it * 1e3:.0f} ms per iteration' if extra else '')
+                      + f'; value = {max_iter} / (set-up + {max_iter} x per-iteration + post) = whole-fit it/s')
+            return dict(kind='reference', value=max_iter / fit_full_s, pg_only_its=1.0 / it, sample=sample, fit_full_s=fit_full_s,
+                        step_ms=(m * it * 1e3) if extra else first['fit_s'] * 1e3, parts=first, iter_ms=[round(t * 1e3, 2) for t in iter_s])
+        except MemoryError:
+            why = 'MemoryError inside the reference fit'
+    n_sample = min(n_full, 16000)
+    vals = [oracle_sample(config, n_full, n_sample, 20, max_iter) for _ in range(max(1, min(steps, 3)))]
+    sample = (f'FALLBACK ({why}): first {n_sample} rows of {config} (n={n_full}); NumPy oracle = reference algorithm '
+              f'(Gram + 20 PG iterations, 3 passes over Q each); it/s scaled by ({n_sample}/{n_full})^2 '
+              f'to the full problem, whole-fit equivalent incl. Gram')
+    return dict(kind='port', value=float(np.mean([v['its_full_whole_fit'] for v in vals])),
+                pg_only_its=float(np.mean([v['its_full_pg_only'] for v in vals])), sample=sample,
+                fit_full_s=float(np.mean([v['fit_full_s'] for v in vals])),
+                step_ms=float(np.mean([v['gram_s'] + v['pg_s'] for v in vals]) * 1e3), parts=None, iter_ms=None)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from optiml_b200.configs import CONFIGS
-    use_all_host_threads()
     n_full = args.n or CONFIGS[args.config]['n']
-    n_sample = min(n_full, 16000)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        r = oracle_sample(args.config, n_full, n_sample, 20, args.max_iter)
-        if i >= args.warmup:
-            vals.append(r)
-    its = float(np.mean([v['its_full_whole_fit'] for v in vals]))
-    ms = float(np.mean([v['gram_s'] + v['pg_s'] for v in vals]) * 1e3)
-    sample = (f'first {n_sample} rows of {args.config} (n={n_full}); NumPy oracle = reference algorithm '
-              f'(Gram + 20 PG iterations, 3 passes over Q each); it/s scaled by ({n_sample}/{n_full})^2 '
-              f'to the full problem, whole-fit equivalent incl. Gram')
-    line = {'impl': 'reference', 'metric': metric_name(args.config, n_full, CONFIGS[args.config]['d']), 'value': its, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'{args.config} DualSVC GaussianKernel C=1 n={n_full} d={CONFIGS[args.config]["d"]} '
-                                   f'max_iter={args.max_iter}',
-                       'sample': sample},
-            'cpu_baseline': {'value': its, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port', 'sample': sample,
-                             'pg_only_its': float(np.mean([v['its_full_pg_only'] for v in vals]))},
-            'e2e': {'value': its, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    d = CONFIGS[args.config]['d']
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    r = reference_measure(args.config, n_full, args.max_iter, steps=args.steps, warmup=args.warmup)
+    line = {'impl': 'reference', 'metric': metric_name(args.config, n_full, d), 'value': r['value'], 'unit': UNIT,
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['step_ms'],
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': bench_config(args.config, n_full, d, args.max_iter, max(world, args.gpus)),
+            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': host_threads(), 'kind': r['kind'], 'sample': r['sample'],
+                             'pg_only_its': r['pg_only_its'], 'whole_fit_s': r['fit_full_s'], 'parts': r['parts'],
+                             'iter_ms_samples': r['iter_ms']},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -197,6 +316,31 @@ def pinned_array(shape, dtype=np.float64):
     N.call('svmb200_host_alloc_pinned', nbytes, C.byref(p))
     buf = (C.c_char * nbytes).from_address(p.value)
     return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def parity_block(args, m, n):
+    """The last fit against the REAL reference's own run of this config (golden vectors made by
+    tests/golden/make_golden_c4_full.py from the imported reference): north_star's bar is max |delta alpha| <= 1e-8 and an
+    identical support set."""
+    gpath = os.path.join(ROOT, 'tests', 'golden', 'c4_full_svc_gaussian.npz')
+    if not (args.config == 'C4' and n == 50000 and os.path.exists(gpath)):
+        return None
+    g = np.load(gpath)
+    k = min(len(m.train_loss_history), len(g['f_hist'])) - 1
+    if k < 1:
+        return None
+    out = {'against': 'tests/golden/c4_full_svc_gaussian.npz (unmodified reference, 1000 iterations, 954.6 s on 8 host cores)',
+           'iterations_compared': int(k),
+           'f_hist_max_rel': float(np.max(np.abs(np.array(m.train_loss_history)[:k + 1] - g['f_hist'][:k + 1]) /
+                                          np.maximum(1.0, np.abs(g['f_hist'][:k + 1]))))}
+    if m.optimizer.iter == int(g['iter']):
+        out.update({'max_abs_dalpha': float(np.abs(m.alphas_ - g['alphas']).max()),
+                    'same_support': bool(np.array_equal(m.support_, g['support'])),
+                    'f_x_rel': float(abs(m.optimizer.f_x - float(g['f_hist'][-1])) / abs(float(g['f_hist'][-1]))),
+                    'intercept_abs': float(abs(m.intercept_ - float(g['intercept']))),
+                    'meets_north_star': bool(np.abs(m.alphas_ - g['alphas']).max() <= 1e-8 and
+                                             np.array_equal(m.support_, g['support']))})
+    return out
 
 
 def run_b200(args):
@@ -301,6 +445,7 @@ def run_b200(args):
 
     if rank != 0:
         return
+    parity = parity_block(args, m, n)
     peak, peak_src = measured_peak()
     bytes_per_launch = 8.0 * n * n / world
     mv_avg_ms = mv_ms / max(mv_launches, 1)
@@ -316,11 +461,11 @@ def run_b200(args):
         'metric': metric_name(args.config, n, d), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'{args.config} DualSVC GaussianKernel C=1 n={n} d={d} max_iter={args.max_iter} '
-                               f'(make_classification random_state=0)', 'parallelism': f'row-block x{world}', 'exchange': ctx.exchange,
-                   'host': 'gc.collect() + gc.freeze() after warm-up (a full Python GC pass is ~0.2 s with torch/sklearn loaded)',
-                   'l2': f'inputs larger than L2: Q shard = {8.0 * n * n / world / 1e9:.2f} GB per GPU, streamed once '
-                         'per iteration'},
+        'config': bench_config(args.config, n, d, args.max_iter, world),
+        'exchange': ctx.exchange,
+        'host_note': 'gc.collect() + gc.freeze() after warm-up (a full Python GC pass is ~0.2 s with torch/sklearn loaded); '
+                     'the value leg runs with per-launch CUDA-event profiling on (4 cudaEventRecord per iteration)',
+        'parity': parity,
         'fit_s': dev_ms / args.steps / 1e3, 'pg_its_per_s': iters_total / (pg_ms / 1e3),
         'hbm_gbps_pg_loop': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9,
         'frac_of_8TBps_nominal': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9 / world / 8000.0,
@@ -340,15 +485,11 @@ def run_b200(args):
         'gpu_launches': int(launches), 'clocks': clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        use_all_host_threads()
-        n_sample = min(n, 12000)
-        r = oracle_sample(args.config, n, n_sample, 20, args.max_iter)
+        # release the GPU arm's host copies first: the reference needs ~4.6 x 8 n^2 bytes of host memory
+        r = reference_measure(args.config, n, args.max_iter)
         line['cpu_baseline'] = {
-            'value': r['its_full_whole_fit'], 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
-            'sample': f'first {n_sample} rows of {args.config}: NumPy oracle (reference algorithm, 3 passes over Q per '
-                      f'iteration) Gram {r["gram_s"]:.2f}s + 20 PG iterations {r["pg_s"]:.2f}s; it/s scaled by '
-                      f'({n_sample}/{n})^2 to n={n}, whole-fit equivalent',
-            'pg_only_its': r['its_full_pg_only'],
+            'value': r['value'], 'unit': UNIT, 'cores': host_threads(), 'kind': r['kind'], 'sample': r['sample'],
+            'pg_only_its': r['pg_only_its'], 'whole_fit_s': r['fit_full_s'], 'parts': r['parts'],
             'reference_full_run_note': 'the unmodified reference solver needed 954.6 s for the 1000 PG iterations of '
                                        'this config on the 8 host cores of the build container '
                                        '(tests/golden/c4_full_svc_gaussian.npz)'}

@@ -1,4 +1,8 @@
-"""Import the REAL reference (dmeoli/optiml) from /root/reference  --  TEST INFRASTRUCTURE ONLY.
+"""Import the REAL reference (dmeoli/optiml)  --  TEST / BENCHMARK INFRASTRUCTURE ONLY.
+
+Where it is looked for, in order: ``$OPTIML_REFERENCE_ROOT``; ``baseline/_ref`` (the unmodified reference installed by
+``pip install --no-deps --target baseline/_ref``, git-ignored, travels to the GPU box: what ``bench.py --impl reference``
+and its ``cpu_baseline`` leg time); ``/root/reference`` (the build container only).
 
 The reference's dual-BCQP path is pure NumPy, but ``import optiml.ml.svm`` also imports four
 third-party packages that are absent from this image and that the path never calls
@@ -12,7 +16,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('OPTIML_REFERENCE_ROOT', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    for cand in (os.environ.get('OPTIML_REFERENCE_ROOT'), os.path.join(_REPO, 'baseline', '_ref'), '/root/reference'):
+        if cand and os.path.isdir(os.path.join(cand, 'optiml')):
+            return cand
+    return os.environ.get('OPTIML_REFERENCE_ROOT', '/root/reference')
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available():

@@ -120,6 +120,19 @@ class PGResult:
     __slots__ = ('x', 'f_x', 'g_x', 'iter', 'status', 'f_hist', 'ng_hist', 'n_clipped')
 
 
+class SVRBlockOperator:
+    """[[M, -M], [-M, M]] @ v without the 2n x 2n matrix (optiml/ml/svm/_base.py:1098-1099 builds it densely): for
+    sizes where three passes over the materialised block matrix are impractical.  ``passes=1`` only."""
+
+    def __init__(self, M):
+        self.M = np.asarray(M, dtype=np.float64)
+        self.n = self.M.shape[0]
+
+    def __matmul__(self, v):
+        w = self.M @ (v[:self.n] - v[self.n:])
+        return np.hstack((w, -w))
+
+
 def projected_gradient(Q, q, ub, lb=None, x0=None, eps=1e-6, max_iter=1000, passes=3, callback=None):
     """optiml/opti/constrained/projected_gradient.py:76-143 with the start point of
     optiml/opti/constrained/_base.py:59-65 (lb = 0, x0 = (lb+ub)/2).
@@ -133,7 +146,10 @@ def projected_gradient(Q, q, ub, lb=None, x0=None, eps=1e-6, max_iter=1000, pass
     ``callback(k, x, f, ng)`` mirrors the per-iteration callback point
     (``projected_gradient.py:95-98``: after the norm, before the stopping tests).
     """
-    Q = np.asarray(Q, dtype=np.float64)
+    if not isinstance(Q, SVRBlockOperator):
+        Q = np.asarray(Q, dtype=np.float64)
+    elif passes != 1:
+        raise ValueError('the block operator offers the single-pass form only')
     q = np.asarray(q, dtype=np.float64)
     ub = np.asarray(ub, dtype=np.float64)
     lb = np.zeros_like(ub) if lb is None else np.asarray(lb, dtype=np.float64)

@@ -37,3 +37,52 @@ def test_c1_trajectory_is_stable():
     assert fit.pg.n_clipped >= 990                          # 998 of 1000 steps hit a bound
     assert np.abs(pert.x - fit.pg.x).max() < 1e-12
     assert np.array_equal(pert.x > 1e-6, fit.pg.x > 1e-6)
+
+
+def test_c2_trajectory_is_chaotic():
+    """BASELINE config C2 (DualSVR, PolyKernel(3)) on a reduced sample: free line-search steps dominate (unlike C1/C4)
+    and a +-1 ulp change of the Gram matrix moves the reference algorithm's own alpha by ~1e-2 after 1000 iterations --
+    six orders above north_star's 1e-8 -- after a common prefix that agrees to rounding."""
+    spec, X, y = make_config('C2', n=1500)
+    n = len(y)
+    M = O.poly_kernel(X, degree=3) + 1.0
+    q, ub = np.hstack((-y, y)) + 0.1, np.ones(2 * n)
+    base = O.projected_gradient(O.SVRBlockOperator(M), q, ub, passes=1)
+    rng = np.random.default_rng(0)
+    E = rng.integers(-1, 2, size=M.shape)
+    E = np.triu(E) + np.triu(E, 1).T
+    pert = O.projected_gradient(O.SVRBlockOperator(M * (1 + E * 2.2e-16)), q, ub, passes=1)
+    assert base.iter == pert.iter == 1000
+    assert base.n_clipped < 600                               # hundreds of free steps (C1: 2 of 1000)
+    assert np.abs(pert.x - base.x).max() > 1e-4               # ~1e-2 measured
+    assert np.abs(pert.f_hist[:50] - base.f_hist[:50]).max() <= 1e-9 * np.abs(base.f_hist[:50]).max()
+
+
+def test_block_operator_is_the_materialised_svr_hessian():
+    """The single-pass block form used above is the reference's 2n x 2n Hessian (ml/svm/_base.py:1098-1099, 1178)."""
+    spec, X, y = make_config('C2', n=300)
+    fit = O.svr_dual_fit(X, y, kind='poly', max_iter=10, passes=1)
+    n = len(y)
+    blk = O.projected_gradient(O.SVRBlockOperator(fit.K + 1.0), np.hstack((-y, y)) + 0.1, np.ones(2 * n), max_iter=10, passes=1)
+    assert np.abs(blk.x - fit.pg.x).max() <= 1e-11               # (40 iterations: 6e-8 -- the map amplifies even here)
+    import pytest
+    with pytest.raises(ValueError):
+        O.projected_gradient(O.SVRBlockOperator(fit.K + 1.0), np.hstack((-y, y)), np.ones(2 * n), passes=3)
+
+
+def test_c2_full_size_golden_states_pin_the_oracle(golden):
+    """Full-size C2: from every stored state of the REAL reference's trajectory the oracle reaches the reference's state
+    five iterations later (the GPU test of the same name does this with the device loop), and the stored 1-ulp
+    envelope of the reference algorithm is ~2e-2."""
+    g = golden('c2_full_states')
+    spec, X, y = make_config('C2')
+    n = len(y)
+    M = O.poly_kernel(X, degree=3) + 1.0
+    q, ub = np.hstack((-y, y)) + 0.1, np.ones(2 * n)
+    steps = int(g['steps'])
+    for k in g['ks']:
+        k = int(k)
+        r = O.projected_gradient(O.SVRBlockOperator(M), q, ub, x0=g[f'x_{k}'], max_iter=steps, passes=1)
+        assert np.abs(r.x - g[f'x_{k + steps}']).max() <= (1e-10 if k == 0 else 1e-12)
+    assert 1e-3 < float(g['env_dalpha']) < 1e-1
+    assert g['env_clipped'].max() < 100                       # < 10 % of the steps hit a bound
