@@ -93,6 +93,7 @@ extern "C" int svmb200_comm_unique_id(void* id128) {
 extern "C" int svmb200_comm_init(svmb200_ctx* ctx, const void* id128, int rank, int nranks) {
     SVM_TRY(svm_use(ctx));
     SVM_CHECK_ARG(id128 != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / size");
+    SVM_CHECK_ARG(nranks <= SVM_MAX_RANKS, "more ranks than SVM_MAX_RANKS (16)");
     if (ctx->nccl_comm) {
         svmb200_set_error("communicator already initialised");
         return SVMB200_ERR_STATE;
@@ -176,12 +177,19 @@ extern "C" int svmb200_comm_p2p_enabled(svmb200_ctx* ctx, int* enabled) {
     return SVMB200_OK;
 }
 
+// Tear-down of the peer mappings.  Peers may still be executing matvec launches that STORE into this rank's arena when
+// a rank leaves early (an exception on one rank of a sharded fit): freeing the arena then turns their stores into
+// illegal-address faults (sticky CUDA error, Xid) instead of the clean exchange time-out.  A cross-rank barrier cannot
+// be relied on from an error path (the peer may be the one that died), so a multi-rank context leaves its arena
+// allocated and its peer mappings open until the process exits -- 64 MB, reclaimed by the driver with the process.
 static void p2p_release(svmb200_ctx* ctx) {
+    const bool peers_may_still_store = ctx->nranks > 1;
     for (int r = 0; r < SVM_MAX_RANKS; ++r) {
-        if (ctx->peer_arena[r] && ctx->peer_arena[r] != ctx->arena) cudaIpcCloseMemHandle(ctx->peer_arena[r]);
+        if (!peers_may_still_store && ctx->peer_arena[r] && ctx->peer_arena[r] != ctx->arena)
+            cudaIpcCloseMemHandle(ctx->peer_arena[r]);
         ctx->peer_arena[r] = nullptr;
     }
-    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->arena && !peers_may_still_store) cudaFree(ctx->arena);
     ctx->arena = nullptr;
     ctx->arena_bytes = 0;
     ctx->p2p_enabled = false;

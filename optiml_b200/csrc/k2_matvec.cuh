@@ -41,6 +41,7 @@ struct MatvecArgs {
     int nranks_x;
     unsigned tag;
     ulonglong2* peer_w[SVM_MAX_RANKS];           // this rank's slot in rank r's gathered buffer
+    const int* fault;       // the context's sticky exchange-fault flag (see ll_load), or null
 };
 
 #ifndef SVMB200_HOST_EMULATION
@@ -49,17 +50,22 @@ __device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned tag) 
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t)
                  : "memory");
 }
-// bounded spin (20 s: a peer died) -> fault flag; the host turns it into an error
+// Bounded spin: after 20 s without the entry (a peer died or fell out of step) the reader raises the context's fault
+// flag and gives up.  The flag is sticky and context-fatal: every later wait -- of this thread, of the other threads, of
+// the launches already enqueued behind this one -- sees it (first miss and every 1024 spins) and returns at once, K2 / K3
+// return at entry, and the host turns it into SVMB200_ERR_STATE at its next poll: one 20 s time-out per failure, not one
+// per missing entry.  The values computed after a fault are garbage and are never handed out.
 __device__ __forceinline__ double ll_load(const ulonglong2* p, unsigned tag, int* fault) {
     unsigned long long w0, w1, t0 = 0, now = 0;
     for (unsigned spins = 0;; ++spins) {
         asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
         if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
-        if ((spins & 1023u) == 1023u) {
+        if ((spins & 1023u) == 0u) {
+            if (*reinterpret_cast<volatile int*>(fault)) break;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
             else if (now - t0 > 20000000000ull) {
-                *fault = 1;
+                *reinterpret_cast<volatile int*>(fault) = 1;
                 break;
             }
         }
@@ -86,8 +92,9 @@ __device__ __forceinline__ double ll_load(const ulonglong2* p, unsigned tag, int
         w0 = __atomic_load_n(&p->x, __ATOMIC_ACQUIRE);
         w1 = __atomic_load_n(&p->y, __ATOMIC_ACQUIRE);
         if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+        if ((spins & 1023u) == 0u && __atomic_load_n(fault, __ATOMIC_ACQUIRE)) break;  // sticky: somebody already timed out
         if (emu::spin_wait(spins)) {  // yields the host thread; true after 20 s
-            *fault = 1;
+            __atomic_store_n(fault, 1, __ATOMIC_RELEASE);
             break;
         }
     }
@@ -98,6 +105,7 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) { return *p
 
 __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const MatvecArgs a) {
     if (a.done != nullptr && *a.done) return;
+    if (a.fault != nullptr && *a.fault) return;  // the exchange is broken: nothing downstream will be used
     constexpr int R = MV_R, NT = MV_NT, U = MV_U;
     const unsigned items_per_group = (unsigned)(MV_BPG * a.nseg);
     const unsigned group = blockIdx.x / items_per_group;
@@ -269,6 +277,7 @@ struct MatvecMultiArgs {
     unsigned tag;
     long long xstride, share_off;
     ulonglong2* peer_w[SVM_MAX_RANKS];
+    const int* fault;   // the context's sticky exchange-fault flag, or null
 };
 
 template <int NB>
@@ -284,6 +293,7 @@ __global__ void __launch_bounds__(MV_NT * MultiCfg<NB>::H, MultiCfg<NB>::MINB) m
         any = any || live[b];
     }
     if (!any) return;
+    if (a.fault != nullptr && *a.fault) return;
     const int half = (int)threadIdx.x / NT;         // which group of 256 threads (whole warps)
     const int tid = (int)threadIdx.x - half * NT;   // the thread's index inside its group: the column it starts at
     const unsigned items_per_group = (unsigned)(BPG * a.nseg);

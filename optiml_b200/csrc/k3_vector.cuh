@@ -136,6 +136,7 @@ __device__ __forceinline__ void pg_vector_body(const VecArgs& a, const long long
     // `done` is raised inside the stop branch below, which every CTA of that launch takes anyway;
     // a CTA that starts late and already sees the flag returns here instead -- same outcome.
     if (*reinterpret_cast<volatile int*>(&st->done)) return;
+    if (a.fault != nullptr && *reinterpret_cast<volatile int*>(a.fault)) return;  // broken exchange: see ll_load
     const int tid = threadIdx.x;
     const long long n = a.n;
     const long long chunk = (n + a.nctas - 1) / a.nctas;
@@ -276,6 +277,7 @@ __device__ __forceinline__ void fw_vector_body(const VecArgs& a, const long long
     __shared__ double sm[VP_NT / 32][4];
     PGDeviceState* st = a.st;
     if (*reinterpret_cast<volatile int*>(&st->done)) return;
+    if (a.fault != nullptr && *reinterpret_cast<volatile int*>(a.fault)) return;  // broken exchange: see ll_load
     const int tid = threadIdx.x;
     const long long n = a.n;
     const long long chunk = (n + a.nctas - 1) / a.nctas;
@@ -478,6 +480,7 @@ __device__ __forceinline__ void al_vector_body(const VecArgs& a, const ALArgs& a
         __threadfence();
         if (*reinterpret_cast<volatile long long*>(&st->done_k) != k) return;
     }
+    if (a.fault != nullptr && *reinterpret_cast<volatile int*>(a.fault)) return;  // broken exchange: see ll_load
     const int tid = threadIdx.x;
     const long long n = a.n;
     const long long chunk = (n + a.nctas - 1) / a.nctas;

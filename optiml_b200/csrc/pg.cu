@@ -87,9 +87,11 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
     const int64_t ngroups = (nrows + MV_GROUP - 1) / MV_GROUP;
     a.nranks_x = 0;
     a.tag = 0;
+    a.fault = nullptr;
     if (xt != nullptr) {
         a.nranks_x = xt->nranks;
         a.tag = xt->tag;
+        a.fault = reinterpret_cast<const int*>(ctx->arena + ARENA_LOCAL_OFF + 8);
         for (int r = 0; r < xt->nranks; ++r) a.peer_w[r] = xt->peer_w[r];
     }
     const int64_t nitems = ngroups * MV_BPG * a.nseg;
@@ -168,6 +170,7 @@ static int launch_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows
         a.tag = xt->tag;
         a.xstride = xstride;
         a.share_off = share_off;
+        a.fault = reinterpret_cast<const int*>(ctx->arena + ARENA_LOCAL_OFF + 8);
         for (int r = 0; r < xt->nranks; ++r) a.peer_w[r] = xt->peer_w[r];
     }
     const int64_t ngroups = (nrows + MV_GROUP - 1) / MV_GROUP;
@@ -634,11 +637,13 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
 #undef PG_CUDA
     pg->last_passes = 0;
     if (pg->p2p) {
-        // Optional (SVMB200_P2P_CREATE_BARRIER=1, off by default until it has been timed on hardware): a one-double
-        // all-gather before the first fused product of this solver.  Every rank's previous solve has then left the
-        // arena, which turns the inter-solve margin of the fused exchange into a guarantee.
+        // A one-double all-gather, in stream order, before the first fused product of this solver: it completes on a
+        // rank only when EVERY rank has reached it, i.e. when every rank's previous solve -- whose last vector launch
+        // may still be reading arena regions that this solve's layout overlaps -- has left the arena.  Without it the
+        // fused exchange would be correct between two solves only by timing.  (SVMB200_P2P_CREATE_BARRIER=0 removes it
+        // for A/B timing; ~30 us per solve.)
         const char* ev = getenv("SVMB200_P2P_CREATE_BARRIER");
-        if (ev != nullptr && atoi(ev) != 0) {
+        if (ev == nullptr || atoi(ev) != 0) {
             rc = svm_comm_allgather(ctx, pg->w, 1);
             if (rc != SVMB200_OK) return fail(rc);
         }
@@ -665,7 +670,9 @@ static int pg_poll(svmb200_pg* pg) {
         int fault = 0;
         SVM_CUDA(cudaMemcpy(&fault, pg->ctx->arena + ARENA_LOCAL_OFF + 8, sizeof(int), cudaMemcpyDeviceToHost));
         if (fault) {
-            svmb200_set_error("peer exchange timed out: a rank stopped publishing its product shard");
+            // sticky and context-fatal: the sequence numbers of the ranks can no longer be trusted to agree
+            svmb200_set_error("peer exchange timed out: a rank stopped publishing its product shard (the context's "
+                              "exchange is unusable from here on: destroy it and every peer's, then start over)");
             return SVMB200_ERR_STATE;
         }
     }

@@ -31,35 +31,53 @@ class Context:
         self.rank, self.nranks = 0, 1
         # large device buffers (the Hessian shard) are recycled between fits: cudaMalloc/cudaFree of
         # tens of GB costs ~0.1 s each, more than the Gram build itself
-        self._pool = {}
+        self._pool = []  # (nbytes, device pointer), oldest first
         self._finalizer = weakref.finalize(self, N.load_library().svmb200_ctx_destroy, h)
 
     # ---------------------------------------------------------------- memory
     POOL_MIN_BYTES = 1 << 20
     POOL_MAX_BUFFERS = 4
+    POOL_SLACK = 1.5   # parked bytes never exceed this multiple of the largest parked buffer (one Hessian shard + X)
 
     def malloc(self, nbytes):
-        cached = self._pool.get(int(nbytes))
-        if cached:
-            return cached.pop()
+        nbytes = int(nbytes)
+        for i in range(len(self._pool) - 1, -1, -1):
+            if self._pool[i][0] == nbytes:
+                return self._pool.pop(i)[1]
         p = C.c_void_p()
-        N.call('svmb200_malloc', self.handle, int(nbytes), C.byref(p))
+        try:
+            N.call('svmb200_malloc', self.handle, nbytes, C.byref(p))
+        except N.NativeError:
+            if not self._pool:
+                raise
+            self.trim()  # parked buffers of other sizes (earlier fits) may be what is in the way: give them back, retry once
+            N.call('svmb200_malloc', self.handle, nbytes, C.byref(p))
         return p.value
 
     def free(self, dptr, nbytes=0):
+        """Buffers of >= 1 MB are parked for the next fit of the same size (exact-size reuse): at most four, and never more
+        bytes in total than 1.5x the largest parked one -- fits of varying n (CV folds, other data sets) evict the oldest
+        parked buffers instead of accumulating Hessian-sized ones."""
         if not dptr:
             return
-        if nbytes >= self.POOL_MIN_BYTES and sum(len(v) for v in self._pool.values()) < self.POOL_MAX_BUFFERS:
-            self._pool.setdefault(int(nbytes), []).append(dptr)  # keep for the next fit
+        nbytes = int(nbytes)
+        if nbytes < self.POOL_MIN_BYTES:
+            N.call('svmb200_free', self.handle, C.c_void_p(dptr))
             return
-        N.call('svmb200_free', self.handle, C.c_void_p(dptr))
+        self._pool.append((nbytes, dptr))
+        while len(self._pool) > self.POOL_MAX_BUFFERS or \
+                sum(sz for sz, _ in self._pool) > self.POOL_SLACK * max(sz for sz, _ in self._pool):
+            _, victim = self._pool.pop(0)  # oldest first
+            N.call('svmb200_free', self.handle, C.c_void_p(victim))
+
+    def pooled_bytes(self):
+        return sum(sz for sz, _ in self._pool)
 
     def trim(self):
         """Return pooled buffers to the driver."""
-        for lst in self._pool.values():
-            for dptr in lst:
-                N.call('svmb200_free', self.handle, C.c_void_p(dptr))
-        self._pool = {}
+        pool, self._pool = self._pool, []
+        for _, dptr in pool:
+            N.call('svmb200_free', self.handle, C.c_void_p(dptr))
 
     def memset(self, dptr, value, nbytes):
         N.call('svmb200_memset', self.handle, C.c_void_p(dptr), int(value), int(nbytes))

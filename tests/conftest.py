@@ -26,9 +26,22 @@ def _library_is_built():
     """A fresh checkout has no optiml_b200/_lib/libsvmb200.so (build artefacts are not in the history): build it once per
     session (nvcc cross-compiles without a GPU) so that no test depends on test order.  A library that is already there
     is left alone -- on the GPU box the shipped one is the one under test."""
+    import shutil
+    import subprocess
+    import warnings
     from optiml_b200.csrc import build as B
-    if not os.path.exists(B.LIB):
+    if os.path.exists(B.LIB):
+        return
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    if not (os.path.exists(nvcc) or shutil.which(nvcc)):
+        # no CUDA toolkit: the oracle / golden / host-logic / emulation tests need none; the tests that load the real
+        # library fail on their own with _native.load_library()'s message instead of the whole session erroring here
+        warnings.warn(f'{nvcc} not found: libsvmb200.so was not built; tests that load it will fail')
+        return
+    try:
         B.build()
+    except (subprocess.CalledProcessError, OSError) as e:
+        warnings.warn(f'building libsvmb200.so failed ({e}); tests that load it will fail')
 
 
 @pytest.fixture(autouse=True)

@@ -82,6 +82,8 @@ def main():
                   f'ranks_identical={same_across_ranks} bitwise_equal_to_1gpu={single_ok} golden={golden_ok}', flush=True)
             ok = ok and same_across_ranks and single_ok and (golden_ok is not False)
         dist.barrier()
+    if int(os.environ.get('SVMB200_CHECK_STRESS', '600')) > 0:
+        ok = back_to_back_stress(dist, runtime, ctx, rank, world, local_rank, int(os.environ.get('SVMB200_CHECK_STRESS', '600'))) and ok
     if os.environ.get('SVMB200_CHECK_SHARED_GRAM', '0') == '1':
         ok = shared_gram_cases(dist, runtime, ctx, rank, world, local_rank) and ok
     flag = torch.tensor([1 if ok else 0], device='cuda')
@@ -90,6 +92,71 @@ def main():
     if rank == 0:
         print('MULTIGPU_CHECK', 'PASS' if ok else 'FAIL', flush=True)
     sys.exit(0 if int(flag.item()) else 1)
+
+
+def back_to_back_stress(dist, runtime, ctx, rank, world, local_rank, solves):
+    """`solves` short solves back to back on resident matrices of ALTERNATING sizes -- the arena layouts of consecutive
+    solves differ and overlap across buffer parities, one size leaves the last rank without rows (all-gather path), one
+    is a lockstep-free SVR block problem -- with nothing on the host between them but solver tear-down and set-up.  No
+    stall (a lost tagged entry would spin into the 20 s time-out and raise), every repeat of a problem bit-identical to
+    its first solve, to every other rank and to one GPU.  Run with and without the creation barrier to time it."""
+    import time
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import ProjectedGradient
+    from optiml_b200.runtime import DeviceHessian
+    rng = np.random.default_rng(11)
+    sizes = [700, 2048 + 5, 64 * (world - 1), 1333, 4096, 130]
+    problems = []
+    for n in sizes:
+        if n < 2:
+            continue
+        G = rng.standard_normal((n + 5, n))
+        problems.append((G.T @ G / n, rng.standard_normal(n), np.full(n, 1.5)))
+
+    def run_all(context, count, iters):
+        hess = [DeviceHessian.from_host(context, Q) for Q, _, _ in problems]
+        quads = [Quadratic(h, q) for h, (_, q, _) in zip(hess, problems)]
+        first, stable = {}, True
+        context.sync()
+        t0 = time.perf_counter()
+        for i in range(count):
+            j = i % len(problems)
+            x = ProjectedGradient(quad=quads[j], ub=problems[j][2], max_iter=iters[i % len(iters)]).minimize().x
+            dg = hashlib.sha256(x.tobytes()).hexdigest()
+            key = (j, iters[i % len(iters)])
+            stable = stable and first.setdefault(key, dg) == dg
+        context.sync()
+        dt = time.perf_counter() - t0
+        for h in hess:
+            h.release()
+        return first, stable, dt
+
+    iters = (3, 7, 1, 12, 5)   # coprime with the number of problems: every (problem, length) pair comes up
+    ok = True
+    # the unguarded arm is opt-in (A/B timing): without the barrier the exchange is correct between solves by timing only
+    for barrier in (('1', '0') if os.environ.get('SVMB200_CHECK_STRESS_AB', '0') == '1' else ('1',)):
+        os.environ['SVMB200_P2P_CREATE_BARRIER'] = barrier
+        first, stable, dt = run_all(ctx, solves, iters)
+        blob = repr(sorted(first.items()))
+        every = [None] * world
+        dist.all_gather_object(every, (blob, stable))
+        same = len(set(b for b, _ in every)) == 1 and all(st for _, st in every)
+        single = None
+        if rank == 0:
+            solo = runtime.Context(device=local_rank)
+            runtime.set_default_context(solo)
+            try:
+                f1, s1, _ = run_all(solo, len(problems) * len(iters), iters)
+                single = bool(s1 and f1 == first)
+            finally:
+                runtime.set_default_context(ctx)
+            print(f'[multigpu N={world}] stress: {solves} back-to-back solves, sizes {[len(q) for _, q, _ in problems]}, '
+                  f'creation barrier {"on" if barrier == "1" else "OFF"}: {dt / solves * 1e3:.3f} ms per solve, '
+                  f'repeats_bit_identical_on_all_ranks={same} bitwise_equal_to_1gpu={single}', flush=True)
+            ok = ok and same and single
+        dist.barrier()
+    os.environ.pop('SVMB200_P2P_CREATE_BARRIER', None)
+    return ok
 
 
 def shared_gram_cases(dist, runtime, ctx, rank, world, local_rank):

@@ -109,11 +109,12 @@ def test_sharded_solve_is_bit_identical_to_one_rank(kind, layout, n, nranks, exc
         gathers = lib.emu_allgather_calls()
         many = run_ranks(nranks, exchange, lambda ctx: solve(kind, shard_hessian(ctx, M, layout), q, ub, max_iter))
         gathers = lib.emu_allgather_calls() - gathers
-        # the fused exchange needs no collective; a problem that leaves a rank without rows falls back to the all-gather
-        # (an empty rank publishes nothing, nobody would wait for it, and it could be lapped: csrc/pg.cu, bcqp_create)
+        # the fused exchange needs no collective per ITERATION -- only the one-double barrier at solver creation; a
+        # problem that leaves a rank without rows falls back to the all-gather (an empty rank publishes nothing, nobody
+        # would wait for it, and it could be lapped: csrc/pg.cu, bcqp_create)
         rows_per_rank = -(-(-(-n // nranks)) // 64) * 64     # ceil(n / P) rounded up to the 64-row group
         fused = exchange == 'p2p' and (nranks - 1) * rows_per_rank < n
-        assert gathers == 0 if fused else gathers >= nranks * max_iter
+        assert gathers == nranks if fused else gathers >= nranks * max_iter
     for rank_state in many:
         for a, b in zip(one, rank_state):
             assert np.array_equal(a, b)
@@ -146,8 +147,9 @@ def test_sharded_lockstep_batch_is_bit_identical_to_one_rank(kind, count, nranks
             gathers = lib.emu_allgather_calls()
             states = run_ranks(nranks, exchange, body)
             gathers = lib.emu_allgather_calls() - gathers
-            # the fused exchange needs no collective at all; the fallback gathers every problem's shard every pass
-            assert gathers == 0 if exchange == 'p2p' else gathers >= nranks * count * 8
+            # the fused exchange needs no collective per pass (one creation barrier per member); the fallback gathers
+            # every problem's shard every pass
+            assert gathers == nranks * count if exchange == 'p2p' else gathers >= nranks * count * 8
             for rank_states in states:
                 for sa, sb in zip(one, rank_states):
                     for a, b in zip(sa, sb):
@@ -302,9 +304,10 @@ def test_rank_without_rows_cannot_be_lapped():
         assert np.array_equal(state, one)
 
 
-def test_optional_barrier_before_the_first_fused_product(monkeypatch):
-    """SVMB200_P2P_CREATE_BARRIER=1: one tiny all-gather per solver creation, then the fused exchange as before --
-    same bits, and exactly `ranks x solves` collectives"""
+def test_barrier_before_the_first_fused_product(monkeypatch):
+    """One tiny all-gather per solver creation (the guarantee that every rank's previous solve has left the arena), then
+    the fused exchange -- same bits, exactly `ranks x solves` collectives; SVMB200_P2P_CREATE_BARRIER=0 removes it (A/B
+    timing only)"""
     from optiml_b200.opti import Quadratic
     from optiml_b200.opti.constrained import ProjectedGradient
     rng = np.random.default_rng(6)
@@ -316,9 +319,35 @@ def test_optional_barrier_before_the_first_fused_product(monkeypatch):
 
     with emulated_device() as lib:
         one = run_ranks(1, 'nccl', body)[0]
-        monkeypatch.setenv('SVMB200_P2P_CREATE_BARRIER', '1')
+        monkeypatch.delenv('SVMB200_P2P_CREATE_BARRIER', raising=False)
         gathers = lib.emu_allgather_calls()
         many = run_ranks(2, 'p2p', body)
         assert lib.emu_allgather_calls() - gathers == 2 * len(sizes)
+        monkeypatch.setenv('SVMB200_P2P_CREATE_BARRIER', '0')
+        gathers = lib.emu_allgather_calls()
+        unguarded = run_ranks(2, 'p2p', body)
+        assert lib.emu_allgather_calls() - gathers == 0
+    for state in many + unguarded:
+        assert all(np.array_equal(a, b) for a, b in zip(one, state))
+
+
+def test_many_back_to_back_solves_of_alternating_sizes():
+    """The hardware stress of tests/multigpu_check.py in small: 48 solves back to back on three ranks, sizes alternating so
+    that consecutive arena layouts overlap across parities and one size leaves the last rank without rows (that one
+    takes the all-gather) -- every repeat bit-identical to one rank, nobody stalls."""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import ProjectedGradient
+    rng = np.random.default_rng(12)
+    sizes = (200, 128, 330, 90)      # 128 on 3 ranks: 64-row shards, rank 2 owns nothing
+    problems = [(S.psd(rng, n), rng.standard_normal(n), np.full(n, 1.5)) for n in sizes]
+    iters = (3, 1, 5)
+
+    def body(ctx):
+        quads = [Quadratic(shard_hessian(ctx, M), q) for M, q, _ in problems]
+        return [ProjectedGradient(quad=quads[i % 4], ub=problems[i % 4][2], max_iter=iters[i % 3]).minimize().x for i in range(48)]
+
+    with emulated_device():
+        one = run_ranks(1, 'nccl', body)[0]
+        many = run_ranks(3, 'p2p', body)
     for state in many:
         assert all(np.array_equal(a, b) for a, b in zip(one, state))

@@ -4,9 +4,7 @@ streaming pass, signed Hessian views, lockstep batches and the one-vs-rest / mul
 The checks are the ones the CPU suite runs on the host emulation of the kernels (tests/shared_gram_checks.py), at
 sizes that need several column segments and row groups, plus the reference's one-vs-rest recipes against its goldens.
 
-FIRST HARDWARE RUN PENDING: round 1's GPU budget was spent before this row was written, so these tests have only
-run on the emulation (real kernel source, CPU).  They are marked xfail(strict=False) until a B200 run confirms them,
-so that an unverified row cannot turn the verified suite red; DESIGN.md section 6.4 says the same.
+First hardware runs: the driver's round-1 GPU test pass and profiles/r2_s1_pytest_gpu.log (all 15 green).
 """
 import warnings
 
@@ -15,8 +13,7 @@ import pytest
 
 import shared_gram_checks as S
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='first hardware run pending (verified on the host emulation only)')]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('n,count', [(1000, 2), (8200, 3), (9001, 4), (2500, 7)])
