@@ -158,10 +158,12 @@ int svmb200_pg_scalars(svmb200_pg* pg, double* vals6);
 int svmb200_pg_history(svmb200_pg* pg, double* f_hist_host, double* ng_hist_host, int64_t* count);
 /* timing of the last svmb200_pg_run: device milliseconds and number of Q passes (matvec launches) */
 int svmb200_pg_stats(svmb200_pg* pg, float* ms, int64_t* passes, float* matvec_ms);
-/* when on, every iteration of svmb200_pg_run is bracketed by CUDA events: K2 (matvec_ms above),
- * the all-gather and K3; svmb200_pg_stats_ex returns the three sums of the last run */
+/* when on, ONE ITERATION IN 16 of svmb200_pg_run is bracketed by CUDA events: K2 (matvec_ms above), the all-gather
+ * and K3 (events serialise the programmatic launches around them, so they are sampled); svmb200_pg_stats_ex returns
+ * the three sums over the sampled iterations of the last run, svmb200_pg_profile_samples how many those were */
 int svmb200_pg_set_profile(svmb200_pg* pg, int on);
 int svmb200_pg_stats_ex(svmb200_pg* pg, float* matvec_ms, float* comm_ms, float* vector_ms);
+int svmb200_pg_profile_samples(svmb200_pg* pg, int64_t* samples);
 int svmb200_pg_device_x(svmb200_pg* pg, double** dx); /* device pointer of the iterate (nvars)     */
 int svmb200_pg_destroy(svmb200_pg* pg);
 
@@ -246,6 +248,24 @@ int svmb200_masked_product(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_
 int svmb200_decision(svmb200_ctx* ctx, const double* sv_host, int64_t nsv, const double* dual_coef_host,
                      const double* x_host, int64_t m, int64_t d, int kernel, double gamma, double coef0,
                      double degree, double intercept, double* out_host);
+
+/* The same with the support vectors already in HBM (dsv: nsv x d doubles, leading dimension ldsv, even): what fit
+ * leaves behind (svmb200_gather_rows), so that predict does not upload them again on every call.                */
+int svmb200_decision_device(svmb200_ctx* ctx, const double* dsv, int64_t nsv, int64_t ldsv,
+                            const double* dual_coef_host, const double* x_host, int64_t m, int64_t d, int kernel,
+                            double gamma, double coef0, double degree, double intercept, double* out_host);
+
+/* ---- device-side replacements of the O(n d) host steps of fit (csrc/devmath.cu) -------------------------------
+ * X.var() of kernels.py:93, 127 (gamma='scale') over the rows x cols logical elements of a device matrix,
+ * BIT-IDENTICAL to NumPy (same pairwise-summation tree), and the all-finite test of the input validation
+ * (sklearn check_pairwise_arrays, kernels.py:50, 92, 126) in the same pass: *nonfinite = 1 if any element is NaN or
+ * +-inf.  want_variance = 0: finite test only.                                                                      */
+int svmb200_device_variance(svmb200_ctx* ctx, const double* dX, int64_t rows, int64_t cols, int64_t ld,
+                            int want_variance, double* var, int* nonfinite);
+/* support_vectors_ = X[sv] (ml/svm/_base.py:869, 1425) gathered in HBM: dOut[i][:] = dX[idx_host[i]][:], pad columns
+ * zero.  Asynchronous on the context's stream.                                                                      */
+int svmb200_gather_rows(svmb200_ctx* ctx, const double* dX, int64_t nrows_src, int64_t ld_src, int64_t d,
+                        const int64_t* idx_host, int64_t nidx, double* dOut, int64_t ld_out);
 
 /* ---- host-pointer convenience entry points (what a reference-side binding would call) ------- */
 /* kernels.py Kernel.__call__(X, Y=None): out is nx x ny row-major on the host. y_host NULL => Y is X */

@@ -76,11 +76,16 @@ PROTOTYPES = {
     'svmb200_pg_stats': [c_vp, C.POINTER(C.c_float), C.POINTER(i64), C.POINTER(C.c_float)],
     'svmb200_pg_set_profile': [c_vp, C.c_int],
     'svmb200_pg_stats_ex': [c_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)],
+    'svmb200_pg_profile_samples': [c_vp, C.POINTER(i64)],
     'svmb200_pg_device_x': [c_vp, C.POINTER(c_vp)],
     'svmb200_pg_destroy': [c_vp],
     'svmb200_masked_product': [c_vp, c_vp, i64, i64, i64, i64, c_vp, c_vp],
     'svmb200_decision': [c_vp, c_vp, i64, c_vp, c_vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_double,
                          C.c_double, c_vp],
+    'svmb200_decision_device': [c_vp, c_vp, i64, i64, c_vp, c_vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                C.c_double, c_vp],
+    'svmb200_device_variance': [c_vp, c_vp, i64, i64, i64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)],
+    'svmb200_gather_rows': [c_vp, c_vp, i64, i64, i64, c_vp, i64, c_vp, i64],
     'svmb200_kernel_matrix_host': [c_vp, c_vp, i64, c_vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_double,
                                    c_vp],
     'svmb200_host_variance': [c_vp, i64, C.c_int, C.POINTER(C.c_double)],

@@ -81,6 +81,8 @@ extern "C" int svmb200_ctx_destroy(svmb200_ctx* ctx) {
         if (ctx->norm_buf) cudaFree(ctx->norm_buf);
         if (ctx->mp_buf) cudaFree(ctx->mp_buf);
         if (ctx->batch_buf) cudaFree(ctx->batch_buf);
+        if (ctx->idx_buf) cudaFree(ctx->idx_buf);
+        svm_release_variance_cache(ctx);
         cudaStreamDestroy(ctx->stream);
     }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -229,17 +231,14 @@ extern "C" int svmb200_kernel_matrix_host(svmb200_ctx* ctx, const double* x_host
     return SVMB200_OK;
 }
 
-extern "C" int svmb200_decision(svmb200_ctx* ctx, const double* sv_host, int64_t nsv, const double* dual_coef_host,
-                                const double* x_host, int64_t m, int64_t d, int kernel, double gamma, double coef0,
-                                double degree, double intercept, double* out_host) {
-    SVM_TRY(svm_use(ctx));
-    SVM_CHECK_ARG(sv_host && dual_coef_host && x_host && out_host, "null argument");
-    SVM_CHECK_ARG(nsv > 0 && m > 0 && d > 0, "empty operand");
-    // k(SV_i, X_j) == k(X_j, SV_i) term by term for the three kernels, so the block K(X_chunk, SV)
-    // (rows = test points) is built with K1 and contracted with dual_coef by the streaming matvec K2.
-    DevBuf dsv, dx, dcoef, dblock, dres;
-    int64_t ldsv = 0, ldx = 0;
-    SVM_TRY(upload_padded(ctx, sv_host, nsv, d, dsv, &ldsv));
+// out[j] = sum_i dual_coef[i] k(SV_i, X_j) + b with the support vectors already in HBM (dsv: nsv x d, leading dimension
+// ldsv).  k(SV_i, X_j) == k(X_j, SV_i) term by term for every kernel here, so the block K(X_chunk, SV) (rows = test
+// points) is built with K1 and contracted with dual_coef by the streaming matvec K2; blocks of <= 2 GiB.
+static int decision_core(svmb200_ctx* ctx, const double* dsv, int64_t nsv, int64_t ldsv, const double* dual_coef_host,
+                         const double* x_host, int64_t m, int64_t d, int kernel, double gamma, double coef0, double degree,
+                         double intercept, double* out_host) {
+    DevBuf dx, dcoef, dblock, dres;
+    int64_t ldx = 0;
     SVM_TRY(upload_padded(ctx, x_host, m, d, dx, &ldx));
     const int64_t ldo = svmb200_padded_ld(nsv);
     SVM_TRY(dcoef.alloc((size_t)ldo * sizeof(double)));
@@ -251,7 +250,7 @@ extern "C" int svmb200_decision(svmb200_ctx* ctx, const double* sv_host, int64_t
     SVM_TRY(dres.alloc((size_t)m * sizeof(double)));
     for (int64_t r0 = 0; r0 < m; r0 += rows_per_block) {
         const int64_t nr = std::min(rows_per_block, m - r0);
-        SVM_TRY(svmb200_gram(ctx, dx.d(), m, ldx, dsv.d(), nsv, ldsv, d, 0, kernel, gamma, coef0, degree, nullptr,
+        SVM_TRY(svmb200_gram(ctx, dx.d(), m, ldx, dsv, nsv, ldsv, d, 0, kernel, gamma, coef0, degree, nullptr,
                              nullptr, 0.0, r0, nr, dblock.d(), ldo));
         SVM_TRY(svm_launch_matvec(ctx, dblock.d(), nr, ldo, dcoef.d(), dres.d() + r0, nullptr));
     }
@@ -259,6 +258,28 @@ extern "C" int svmb200_decision(svmb200_ctx* ctx, const double* sv_host, int64_t
     SVM_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int64_t j = 0; j < m; ++j) out_host[j] += intercept;
     return SVMB200_OK;
+}
+
+extern "C" int svmb200_decision(svmb200_ctx* ctx, const double* sv_host, int64_t nsv, const double* dual_coef_host,
+                                const double* x_host, int64_t m, int64_t d, int kernel, double gamma, double coef0,
+                                double degree, double intercept, double* out_host) {
+    SVM_TRY(svm_use(ctx));
+    SVM_CHECK_ARG(sv_host && dual_coef_host && x_host && out_host, "null argument");
+    SVM_CHECK_ARG(nsv > 0 && m > 0 && d > 0, "empty operand");
+    DevBuf dsv;
+    int64_t ldsv = 0;
+    SVM_TRY(upload_padded(ctx, sv_host, nsv, d, dsv, &ldsv));
+    return decision_core(ctx, dsv.d(), nsv, ldsv, dual_coef_host, x_host, m, d, kernel, gamma, coef0, degree, intercept,
+                         out_host);
+}
+
+extern "C" int svmb200_decision_device(svmb200_ctx* ctx, const double* dsv, int64_t nsv, int64_t ldsv,
+                                       const double* dual_coef_host, const double* x_host, int64_t m, int64_t d, int kernel,
+                                       double gamma, double coef0, double degree, double intercept, double* out_host) {
+    SVM_TRY(svm_use(ctx));
+    SVM_CHECK_ARG(dsv && dual_coef_host && x_host && out_host, "null argument");
+    SVM_CHECK_ARG(nsv > 0 && m > 0 && d > 0 && ldsv >= d && ldsv % 2 == 0, "bad operand");
+    return decision_core(ctx, dsv, nsv, ldsv, dual_coef_host, x_host, m, d, kernel, gamma, coef0, degree, intercept, out_host);
 }
 
 extern "C" int svmb200_bcqp_pg_host(svmb200_ctx* ctx, const double* Q_host, const double* q_host, const double* lb_host,

@@ -40,7 +40,7 @@ struct svmb200_ctx {
     size_t pg_slab_bytes = 0;
     bool pg_slab_busy = false;
     void* pg_pinned = nullptr;
-    cudaEvent_t pg_ev0 = nullptr, pg_ev1 = nullptr;
+    cudaEvent_t pg_ev0 = nullptr, pg_ev1 = nullptr, pg_ev_poll[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> event_pool;
     size_t event_pool_used = 0;
     // small per-call scratch, grown on demand and reused in stream order: row norms of K1, operands of K5
@@ -51,12 +51,18 @@ struct svmb200_ctx {
     // argument blocks of a batched solve (one VecArgs / ALArgs per problem, read by the batch vector kernels)
     void* batch_buf = nullptr;
     size_t batch_bytes = 0;
+    // device-side X.var() (devmath.cu): leaf table of NumPy's pairwise tree, leaf sums, pinned staging -- cached per size
+    void* var_cache = nullptr;
+    // row indices of a device gather (support vectors)
+    void* idx_buf = nullptr;
+    size_t idx_bytes = 0;
 };
 
 // grow-only device scratch; safe to reuse without a sync because every user runs on ctx->stream
 int svm_scratch_reserve(svmb200_ctx* ctx, void** buf, size_t* have, size_t need);
 
 void svm_release_solver_cache(svmb200_ctx* ctx);
+void svm_release_variance_cache(svmb200_ctx* ctx);
 
 // arena layout
 constexpr size_t ARENA_LOCAL_OFF = 256;    // [+8] int fault: set by a reader whose bounded spin expired
@@ -97,6 +103,39 @@ static inline int svm_use(svmb200_ctx* ctx) {
 }
 
 static inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- programmatic dependent launch (PDL): the kernels of the solver loop form a strict chain (K2 -> K3 -> K2 ...), each
+// a few hundred microseconds or less at 8 GPUs, so the 2-3 us between the end of one grid and the first instruction of the
+// next are paid twice per iteration.  A kernel launched with the programmatic-serialisation attribute may be SCHEDULED
+// while its predecessor is still running (as soon as every CTA of the predecessor has passed pdl_launch_dependents());
+// its CTAs sit in pdl_wait() until the predecessor grid has completed and its memory is visible.  Correctness is that of
+// the plain stream order: nothing is read or written before pdl_wait().
+#ifndef SVMB200_HOST_EMULATION
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t svm_launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#else
+static inline void pdl_wait() {}
+static inline void pdl_launch_dependents() {}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t svm_launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t, Args... args) {
+    emu::launch(grid, block, 0, [=]() { kernel(KArgs(args)...); });
+    return cudaSuccess;
+}
+#endif
 
 // internal cross-file entry points
 int svm_comm_allgather(svmb200_ctx* ctx, double* dbuf, int64_t count_per_rank);  // in place, on ctx->stream

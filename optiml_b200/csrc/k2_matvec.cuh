@@ -104,6 +104,8 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) { return *p
 #endif
 
 __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const MatvecArgs a) {
+    pdl_wait();               // u (and the done flag) come from the vector launch before this one
+    pdl_launch_dependents();  // once every CTA of this grid has started, the vector launch may be scheduled behind it
     if (a.done != nullptr && *a.done) return;
     if (a.fault != nullptr && *a.fault) return;  // the exchange is broken: nothing downstream will be used
     constexpr int R = MV_R, NT = MV_NT, U = MV_U;
@@ -285,6 +287,8 @@ __global__ void __launch_bounds__(MV_NT * MultiCfg<NB>::H, MultiCfg<NB>::MINB) m
     constexpr int R = MultiCfg<NB>::R, NT = MV_NT, U = MultiCfg<NB>::U, H = MultiCfg<NB>::H, BPG = MV_GROUP / (R * H);
     static_assert(NB >= 1 && NB <= MV_MULTI_MAX && NB * MV_GROUP <= NT * H && MV_GROUP % (R * H) == 0 && NT * H <= 1024,
                   "bad multi-vector shape");
+    pdl_wait();
+    pdl_launch_dependents();
     bool live[NB];
     bool any = false;
 #pragma unroll

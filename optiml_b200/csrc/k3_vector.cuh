@@ -632,14 +632,20 @@ __device__ __forceinline__ void al_vector_body(const VecArgs& a, const ALArgs& a
 // blocks live in device memory.  A problem that has finished ignores the launches that follow (its `done` flag).
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const long long k) {
+    pdl_wait();               // the product this launch consumes (and the previous vector launch) must be complete
+    pdl_launch_dependents();  // the next product may be scheduled behind us; it waits for our completion itself
     pg_vector_body<MODE>(a, k);
 }
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const long long k) {
+    pdl_wait();               // the product this launch consumes (and the previous vector launch) must be complete
+    pdl_launch_dependents();  // the next product may be scheduled behind us; it waits for our completion itself
     fw_vector_body<MODE>(a, k);
 }
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) al_vector_kernel(const VecArgs a, const ALArgs al, const long long k) {
+    pdl_wait();
+    pdl_launch_dependents();
     al_vector_body<MODE>(a, al, k);
 }
 // The argument blocks are constant over a run except for the fused exchange: the tag and the parity of the gathered
@@ -655,12 +661,16 @@ __device__ __forceinline__ VecArgs batch_args(const VecArgs* __restrict__ args, 
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) pg_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k,
                                                                 const unsigned tag, const int parity) {
+    pdl_wait();
+    pdl_launch_dependents();
     const VecArgs a = batch_args(args, tag, parity);
     pg_vector_body<MODE>(a, k);
 }
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) fw_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k,
                                                                 const unsigned tag, const int parity) {
+    pdl_wait();
+    pdl_launch_dependents();
     const VecArgs a = batch_args(args, tag, parity);
     fw_vector_body<MODE>(a, k);
 }
@@ -668,6 +678,8 @@ template <int MODE>
 __global__ void __launch_bounds__(VP_NT) al_vector_batch_kernel(const VecArgs* __restrict__ args,
                                                                 const ALArgs* __restrict__ als, const long long k,
                                                                 const unsigned tag, const int parity) {
+    pdl_wait();
+    pdl_launch_dependents();
     const VecArgs a = batch_args(args, tag, parity);
     const ALArgs al = als[blockIdx.y];
     al_vector_body<MODE>(a, al, k);

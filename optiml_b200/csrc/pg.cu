@@ -99,9 +99,8 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
         svmb200_set_error("matvec: grid too large");
         return SVMB200_ERR_ARG;
     }
-    matvec_seg_kernel<<<(unsigned)nitems, MV_NT, 0, ctx->stream>>>(a);
+    SVM_CUDA(svm_launch_chained(matvec_seg_kernel, dim3((unsigned)nitems), dim3(MV_NT), ctx->stream, a));
     ctx->launches++;
-    SVM_CUDA(cudaGetLastError());
     return SVMB200_OK;
 }
 
@@ -175,12 +174,14 @@ static int launch_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows
     }
     const int64_t ngroups = (nrows + MV_GROUP - 1) / MV_GROUP;
     int64_t nitems = 0;
+    cudaError_t launch_err = cudaSuccess;
     switch (nb) {
 #define LAUNCH_MULTI(NB)                                                                                \
     case NB:                                                                                            \
         nitems = ngroups * (MV_GROUP / (MultiCfg<NB>::R * MultiCfg<NB>::H)) * a.nseg;                   \
         if (nitems >= (1ll << 31)) break;                                                               \
-        matvec_seg_multi_kernel<NB><<<(unsigned)nitems, MV_NT * MultiCfg<NB>::H, 0, ctx->stream>>>(a);  \
+        launch_err = svm_launch_chained(matvec_seg_multi_kernel<NB>, dim3((unsigned)nitems),            \
+                                        dim3(MV_NT * MultiCfg<NB>::H), ctx->stream, a);                 \
         break;
         LAUNCH_MULTI(1)
         LAUNCH_MULTI(2)
@@ -193,7 +194,7 @@ static int launch_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows
         return SVMB200_ERR_ARG;
     }
     ctx->launches++;
-    SVM_CUDA(cudaGetLastError());
+    SVM_CUDA(launch_err);
     return SVMB200_OK;
 }
 
@@ -248,7 +249,10 @@ struct svmb200_pg {
     double* sgn = nullptr;  // label signs (Q = (s s') o resident matrix), or null
     double *part = nullptr, *hist_f = nullptr, *hist_ng = nullptr;
     PGDeviceState* st = nullptr;
-    PGDeviceState* st_host = nullptr;  // pinned
+    PGDeviceState* st_host = nullptr;  // pinned; points at the slot of the most recent completed poll
+    unsigned char* pinned = nullptr;   // 256 bytes: two poll slots of {PGDeviceState, fault flag}
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+    int64_t last_samples = 0;          // iterations of the last run that carried profiling events
     // host-side cursor
     int64_t k_next = 0;     // next iteration whose STEP kernel has not been enqueued
     bool finished = false;  // device reported done
@@ -261,6 +265,9 @@ struct svmb200_pg {
     void* slab = nullptr;        // all device buffers below live in this slab
     bool slab_private = false;   // true: allocated for this solver only (the context's slab was busy)
 };
+
+constexpr size_t POLL_SLOT_BYTES = 128;  // {PGDeviceState, ..., int fault} per poll slot of the pinned block
+constexpr int64_t PROFILE_STRIDE = 16;   // with profiling on, one iteration in this many carries CUDA events
 
 static unsigned exchange_tag(unsigned long long seq) { return (unsigned)(seq % 0xfffffffful) + 1u; }  // never 0
 
@@ -305,11 +312,12 @@ static VecArgs make_vec_args(svmb200_pg* pg) {
 template <int MODE>
 static int launch_vec(svmb200_pg* pg, long long k) {
     VecArgs a = make_vec_args(pg);
-    if (pg->solver == 2) al_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, pg->al, MODE == VP_INIT ? -1 : k);
-    else if (pg->solver == 1) fw_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
-    else pg_vector_kernel<MODE><<<pg->nctas, VP_NT, 0, pg->ctx->stream>>>(a, k);
+    const dim3 grid((unsigned)pg->nctas), block(VP_NT);
+    cudaStream_t s = pg->ctx->stream;
+    if (pg->solver == 2) SVM_CUDA(svm_launch_chained(al_vector_kernel<MODE>, grid, block, s, a, pg->al, (long long)(MODE == VP_INIT ? -1 : k)));
+    else if (pg->solver == 1) SVM_CUDA(svm_launch_chained(fw_vector_kernel<MODE>, grid, block, s, a, k));
+    else SVM_CUDA(svm_launch_chained(pg_vector_kernel<MODE>, grid, block, s, a, k));
     pg->ctx->launches++;
-    SVM_CUDA(cudaGetLastError());
     return SVMB200_OK;
 }
 
@@ -319,7 +327,7 @@ static int pg_product(svmb200_pg* pg, bool timed) {
     // w[row0 : row0+nrows] = Q_shard u, then all ranks exchange their shards (K4)
     svmb200_ctx* ctx = pg->ctx;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-    if (timed && pg->profile) {
+    if (timed) {
         e0 = pooled_event(ctx);
         e1 = pooled_event(ctx);
         e2 = pooled_event(ctx);
@@ -377,6 +385,10 @@ void svm_release_solver_cache(svmb200_ctx* ctx) {
     if (ctx->pg_ev0) cudaEventDestroy(ctx->pg_ev0);
     if (ctx->pg_ev1) cudaEventDestroy(ctx->pg_ev1);
     ctx->pg_ev0 = ctx->pg_ev1 = nullptr;
+    for (cudaEvent_t& e : ctx->pg_ev_poll) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
     if (ctx->pg_slab) cudaFree(ctx->pg_slab);
     ctx->pg_slab = nullptr;
     ctx->pg_slab_bytes = 0;
@@ -391,9 +403,11 @@ extern "C" int svmb200_pg_destroy(svmb200_pg* pg) {
         cudaStreamSynchronize(pg->ctx->stream);
         if (pg->slab_private) {
             if (pg->slab) cudaFree(pg->slab);
-            if (pg->st_host) cudaFreeHost(pg->st_host);
+            if (pg->pinned) cudaFreeHost(pg->pinned);
             if (pg->ev0) cudaEventDestroy(pg->ev0);
             if (pg->ev1) cudaEventDestroy(pg->ev1);
+            for (cudaEvent_t e : pg->ev_poll)
+                if (e) cudaEventDestroy(e);
         } else if (pg->slab) {
             pg->ctx->pg_slab_busy = false;  // workspace, pinned block and events go back to the context
             pg->ctx->event_pool_used = 0;
@@ -534,20 +548,27 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
             if (!ctx->pg_pinned) PG_CUDA(cudaMallocHost(&ctx->pg_pinned, 256));
             if (!ctx->pg_ev0) PG_CUDA(cudaEventCreate(&ctx->pg_ev0));
             if (!ctx->pg_ev1) PG_CUDA(cudaEventCreate(&ctx->pg_ev1));
+            for (cudaEvent_t& e : ctx->pg_ev_poll)
+                if (!e) PG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->pg_slab_busy = true;
             ctx->event_pool_used = 0;
             pg->slab = ctx->pg_slab;
             pg->slab_private = false;
-            pg->st_host = static_cast<PGDeviceState*>(ctx->pg_pinned);
+            pg->pinned = static_cast<unsigned char*>(ctx->pg_pinned);
             pg->ev0 = ctx->pg_ev0;
             pg->ev1 = ctx->pg_ev1;
+            pg->ev_poll[0] = ctx->pg_ev_poll[0];
+            pg->ev_poll[1] = ctx->pg_ev_poll[1];
         } else {
             pg->slab_private = true;  // a second live solver on the same context: private workspace
             PG_CUDA(cudaMalloc(&pg->slab, total));
-            PG_CUDA(cudaMallocHost(&pg->st_host, sizeof(PGDeviceState)));
+            PG_CUDA(cudaMallocHost(&pg->pinned, 256));
             PG_CUDA(cudaEventCreate(&pg->ev0));
             PG_CUDA(cudaEventCreate(&pg->ev1));
+            for (cudaEvent_t& e : pg->ev_poll) PG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
+        static_assert(sizeof(PGDeviceState) <= POLL_SLOT_BYTES - sizeof(int), "poll slot too small");
+        pg->st_host = reinterpret_cast<PGDeviceState*>(pg->pinned);
         base = static_cast<unsigned char*>(pg->slab);
         size_t off = 0;
         auto take = [&](size_t b) { unsigned char* q = base + off; off += b; return reinterpret_cast<double*>(q); };
@@ -662,21 +683,39 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     return SVMB200_OK;
 }
 
-static int pg_poll(svmb200_pg* pg) {
-    SVM_CUDA(cudaMemcpyAsync(pg->st_host, pg->st, sizeof(PGDeviceState), cudaMemcpyDeviceToHost, pg->ctx->stream));
-    SVM_CUDA(cudaStreamSynchronize(pg->ctx->stream));
+// A poll is a copy of the device state block (and of the exchange fault flag) into one of two pinned slots, followed by an
+// event.  pg_run enqueues the NEXT batch of iterations before it waits for the poll of the previous one, so the stream
+// never runs dry while the host looks at the stopping flags (a drained stream costs a launch latency per batch: 2.5 % of
+// a C1-sized solve).
+static int poll_enqueue(svmb200_pg* pg, int slot) {
+    cudaStream_t s = pg->ctx->stream;
+    unsigned char* dst = pg->pinned + (size_t)slot * POLL_SLOT_BYTES;
+    SVM_CUDA(cudaMemcpyAsync(dst, pg->st, sizeof(PGDeviceState), cudaMemcpyDeviceToHost, s));
+    int* fault = reinterpret_cast<int*>(dst + POLL_SLOT_BYTES - sizeof(int));
+    *fault = 0;
+    if (pg->p2p)
+        SVM_CUDA(cudaMemcpyAsync(fault, pg->ctx->arena + ARENA_LOCAL_OFF + 8, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SVM_CUDA(cudaEventRecord(pg->ev_poll[slot], s));
+    return SVMB200_OK;
+}
+
+static int poll_wait(svmb200_pg* pg, int slot) {
+    SVM_CUDA(cudaEventSynchronize(pg->ev_poll[slot]));
+    unsigned char* src = pg->pinned + (size_t)slot * POLL_SLOT_BYTES;
+    pg->st_host = reinterpret_cast<PGDeviceState*>(src);
     if (pg->st_host->done) pg->finished = true;
-    if (pg->p2p) {
-        int fault = 0;
-        SVM_CUDA(cudaMemcpy(&fault, pg->ctx->arena + ARENA_LOCAL_OFF + 8, sizeof(int), cudaMemcpyDeviceToHost));
-        if (fault) {
-            // sticky and context-fatal: the sequence numbers of the ranks can no longer be trusted to agree
-            svmb200_set_error("peer exchange timed out: a rank stopped publishing its product shard (the context's "
-                              "exchange is unusable from here on: destroy it and every peer's, then start over)");
-            return SVMB200_ERR_STATE;
-        }
+    if (*reinterpret_cast<const int*>(src + POLL_SLOT_BYTES - sizeof(int))) {
+        // sticky and context-fatal: the sequence numbers of the ranks can no longer be trusted to agree
+        svmb200_set_error("peer exchange timed out: a rank stopped publishing its product shard (the context's "
+                          "exchange is unusable from here on: destroy it and every peer's, then start over)");
+        return SVMB200_ERR_STATE;
     }
     return SVMB200_OK;
+}
+
+static int pg_poll(svmb200_pg* pg) {
+    SVM_TRY(poll_enqueue(pg, 0));
+    return poll_wait(pg, 0);
 }
 
 extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, int* status) {
@@ -686,34 +725,53 @@ extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, in
     pg->mv_ev.clear();  // pooled events: reused, never destroyed per run
     ctx->event_pool_used = 0;
     pg->last_passes = 0;
+    pg->last_samples = 0;
     pg->last_ms = pg->last_mv_ms = pg->last_comm_ms = pg->last_vec_ms = 0.f;
     SVM_CUDA(cudaEventRecord(pg->ev0, ctx->stream));
     if (!pg->finished) {
         const bool to_end = max_new < 0;
         int64_t budget = to_end ? (pg->max_iter - pg->k_next) : max_new;
         if (budget > pg->max_iter - pg->k_next) budget = pg->max_iter - pg->k_next;
-        // enqueue in batches; the device-side done flag turns the remainder of a batch into no-ops
+        // enqueue in batches; the device-side done flag turns the remainder of a batch (and the batch enqueued behind it
+        // before its poll came back) into no-ops
         const int64_t BATCH = 64;
-        while (budget > 0 && !pg->finished) {
+        int pending = -1, slot = 0;
+        int rc = SVMB200_OK;
+        while (budget > 0 && !pg->finished && rc == SVMB200_OK) {
             const int64_t nb = budget < BATCH ? budget : BATCH;
-            for (int64_t i = 0; i < nb; ++i) {
-                SVM_TRY(pg_product(pg, true));
-                SVM_TRY(launch_vec<VP_STEP>(pg, pg->k_next));
-                if (pg->profile) {
+            for (int64_t i = 0; i < nb && rc == SVMB200_OK; ++i) {
+                // profiling events serialise the programmatic launches around them: sample one iteration in PROFILE_STRIDE
+                const bool sample = pg->profile && (pg->k_next % PROFILE_STRIDE) == 0;
+                rc = pg_product(pg, sample);
+                if (rc == SVMB200_OK) rc = launch_vec<VP_STEP>(pg, pg->k_next);
+                if (rc == SVMB200_OK && sample) {
                     cudaEvent_t e3 = pooled_event(ctx);
                     if (!e3) {
                         svmb200_set_error("cannot create profiling events");
-                        return SVMB200_ERR_CUDA;
+                        rc = SVMB200_ERR_CUDA;
+                    } else if (cudaEventRecord(e3, ctx->stream) != cudaSuccess) {
+                        svmb200_set_error("cudaEventRecord failed");
+                        rc = SVMB200_ERR_CUDA;
+                    } else {
+                        pg->mv_ev.push_back(e3);
+                        pg->last_samples++;
                     }
-                    SVM_CUDA(cudaEventRecord(e3, ctx->stream));
-                    pg->mv_ev.push_back(e3);
                 }
                 pg->k_next++;
             }
             budget -= nb;
-            SVM_TRY(pg_poll(pg));
-            if (pg->finished) pg->k_next = pg->st_host->iter;
+            if (rc == SVMB200_OK) rc = poll_enqueue(pg, slot);
+            if (rc == SVMB200_OK && pending >= 0) rc = poll_wait(pg, pending);  // the batch BEFORE the one just enqueued
+            pending = slot;
+            slot ^= 1;
         }
+        if (pending >= 0) {
+            // the last poll is always collected: its copy targets pinned memory that outlives this call
+            const int rc2 = poll_wait(pg, pending);
+            if (rc == SVMB200_OK) rc = rc2;
+        }
+        SVM_TRY(rc);
+        if (pg->finished) pg->k_next = pg->st_host->iter;
         if (!pg->finished) {
             // make the state at callback point k_next visible (f, |d|, stopping tests); the augmented Lagrangian
             // needs w = Q xe for that (value and gradient at xe), the box-constrained solvers carry g along
@@ -805,11 +863,11 @@ static int launch_vec_batch(svmb200_ctx* ctx, int solver, int nctas, int count, 
     const dim3 grid((unsigned)nctas, (unsigned)count);
     const unsigned tag = bx.p2p ? exchange_tag(bx.seq) : 0u;
     const int parity = bx.p2p ? (int)(bx.seq & 1) : 0;
-    if (solver == 2) al_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, dal, k, tag, parity);
-    else if (solver == 1) fw_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, k, tag, parity);
-    else pg_vector_batch_kernel<MODE><<<grid, VP_NT, 0, ctx->stream>>>(dva, k, tag, parity);
+    const dim3 block(VP_NT);
+    if (solver == 2) SVM_CUDA(svm_launch_chained(al_vector_batch_kernel<MODE>, grid, block, ctx->stream, dva, dal, k, tag, parity));
+    else if (solver == 1) SVM_CUDA(svm_launch_chained(fw_vector_batch_kernel<MODE>, grid, block, ctx->stream, dva, k, tag, parity));
+    else SVM_CUDA(svm_launch_chained(pg_vector_batch_kernel<MODE>, grid, block, ctx->stream, dva, k, tag, parity));
     ctx->launches++;
-    SVM_CUDA(cudaGetLastError());
     return SVMB200_OK;
 }
 
@@ -990,6 +1048,14 @@ extern "C" int svmb200_pg_stats_ex(svmb200_pg* pg, float* matvec_ms, float* comm
     if (matvec_ms) *matvec_ms = pg->last_mv_ms;
     if (comm_ms) *comm_ms = pg->last_comm_ms;
     if (vector_ms) *vector_ms = pg->last_vec_ms;
+    return SVMB200_OK;
+}
+
+// iterations of the last svmb200_pg_run whose launches were bracketed by CUDA events (profiling samples one iteration
+// in 16: the events serialise the programmatic launches around them); the *_ms sums of svmb200_pg_stats_ex cover these
+extern "C" int svmb200_pg_profile_samples(svmb200_pg* pg, int64_t* samples) {
+    SVM_CHECK_ARG(pg != nullptr && samples != nullptr, "null argument");
+    *samples = pg->last_samples;
     return SVMB200_OK;
 }
 

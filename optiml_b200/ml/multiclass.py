@@ -39,20 +39,28 @@ def fit_shared_gram(estimator, X, targets):
     if not targets:
         return []
     clones = [clone(estimator) for _ in targets]
-    X, _ = _dense_f64(X, None)
+    X, _ = _dense_f64(X, None, finite=False)  # the all-finite test runs on the device copy (_build_hessian)
     head = clones[0]
     head._bcqp_solver_class()  # raises for the branches outside the dual path before any device work
     # K1 once: M = K + bias without label signs (SVC: the solvers apply them; SVR: the block signs are implicit)
     shared = head._build_hessian(X, None, 'svr' if isinstance(estimator, SVR) else 'plain', None, head._bias())
     gram_s = head.fit_times_['gram_s']
-    plans = [est._plan_fit(X, t, shared=shared) for est, t in zip(clones, targets)]
-    t0 = time.perf_counter()
-    minimize_batch([p['solver'] for p in plans])
-    solve_s = time.perf_counter() - t0
-    for est, plan in zip(clones, plans):
-        # wall-clock of the shared steps: every clone reports the whole batch
-        est.fit_times_ = {'gram_s': gram_s, 'solve_s': solve_s, 'batch': len(clones)}
-        est._finish_fit(plan)
+    dX, owned = head._train_X_device   # every clone gathers its support vectors from this one copy of X in HBM
+    try:
+        plans = [est._plan_fit(X, t, shared=shared) for est, t in zip(clones, targets)]
+        t0 = time.perf_counter()
+        minimize_batch([p['solver'] for p in plans])
+        solve_s = time.perf_counter() - t0
+        for est, plan in zip(clones, plans):
+            # wall-clock of the shared steps: every clone reports the whole batch
+            est.fit_times_ = {'gram_s': gram_s, 'solve_s': solve_s, 'batch': len(clones)}
+            est._train_X_device = (dX, False)
+            est._finish_fit(plan)
+    finally:
+        for est in clones:
+            est._train_X_device = None
+        if owned:
+            dX.release()
     return clones
 
 

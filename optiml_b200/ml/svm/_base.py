@@ -25,7 +25,7 @@ from ... import _native as N
 from ...opti import Optimizer, Quadratic
 from ...opti.constrained import AugmentedLagrangianQuadratic, BoxConstrainedQuadraticOptimizer, ProjectedGradient
 from ...opti.unconstrained.stochastic import StochasticOptimizer, StochasticMomentumOptimizer
-from ...runtime import DeviceHessian, default_context
+from ...runtime import DeviceHessian, DeviceMatrix, default_context
 
 _SCOPE = ('optiml_b200 implements the dual formulation solved by a BoxConstrainedQuadraticOptimizer '
           '(ProjectedGradient, FrankWolfe; reg_intercept=True) or, as its augmented-Lagrangian relaxation, by a '
@@ -100,6 +100,7 @@ class SVM(BaseEstimator):
             self.coef_ = np.zeros(0)
         self.intercept_ = 0.
         self.support_ = np.zeros(0)
+        self._sv_device = None
         self.support_vectors_ = np.zeros(0)
         if self.dual:
             self.alphas_ = np.zeros(0)
@@ -167,24 +168,74 @@ class SVM(BaseEstimator):
         ctx = default_context()
         n, d = X.shape
         t0 = time.perf_counter()
-        kid, gamma, coef0, degree = self.kernel.gram_spec(X)
         dX = X_device if X_device is not None else ctx.upload_matrix(X)
+        # gamma='scale' needs X.var(), the input validation an all-finite test: both from the copy in HBM, one pass
+        kid, gamma, coef0, degree = self.kernel.gram_spec(X, device=dX)
         dS = ctx.upload_vector(signs) if signs is not None else None
         H = DeviceHessian(ctx, n, layout)
         sp = C.c_void_p(dS.dptr) if dS is not None else None
         N.call('svmb200_gram', ctx.handle, C.c_void_p(dX.dptr), n, dX.ld, C.c_void_p(dX.dptr), n, dX.ld, d, 1, kid,
                gamma, coef0, degree, sp, sp, float(bias), H.row0, H.nrows, C.c_void_p(H.matrix.dptr), H.ld)
         ctx.sync()
-        if X_device is None:
-            dX.release()
         if dS is not None:
             dS.release()
+        # X stays in HBM until the support vectors have been gathered from it (_set_support_vectors)
+        self._train_X_device = (dX, X_device is None)
         self.fit_times_ = {'gram_s': time.perf_counter() - t0}  # gamma + upload + Gram kernel (wall clock)
         return H
+
+    # ------------------------------------------------------------------ support vectors: device-resident, host copy on demand
+    @property
+    def support_vectors_(self):
+        """``X[support_]`` (ml/svm/_base.py:869, 1425).  After a kernelised fit the rows are gathered in HBM, where
+        ``decision_function`` needs them, from the copy of X the fit uploaded -- a snapshot of the training data at fit
+        time, like the reference's; the host array is materialised on first access (50 MB at n = 50 000, d = 128: the
+        copy into fresh host memory alone was 8 ms of every fit on every rank)."""
+        if self._sv_host is None and self._sv_device is not None:
+            self._sv_host = self._sv_device.to_host()
+        return self._sv_host
+
+    @support_vectors_.setter
+    def support_vectors_(self, value):
+        self._sv_host, self._sv_device = value, None
+
+    def _set_support_vectors(self, X):
+        dX, owned = getattr(self, '_train_X_device', None) or (None, False)
+        self._train_X_device = None
+        if dX is not None and dX.dptr and not isinstance(self.kernel, LinearKernel) and len(self.support_):
+            ctx = dX.ctx
+            idx = np.ascontiguousarray(self.support_, dtype=np.int64)
+            sv = DeviceMatrix(ctx, len(idx), dX.cols, dX.ld)
+            N.call('svmb200_gather_rows', ctx.handle, C.c_void_p(dX.dptr), dX.rows, dX.ld, dX.cols,
+                   idx.ctypes.data_as(C.c_void_p), len(idx), C.c_void_p(sv.dptr), sv.ld)
+            self._sv_host, self._sv_device = None, sv
+        else:
+            self.support_vectors_ = gather_rows(X, self.support_)
+        if dX is not None and owned:
+            dX.release()
+
+    def __getstate__(self):
+        """Fitted estimators pickle / deep-copy without device handles: the support vectors travel as the host array."""
+        state = super().__getstate__()
+        if state.get('_sv_device') is not None:
+            state['_sv_host'] = self.support_vectors_
+        state['_sv_device'] = None
+        state['_train_X_device'] = None
+        return state
 
     def decision_function(self, X):
         """ml/svm/_base.py:284-287.  ``gamma='scale'`` is resolved from ``support_vectors_`` (the first
         argument of the reference's kernel call), not from the training matrix."""
+        if self.dual and not isinstance(self.kernel, LinearKernel) and self._sv_device is not None and self._sv_device.dptr:
+            # support vectors already in HBM (left there by fit): no upload, gamma='scale' from the device copy
+            X, _ = _dense_f64(X, None)
+            dsv = self._sv_device
+            coef = np.ascontiguousarray(self.dual_coef_, dtype=np.float64)
+            kid, gamma, coef0, degree = self.kernel.gram_spec(None, device=dsv)
+            out = np.empty(X.shape[0])
+            N.call('svmb200_decision_device', dsv.ctx.handle, C.c_void_p(dsv.dptr), dsv.rows, dsv.ld, N.ptr(coef), N.ptr(X),
+                   X.shape[0], X.shape[1], kid, gamma, coef0, degree, float(self.intercept_), N.ptr(out))
+            return out
         if self.dual and not isinstance(self.kernel, LinearKernel):
             X, _ = _dense_f64(X, None)
             sv = np.ascontiguousarray(self.support_vectors_, dtype=np.float64)
@@ -260,7 +311,7 @@ class SVC(ClassifierMixin, SVM):
             raise NotImplementedError  # ml/svm/_base.py:771-774
         if self.loss != Hinge:
             raise TypeError(f'{self.loss} is not an allowed loss')
-        X, _ = _dense_f64(X, None)
+        X, _ = _dense_f64(X, None, finite=False)  # the all-finite test runs on the device copy (_build_hessian)
         n = len(y)
         ys = y.astype(np.float64)
 
@@ -285,7 +336,8 @@ class SVC(ClassifierMixin, SVM):
         # support set, dual coefficients, intercept (ml/svm/_base.py:867-880)
         sv = self.alphas_ > 1e-6
         self.support_ = np.arange(n)[sv]
-        self.support_vectors_, sv_y, alphas = gather_rows(X, self.support_), y[sv], self.alphas_[sv]
+        self._set_support_vectors(X)
+        sv_y, alphas = y[sv], self.alphas_[sv]
         self.dual_coef_ = alphas * sv_y
         if isinstance(self.kernel, LinearKernel):
             self.coef_ = np.dot(self.dual_coef_, self.support_vectors_)
@@ -343,7 +395,7 @@ class SVR(RegressorMixin, SVM):
             raise NotImplementedError  # ml/svm/_base.py:1325-1328
         if self.loss != EpsilonInsensitive:
             raise TypeError(f'{self.loss} is not an allowed loss')
-        X, _ = _dense_f64(X, None)
+        X, _ = _dense_f64(X, None, finite=False)  # the all-finite test runs on the device copy (_build_hessian)
         y = y.astype(np.float64).ravel()
         n = len(y)
 
@@ -371,7 +423,8 @@ class SVR(RegressorMixin, SVM):
         # ml/svm/_base.py:1423-1437
         sv = np.logical_or(alphas_p > 1e-6, alphas_n > 1e-6)
         self.support_ = np.arange(n)[sv]
-        self.support_vectors_, sv_y = gather_rows(X, self.support_), y[sv]
+        self._set_support_vectors(X)
+        sv_y = y[sv]
         self.dual_coef_ = alphas_p[sv] - alphas_n[sv]
         if isinstance(self.kernel, LinearKernel):
             self.coef_ = np.dot(self.dual_coef_, self.support_vectors_)

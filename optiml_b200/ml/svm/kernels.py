@@ -19,11 +19,13 @@ def _check_gamma(gamma):
         raise ValueError('gamma must be > 0')
 
 
-def _dense_f64(X, Y):
+def _dense_f64(X, Y, finite=True):
     """sklearn's pairwise validation (2-D, finite, matching feature counts), then dense float64:
-    sparse / float32 inputs are converted (the reference keeps float32 Grams in float32)."""
+    sparse / float32 inputs are converted (the reference keeps float32 Grams in float32).
+    ``finite=False``: the caller runs the all-finite test on the device copy (``device_variance``) -- sklearn's is a full
+    single-threaded pass over X on the host (6.6 ms at n = 50 000, d = 128, on every rank of a sharded fit)."""
     same = Y is None or Y is X
-    X, Y = check_pairwise_arrays(X, None if same else Y, accept_sparse='csr')
+    X, Y = check_pairwise_arrays(X, None if same else Y, accept_sparse='csr', ensure_all_finite=bool(finite))
     dense = [np.ascontiguousarray(A.toarray() if hasattr(A, 'toarray') else A, dtype=np.float64) for A in (X, Y)]
     return dense[0], (None if same else dense[1])
 
@@ -49,6 +51,21 @@ def variance(X):
     return X.var()
 
 
+def device_variance(dX, X_host=None, want_variance=True):
+    """``X.var()`` bit for bit from the copy of X in HBM (svmb200_device_variance: NumPy's pairwise-summation tree, leaves on
+    the device) and, in the same pass, the all-finite test of sklearn's input validation -- a non-finite element raises
+    sklearn's own ValueError (from ``assert_all_finite`` on the host copy when there is one)."""
+    v, bad = C.c_double(0), C.c_int(0)
+    N.call('svmb200_device_variance', dX.ctx.handle, C.c_void_p(dX.dptr), dX.rows, dX.cols, dX.ld, int(bool(want_variance)),
+           C.byref(v), C.byref(bad))
+    if bad.value:
+        if X_host is not None:
+            from sklearn.utils import assert_all_finite
+            assert_all_finite(X_host)
+        raise ValueError('Input contains NaN or infinity.')
+    return v.value
+
+
 def gather_rows(X, idx):
     """``X[idx]`` for a C-contiguous float64 matrix and int64 row indices (threaded copy into fresh memory)"""
     idx = np.ascontiguousarray(idx, dtype=np.int64)
@@ -66,18 +83,23 @@ class Kernel(BaseEstimator):
 
     kernel_id = None
 
-    def resolve_gamma(self, X):
+    def resolve_gamma(self, X, device=None):
         """'scale' -> 1/(d * X.var()), 'auto' -> 1/d, evaluated on the FIRST argument of the call
-        exactly as kernels.py:93-94 / 127-128 do (on the host, bit-identical to NumPy's X.var())."""
+        exactly as kernels.py:93-94 / 127-128 do (bit-identical to NumPy's X.var()).  ``device``: the DeviceMatrix that
+        holds X in HBM -- the variance and the all-finite test of the input then run there (``X`` may be None)."""
         gamma = getattr(self, 'gamma', None)
+        d = device.cols if device is not None else X.shape[1]
+        if device is not None:
+            var = device_variance(device, X, want_variance=(gamma == 'scale'))
+        elif gamma == 'scale':
+            var = variance(X)
         if gamma is None:
             return 1.
-        return (1. / (X.shape[1] * variance(X)) if gamma == 'scale' else
-                1. / X.shape[1] if gamma == 'auto' else gamma)
+        return (1. / (d * var) if gamma == 'scale' else 1. / d if gamma == 'auto' else gamma)
 
-    def gram_spec(self, X):
+    def gram_spec(self, X, device=None):
         """(kernel_id, gamma, coef0, degree) for a call whose first argument is X."""
-        return (self.kernel_id, float(self.resolve_gamma(X)), float(getattr(self, 'coef0', 0.)),
+        return (self.kernel_id, float(self.resolve_gamma(X, device)), float(getattr(self, 'coef0', 0.)),
                 float(getattr(self, 'degree', 1)))
 
     def __call__(self, X, Y=None):

@@ -141,3 +141,6 @@ class DeviceLoopMixin:
         cm, vm = C.c_float(0), C.c_float(0)
         N.call('svmb200_pg_stats_ex', h, C.byref(mv), C.byref(cm), C.byref(vm))
         self.comm_ms, self.vector_ms = float(cm.value), float(vm.value)
+        ns = C.c_int64(0)
+        N.call('svmb200_pg_profile_samples', h, C.byref(ns))
+        self.profile_samples = int(ns.value)   # iterations that carried CUDA events (one in 16 with profiling on)

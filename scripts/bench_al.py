@@ -40,12 +40,12 @@ def main():
                 fit_s = time.perf_counter() - t0
                 o = m.optimizer
                 m.obj.release()
-            passes = max(o.q_passes, 1)
+            passes = max(o.profile_samples, 1)
             print(json.dumps(dict(case=f'C4 n={n} SVC {name} reg_intercept={ri}', iters=o.iter + 1, status=o.status,
                                   fit_s=round(fit_s, 4), loop_ms=round(o.device_ms, 2),
                                   its_per_s=round((o.iter + 1) / (o.device_ms / 1e3), 1),
                                   matvec_us=round(1e3 * o.matvec_ms / passes, 2), vector_us=round(1e3 * o.vector_ms / passes, 2),
-                                  hbm_gbps=round(8.0 * n * n * passes / (o.device_ms / 1e3) / 1e9, 1),
+                                  hbm_gbps=round(8.0 * n * n * o.q_passes / (o.device_ms / 1e3) / 1e9, 1),
                                   primal_cost=float(m.train_loss_history[-1]), n_sv=int(len(m.support_)))), flush=True)
 
 

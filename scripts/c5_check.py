@@ -23,8 +23,8 @@ for rep in range(2):
     res = dict(n=n, d=X.shape[1], n_gpus=ctx.nranks, exchange=ctx.exchange, fit_s=dt, pg_ms=m.optimizer.device_ms,
                iters=m.optimizer.iter, status=m.optimizer.status, f_x=m.optimizer.f_x, n_sv=len(m.support_),
                intercept=m.intercept_, its_per_s=m.optimizer.iter / (m.optimizer.device_ms / 1e3),
-               matvec_us=1e3 * m.optimizer.matvec_ms / m.optimizer.q_passes,
-               hbm_gbps_per_gpu=8.0 * n * n / ctx.nranks / (m.optimizer.matvec_ms / m.optimizer.q_passes / 1e3) / 1e9,
+               matvec_us=1e3 * m.optimizer.matvec_ms / max(m.optimizer.profile_samples, 1),
+               hbm_gbps_per_gpu=8.0 * n * n / ctx.nranks / (m.optimizer.matvec_ms / max(m.optimizer.profile_samples, 1) / 1e3) / 1e9,
                hessian_gb_per_gpu=8.0 * n * n / ctx.nranks / 1e9)
     if rep == 0:
         m.obj.release()

@@ -111,6 +111,8 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaEventCreate(cudaEvent_t* e);
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);

@@ -348,3 +348,15 @@ def test_one_vs_rest_host_contract_labels_clone_pickle():
         back = pickle.loads(blob)
         assert np.array_equal(back.predict(X), pred)
         assert lib.emu_sticky_error() == 0
+
+
+def test_device_variance_is_bit_identical_to_numpy():
+    import device_path_checks as D
+    with emulated_device():
+        D.check_device_variance([(1, 1), (3, 2), (7, 1), (1, 9), (129, 1), (300, 7), (257, 16), (1000, 33), (2049, 5), (40, 40)])
+
+
+def test_fit_keeps_the_host_passes_off_the_path():
+    import device_path_checks as D
+    with emulated_device():
+        D.check_fit_keeps_host_passes_off_the_path(n=150, d=5)

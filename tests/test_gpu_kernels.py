@@ -127,3 +127,19 @@ def test_extra_kernel_svc_fit(golden, name, kern):
     assert np.array_equal(m.support_, ex[f'iris_{name}_support'])
     assert abs(m.intercept_ - float(ex[f'iris_{name}_intercept'])) <= 1e-8
     assert np.abs(m.decision_function(iris['X_test']) - ex[f'iris_{name}_decision']).max() <= 1e-8
+
+
+def test_device_variance_is_bit_identical_to_numpy():
+    """svmb200_device_variance (gamma='scale', kernels.py:93, 127) incl. every BASELINE shape"""
+    import device_path_checks as D
+    from optiml_b200.configs import make_config
+    from optiml_b200.runtime import default_context
+    D.check_device_variance([(1, 1), (3, 2), (129, 1), (300, 7), (2049, 5), (70001, 3), (20000, 131), (123457, 9)])
+    for cfg, n in (('C1', None), ('C2', None), ('C3', 6000), ('C4', None), ('C5', 30000)):
+        spec, X, y = make_config(cfg, n=n)
+        assert D.device_var(default_context(), X) == (X.var(), 0)
+
+
+def test_fit_keeps_the_host_passes_off_the_path():
+    import device_path_checks as D
+    D.check_fit_keeps_host_passes_off_the_path(n=3000, d=20)
