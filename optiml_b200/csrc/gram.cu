@@ -54,6 +54,7 @@ struct GramArgs {
     int exclusive;  // 0: groups run free; 1: ping-pong on the tensor pipe; 2: lockstep phases (see kernel)
     int backoff;    // 1: the producers sleep between polls of a full ring (default); 0: they spin (A/B: SVMB200_GRAM_BACKOFF)
     double gamma, coef0, degree, bias;
+    int int_degree;  // degree when it is an integer in [1, 64] (poly: binary powering instead of pow()), else 0
 };
 
 #ifndef SVMB200_HOST_EMULATION
@@ -112,6 +113,17 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+// The n x n output is written once and never read by this kernel; X (51 MB at C4) is re-read by every row of tiles.
+// With default stores the 20 GB output stream evicted X from the 126 MB L2 again and again: 10.8 GB of DRAM reads for
+// 51 MB of operands (profiles/r1_gram_kernel_ncu.txt).  Output stores carry an evict-first L2 policy instead.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_evict_first_f64x2(double* ptr, double2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(ptr), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 #define SVM_PTX(...) asm volatile(__VA_ARGS__)
 #else
 // tests/cuda_emu compiles this file for the host: the PTX wrappers map onto the emulation's shared-memory offsets,
@@ -127,11 +139,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     emu::tma_load_2d(dst, map, bar, c0, c1);
 }
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) { emu::dmma_m8n8k4(c0, c1, a, b); }
+__device__ __forceinline__ uint64_t l2_evict_first_policy() { return 0; }
+__device__ __forceinline__ void st_evict_first_f64x2(double* ptr, double2 v, uint64_t) { *reinterpret_cast<double2*>(ptr) = v; }
 #define SVM_PTX(...) ((void)0)
 #endif
 
 // pow() stays out of line (the poly epilogue is unrolled 64x per thread and pow is ~300 instructions).
 __device__ __noinline__ double pow_outofline(double x, double y) { return pow(x, y); }
+// x ** n for a small positive integer n (PolyKernel's default degree = 3, kernels.py:79, 95) by binary powering with
+// separately rounded products: n = 2 is NumPy's own fast path (np.square, exact same bits); n = 3 is (x*x)*x, two
+// roundings against libm pow's one (<= ~1.5 ulp apart, SURVEY.md A.12: far inside the 1e-12 Gram bar).  pow() was
+// ~300 instructions per output and made the poly Gram 6x slower than the Gaussian one per element.
+__device__ __forceinline__ double ipow_rn(double x, int n) {
+    double r = 1.0, b = x;
+    bool first = true;
+    for (;;) {
+        if (n & 1) {
+            r = first ? b : __dmul_rn(r, b);
+            first = false;
+        }
+        n >>= 1;
+        if (n == 0) break;
+        b = __dmul_rn(b, b);
+    }
+    return r;
+}
 __device__ __noinline__ double tanh_outofline(double x) { return tanh(x); }
 
 // exp(x), x <= 0, for the Gaussian epilogue, evaluated for EIGHT independent arguments in lock-step so
@@ -365,6 +397,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const long long tile_r0 = p.row0 + (long long)tm * BM, tile_c0 = (long long)tn * BN;
         const bool edge = tile_r0 + BM > p.row0 + p.nrows || tile_c0 + BN > p.nb ||
                           (p.same && tile_r0 < tile_c0 + BN && tile_c0 < tile_r0 + BM);
+        const uint64_t out_policy = l2_evict_first_policy();
         auto epilogue = [&](auto edge_tag) {
             constexpr bool EDGE = decltype(edge_tag)::value;
 #pragma unroll
@@ -390,11 +423,19 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                     exp8(x, val);
                 } else if (KERNEL == SVMB200_KERNEL_POLY) {
+                    if (p.int_degree > 0) {
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni)
+                        for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e)  // separately rounded product and sum (NumPy semantics)
-                            val[ni * 2 + e] = pow_outofline(__dadd_rn(__dmul_rn(p.gamma, acc[mi][ni][e]), p.coef0), p.degree);
+                            for (int e = 0; e < 2; ++e)  // separately rounded product and sum (NumPy semantics)
+                                val[ni * 2 + e] = ipow_rn(__dadd_rn(__dmul_rn(p.gamma, acc[mi][ni][e]), p.coef0), p.int_degree);
+                    } else {
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                val[ni * 2 + e] = pow_outofline(__dadd_rn(__dmul_rn(p.gamma, acc[mi][ni][e]), p.coef0), p.degree);
+                    }
                 } else if (KERNEL == SVMB200_KERNEL_SIGMOID) {
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni)
@@ -424,7 +465,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                         ve[e] = o;
                     }
-                    *reinterpret_cast<double2*>(orow + c) = v;
+                    st_evict_first_f64x2(orow + c, v, out_policy);
                 }
             }
         };
@@ -692,6 +733,8 @@ extern "C" int svmb200_gram(svmb200_ctx* ctx, const double* dA, int64_t na, int6
         a.coef0 = coef0;
         a.degree = degree;
         a.bias = bias;
+        a.int_degree = (degree >= 1.0 && degree <= 64.0 && degree == (double)(int)degree) ? (int)degree : 0;
+        if (getenv("SVMB200_POLY_LIBM_POW") != nullptr && atoi(getenv("SVMB200_POLY_LIBM_POW")) != 0) a.int_degree = 0;  // A/B
         if (kernel == SVMB200_KERNEL_LINEAR) rc = launch_gram<SVMB200_KERNEL_LINEAR>(ctx, ma, mb, a);
         else if (kernel == SVMB200_KERNEL_POLY) rc = launch_gram<SVMB200_KERNEL_POLY>(ctx, ma, mb, a);
         else if (kernel == SVMB200_KERNEL_SIGMOID) rc = launch_gram<SVMB200_KERNEL_SIGMOID>(ctx, ma, mb, a);
