@@ -218,6 +218,20 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { emu::name
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { emu::named_barrier(id, nthreads, false); }
 #endif
 
+// Tile order.  A tile needs one 128-row A panel and one 64-row B panel; with the plain row-major order a B panel is
+// re-read once per tile ROW, i.e. after a full sweep over X plus as many bytes of output stores: at C4 that thrashed the L2
+// (10.8 GB of DRAM reads for 51 MB of operands, profiles/r1_gram_kernel_ncu.txt; 7.6 GB with evict-first stores).  Tiles
+// are therefore enumerated in BANDS of GRAM_BAND tile rows, column by column inside a band: the ~300 tiles in flight
+// share a handful of B panels and the band's A panels (4 MB), and X comes from DRAM once per band (tiles_m / 32 times).
+constexpr int GRAM_BAND = 32;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+    const int per_band = GRAM_BAND * tiles_n;
+    const int band = tile / per_band, within = tile - band * per_band;
+    const int rows = (tiles_m - band * GRAM_BAND) < GRAM_BAND ? (tiles_m - band * GRAM_BAND) : GRAM_BAND;
+    tn = within / rows;
+    tm = band * GRAM_BAND + (within - tn * rows);
+}
+
 template <bool V>
 struct EdgeTile {
     static constexpr bool value = V;
@@ -263,7 +277,8 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
-                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+                int tm, tn;
+                tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
                 const int arow = (int)p.row0 + tm * BM;
                 const int brow = tn * BN;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -316,7 +331,8 @@ gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (int round = 0; round < rounds; ++round) {
         const int tile = blockIdx.x + (2 * round + grp) * gridDim.x;
         const bool has_tile = tile < ntiles;
-        const int tm = has_tile ? tile / p.tiles_n : 0, tn = has_tile ? tile % p.tiles_n : 0;
+        int tm = 0, tn = 0;
+        if (has_tile) tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
         double acc[8][4][2];
         if (has_tile) {
 #pragma unroll

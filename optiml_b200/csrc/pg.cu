@@ -99,7 +99,12 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
         svmb200_set_error("matvec: grid too large");
         return SVMB200_ERR_ARG;
     }
-    SVM_CUDA(svm_launch_chained(matvec_seg_kernel, dim3((unsigned)nitems), dim3(MV_NT), ctx->stream, a));
+    static const bool l2_hint = [] {
+        const char* ev = getenv("SVMB200_MATVEC_L2_HINT");
+        return ev != nullptr && atoi(ev) != 0;
+    }();
+    if (l2_hint) SVM_CUDA(svm_launch_chained(matvec_seg_kernel<true>, dim3((unsigned)nitems), dim3(MV_NT), ctx->stream, a));
+    else SVM_CUDA(svm_launch_chained(matvec_seg_kernel<false>, dim3((unsigned)nitems), dim3(MV_NT), ctx->stream, a));
     ctx->launches++;
     return SVMB200_OK;
 }
