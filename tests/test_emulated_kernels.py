@@ -360,3 +360,27 @@ def test_fit_keeps_the_host_passes_off_the_path():
     import device_path_checks as D
     with emulated_device():
         D.check_fit_keeps_host_passes_off_the_path(n=150, d=5)
+
+
+def test_gram_tile_bands_cover_every_tile_once():
+    """K1 enumerates its tiles in bands of 32 tile rows (L2 reuse of X); more than one band, a ragged last band and a row
+    shard that starts inside a band must still produce every output exactly once"""
+    from optiml_b200.runtime import default_context
+    with emulated_device():
+        ctx = default_context()
+        rng = np.random.default_rng(0)
+        n, d = 4230, 3                      # 34 tile rows: one full band + a band of two
+        X = rng.standard_normal((n, d))
+        want = X @ X.T
+        dX = ctx.upload_matrix(X)
+        ld = N.padded_ld(n)
+        for r0, nr in ((0, n), (100, 4120)):
+            dQ = ctx.malloc(nr * ld * 8)
+            ctx.memset(dQ, 0xFF, nr * ld * 8)
+            N.call('svmb200_gram', ctx.handle, C.c_void_p(dX.dptr), n, dX.ld, C.c_void_p(dX.dptr), n, dX.ld, d, 1,
+                   N.KERNEL_LINEAR, 1.0, 0., 1., None, None, 0.0, r0, nr, C.c_void_p(dQ), ld)
+            out = np.empty((nr, ld))
+            ctx.d2h(out, dQ)
+            assert np.abs(out[:, :n] - want[r0:r0 + nr]).max() <= 1e-14 and np.all(out[:, n:] == 0)
+            ctx.free(dQ)
+        dX.release()
