@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument('--n', type=int, default=None, help='override the sample count (debug)')
     ap.add_argument('--max-iter', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--devices', default=None,
+                    help="ONE process driving several GPUs (comma-separated indices or 'all'): the single-process device "
+                         "group instead of torchrun ranks; not a driver mode, used to compare the two launch models")
     return ap.parse_args()
 
 
@@ -356,8 +359,20 @@ def run_b200(args):
     from optiml_b200.configs import make_config
     from optiml_b200.ml.svm import DualSVC
     from optiml_b200.ml.svm.kernels import GaussianKernel
-    from optiml_b200.runtime import default_context
+    from optiml_b200.runtime import default_context, use_devices
 
+    group_size = 1
+    if args.devices and world == 1:
+        if args.devices.strip().lower() == 'all':
+            import ctypes as C
+            from optiml_b200 import _native as N
+            cnt = C.c_int(0)
+            N.call('svmb200_device_count', C.byref(cnt))
+            devs = list(range(cnt.value))
+        else:
+            devs = [int(t) for t in args.devices.split(',')]
+        use_devices(devs)
+        group_size = len(devs)
     ctx = default_context()
     spec, X0, y0 = make_config(args.config, n=args.n)
     n, d = X0.shape
@@ -448,7 +463,8 @@ def run_b200(args):
         return
     parity = parity_block(args, m, n)
     peak, peak_src = measured_peak()
-    bytes_per_launch = 8.0 * n * n / world
+    gpus = world * group_size
+    bytes_per_launch = 8.0 * n * n / gpus
     mv_avg_ms = mv_ms / max(mv_samples, 1)  # CUDA events bracket one K2 launch in 16 (they serialise programmatic launches)
     achieved = bytes_per_launch / (mv_avg_ms / 1e3) / 1e9
     traffic = None
@@ -456,21 +472,23 @@ def run_b200(args):
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
-        if tj.get('n') == n and tj.get('n_gpus', 1) == world:
+        if tj.get('n') == n and tj.get('n_gpus', 1) == gpus:
             traffic = tj.get('dram_bytes_per_launch')
     line = {
-        'metric': metric_name(args.config, n, d), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': metric_name(args.config, n, d), 'value': value, 'unit': UNIT, 'n_gpus': gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': bench_config(args.config, n, d, args.max_iter, world),
-        'exchange': ctx.exchange,
+        'config': bench_config(args.config, n, d, args.max_iter, gpus),
+        'exchange': ctx.exchange if group_size == 1 else 'p2p',
+        'launch_model': 'one process, one host thread, %d GPUs (device group)' % group_size if group_size > 1 else
+                        ('torchrun, one process per GPU' if world > 1 else 'one process, one GPU'),
         'host_note': 'gc.collect() + gc.freeze() after warm-up (a full Python GC pass is ~0.2 s with torch/sklearn loaded); '
                      'in the value leg one iteration in 16 is bracketed by CUDA events (roofline / per_iteration_us); the '
                      'e2e leg runs without them',
         'parity': parity,
         'fit_s': dev_ms / args.steps / 1e3, 'pg_its_per_s': iters_total / (pg_ms / 1e3),
         'hbm_gbps_pg_loop': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9,
-        'frac_of_8TBps_nominal': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9 / world / 8000.0,
+        'frac_of_8TBps_nominal': 8.0 * n * n * mv_launches / (pg_ms / 1e3) / 1e9 / gpus / 8000.0,
         'iters_per_step': iters_total / args.steps, 'status': status, 'f_x': fx, 'n_sv': nsv,
         'wall_s_value_leg': wall_s, 'step_wall_s': step_s, 'step_parts': step_parts,
         'per_iteration_us': {'matvec': 1e3 * mv_ms / max(mv_samples, 1), 'allgather': 1e3 * comm_ms / max(mv_samples, 1),

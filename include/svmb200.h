@@ -234,6 +234,22 @@ int svmb200_pg_run_batch(svmb200_pg* const* pgs, int count, int64_t* iters, int*
 int svmb200_matvec_multi(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* const* du,
                          double* const* dw, int count);
 
+/* ---- one process, N GPUs ----------------------------------------------------------------------------------------
+ * The reference's API is ONE Python process calling SVC.fit (ml/svm/_base.py:631-636).  svmb200_comm_local_group turns
+ * n contexts of the calling thread (one per device) into ranks 0..n-1 whose exchange arenas are mapped by plain peer
+ * access (no torchrun, no NCCL, no IPC).  Solvers created on such contexts (svmb200_{pg,fw,al}_create*, one per rank
+ * with that rank's shard) defer their first product; svmb200_pg_start_group issues it for all ranks, and
+ * svmb200_pg_run_group advances all of them, enqueuing iteration-major over the ranks.  State, history and statistics
+ * are read from the rank-0 solver with the calls above (the state is replicated).                                    */
+int svmb200_comm_local_group(svmb200_ctx** ctxs, int n, size_t arena_bytes);
+/* device-to-device copy between two contexts of this process (replicates X over the ranks of the group) */
+int svmb200_copy_peer(svmb200_ctx* dst_ctx, void* dst, svmb200_ctx* src_ctx, const void* src, size_t bytes);
+int svmb200_pg_start_group(svmb200_pg* const* pgs, int count);
+int svmb200_pg_run_group(svmb200_pg* const* pgs, int count, int64_t max_new, int64_t* iter, int* status);
+/* svmb200_masked_product for all ranks of the group at once (dQ[r]: rank r's shard); v_host receives all n rows */
+int svmb200_masked_product_group(svmb200_ctx* const* ctxs, const double* const* dQ, int count, int64_t n, int64_t ld,
+                                 const double* beta_host, double* v_host);
+
 /* ---- K5: masked product for the intercept ---------------------------------------------------
  * Replaces the Python loop  ml/svm/_base.py:877-880 / :1433-1437:
  * v[i] = sum_m M[i][m] * beta[m] over the rank's rows (all-gathered when a communicator is attached),

@@ -79,6 +79,11 @@ PROTOTYPES = {
     'svmb200_pg_profile_samples': [c_vp, C.POINTER(i64)],
     'svmb200_pg_device_x': [c_vp, C.POINTER(c_vp)],
     'svmb200_pg_destroy': [c_vp],
+    'svmb200_copy_peer': [c_vp, c_vp, c_vp, c_vp, C.c_size_t],
+    'svmb200_comm_local_group': [C.POINTER(c_vp), C.c_int, C.c_size_t],
+    'svmb200_pg_start_group': [C.POINTER(c_vp), C.c_int],
+    'svmb200_pg_run_group': [C.POINTER(c_vp), C.c_int, i64, C.POINTER(i64), C.POINTER(C.c_int)],
+    'svmb200_masked_product_group': [C.POINTER(c_vp), C.POINTER(c_vp), C.c_int, i64, i64, c_vp, c_vp],
     'svmb200_masked_product': [c_vp, c_vp, i64, i64, i64, i64, c_vp, c_vp],
     'svmb200_decision': [c_vp, c_vp, i64, c_vp, c_vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_double,
                          C.c_double, c_vp],

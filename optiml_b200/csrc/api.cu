@@ -141,6 +141,22 @@ extern "C" int svmb200_d2d(svmb200_ctx* ctx, void* dst, const void* src, size_t 
     SVM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return SVMB200_OK;
 }
+// copy between two contexts of this process (replicating X over the ranks of a single-process group): waits for the
+// source context's stream on the host, then enqueues the copy on the destination context's stream
+extern "C" int svmb200_copy_peer(svmb200_ctx* dst_ctx, void* dst, svmb200_ctx* src_ctx, const void* src, size_t bytes) {
+    SVM_CHECK_ARG(dst_ctx != nullptr && src_ctx != nullptr && dst != nullptr && src != nullptr, "null argument");
+    SVM_TRY(svm_use(src_ctx));
+    SVM_CUDA(cudaStreamSynchronize(src_ctx->stream));
+    SVM_TRY(svm_use(dst_ctx));
+#ifndef SVMB200_HOST_EMULATION
+    if (dst_ctx->device != src_ctx->device) {
+        SVM_CUDA(cudaMemcpyPeerAsync(dst, dst_ctx->device, src, src_ctx->device, bytes, dst_ctx->stream));
+        return SVMB200_OK;
+    }
+#endif
+    SVM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, dst_ctx->stream));
+    return SVMB200_OK;
+}
 extern "C" int svmb200_sync(svmb200_ctx* ctx) {
     SVM_TRY(svm_use(ctx));
     SVM_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -165,6 +165,54 @@ extern "C" int svmb200_comm_p2p_attach(svmb200_ctx* ctx, const void* handles, in
     return SVMB200_OK;
 }
 
+// One process, N GPUs: the reference's API is a single Python process calling SVC.fit (ml/svm/_base.py:631-636).  The
+// contexts of `ctxs` (one per device, all owned by the calling thread) become ranks 0..n-1 of a group whose exchange
+// arenas are mapped by plain peer access -- no torchrun, no torch.distributed, no NCCL, no IPC.
+extern "C" int svmb200_comm_local_group(svmb200_ctx** ctxs, int n, size_t arena_bytes) {
+    SVM_CHECK_ARG(ctxs != nullptr && n >= 1 && n <= SVM_MAX_RANKS && arena_bytes >= (1u << 20), "bad argument");
+    for (int i = 0; i < n; ++i) {
+        SVM_CHECK_ARG(ctxs[i] != nullptr, "null context");
+        SVM_CHECK_ARG(ctxs[i]->nranks == 1 && ctxs[i]->nccl_comm == nullptr && ctxs[i]->arena == nullptr,
+                      "context already belongs to a communicator");
+#ifndef SVMB200_HOST_EMULATION
+        for (int j = 0; j < i; ++j) SVM_CHECK_ARG(ctxs[j]->device != ctxs[i]->device, "one context per device");
+#endif
+    }
+    if (n == 1) return SVMB200_OK;
+    for (int i = 0; i < n; ++i) {
+        SVM_CUDA(cudaSetDevice(ctxs[i]->device));
+        for (int j = 0; j < n; ++j) {
+            if (j == i || ctxs[j]->device == ctxs[i]->device) continue;
+            int can = 0;
+            SVM_CUDA(cudaDeviceCanAccessPeer(&can, ctxs[i]->device, ctxs[j]->device));
+            if (!can) {
+                svmb200_set_error("device %d cannot access device %d: no peer path for the fused exchange", ctxs[i]->device,
+                                  ctxs[j]->device);
+                return SVMB200_ERR_CUDA;
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                svmb200_set_error("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", ctxs[i]->device, ctxs[j]->device,
+                                  cudaGetErrorString(e));
+                return SVMB200_ERR_CUDA;
+            }
+            cudaGetLastError();  // clear cudaErrorPeerAccessAlreadyEnabled
+        }
+        SVM_CUDA(cudaMalloc(&ctxs[i]->arena, arena_bytes));
+        SVM_CUDA(cudaMemset(ctxs[i]->arena, 0, arena_bytes));
+        ctxs[i]->arena_bytes = arena_bytes;
+    }
+    for (int i = 0; i < n; ++i) {
+        for (int r = 0; r < n; ++r) ctxs[i]->peer_arena[r] = ctxs[r]->arena;
+        ctxs[i]->rank = i;
+        ctxs[i]->nranks = n;
+        ctxs[i]->p2p_enabled = true;
+        ctxs[i]->local_group = true;
+        ctxs[i]->xseq = 0;
+    }
+    return SVMB200_OK;
+}
+
 extern "C" int svmb200_comm_p2p_disable(svmb200_ctx* ctx) {
     SVM_CHECK_ARG(ctx != nullptr, "null argument");
     ctx->p2p_enabled = false;  // keep the mappings; the solver falls back to ncclAllGather
@@ -183,6 +231,16 @@ extern "C" int svmb200_comm_p2p_enabled(svmb200_ctx* ctx, int* enabled) {
 // be relied on from an error path (the peer may be the one that died), so a multi-rank context leaves its arena
 // allocated and its peer mappings open until the process exits -- 64 MB, reclaimed by the driver with the process.
 static void p2p_release(svmb200_ctx* ctx) {
+    if (ctx->local_group) {
+        // one host thread owns every rank: the caller destroys the group's contexts together, after their streams idle
+        for (int r = 0; r < SVM_MAX_RANKS; ++r) ctx->peer_arena[r] = nullptr;
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+        ctx->p2p_enabled = false;
+        ctx->local_group = false;
+        return;
+    }
     const bool peers_may_still_store = ctx->nranks > 1;
     for (int r = 0; r < SVM_MAX_RANKS; ++r) {
         if (!peers_may_still_store && ctx->peer_arena[r] && ctx->peer_arena[r] != ctx->arena)
@@ -215,6 +273,10 @@ extern "C" int svmb200_comm_destroy(svmb200_ctx* ctx) {
 
 int svm_comm_allgather(svmb200_ctx* ctx, double* dbuf, int64_t count_per_rank) {
     if (ctx->nranks <= 1) return SVMB200_OK;
+    if (ctx->local_group) {
+        svmb200_set_error("a single-process group has no collective: this operation needs the fused exchange or a per-shard call");
+        return SVMB200_ERR_STATE;
+    }
     if (!ctx->nccl_comm) {
         svmb200_set_error("multi-rank context without communicator");
         return SVMB200_ERR_STATE;

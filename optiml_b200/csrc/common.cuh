@@ -33,6 +33,10 @@ struct svmb200_ctx {
     size_t arena_bytes = 0;
     unsigned char* peer_arena[SVM_MAX_RANKS] = {};  // peer_arena[r] = rank r's arena as mapped here (self: local)
     unsigned long long xseq = 0;                  // number of fused exchanges issued so far (same on all ranks)
+    // single-process group (svmb200_comm_local_group): the ranks are contexts of ONE host thread, the arenas are plain
+    // peer pointers (cudaDeviceEnablePeerAccess, no IPC, no NCCL).  Solvers are then created with a deferred first
+    // product and advanced by svmb200_pg_run_group, which enqueues iteration-major over the ranks.
+    bool local_group = false;
     // solver workspace recycled between solves (pg.cu): one device slab, one pinned state block, an event pool.
     // cudaMalloc / cudaMallocHost / cudaEventCreate / cudaFree are slow and jittery (tens to hundreds of ms when
     // the host is busy); a fit issues none of them after the first one of its size.

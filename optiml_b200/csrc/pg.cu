@@ -258,6 +258,7 @@ struct svmb200_pg {
     unsigned char* pinned = nullptr;   // 256 bytes: two poll slots of {PGDeviceState, fault flag}
     cudaEvent_t ev_poll[2] = {nullptr, nullptr};
     int64_t last_samples = 0;          // iterations of the last run that carried profiling events
+    bool deferred_start = false;       // single-process group: first product + INIT are issued by svmb200_pg_start_group
     // host-side cursor
     int64_t k_next = 0;     // next iteration whose STEP kernel has not been enqueued
     bool finished = false;  // device reported done
@@ -662,6 +663,21 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     }
 #undef PG_CUDA
     pg->last_passes = 0;
+    if (ctx->local_group && P > 1) {
+        // one host thread drives every rank: it cannot issue a collective, and a vector launch that waits for a peer's
+        // entries must not be enqueued before that peer's product exists in ITS stream order either (the host emulation
+        // runs launches synchronously) -- so the first product and INIT are issued for all ranks together, iteration-major,
+        // by svmb200_pg_start_group.  No creation barrier is needed: the host has seen every rank's previous solve end.
+        if (!pg->p2p) {
+            svmb200_set_error("a single-process group needs the fused exchange: every rank must own rows of the matrix "
+                              "(n > %lld) and the gathered buffers must fit the arena", (long long)((P - 1) * rpr));
+            return fail(SVMB200_ERR_ARG);
+        }
+        pg->deferred_start = true;
+        pg->k_next = 0;
+        *out = pg;
+        return SVMB200_OK;
+    }
     if (pg->p2p) {
         // A one-double all-gather, in stream order, before the first fused product of this solver: it completes on a
         // rank only when EVERY rank has reached it, i.e. when every rank's previous solve -- whose last vector launch
@@ -718,87 +734,174 @@ static int poll_wait(svmb200_pg* pg, int slot) {
     return SVMB200_OK;
 }
 
-static int pg_poll(svmb200_pg* pg) {
-    SVM_TRY(poll_enqueue(pg, 0));
-    return poll_wait(pg, 0);
-}
-
-extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, int* status) {
-    SVM_CHECK_ARG(pg != nullptr, "null solver");
-    svmb200_ctx* ctx = pg->ctx;
-    SVM_TRY(svm_use(ctx));
-    pg->mv_ev.clear();  // pooled events: reused, never destroyed per run
-    ctx->event_pool_used = 0;
-    pg->last_passes = 0;
-    pg->last_samples = 0;
-    pg->last_ms = pg->last_mv_ms = pg->last_comm_ms = pg->last_vec_ms = 0.f;
-    SVM_CUDA(cudaEventRecord(pg->ev0, ctx->stream));
-    if (!pg->finished) {
+// The ranks of a single-process group (count > 1), or one solver (count == 1): `max_new` more iterations (< 0: to the
+// end).  Launches are enqueued ITERATION-MAJOR over the ranks -- every rank's product k, then every rank's vector launch
+// k -- so that in each stream a launch that waits for a peer's entries comes after that peer's product has been
+// enqueued in its own stream; the ranks' state is replicated, so they stop together.
+static int run_many(svmb200_pg* const* pgs, int count, int64_t max_new) {
+    svmb200_pg* p0 = pgs[0];
+    for (int r = 0; r < count; ++r) {
+        svmb200_pg* pg = pgs[r];
+        SVM_TRY(svm_use(pg->ctx));
+        if (r == 0) {
+            pg->mv_ev.clear();  // pooled events: reused, never destroyed per run
+            pg->ctx->event_pool_used = 0;
+        }
+        pg->last_passes = 0;
+        pg->last_samples = 0;
+        pg->last_ms = pg->last_mv_ms = pg->last_comm_ms = pg->last_vec_ms = 0.f;
+        SVM_CUDA(cudaEventRecord(pg->ev0, pg->ctx->stream));
+    }
+    if (!p0->finished) {
         const bool to_end = max_new < 0;
-        int64_t budget = to_end ? (pg->max_iter - pg->k_next) : max_new;
-        if (budget > pg->max_iter - pg->k_next) budget = pg->max_iter - pg->k_next;
+        int64_t budget = to_end ? (p0->max_iter - p0->k_next) : max_new;
+        if (budget > p0->max_iter - p0->k_next) budget = p0->max_iter - p0->k_next;
         // enqueue in batches; the device-side done flag turns the remainder of a batch (and the batch enqueued behind it
         // before its poll came back) into no-ops
         const int64_t BATCH = 64;
         int pending = -1, slot = 0;
         int rc = SVMB200_OK;
-        while (budget > 0 && !pg->finished && rc == SVMB200_OK) {
+        while (budget > 0 && !p0->finished && rc == SVMB200_OK) {
             const int64_t nb = budget < BATCH ? budget : BATCH;
             for (int64_t i = 0; i < nb && rc == SVMB200_OK; ++i) {
                 // profiling events serialise the programmatic launches around them: sample one iteration in PROFILE_STRIDE
-                const bool sample = pg->profile && (pg->k_next % PROFILE_STRIDE) == 0;
-                rc = pg_product(pg, sample);
-                if (rc == SVMB200_OK) rc = launch_vec<VP_STEP>(pg, pg->k_next);
-                if (rc == SVMB200_OK && sample) {
-                    cudaEvent_t e3 = pooled_event(ctx);
-                    if (!e3) {
-                        svmb200_set_error("cannot create profiling events");
-                        rc = SVMB200_ERR_CUDA;
-                    } else if (cudaEventRecord(e3, ctx->stream) != cudaSuccess) {
-                        svmb200_set_error("cudaEventRecord failed");
-                        rc = SVMB200_ERR_CUDA;
-                    } else {
-                        pg->mv_ev.push_back(e3);
-                        pg->last_samples++;
-                    }
+                // (rank 0 only)
+                const bool sample = p0->profile && (p0->k_next % PROFILE_STRIDE) == 0;
+                for (int r = 0; r < count && rc == SVMB200_OK; ++r) {
+                    if (count > 1) rc = svm_use(pgs[r]->ctx);
+                    if (rc == SVMB200_OK) rc = pg_product(pgs[r], sample && r == 0);
                 }
-                pg->k_next++;
+                for (int r = 0; r < count && rc == SVMB200_OK; ++r) {
+                    if (count > 1) rc = svm_use(pgs[r]->ctx);
+                    if (rc == SVMB200_OK) rc = launch_vec<VP_STEP>(pgs[r], pgs[r]->k_next);
+                    if (rc == SVMB200_OK && sample && r == 0) {
+                        cudaEvent_t e3 = pooled_event(p0->ctx);
+                        if (!e3) {
+                            svmb200_set_error("cannot create profiling events");
+                            rc = SVMB200_ERR_CUDA;
+                        } else if (cudaEventRecord(e3, p0->ctx->stream) != cudaSuccess) {
+                            svmb200_set_error("cudaEventRecord failed");
+                            rc = SVMB200_ERR_CUDA;
+                        } else {
+                            p0->mv_ev.push_back(e3);
+                            p0->last_samples++;
+                        }
+                    }
+                    pgs[r]->k_next++;
+                }
             }
             budget -= nb;
-            if (rc == SVMB200_OK) rc = poll_enqueue(pg, slot);
-            if (rc == SVMB200_OK && pending >= 0) rc = poll_wait(pg, pending);  // the batch BEFORE the one just enqueued
+            for (int r = 0; r < count && rc == SVMB200_OK; ++r) {
+                if (count > 1) rc = svm_use(pgs[r]->ctx);
+                if (rc == SVMB200_OK) rc = poll_enqueue(pgs[r], slot);
+            }
+            if (pending >= 0)  // the batch BEFORE the one just enqueued
+                for (int r = 0; r < count && rc == SVMB200_OK; ++r) rc = poll_wait(pgs[r], pending);
             pending = slot;
             slot ^= 1;
         }
         if (pending >= 0) {
             // the last poll is always collected: its copy targets pinned memory that outlives this call
-            const int rc2 = poll_wait(pg, pending);
-            if (rc == SVMB200_OK) rc = rc2;
+            for (int r = 0; r < count; ++r) {
+                const int rc2 = poll_wait(pgs[r], pending);
+                if (rc == SVMB200_OK) rc = rc2;
+            }
         }
         SVM_TRY(rc);
-        if (pg->finished) pg->k_next = pg->st_host->iter;
-        if (!pg->finished) {
+        for (int r = 0; r < count; ++r) {
+            if (pgs[r]->finished != p0->finished) {
+                svmb200_set_error("the ranks of a group disagree on the stopping test (replicated state diverged)");
+                return SVMB200_ERR_STATE;
+            }
+            if (pgs[r]->finished) pgs[r]->k_next = pgs[r]->st_host->iter;
+        }
+        if (!p0->finished) {
             // make the state at callback point k_next visible (f, |d|, stopping tests); the augmented Lagrangian
             // needs w = Q xe for that (value and gradient at xe), the box-constrained solvers carry g along
-            if (pg->solver == 2) SVM_TRY(pg_product(pg, false));
-            SVM_TRY(launch_vec<VP_FINALISE>(pg, pg->k_next));
-            SVM_TRY(pg_poll(pg));
+            if (p0->solver == 2)
+                for (int r = 0; r < count; ++r) {
+                    SVM_TRY(svm_use(pgs[r]->ctx));
+                    SVM_TRY(pg_product(pgs[r], false));
+                }
+            for (int r = 0; r < count; ++r) {
+                SVM_TRY(svm_use(pgs[r]->ctx));
+                SVM_TRY(launch_vec<VP_FINALISE>(pgs[r], pgs[r]->k_next));
+                SVM_TRY(poll_enqueue(pgs[r], 0));
+            }
+            for (int r = 0; r < count; ++r) SVM_TRY(poll_wait(pgs[r], 0));
         }
     }
-    SVM_CUDA(cudaEventRecord(pg->ev1, ctx->stream));
-    SVM_CUDA(cudaEventSynchronize(pg->ev1));
-    SVM_CUDA(cudaEventElapsedTime(&pg->last_ms, pg->ev0, pg->ev1));
-    for (size_t i = 0; i + 3 < pg->mv_ev.size(); i += 4) {
-        float ms = 0.f;
-        SVM_CUDA(cudaEventElapsedTime(&ms, pg->mv_ev[i], pg->mv_ev[i + 1]));
-        pg->last_mv_ms += ms;
-        SVM_CUDA(cudaEventElapsedTime(&ms, pg->mv_ev[i + 1], pg->mv_ev[i + 2]));
-        pg->last_comm_ms += ms;
-        SVM_CUDA(cudaEventElapsedTime(&ms, pg->mv_ev[i + 2], pg->mv_ev[i + 3]));
-        pg->last_vec_ms += ms;
+    for (int r = 0; r < count; ++r) {
+        svmb200_pg* pg = pgs[r];
+        SVM_TRY(svm_use(pg->ctx));
+        SVM_CUDA(cudaEventRecord(pg->ev1, pg->ctx->stream));
     }
+    for (int r = 0; r < count; ++r) {
+        svmb200_pg* pg = pgs[r];
+        SVM_CUDA(cudaEventSynchronize(pg->ev1));
+        SVM_CUDA(cudaEventElapsedTime(&pg->last_ms, pg->ev0, pg->ev1));
+    }
+    for (size_t i = 0; i + 3 < p0->mv_ev.size(); i += 4) {
+        float ms = 0.f;
+        SVM_CUDA(cudaEventElapsedTime(&ms, p0->mv_ev[i], p0->mv_ev[i + 1]));
+        p0->last_mv_ms += ms;
+        SVM_CUDA(cudaEventElapsedTime(&ms, p0->mv_ev[i + 1], p0->mv_ev[i + 2]));
+        p0->last_comm_ms += ms;
+        SVM_CUDA(cudaEventElapsedTime(&ms, p0->mv_ev[i + 2], p0->mv_ev[i + 3]));
+        p0->last_vec_ms += ms;
+    }
+    return SVMB200_OK;
+}
+
+extern "C" int svmb200_pg_run(svmb200_pg* pg, int64_t max_new, int64_t* iter, int* status) {
+    SVM_CHECK_ARG(pg != nullptr, "null solver");
+    SVM_CHECK_ARG(!pg->deferred_start, "a solver of a single-process group runs through svmb200_pg_run_group");
+    SVM_TRY(run_many(&pg, 1, max_new));
     if (iter) *iter = pg->st_host->iter;
     if (status) *status = pg->st_host->done ? pg->st_host->status : SVMB200_STATUS_UNKNOWN;
+    return SVMB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ single-process group
+static int check_group(svmb200_pg* const* pgs, int count) {
+    SVM_CHECK_ARG(pgs != nullptr && count >= 1 && count <= SVM_MAX_RANKS, "bad argument");
+    for (int r = 0; r < count; ++r) {
+        const svmb200_pg* p = pgs[r];
+        SVM_CHECK_ARG(p != nullptr && p->ctx != nullptr, "null solver");
+        SVM_CHECK_ARG(p->ctx->local_group && p->ctx->nranks == count && p->ctx->rank == r,
+                      "pass one solver per rank of the single-process group, in rank order");
+        SVM_CHECK_ARG(p->n == pgs[0]->n && p->solver == pgs[0]->solver && p->max_iter == pgs[0]->max_iter &&
+                          p->svr == pgs[0]->svr && p->k_next == pgs[0]->k_next,
+                      "the solvers of a group must pose the same problem and be in the same state");
+    }
+    return SVMB200_OK;
+}
+
+// first product (g0 = Q x0 + q) and INIT launch of solvers that were created on the ranks of a single-process group
+extern "C" int svmb200_pg_start_group(svmb200_pg* const* pgs, int count) {
+    SVM_TRY(check_group(pgs, count));
+    for (int r = 0; r < count; ++r) SVM_CHECK_ARG(pgs[r]->deferred_start, "solver already started");
+    if (pgs[0]->solver != 2)
+        for (int r = 0; r < count; ++r) {
+            SVM_TRY(svm_use(pgs[r]->ctx));
+            SVM_TRY(pg_product(pgs[r], false));
+        }
+    for (int r = 0; r < count; ++r) {
+        SVM_TRY(svm_use(pgs[r]->ctx));
+        SVM_TRY(launch_vec<VP_INIT>(pgs[r], 0));
+        pgs[r]->deferred_start = false;
+    }
+    return SVMB200_OK;
+}
+
+// svmb200_pg_run for every rank of a single-process group at once (one host thread, no collective): iter / status are
+// those of the replicated state
+extern "C" int svmb200_pg_run_group(svmb200_pg* const* pgs, int count, int64_t max_new, int64_t* iter, int* status) {
+    SVM_TRY(check_group(pgs, count));
+    for (int r = 0; r < count; ++r) SVM_CHECK_ARG(!pgs[r]->deferred_start, "call svmb200_pg_start_group first");
+    SVM_TRY(run_many(pgs, count, max_new));
+    if (iter) *iter = pgs[0]->st_host->iter;
+    if (status) *status = pgs[0]->st_host->done ? pgs[0]->st_host->status : SVMB200_STATUS_UNKNOWN;
     return SVMB200_OK;
 }
 
@@ -910,6 +1013,7 @@ extern "C" int svmb200_pg_run_batch(svmb200_pg* const* pgs, int count, int64_t* 
         SVM_CHECK_ARG(p->solver == p0->solver && p->max_iter == p0->max_iter,
                       "the solvers of a batch must be of one kind and share the iteration limit");
         SVM_CHECK_ARG(p->k_next == 0 && !p->finished, "a batch takes solvers that have not run yet");
+        SVM_CHECK_ARG(!p->deferred_start, "lockstep batches are not available on a single-process group");
         for (int c = 0; c < b; ++c) SVM_CHECK_ARG(pgs[c] != p, "a solver is listed twice");
     }
     svmb200_ctx* ctx = p0->ctx;
@@ -1161,7 +1265,19 @@ extern "C" int svmb200_masked_product(svmb200_ctx* ctx, const double* dQ, int64_
     cudaMemsetAsync(dw, 0, (size_t)(rpr * P) * sizeof(double), s);
     cudaMemcpyAsync(du, beta_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s);
     rc = svm_launch_matvec(ctx, dQ, nrows, ld, du, dw + (size_t)ctx->rank * rpr, nullptr);
-    if (rc == SVMB200_OK && P > 1) rc = svm_comm_allgather(ctx, dw, rpr);
+    if (rc == SVMB200_OK && P > 1 && !ctx->local_group) rc = svm_comm_allgather(ctx, dw, rpr);
+    if (rc == SVMB200_OK && ctx->local_group && P > 1) {
+        // single-process group: no collective -- this call fills rows [row0, row0 + nrows) of v_host, the caller makes it
+        // once per rank with the same v_host
+        if (nrows > 0)
+            cudaMemcpyAsync(v_host + row0, dw + (size_t)ctx->rank * rpr, (size_t)nrows * sizeof(double), cudaMemcpyDeviceToHost, s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            svmb200_set_error("masked_product: %s", cudaGetErrorString(e));
+            rc = SVMB200_ERR_CUDA;
+        }
+        return rc;
+    }
     if (rc == SVMB200_OK) {
         cudaMemcpyAsync(v_host, dw, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
         cudaError_t e = cudaStreamSynchronize(s);
@@ -1171,4 +1287,35 @@ extern "C" int svmb200_masked_product(svmb200_ctx* ctx, const double* dQ, int64_
         }
     }
     return rc;
+}
+
+// The same for every rank of a single-process group at once: count contexts (rank order) with their shards dQ[r];
+// all products run concurrently, v_host receives the n results.
+extern "C" int svmb200_masked_product_group(svmb200_ctx* const* ctxs, const double* const* dQ, int count, int64_t n, int64_t ld,
+                                            const double* beta_host, double* v_host) {
+    SVM_CHECK_ARG(ctxs != nullptr && dQ != nullptr && count >= 1 && count <= SVM_MAX_RANKS && beta_host && v_host, "bad argument");
+    SVM_CHECK_ARG(ld >= n && ld % 2 == 0, "ld must be >= n and even");
+    const int64_t rpr = rows_per_rank(n, count);
+    for (int r = 0; r < count; ++r) {
+        svmb200_ctx* ctx = ctxs[r];
+        SVM_CHECK_ARG(ctx != nullptr && ctx->nranks == count && ctx->rank == r && (count == 1 || ctx->local_group),
+                      "pass the contexts of the single-process group in rank order");
+        SVM_TRY(svm_use(ctx));
+        int64_t row0 = 0, nrows = 0;
+        SVM_TRY(svmb200_shard_rows(n, r, count, &row0, &nrows));
+        SVM_CHECK_ARG(nrows == 0 || dQ[r] != nullptr, "null shard");
+        SVM_TRY(svm_scratch_reserve(ctx, &ctx->mp_buf, &ctx->mp_bytes, (size_t)(ld + rpr * count) * sizeof(double)));
+        double* du = static_cast<double*>(ctx->mp_buf);
+        double* dw = du + ld;
+        cudaStream_t s = ctx->stream;
+        SVM_CUDA(cudaMemsetAsync(du, 0, (size_t)ld * sizeof(double), s));
+        SVM_CUDA(cudaMemcpyAsync(du, beta_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+        SVM_TRY(svm_launch_matvec(ctx, dQ[r], nrows, ld, du, dw, nullptr));
+        if (nrows > 0) SVM_CUDA(cudaMemcpyAsync(v_host + row0, dw, (size_t)nrows * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    for (int r = 0; r < count; ++r) {
+        SVM_TRY(svm_use(ctxs[r]));
+        SVM_CUDA(cudaStreamSynchronize(ctxs[r]->stream));
+    }
+    return SVMB200_OK;
 }

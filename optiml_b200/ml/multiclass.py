@@ -64,10 +64,16 @@ def fit_shared_gram(estimator, X, targets):
     return clones
 
 
-def _lockstep_capable(estimator):
-    """The estimator runs a device-resident solver that nothing on the host has to watch."""
+def _lockstep_capable(estimator, n_samples=None):
+    """The estimator runs a device-resident solver that nothing on the host has to watch (and the problem is not one a
+    single-process device group shards over its GPUs: there the clones are fitted one after the other, each on all GPUs)."""
     if not isinstance(estimator, (SVC, SVR)) or estimator.verbose:
         return False
+    if n_samples is not None:
+        from ..runtime import default_context
+        group = default_context().group
+        if group is not None and group.wants(int(n_samples)):
+            return False
     try:
         estimator._bcqp_solver_class()
     except (NotImplementedError, TypeError):
@@ -79,7 +85,7 @@ class OneVsRestClassifier(_skmc.OneVsRestClassifier):
     """``sklearn.multiclass.OneVsRestClassifier`` whose binary ``SVC`` problems share one Gram matrix."""
 
     def fit(self, X, y, **fit_params):
-        if fit_params or not isinstance(self.estimator, SVC) or not _lockstep_capable(self.estimator):
+        if fit_params or not isinstance(self.estimator, SVC) or not _lockstep_capable(self.estimator, np.shape(X)[0]):
             return super().fit(X, y, **fit_params)
         self._validate_params()
         # label handling of sklearn/multiclass.py OneVsRestClassifier.fit
@@ -104,7 +110,7 @@ class MultiOutputRegressor(_skmo.MultiOutputRegressor):
     def fit(self, X, y, sample_weight=None, **fit_params):
         y_arr = np.asarray(y)
         if sample_weight is not None or fit_params or not isinstance(self.estimator, SVR) or \
-                not _lockstep_capable(self.estimator) or y_arr.ndim != 2 or y_arr.shape[1] < 2:
+                not _lockstep_capable(self.estimator, np.shape(X)[0]) or y_arr.ndim != 2 or y_arr.shape[1] < 2:
             return super().fit(X, y, sample_weight=sample_weight, **fit_params)
         self._validate_params()
         self.estimators_ = fit_shared_gram(self.estimator, X, [y_arr[:, i] for i in range(y_arr.shape[1])])

@@ -25,7 +25,7 @@ from ... import _native as N
 from ...opti import Optimizer, Quadratic
 from ...opti.constrained import AugmentedLagrangianQuadratic, BoxConstrainedQuadraticOptimizer, ProjectedGradient
 from ...opti.unconstrained.stochastic import StochasticOptimizer, StochasticMomentumOptimizer
-from ...runtime import DeviceHessian, DeviceMatrix, default_context
+from ...runtime import DeviceHessian, DeviceMatrix, GroupHessian, default_context, make_hessian
 
 _SCOPE = ('optiml_b200 implements the dual formulation solved by a BoxConstrainedQuadraticOptimizer '
           '(ProjectedGradient, FrankWolfe; reg_intercept=True) or, as its augmented-Lagrangian relaxation, by a '
@@ -171,14 +171,27 @@ class SVM(BaseEstimator):
         dX = X_device if X_device is not None else ctx.upload_matrix(X)
         # gamma='scale' needs X.var(), the input validation an all-finite test: both from the copy in HBM, one pass
         kid, gamma, coef0, degree = self.kernel.gram_spec(X, device=dX)
-        dS = ctx.upload_vector(signs) if signs is not None else None
-        H = DeviceHessian(ctx, n, layout)
-        sp = C.c_void_p(dS.dptr) if dS is not None else None
-        N.call('svmb200_gram', ctx.handle, C.c_void_p(dX.dptr), n, dX.ld, C.c_void_p(dX.dptr), n, dX.ld, d, 1, kid,
-               gamma, coef0, degree, sp, sp, float(bias), H.row0, H.nrows, C.c_void_p(H.matrix.dptr), H.ld)
-        ctx.sync()
-        if dS is not None:
-            dS.release()
+        H = make_hessian(ctx, n, layout)
+        if isinstance(H, GroupHessian):
+            # one process, N GPUs: X is replicated over NVLink, every rank builds its row shard, all at once
+            copies = ctx.group.replicate(dX)
+            sign_copies = [c.upload_vector(signs) if signs is not None else None for c in ctx.group.ctxs]
+            for part, dXr, dSr in zip(H.parts, copies, sign_copies):
+                sp = C.c_void_p(dSr.dptr) if dSr is not None else None
+                N.call('svmb200_gram', part.ctx.handle, C.c_void_p(dXr.dptr), n, dXr.ld, C.c_void_p(dXr.dptr), n, dXr.ld, d, 1,
+                       kid, gamma, coef0, degree, sp, sp, float(bias), part.row0, part.nrows, C.c_void_p(part.matrix.dptr),
+                       part.ld)
+            ctx.group.sync()
+            for m in copies + [v for v in sign_copies if v is not None]:
+                m.release()
+        else:
+            dS = ctx.upload_vector(signs) if signs is not None else None
+            sp = C.c_void_p(dS.dptr) if dS is not None else None
+            N.call('svmb200_gram', ctx.handle, C.c_void_p(dX.dptr), n, dX.ld, C.c_void_p(dX.dptr), n, dX.ld, d, 1, kid,
+                   gamma, coef0, degree, sp, sp, float(bias), H.row0, H.nrows, C.c_void_p(H.matrix.dptr), H.ld)
+            ctx.sync()
+            if dS is not None:
+                dS.release()
         # X stays in HBM until the support vectors have been gathered from it (_set_support_vectors)
         self._train_X_device = (dX, X_device is None)
         self.fit_times_ = {'gram_s': time.perf_counter() - t0}  # gamma + upload + Gram kernel (wall clock)

@@ -2,7 +2,7 @@
 uses (reference: optiml/opti/_base.py).  Matrix work is done by the svmb200 CUDA library."""
 import numpy as np
 
-from ..runtime import DeviceHessian, default_context
+from ..runtime import DeviceHessian, GroupHessian, default_context, hessian_from_host
 
 
 class OptimizationFunction:
@@ -48,7 +48,7 @@ class Quadratic(OptimizationFunction):
 
     def __init__(self, Q, q):
         q = np.array(q, dtype=float)
-        if isinstance(Q, DeviceHessian):
+        if isinstance(Q, (DeviceHessian, GroupHessian)):
             self._device, self._host_Q = Q, None
             n = Q.nvars
         else:
@@ -77,7 +77,7 @@ class Quadratic(OptimizationFunction):
         if self._device is None:
             if self._host_Q is None:
                 raise RuntimeError('the device copy of Q was released and no host copy exists')
-            self._device = DeviceHessian.from_host(ctx or default_context(), self._host_Q)
+            self._device = hessian_from_host(ctx or default_context(), self._host_Q)
         return self._device
 
     def release(self):

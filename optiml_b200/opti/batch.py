@@ -28,6 +28,8 @@ def batchable(solvers):
     if len({int(s.max_iter) for s in solvers}) != 1:
         return False
     H0 = first.f.device_hessian()
+    if len(H0.shards()) != 1:
+        return False   # a single-process device group advances one problem at a time (no lockstep batches there)
     for s in solvers:
         H = s.f.device_hessian()
         if H.matrix is not H0.matrix or H.layout != H0.layout or (H.row0, H.nrows) != (H0.row0, H0.nrows):

@@ -12,6 +12,47 @@ import numpy as np
 from ... import _native as N
 
 
+class GroupHandle(C.c_void_p):
+    """Solver handles of the ranks of a single-process device group (runtime.DeviceGroup).  It IS the rank-0 handle
+    wherever one handle is expected -- state, histories and statistics are replicated -- and carries its peers for the
+    calls that drive all ranks: run and destroy."""
+    peers = ()
+
+
+def create_solvers(symbol, H, tail):
+    """``symbol(ctx, shard, n, ld, row0, nrows, layout[, signs], *tail(h))`` for every shard of the resident matrix H:
+    one handle under torchrun / on one GPU, one per rank (started together) on a single-process device group."""
+    layout = N.HESSIAN_SVR if H.layout == 'svr' else N.HESSIAN_PLAIN
+    handles = []
+    try:
+        for part in H.shards():
+            h = C.c_void_p()
+            head = (part.ctx.handle, C.c_void_p(part.matrix.dptr), part.n, part.ld, part.row0, part.nrows, layout)
+            if H.signs is not None:
+                # Q = (s s') o M on a shared, unsigned resident matrix (one-vs-rest, SURVEY.md 8f-4)
+                N.call(symbol + '_signed', *head, N.ptr(H.signs), *tail(h))
+            else:
+                N.call(symbol, *head, *tail(h))
+            handles.append(h)
+        if len(handles) == 1:
+            return handles[0]
+        arr = (C.c_void_p * len(handles))(*[h.value for h in handles])
+        N.call('svmb200_pg_start_group', arr, len(handles))
+    except Exception:
+        for h in handles:
+            N.load_library().svmb200_pg_destroy(h)
+        raise
+    gh = GroupHandle(handles[0].value)
+    gh.peers = tuple(handles)
+    return gh
+
+
+def destroy_solvers(h):
+    lib = N.load_library()
+    for peer in (getattr(h, 'peers', None) or (h,)):
+        lib.svmb200_pg_destroy(peer)
+
+
 class DeviceLoopMixin:
     # subclasses set these
     _create_symbol = None          # C entry point that builds the solver handle
@@ -30,17 +71,9 @@ class DeviceLoopMixin:
         if self.ub.size != n or self.lb.size != n or self.x.size != n:
             raise ValueError('bounds / start point size does not match with Q')
         q, lb, ub, x0 = (np.ascontiguousarray(v, dtype=np.float64) for v in (self.f.q, self.lb, self.ub, self.x))
-        h = C.c_void_p()
-        layout = N.HESSIAN_SVR if H.layout == 'svr' else N.HESSIAN_PLAIN
-        if H.signs is not None:
-            # Q = (s s') o M on a shared, unsigned resident matrix (one-vs-rest)
-            N.call(self._create_symbol + '_signed', H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows,
-                   layout, N.ptr(H.signs), N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0), float(self.eps),
-                   int(self.max_iter), *self._extra_create_args(), C.byref(h))
-        else:
-            N.call(self._create_symbol, H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows, layout,
-                   N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0), float(self.eps), int(self.max_iter),
-                   *self._extra_create_args(), C.byref(h))
+        h = create_solvers(self._create_symbol, H,
+                           lambda hh: (N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0), float(self.eps), int(self.max_iter),
+                                       *self._extra_create_args(), C.byref(hh)))
         if profile:
             N.call('svmb200_pg_set_profile', h, 1)
         return h, n
@@ -48,7 +81,12 @@ class DeviceLoopMixin:
     @staticmethod
     def _run(h, max_new):
         it, st = C.c_int64(0), C.c_int(0)
-        N.call('svmb200_pg_run', h, int(max_new), C.byref(it), C.byref(st))
+        peers = getattr(h, 'peers', None)
+        if peers:
+            arr = (C.c_void_p * len(peers))(*[p.value for p in peers])
+            N.call('svmb200_pg_run_group', arr, len(peers), int(max_new), C.byref(it), C.byref(st))
+        else:
+            N.call('svmb200_pg_run', h, int(max_new), C.byref(it), C.byref(st))
         return int(it.value), N.STATUS[st.value]
 
     def _pull_state(self, h, n):
@@ -90,7 +128,7 @@ class DeviceLoopMixin:
                 self._minimize_stepwise(h, n)
             self._after_run(h, n)
         finally:
-            N.load_library().svmb200_pg_destroy(h)
+            destroy_solvers(h)
         if self.verbose:
             print('\n')
         return self

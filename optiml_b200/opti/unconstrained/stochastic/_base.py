@@ -15,7 +15,7 @@ import numpy as np
 from .schedules import constant
 from ... import Optimizer
 from ...constrained import AugmentedLagrangianQuadratic
-from ...constrained._device_loop import DeviceLoopMixin
+from ...constrained._device_loop import DeviceLoopMixin, create_solvers, destroy_solvers
 from .... import _native as N
 
 
@@ -86,7 +86,9 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
             raise ValueError('start point size does not match with Q')
         if self.random_state is None:
             # an unseeded start point (opti/_base.py:40-41) differs from rank to rank: all ranks take rank 0's
-            self.x = H.ctx.broadcast_array(self.x)
+            # (under torchrun; the ranks of a single-process group are created from this one array anyway)
+            if getattr(H, 'group', None) is None:
+                self.x = H.ctx.broadcast_array(self.x)
         q, lb, ub, x0 = (np.ascontiguousarray(v, dtype=np.float64) for v in (f.q, f.lb, f.ub, self.x))
         a = np.ascontiguousarray(f.A[0]) if f.n_eq else None
         b = float(f.b[0]) if f.n_eq else 0.
@@ -94,16 +96,10 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
         momentum_type = getattr(self, 'momentum_type', 'none')
         mom = self._draw(self.momentum, self.epochs + 1) if momentum_type != 'none' else None
         k = self._rule_constants()
-        h = C.c_void_p()
-        layout = N.HESSIAN_SVR if H.layout == 'svr' else N.HESSIAN_PLAIN
-        tail = (N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0), N.ptr(a), b, float(f.rho), N.RULES[self._rule],
-                N.MOMENTUM[momentum_type], N.ptr(lr), N.ptr(mom), float(k['decay']), float(k['beta1']), float(k['beta2']),
-                float(k['offset']), float(self.tol), int(self.epochs), C.byref(h))
-        if H.signs is not None:  # Q = (s s') o M on a shared, unsigned resident matrix
-            N.call('svmb200_al_create_signed', H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows, layout,
-                   N.ptr(H.signs), *tail)
-        else:
-            N.call('svmb200_al_create', H.ctx.handle, C.c_void_p(H.matrix.dptr), H.n, H.ld, H.row0, H.nrows, layout, *tail)
+        h = create_solvers('svmb200_al_create', H, lambda hh: (
+            N.ptr(q), N.ptr(lb), N.ptr(ub), N.ptr(x0), N.ptr(a), b, float(f.rho), N.RULES[self._rule],
+            N.MOMENTUM[momentum_type], N.ptr(lr), N.ptr(mom), float(k['decay']), float(k['beta1']), float(k['beta2']),
+            float(k['offset']), float(self.tol), int(self.epochs), C.byref(hh)))
         if profile:
             N.call('svmb200_pg_set_profile', h, 1)
         return h, n
@@ -140,7 +136,7 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
                 self._minimize_stepwise(h, n)
             self._after_run(h, n)
         finally:
-            N.load_library().svmb200_pg_destroy(h)
+            destroy_solvers(h)
         if self.verbose:
             print('\n')
         return self

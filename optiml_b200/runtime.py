@@ -1,9 +1,13 @@
-"""Device runtime of the host mirror: one context (GPU + stream) per process, device-resident
-matrices and the multi-GPU plumbing.
+"""Device runtime of the host mirror: contexts (GPU + stream), device-resident matrices and the multi-GPU plumbing.
 
-Multi-GPU model: one process per GPU (``torchrun``); ``torch.distributed`` is used only to agree on
-the NCCL unique id, the per-iteration exchange itself is an ``ncclAllGather`` issued by the C
-library on its own stream (csrc/comm.cu).
+Two multi-GPU models, same kernels, same row-block partition, bit-identical results:
+
+* one process per GPU (``torchrun``): ``torch.distributed`` is used only for the rendezvous (NCCL unique id, IPC handles of
+  the exchange arenas); the per-iteration exchange is fused into the matvec kernel over NVLink peer memory, with an
+  ``ncclAllGather`` issued by the C library as the fallback (csrc/comm.cu);
+* ONE process, N GPUs (``use_devices([...])`` or ``SVMB200_DEVICES=0,1,...|all``): the reference's API is a single Python
+  process calling ``SVC.fit``; a :class:`DeviceGroup` makes that process drive every GPU from the calling thread -- no
+  torchrun, no torch, no NCCL -- so notebooks and sklearn meta-estimators (``GridSearchCV``) use all GPUs unchanged.
 """
 import ctypes as C
 import os
@@ -29,6 +33,7 @@ class Context:
         self.handle = h
         self.device = int(device)
         self.rank, self.nranks = 0, 1
+        self.group = None   # a DeviceGroup whose GPUs this (solo) context may fan large problems out to
         # large device buffers (the Hessian shard) are recycled between fits: cudaMalloc/cudaFree of
         # tens of GB costs ~0.1 s each, more than the Gram build itself
         self._pool = []  # (nbytes, device pointer), oldest first
@@ -270,6 +275,10 @@ class DeviceHessian:
     def nvars(self):
         return 2 * self.n if self.layout == 'svr' else self.n
 
+    def shards(self):
+        """the per-context shards a solver is created on (one here; a GroupHessian has one per rank)"""
+        return [self]
+
     @classmethod
     def from_host(cls, ctx, Q):
         """Upload (this rank's rows of) a host-resident square matrix."""
@@ -322,21 +331,184 @@ class DeviceHessian:
             self.matrix.release()
 
 
+class DeviceGroup:
+    """One process, N GPUs: ranks 0..N-1 are contexts of the calling thread (one per device) whose exchange arenas are
+    mapped by plain peer access (``svmb200_comm_local_group``).  Problems with at least ``MIN_ROWS_PER_GPU`` rows per GPU
+    are row-block sharded over the group exactly like a ``torchrun`` job (same partition, same kernels, same bits);
+    smaller ones stay on the solo context -- an exchange per iteration costs more than it saves there."""
+
+    MIN_ROWS_PER_GPU = 512
+
+    def __init__(self, devices, arena_bytes=64 << 20):
+        devices = [int(d) for d in devices]
+        if len(devices) < 2 or len(set(devices)) != len(devices):
+            raise ValueError('a device group needs two or more distinct devices')
+        self.ctxs = [Context(device=d) for d in devices]
+        handles = (C.c_void_p * len(devices))(*[c.handle.value for c in self.ctxs])
+        N.call('svmb200_comm_local_group', handles, len(devices), int(arena_bytes))
+        for r, c in enumerate(self.ctxs):
+            c.rank, c.nranks = r, len(devices)
+        self.devices = devices
+
+    def __len__(self):
+        return len(self.ctxs)
+
+    def wants(self, n):
+        """shard an n x n matrix over the group?  (every rank must own rows: the fused exchange has no collective)"""
+        P = len(self.ctxs)
+        rows_per_rank = shard_rows(n, 0, P)[1]
+        return n >= P * self.MIN_ROWS_PER_GPU and (P - 1) * rows_per_rank < n
+
+    def replicate(self, src):
+        """copies of a DeviceMatrix on every rank's device (rank order); the source's own device reuses it in place"""
+        out = []
+        for c in self.ctxs:
+            m = DeviceMatrix(c, src.rows, src.cols, src.ld)
+            N.call('svmb200_copy_peer', c.handle, C.c_void_p(m.dptr), src.ctx.handle, C.c_void_p(src.dptr), src.nbytes)
+            out.append(m)
+        return out
+
+    def sync(self):
+        for c in self.ctxs:
+            c.sync()
+
+    def trim(self):
+        for c in self.ctxs:
+            c.trim()
+
+
+class GroupHessian:
+    """The n x n matrix of a solve, row-block sharded over the ranks of a :class:`DeviceGroup` (``parts[r]`` is rank r's
+    :class:`DeviceHessian`).  Same interface as ``DeviceHessian`` where the solvers and estimators use it."""
+
+    def __init__(self, group, n, layout='plain'):
+        self.group, self.n, self.layout = group, int(n), layout
+        self.parts = [DeviceHessian(c, n, layout) for c in group.ctxs]
+        self.ctx = group.ctxs[0]
+        self.ld = self.parts[0].ld
+        self.signs = None
+        self.row0, self.nrows = 0, self.n
+
+    @property
+    def nvars(self):
+        return 2 * self.n if self.layout == 'svr' else self.n
+
+    @property
+    def matrix(self):
+        return self.parts[0].matrix
+
+    def shards(self):
+        return self.parts
+
+    def with_signs(self, signs):
+        raise NotImplementedError('signed views (lockstep one-vs-rest batches) are not available on a device group')
+
+    @classmethod
+    def from_host(cls, group, Q):
+        Q = np.asarray(Q, dtype=np.float64)
+        n = Q.shape[0]
+        H = cls(group, n, 'plain')
+        for part in H.parts:
+            block = np.zeros((max(part.nrows, 1), part.ld))
+            block[:part.nrows, :n] = Q[part.row0:part.row0 + part.nrows]
+            part.ctx.h2d(part.matrix.dptr, block)
+        return H
+
+    def shard_to_host(self):
+        return np.vstack([p.shard_to_host() for p in self.parts])
+
+    def to_host(self):
+        M = self.shard_to_host()
+        if self.layout == 'svr':
+            return np.vstack((np.hstack((M, -M)), np.hstack((-M, M))))
+        return M
+
+    def product(self, v):
+        """Q @ v: every rank's shard streams concurrently (svmb200_masked_product_group), one host result"""
+        v = np.asarray(v, dtype=np.float64).ravel()
+        beta = np.ascontiguousarray(v[:self.n] - v[self.n:] if self.layout == 'svr' else v)
+        out = np.empty(self.n)
+        P = len(self.parts)
+        ctxs = (C.c_void_p * P)(*[p.ctx.handle.value for p in self.parts])
+        mats = (C.c_void_p * P)(*[p.matrix.dptr for p in self.parts])
+        N.call('svmb200_masked_product_group', ctxs, mats, P, self.n, self.ld, N.ptr(beta), N.ptr(out))
+        return np.concatenate((out, -out)) if self.layout == 'svr' else out
+
+    def release(self):
+        for p in self.parts:
+            p.release()
+
+
+def make_hessian(ctx, n, layout='plain'):
+    """The resident matrix of an n-variable problem: sharded over ``ctx.group`` when there is one and the problem is
+    large enough, on ``ctx`` (this rank's row shard under torchrun) otherwise."""
+    if ctx.group is not None and ctx.group.wants(n):
+        return GroupHessian(ctx.group, n, layout)
+    return DeviceHessian(ctx, n, layout)
+
+
+def hessian_from_host(ctx, Q):
+    if ctx.group is not None and ctx.group.wants(np.shape(Q)[0]):
+        return GroupHessian.from_host(ctx.group, Q)
+    return DeviceHessian.from_host(ctx, Q)
+
+
+_devices = None
+
+
+def use_devices(devices):
+    """Fan large problems of this process out to these GPUs (``None`` / one device: single-GPU).  The environment variable
+    ``SVMB200_DEVICES`` (comma-separated indices, or ``all``) does the same without a code change.  Not for ``torchrun``
+    jobs: there every rank owns one GPU already."""
+    global _devices, _default_ctx
+    _devices = None if devices is None else [int(d) for d in devices]
+    if _default_ctx is not None and _default_ctx.nranks == 1:
+        _attach_group(_default_ctx)
+
+
+def _configured_devices():
+    if _devices is not None:
+        return _devices
+    env = os.environ.get('SVMB200_DEVICES', '').strip()
+    if not env:
+        return None
+    if env.lower() == 'all':
+        count = C.c_int(0)
+        N.call('svmb200_device_count', C.byref(count))
+        return list(range(count.value))
+    return [int(t) for t in env.split(',') if t.strip() != '']
+
+
+def _attach_group(ctx):
+    devs = _configured_devices()
+    if devs is None or len(devs) < 2:
+        if ctx.group is not None:
+            ctx.group = None
+        return
+    if ctx.group is None or ctx.group.devices != devs:
+        ctx.group = DeviceGroup(devs)
+
+
 def default_context():
     """Process-wide context.  Under ``torchrun`` (torch.distributed initialised, world size > 1) the
     context joins an NCCL communicator whose id is broadcast through torch.distributed."""
     global _default_ctx
     if _default_ctx is not None:
         return _default_ctx
-    ctx = Context()
+    devs = _configured_devices()
+    ctx = Context(device=devs[0]) if devs else Context()
+    distributed = False
     import sys
     if 'torch' in sys.modules:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             rank, world = dist.get_rank(), dist.get_world_size()
+            distributed = True
             ctx.attach_communicator(rank, world, broadcast_unique_id(dist, Context.new_unique_id))
             if os.environ.get('SVMB200_EXCHANGE', 'p2p').lower() != 'nccl':
                 ctx.enable_peer_exchange(dist)
+    if not distributed:
+        _attach_group(ctx)
     _default_ctx = ctx
     return ctx
 

@@ -126,6 +126,9 @@ enum { cudaIpcMemLazyEnablePeerAccess = 1 };
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
 cudaError_t cudaIpcCloseMemHandle(void* p);
+enum { cudaErrorPeerAccessAlreadyEnabled = 704 };
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaGetLastError();
 const char* cudaGetErrorString(cudaError_t e);
 

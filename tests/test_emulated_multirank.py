@@ -351,3 +351,94 @@ def test_many_back_to_back_solves_of_alternating_sizes():
         many = run_ranks(3, 'p2p', body)
     for state in many:
         assert all(np.array_equal(a, b) for a, b in zip(one, state))
+
+
+# ---------------------------------------------------------------------------------------------- one process, N GPUs
+@pytest.fixture
+def device_group():
+    """a single-process device group of three emulated GPUs that shards problems from 64 rows per GPU on"""
+    from optiml_b200 import runtime
+    with emulated_device() as lib:
+        saved = runtime.DeviceGroup.MIN_ROWS_PER_GPU
+        runtime.DeviceGroup.MIN_ROWS_PER_GPU = 64
+        runtime.use_devices([0, 1, 2])
+        try:
+            yield runtime
+        finally:
+            runtime.use_devices(None)
+            runtime.DeviceGroup.MIN_ROWS_PER_GPU = saved
+
+
+def test_single_process_group_is_bit_identical_to_one_gpu(device_group):
+    """``SVC.fit`` in ONE Python process on a group of GPUs (runtime.use_devices / SVMB200_DEVICES: no torchrun, no NCCL):
+    same partition and kernels as the torchrun ranks, one host thread enqueuing iteration-major -- alpha, intercept,
+    histories and decision values equal the one-GPU fit bit for bit, for every solver family"""
+    runtime = device_group
+    from optiml_b200.ml.svm import SVC, DualSVC, DualSVR
+    from optiml_b200.ml.svm.kernels import GaussianKernel, PolyKernel
+    from optiml_b200.ml.svm.losses import hinge
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import FrankWolfe, ProjectedGradient
+    from optiml_b200.opti.unconstrained.stochastic import AdaGrad
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((300, 5))
+    y = (X[:, 0] + 0.2 * rng.standard_normal(300) > 0).astype(int)
+    t = X @ rng.standard_normal(5)
+    makers = [lambda: DualSVC(kernel=GaussianKernel(), C=1, max_iter=30),
+              lambda: DualSVR(kernel=PolyKernel(degree=2), C=1, max_iter=25),
+              lambda: DualSVC(kernel=GaussianKernel(), C=1, max_iter=25, optimizer=FrankWolfe),
+              lambda: SVC(loss=hinge, kernel=GaussianKernel(), C=1, reg_intercept=False, dual=True, optimizer=AdaGrad,
+                          learning_rate=1., max_iter=25, random_state=5)]
+
+    def fit_all():
+        out = []
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            for mk in makers:
+                m = mk()
+                m.fit(X, t if isinstance(m, DualSVR) else y)
+                out.append((type(m.obj.device_hessian()).__name__, m.alphas_.copy(), m.intercept_,
+                            np.array(m.train_loss_history), m.decision_function(X[:40]), len(m.support_)))
+                m.obj.release()
+        return out
+
+    grouped = fit_all()
+    assert all(g[0] == 'GroupHessian' for g in grouped)
+    # a generic callback drives the group step by step; a host-resident Q is sharded on upload
+    G = rng.standard_normal((205, 200))
+    Q, q, ub = G.T @ G / 200, rng.standard_normal(200), np.full(200, 1.5)
+    seen = []
+    stepwise = ProjectedGradient(quad=Quadratic(Q, q), ub=ub, max_iter=7, callback=lambda o: seen.append(o.f_x)).minimize()
+    assert len(seen) == stepwise.iter + 1 == 8
+    # small problems stay on the solo context
+    small = DualSVC(kernel=GaussianKernel(), C=1, max_iter=5).fit(X[:100], y[:100])
+    assert type(small.obj.device_hessian()).__name__ == 'DeviceHessian'
+    runtime.use_devices(None)
+    solo = fit_all()
+    assert all(s[0] == 'DeviceHessian' for s in solo)
+    for g, s in zip(grouped, solo):
+        assert np.array_equal(g[1], s[1]) and g[2] == s[2] and np.array_equal(g[3], s[3]) and np.array_equal(g[4], s[4])
+        assert g[5] == s[5]
+    one = ProjectedGradient(quad=Quadratic(Q, q), ub=ub, max_iter=7).minimize()
+    assert np.array_equal(one.x, stepwise.x) and np.allclose(seen, one.f_hist, rtol=0, atol=0)
+
+
+def test_single_process_group_under_sklearn_meta_estimators(device_group):
+    """GridSearchCV / OneVsRestClassifier over the drop-in work unchanged on a device group (clones are fitted one after
+    the other, each on all GPUs; the lockstep batch is a one-context feature)"""
+    from sklearn.model_selection import GridSearchCV
+    from optiml_b200.ml.multiclass import OneVsRestClassifier
+    from optiml_b200.ml.svm import DualSVC
+    from optiml_b200.ml.svm.kernels import GaussianKernel
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((420, 4))
+    y = (X[:, 0] > 0).astype(int)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        gs = GridSearchCV(DualSVC(kernel=GaussianKernel(), max_iter=15), {'C': [0.5, 2.0]}, cv=2).fit(X, y)
+        assert gs.best_estimator_.score(X, y) > 0.8
+        assert type(gs.best_estimator_.obj.device_hessian()).__name__ == 'GroupHessian'
+        y3 = np.digitize(X[:, 1], [-0.5, 0.5])
+        ovr = OneVsRestClassifier(DualSVC(kernel=GaussianKernel(), C=1, max_iter=15)).fit(X, y3)
+        assert len(ovr.estimators_) == 3 and ovr.score(X, y3) > 0.6
+        assert all(type(e.obj.device_hessian()).__name__ == 'GroupHessian' for e in ovr.estimators_)
