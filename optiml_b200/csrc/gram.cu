@@ -643,10 +643,13 @@ int make_tensor_map(svmb200_ctx* ctx, CUtensorMap* map, const double* base, int6
 
 template <int KERNEL>
 int launch_gram(svmb200_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const GramArgs& args) {
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to > 48 KB of dynamic shared memory is a PER-DEVICE function attribute (a single-process device group
+    // launches this kernel on every GPU of the box from one process)
+    static bool configured[64] = {};
+    const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+    if (!configured[dev]) {
         SVM_CUDA(cudaFuncSetAttribute(gram_kernel<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM));
-        configured = true;
+        configured[dev] = true;
     }
     const int ntiles = args.tiles_m * args.tiles_n;
     const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
