@@ -57,6 +57,8 @@ struct svmb200_ctx {
     size_t batch_bytes = 0;
     // device-side X.var() (devmath.cu): leaf table of NumPy's pairwise tree, leaf sums, pinned staging -- cached per size
     void* var_cache = nullptr;
+    // grid barrier of the persistent small-problem kernel (k_persistent.cuh): 256 zeroed bytes
+    unsigned* gbar = nullptr;
     // row indices of a device gather (support vectors)
     void* idx_buf = nullptr;
     size_t idx_bytes = 0;
@@ -131,7 +133,17 @@ static inline cudaError_t svm_launch_chained(void (*kernel)(KArgs...), dim3 grid
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+template <typename Arg>
+static inline cudaError_t svm_launch_cooperative(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Arg arg) {
+    void* params[] = {&arg};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), grid, block, params, smem, stream);
+}
 #else
+template <typename Arg>
+static inline cudaError_t svm_launch_cooperative(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t, Arg arg) {
+    emu::launch_cooperative(grid, block, smem, [=]() { kernel(arg); });
+    return cudaSuccess;
+}
 static inline void pdl_wait() {}
 static inline void pdl_launch_dependents() {}
 template <typename... KArgs, typename... Args>

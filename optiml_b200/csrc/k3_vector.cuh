@@ -54,8 +54,10 @@ struct VecArgs {
     const double* sgn;
 };
 
+// (L1-bypassing load: inside the persistent kernel of k_persistent.cuh the products come from other CTAs of the SAME
+// launch, and a line cached two iterations ago would be stale; between separate launches it makes no difference)
 __device__ __forceinline__ double gathered_at(const VecArgs& a, size_t idx) {
-    return a.gathered_ll != nullptr ? ll_load(a.gathered_ll + idx, a.tag, a.fault) : a.gathered[idx];
+    return a.gathered_ll != nullptr ? ll_load(a.gathered_ll + idx, a.tag, a.fault) : __ldcg(a.gathered + idx);
 }
 
 // w = Q u for Q = (s s') o M:  the vector handed to K2 is s o u and the product that comes back is signed again
@@ -154,10 +156,10 @@ __device__ __forceinline__ void pg_vector_body(const VecArgs& a, const long long
         Quad r;
         r.a = r.b = r.c = 0.0;
         r.m = INFINITY;
-        if (tid < a.nctas) {
-            r.a = part_r[tid];
-            r.b = part_r[VP_MAXC + tid];
-            r.m = part_r[2 * VP_MAXC + tid];
+        if (tid < a.nctas) {  // written by other CTAs: L1-bypassing loads (see gathered_at)
+            r.a = __ldcg(part_r + tid);
+            r.b = __ldcg(part_r + VP_MAXC + tid);
+            r.m = __ldcg(part_r + 2 * VP_MAXC + tid);
         }
         if (MODE == VP_STEP) {
             // u'w: one share per 64-row group, thread-strided in global group order

@@ -15,6 +15,7 @@
 #include "al_math.cuh"
 #include "k2_matvec.cuh"   // K2, K2 x NB (device code)
 #include "k3_vector.cuh"   // K3 vector phases and kernel entry points (device code)
+#include "k_persistent.cuh"  // the whole loop in one cooperative kernel, matrix in shared memory (small problems)
 #include <math.h>
 #include <stdlib.h>
 
@@ -734,6 +735,67 @@ static int poll_wait(svmb200_pg* pg, int slot) {
     return SVMB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------ persistent small-problem loop
+// A projected-gradient solve on one GPU whose matrix fits the shared memory of the SMs (n <= ~2 050 on a B200) runs as
+// ONE cooperative launch (k_persistent.cuh) instead of two launches per iteration.  Same bits; SVMB200_PERSISTENT=0
+// keeps the two-kernel loop (A/B), SVMB200_PERSISTENT_GRID overrides the grid size (tests on the host emulation).
+struct PersistPlan {
+    int grid = 0, rows_per_cta = 0;
+    size_t smem = 0;
+};
+
+static bool persistent_plan(const svmb200_pg* pg, int64_t budget, PersistPlan* plan) {
+    static const int enabled = [] {
+        const char* ev = getenv("SVMB200_PERSISTENT");
+        return ev == nullptr ? 1 : atoi(ev);
+    }();
+    const svmb200_ctx* ctx = pg->ctx;
+    if (!enabled || pg->solver != 0 || ctx->nranks != 1 || pg->profile || budget < 8) return false;
+    if (pg->ld > 2 * PK_NT * PK_UMAX || pg->nrows != pg->n) return false;
+    int grid = ctx->sm_count;
+    if (const char* ev = getenv("SVMB200_PERSISTENT_GRID")) grid = atoi(ev);
+    if (grid < 1 || grid < pg->nctas) return false;
+    const int64_t rows = (pg->n + grid - 1) / grid;
+    const size_t smem = (size_t)rows * pg->ld * sizeof(double);
+    if (rows > PK_RMAX || smem > 225 * 1024) return false;
+    plan->grid = grid;
+    plan->rows_per_cta = (int)rows;
+    plan->smem = smem;
+    return true;
+}
+
+static int launch_persistent(svmb200_pg* pg, const PersistPlan& plan, int64_t niter) {
+    svmb200_ctx* ctx = pg->ctx;
+    if (!ctx->matvec_scratch) ctx->matvec_scratch = new MatvecScratch();
+    MatvecScratch& s = *static_cast<MatvecScratch*>(ctx->matvec_scratch);
+    SVM_TRY(matvec_scratch_reserve(ctx, s, pg->n, pg->ld));
+    if (!ctx->gbar) {
+        SVM_CUDA(cudaMalloc(&ctx->gbar, 256));
+        SVM_CUDA(cudaMemsetAsync(ctx->gbar, 0, 256, ctx->stream));
+    }
+#ifndef SVMB200_HOST_EMULATION
+    static size_t configured[64] = {};  // per-device opt-in to the dynamic shared memory size
+    const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+    if (configured[dev] < plan.smem) {
+        SVM_CUDA(cudaFuncSetAttribute(pg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        configured[dev] = 225 * 1024;
+    }
+#endif
+    PersistArgs a;
+    a.Q = pg->dQ;
+    a.ld = pg->ld;
+    a.n = pg->n;
+    a.rows_per_cta = plan.rows_per_cta;
+    a.prod = s.wpart;
+    a.gbar = ctx->gbar;
+    a.v = make_vec_args(pg);
+    a.k0 = pg->k_next;
+    a.niter = niter;
+    SVM_CUDA(svm_launch_cooperative(pg_persistent_kernel, dim3((unsigned)plan.grid), dim3(PK_NT), plan.smem, ctx->stream, a));
+    ctx->launches++;
+    return SVMB200_OK;
+}
+
 // The ranks of a single-process group (count > 1), or one solver (count == 1): `max_new` more iterations (< 0: to the
 // end).  Launches are enqueued ITERATION-MAJOR over the ranks -- every rank's product k, then every rank's vector launch
 // k -- so that in each stream a launch that waits for a peer's entries comes after that peer's product has been
@@ -761,6 +823,18 @@ static int run_many(svmb200_pg* const* pgs, int count, int64_t max_new) {
         const int64_t BATCH = 64;
         int pending = -1, slot = 0;
         int rc = SVMB200_OK;
+        PersistPlan plan;
+        if (count == 1 && persistent_plan(p0, budget, &plan)) {
+            // one cooperative launch runs the whole budget (it leaves early when the stopping test fires)
+            const int64_t k0 = p0->k_next;
+            rc = launch_persistent(p0, plan, budget);
+            if (rc == SVMB200_OK) rc = poll_enqueue(p0, 0);
+            if (rc == SVMB200_OK) rc = poll_wait(p0, 0);
+            SVM_TRY(rc);
+            p0->k_next = p0->finished ? p0->st_host->iter : k0 + budget;
+            p0->last_passes += p0->k_next - k0;
+            budget = 0;
+        }
         while (budget > 0 && !p0->finished && rc == SVMB200_OK) {
             const int64_t nb = budget < BATCH ? budget : BATCH;
             for (int64_t i = 0; i < nb && rc == SVMB200_OK; ++i) {

@@ -29,6 +29,7 @@
 #include <mutex>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace emu {
@@ -436,6 +437,61 @@ void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::functio
         if (!run_block(r, nt, rng)) break;
     }
     g_run = outer;
+}
+
+// Cooperative launch: one HOST THREAD per block, all alive together -- the fiber runtime (g_run, threadIdx_, the
+// "__shared__" statics, the stack pool) is thread_local, so every block gets its own.  A grid barrier built on global
+// atomics then completes exactly as on the GPU: the polling thread of a block spins on the host (spin_wait yields the
+// CPU) until the other blocks arrive.  An error in any block becomes the launching thread's sticky error.
+void launch_cooperative(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()>& thread_body) {
+    if (g_sticky_error) return;
+    const size_t nblocks = (size_t)grid.x * grid.y;
+    if (block.y != 1 || block.z != 1 || grid.z != 1 || block.x == 0 || block.x > 1024 || nblocks == 0 || nblocks > 160) {
+        fail("unsupported cooperative launch shape (the emulation runs one host thread per block: <= 160 blocks)");
+        return;
+    }
+    ++g_launches;
+    g_blocks += nblocks;
+    std::vector<std::string> errors(nblocks);
+    std::vector<std::thread> threads;
+    const unsigned seed = g_seed + (unsigned)g_launches * 7919u;
+    for (size_t id = 0; id < nblocks; ++id) {
+        threads.emplace_back([&, id]() {
+            const int nt = (int)block.x;
+            BlockRunner r;
+            r.fibers.resize(nt);
+            r.stacks = static_cast<char*>(malloc((size_t)(nt + 1) * STACK_BYTES));
+            if (!r.stacks) {
+                errors[id] = "out of memory for fiber stacks";
+                return;
+            }
+            r.owner = nullptr;
+            r.body = &thread_body;
+            std::vector<unsigned char> smem_storage;
+            if (dynamic_smem_bytes > 0) {
+                smem_storage.assign(dynamic_smem_bytes + 2048, 0xFF);
+                unsigned char* aligned = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_storage.data()) + 1023) & ~uintptr_t(1023));
+                r.smem = aligned + SMEM_WINDOW_SKEW;
+                r.smem_bytes = dynamic_smem_bytes;
+            }
+            g_run = &r;
+            blockDim_ = block;
+            gridDim_ = grid;
+            blockIdx_ = {(unsigned)(id % grid.x), (unsigned)(id / grid.x), 0};
+            std::mt19937 rng(seed + (unsigned)id);
+            run_block(r, nt, rng);
+            g_run = nullptr;
+            if (g_sticky_error) errors[id] = g_sticky_text;
+            free(r.stacks);
+            r.stacks = nullptr;
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (const std::string& e : errors)
+        if (!e.empty()) {
+            fail("cooperative launch: " + e);
+            break;
+        }
 }
 
 // ---------------------------------------------------------------------------------------------- memory

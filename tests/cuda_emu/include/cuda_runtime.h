@@ -58,7 +58,8 @@ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int
 
 // ---- device intrinsics used by the kernels
 static inline void __syncthreads() { emu::syncthreads(); }
-static inline void __threadfence() {}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_block() {}
 static inline void __syncwarp() { emu::syncwarp(); }
 static inline int __double2loint(double v) { long long r; memcpy(&r, &v, 8); return (int)(unsigned)(r & 0xffffffffll); }
 static inline int __double2hiint(double v) { long long r; memcpy(&r, &v, 8); return (int)(unsigned)((unsigned long long)r >> 32); }
@@ -143,4 +144,7 @@ template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFunc
 #include <functional>
 namespace emu {
 void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()>& thread_body);
+// cooperative launch: every block is alive at the same time (one host thread per block) so that a grid barrier built on
+// global atomics can complete; grids of a few dozen blocks only
+void launch_cooperative(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()>& thread_body);
 }

@@ -384,3 +384,42 @@ def test_gram_tile_bands_cover_every_tile_once():
             assert np.abs(out[:, :n] - want[r0:r0 + nr]).max() <= 1e-14 and np.all(out[:, n:] == 0)
             ctx.free(dQ)
         dX.release()
+
+
+@pytest.mark.parametrize('n,grid,layout,order', [(70, 5, 'plain', 0), (600, 40, 'plain', 2), (150, 11, 'svr', 1), (200, 13, 'plain', 0)])
+def test_persistent_loop_is_bit_identical_to_the_two_kernel_loop(monkeypatch, n, grid, layout, order):
+    """k_persistent.cuh: the whole projected-gradient solve as ONE cooperative launch with the matrix in shared memory
+    (what BASELINE config C1 runs on a B200) against the K2 + K3 launch pairs -- same iterates, histories, stopping
+    iteration, with several virtual vector CTAs (n = 600), the SVR block layout, a run that reaches optimality (n = 200)
+    and under reversed / shuffled thread schedules"""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import ProjectedGradient
+    from optiml_b200.runtime import DeviceHessian, default_context
+    rng = np.random.default_rng(n)
+    G = rng.standard_normal((n + 5, n))
+    M = G.T @ G / n
+    nv = 2 * n if layout == 'svr' else n
+    q, ub = rng.standard_normal(nv), np.full(nv, 1.5)
+    iters = 300 if n == 200 else 30
+
+    def solve(persistent_grid):
+        monkeypatch.setenv('SVMB200_PERSISTENT_GRID', str(persistent_grid))
+        with emulated_device(order=order, seed=3) as lib:
+            ctx = default_context()
+            H = DeviceHessian(ctx, n, layout)
+            block = np.zeros((n, H.ld))
+            block[:, :n] = M
+            ctx.h2d(H.matrix.dptr, block)
+            before = lib.emu_launches()
+            o = ProjectedGradient(quad=Quadratic(H, q), ub=ub, max_iter=iters).minimize()
+            launches = lib.emu_launches() - before
+            H.release()
+            return o.x, o.g_x, o.f_hist, o.ng_hist, o.iter, o.status, launches
+
+    two_kernel, persistent = solve(0), solve(grid)
+    assert persistent[6] <= 4 < two_kernel[6]                    # product + INIT, the loop, (FINALISE)
+    assert persistent[4:6] == two_kernel[4:6]
+    if n == 200:
+        assert persistent[5] == 'optimal' and persistent[4] < iters
+    for a, b in zip(two_kernel[:4], persistent[:4]):
+        assert np.array_equal(a, b)
