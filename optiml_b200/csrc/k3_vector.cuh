@@ -131,6 +131,82 @@ __device__ __forceinline__ void tail_accumulate(Quad& a, double d, double x, dou
     else if (d < 0.0) a.m = fmin(a.m, __ddiv_rn(__dsub_rn(lb, x), d));
 }
 
+// One variable (and, for the SVR block layout, its twin j + n) of the vector phase.  The operands do not depend on the
+// step length, so a thread loads those of its first PG_PREFETCH variables BEFORE the reductions that produce t: the
+// kernel is a chain of dependent latencies (loads -> block reduce -> divide -> loads -> update -> block reduce), and this
+// takes one memory round trip (~1 us with the vectors evicted from L2 by the matrix stream) off it.  Same arithmetic,
+// same order of accumulation per thread.
+constexpr int PG_PREFETCH = 2;   // covers the whole slice of a CTA when n <= 65 536 (512 variables per CTA)
+
+struct PGElem {
+    double w, x, q, lb, ub, d, g;
+    double x2, q2, lb2, ub2, d2, g2;
+};
+
+template <int MODE>
+__device__ __forceinline__ PGElem pg_load_elem(const VecArgs& a, long long j, long long n, unsigned rpr) {
+    PGElem e;
+    const unsigned rk = (unsigned)j / rpr;
+    e.w = gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
+    e.x = a.x[j];
+    e.q = a.q[j];
+    e.lb = a.lb[j];
+    e.ub = a.ub[j];
+    e.d = e.g = 0.0;
+    if (MODE != VP_INIT) {
+        e.d = a.d[j];
+        e.g = a.g[j];
+    }
+    e.x2 = e.q2 = e.lb2 = e.ub2 = e.d2 = e.g2 = 0.0;
+    if (a.svr) {
+        const long long i2 = j + n;
+        e.x2 = a.x[i2];
+        e.q2 = a.q[i2];
+        e.lb2 = a.lb[i2];
+        e.ub2 = a.ub[i2];
+        if (MODE != VP_INIT) {
+            e.d2 = a.d[i2];
+            e.g2 = a.g[i2];
+        }
+    }
+    return e;
+}
+
+template <int MODE>
+__device__ __forceinline__ void pg_step_elem(const VecArgs& a, long long j, long long n, double t, const PGElem& e, Quad& acc) {
+    const double wj = apply_sign(a, j, e.w);
+    double x = e.x, g;
+    if (MODE == VP_INIT) {
+        g = __dadd_rn(wj, e.q);  // g = Q x0 + q  (opti/_base.py:291)
+    } else {
+        x = axpy_rn(t, e.d, x);
+        g = axpy_rn(t, wj, e.g);
+        a.x[j] = x;
+    }
+    a.g[j] = g;
+    const double dn = project_dir(g, x, e.lb, e.ub);
+    a.d[j] = dn;
+    tail_accumulate(acc, dn, x, g, e.q, e.lb, e.ub);
+    double uj = dn;
+    if (a.svr) {
+        const long long i2 = j + n;
+        double x2 = e.x2, g2;
+        if (MODE == VP_INIT) {
+            g2 = __dadd_rn(-wj, e.q2);
+        } else {
+            x2 = axpy_rn(t, e.d2, x2);
+            g2 = axpy_rn(t, -wj, e.g2);
+            a.x[i2] = x2;
+        }
+        a.g[i2] = g2;
+        const double dn2 = project_dir(g2, x2, e.lb2, e.ub2);
+        a.d[i2] = dn2;
+        tail_accumulate(acc, dn2, x2, g2, e.q2, e.lb2, e.ub2);
+        uj = __dsub_rn(dn, dn2);
+    }
+    a.u[j] = apply_sign(a, j, uj);
+}
+
 template <int MODE>
 __device__ __forceinline__ void pg_vector_body(const VecArgs& a, const long long k) {
     __shared__ double sm[VP_NT / 32][4];
@@ -150,6 +226,14 @@ __device__ __forceinline__ void pg_vector_body(const VecArgs& a, const long long
     const double* part_r = a.part + (size_t)(k & 1) * 3 * VP_MAXC;
     double* part_w = a.part + (size_t)((MODE == VP_INIT ? k : k + 1) & 1) * 3 * VP_MAXC;
 
+    PGElem pre[PG_PREFETCH];
+    if (MODE != VP_FINALISE) {
+#pragma unroll
+        for (int e = 0; e < PG_PREFETCH; ++e) {
+            const long long j = j0 + tid + (long long)e * VP_NT;
+            if (j < j1) pre[e] = pg_load_elem<MODE>(a, j, n, rpr);
+        }
+    }
     double t = 0.0;
     if (MODE != VP_INIT) {
         // ---- reductions over the whole problem, identical in every CTA
@@ -214,41 +298,14 @@ __device__ __forceinline__ void pg_vector_body(const VecArgs& a, const long long
     Quad acc;
     acc.a = acc.b = acc.c = 0.0;
     acc.m = INFINITY;
-    for (long long j = j0 + tid; j < j1; j += VP_NT) {
-        const unsigned rk = (unsigned)j / rpr;
-        const double wj = apply_sign(a, j, gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr)));
-        double x = a.x[j], q = a.q[j], g;
-        if (MODE == VP_INIT) {
-            g = __dadd_rn(wj, q);  // g = Q x0 + q  (opti/_base.py:291)
-        } else {
-            x = axpy_rn(t, a.d[j], x);
-            g = axpy_rn(t, wj, a.g[j]);
-            a.x[j] = x;
-        }
-        a.g[j] = g;
-        const double lb = a.lb[j], ub = a.ub[j];
-        const double dn = project_dir(g, x, lb, ub);
-        a.d[j] = dn;
-        tail_accumulate(acc, dn, x, g, q, lb, ub);
-        double uj = dn;
-        if (a.svr) {
-            const long long i2 = j + n;
-            double x2 = a.x[i2], q2 = a.q[i2], g2;
-            if (MODE == VP_INIT) {
-                g2 = __dadd_rn(-wj, q2);
-            } else {
-                x2 = axpy_rn(t, a.d[i2], x2);
-                g2 = axpy_rn(t, -wj, a.g[i2]);
-                a.x[i2] = x2;
-            }
-            a.g[i2] = g2;
-            const double lb2 = a.lb[i2], ub2 = a.ub[i2];
-            const double dn2 = project_dir(g2, x2, lb2, ub2);
-            a.d[i2] = dn2;
-            tail_accumulate(acc, dn2, x2, g2, q2, lb2, ub2);
-            uj = __dsub_rn(dn, dn2);
-        }
-        a.u[j] = apply_sign(a, j, uj);
+#pragma unroll
+    for (int e = 0; e < PG_PREFETCH; ++e) {
+        const long long j = j0 + tid + (long long)e * VP_NT;
+        if (j < j1) pg_step_elem<MODE>(a, j, n, t, pre[e], acc);
+    }
+    for (long long j = j0 + tid + (long long)PG_PREFETCH * VP_NT; j < j1; j += VP_NT) {  // chunks > 512 (n > 65 536)
+        const PGElem el = pg_load_elem<MODE>(a, j, n, rpr);
+        pg_step_elem<MODE>(a, j, n, t, el, acc);
     }
     acc = block_reduce(acc, sm);
     if (tid == 0) {

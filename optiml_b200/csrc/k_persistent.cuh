@@ -18,6 +18,7 @@
 constexpr int PK_NT = 256;
 constexpr int PK_RMAX = 16;   // rows per CTA (accumulators per thread)
 constexpr int PK_UMAX = 6;    // 128-bit operand slots per thread: ld <= 2 * PK_NT * PK_UMAX = 3072 columns
+constexpr int PK_SROUNDS = (2 * PK_NT * PK_UMAX / MV_GROUP + PK_NT / 64 - 1) / (PK_NT / 64);  // share rounds: 4 groups each
 
 struct PersistArgs {
     const double* Q;        // n x ld, all rows on this GPU
@@ -44,7 +45,7 @@ __device__ __forceinline__ unsigned pk_arrive(unsigned* p) {
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
     return old;
 }
-__device__ __forceinline__ void pk_backoff(unsigned long long) { __nanosleep(20); }
+__device__ __forceinline__ void pk_backoff(unsigned long long) {}
 __device__ __forceinline__ double2 pk_ld_cg_f64x2(const double2* p) {
     double2 r;
     asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
     double* qs = reinterpret_cast<double*>(emu::dynamic_smem());
 #endif
     __shared__ double red[PK_NT / 32][PK_RMAX];
-    __shared__ double share_red[PK_NT / 32];
+    __shared__ double share_red[PK_SROUNDS][PK_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
     long long r1 = r0 + a.rows_per_cta;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
     for (long long it = 0; it < a.niter; ++it) {
         const long long k = a.k0 + it;
         // ================= phase A: w = Q u for my rows (matvec_seg_kernel's arithmetic, one column segment) =================
+        double u_row = 0.0;
         if (myrows > 0) {
             double2 uv[PK_UMAX];
             const double2* u2 = reinterpret_cast<const double2*>(a.v.u);
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
                 const int c = tid + m * PK_NT;
                 uv[m] = c < nvec ? pk_ld_cg_f64x2(u2 + c) : double2{0.0, 0.0};
             }
+            if (tid < myrows) u_row = __ldcg(a.v.u + r0 + tid);  // for the row's term of u'w below: in flight with the rest
             double acc[PK_RMAX];
 #pragma unroll
             for (int r = 0; r < PK_RMAX; ++r) acc[r] = 0.0;
@@ -136,10 +139,12 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
             // warp butterfly, then fixed-order sum over warps
 #pragma unroll
             for (int r = 0; r < PK_RMAX; ++r) {
-                double v = acc[r];
+                if (r < myrows) {  // uniform over the CTA
+                    double v = acc[r];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) red[wid][r] = v;
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) red[wid][r] = v;
+                }
             }
         }
         __syncthreads();
@@ -151,25 +156,36 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
             v += part;                                   // the segment combine of K2 with its single segment
             const long long rr = r0 + tid;
             const_cast<double*>(a.v.gathered)[rr] = v;
-            a.prod[rr] = __dmul_rn(__ldcg(a.v.u + rr), v);  // term of this row in its group's share of u'w
+            a.prod[rr] = __dmul_rn(u_row, v);            // term of this row in its group's share of u'w
         }
         pk_grid_barrier(a.gbar, gridDim.x);
 
         // ================= phase B: shares of u'w (K2's group combine) + K3's vector phase on the first nctas CTAs =================
         if ((int)blockIdx.x < a.v.nctas) {
-            // warps 2p, 2p+1 take group p, p + 4, ...: butterfly inside each warp, then warp 2p + warp 2p+1
-            for (unsigned g0 = 0; g0 < ngrp; g0 += PK_NT / 64) {
-                const unsigned grp = g0 + (unsigned)(wid >> 1);
-                const long long rr = (long long)grp * MV_GROUP + (wid & 1) * 32 + lane;
-                double dv = (grp < ngrp && rr < a.n) ? __ldcg(a.prod + rr) : 0.0;
+            // warps 2p, 2p+1 take groups p, p + 4, ...: butterfly inside each warp, then warp 2p + warp 2p+1 (K2's tree);
+            // all loads first, so the rounds cost one memory round trip together
+            double dv[PK_SROUNDS];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) dv = __dadd_rn(dv, __shfl_xor_sync(0xffffffffu, dv, o));
-                if (lane == 0) share_red[wid] = dv;
-                __syncthreads();
-                if (tid < PK_NT / 64 && g0 + tid < ngrp)
-                    const_cast<double*>(a.v.gathered)[a.v.rpr + g0 + tid] = __dadd_rn(share_red[2 * tid], share_red[2 * tid + 1]);
-                __syncthreads();
+            for (int r = 0; r < PK_SROUNDS; ++r) {
+                const unsigned grp = (unsigned)r * (PK_NT / 64) + (unsigned)(wid >> 1);
+                const long long rr = (long long)grp * MV_GROUP + (wid & 1) * 32 + lane;
+                dv[r] = (grp < ngrp && rr < a.n) ? __ldcg(a.prod + rr) : 0.0;
             }
+#pragma unroll
+            for (int r = 0; r < PK_SROUNDS; ++r) {
+                if ((unsigned)r * (PK_NT / 64) < ngrp) {  // uniform
+                    double v = dv[r];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    if (lane == 0) share_red[r][wid] = v;
+                }
+            }
+            __syncthreads();
+            if ((unsigned)tid < ngrp) {
+                const int r = tid / (PK_NT / 64), p = tid % (PK_NT / 64);
+                const_cast<double*>(a.v.gathered)[a.v.rpr + tid] = __dadd_rn(share_red[r][2 * p], share_red[r][2 * p + 1]);
+            }
+            __syncthreads();
             __threadfence_block();
             pg_vector_body<VP_STEP>(a.v, k);
         }

@@ -30,6 +30,19 @@ for rep in range(2):
         m.obj.release()
 fh = np.array(m.train_loss_history)
 g_fresh = m.obj.jacobian(m.alphas_)
+# against the CPU oracle (the reference cannot run this size: 346 GB of host matrices): 128 rows spread over all shards of
+# the Hessian, rebuilt with the oracle's kernel -- checks the Gram shards, the streaming product and the gradient the
+# solver carried through 1000 iterations at full C5 size
+from oracle import svm_oracle as O
+rows = np.unique(np.linspace(0, n - 1, 128).astype(np.int64))
+ys = np.where(y == np.unique(y)[1], 1.0, -1.0)
+Krows = O.gaussian_kernel(X[rows], X, gamma=1.0 / (X.shape[1] * X.var()))
+Krows[np.arange(len(rows)), rows] = 1.0                       # the self-Gram's exact diagonal (sklearn semantics)
+g_oracle = (ys[rows, None] * ys[None, :] * (Krows + 1.0)) @ m.alphas_ - 1.0
+sv_mask = m.alphas_ > 1e-6
+kdot_oracle = Krows[:, sv_mask] @ (m.alphas_[sv_mask] * ys[sv_mask])
+dec_oracle = kdot_oracle + m.intercept_
+dec_dev = m.decision_function(X[rows])
 digest = hashlib.sha256(m.alphas_.tobytes()).hexdigest()
 digs = [None] * ctx.nranks
 dist.all_gather_object(digs, digest)
@@ -37,6 +50,10 @@ res.update(monotone_descent=bool(np.all(np.diff(fh) <= 1e-9 * np.abs(fh[:-1]))),
            feasible=bool(m.alphas_.min() >= -1e-12 and m.alphas_.max() <= 1 + 1e-12),
            grad_drift=float(np.abs(g_fresh - m.optimizer.g_x).max() / np.abs(g_fresh).max()),
            f_consistency=float(abs(0.5 * m.alphas_ @ (g_fresh - 1.) - m.optimizer.f_x) / abs(m.optimizer.f_x)),
+           oracle_rows=int(len(rows)),
+           grad_vs_oracle_rows=float(np.abs(m.optimizer.g_x[rows] - g_oracle).max() / np.abs(g_oracle).max()),
+           fresh_grad_vs_oracle_rows=float(np.abs(g_fresh[rows] - g_oracle).max() / np.abs(g_oracle).max()),
+           decision_vs_oracle_rows=float(np.abs(dec_dev - dec_oracle).max() / max(1.0, np.abs(dec_oracle).max())),
            ranks_identical=len(set(digs)) == 1, train_acc_first_4096=float(m.score(X[:4096], y[:4096])))
 if dist.get_rank() == 0:
     print('C5_RESULT ' + json.dumps(res), flush=True)
