@@ -59,6 +59,8 @@ struct svmb200_ctx {
     void* var_cache = nullptr;
     // grid barrier of the persistent small-problem kernel (k_persistent.cuh): 256 zeroed bytes
     unsigned* gbar = nullptr;
+    void* persist_buf = nullptr;   // w / product double buffers and the CTAs' private iterates
+    size_t persist_bytes = 0;
     // row indices of a device gather (support vectors)
     void* idx_buf = nullptr;
     size_t idx_bytes = 0;

@@ -4,14 +4,22 @@
 // BASELINE config C1 (n = 2 000: a 32 MB matrix) is launch-bound on the two-kernel loop: 14 us per iteration for ~1 us of
 // memory traffic ("hard parts").  148 SMs x 227 KB of shared memory hold 33 MB, so here ONE
 // cooperative kernel keeps the whole matrix on chip -- CTA b owns rows [b r, (b+1) r) and loads them once -- and runs all
-// iterations of the solve:
-//     phase A (every CTA)       w = Q u for the CTA's rows, from shared memory; per-row products u_r w_r for the shares
+// iterations of the solve with ONE grid barrier per iteration:
+//     phase A   w = Q u for the CTA's rows, from shared memory, into the w buffer of this iteration's parity;
+//               per-row products u_r w_r for the shares of u'w
 //     grid barrier
-//     phase B (CTA v < nctas)   the 64-row shares of u'w, then the vector phase of K3 (pg_vector_body) as virtual CTA v
-//     grid barrier              stop when the stopping test has fired
+//     phase B   EVERY CTA runs the whole O(n) vector phase on a private copy of x, g, d, u (the vectors are a few
+//               tens of KB; 148 copies live in L2): shares of u'w, reductions, step length, update, new direction.
+//               Nothing has to travel back before the next phase A, so there is no second barrier (a first version ran
+//               phase B on the nctas CTAs of K3's grid and paid two barriers: 13.6 us per iteration, barely better than
+//               two launches -- profiles/r2_s4_persistent_kernel_v1_ncu.txt).  The w / product buffers are double-
+//               buffered by iteration parity: a CTA that is already in phase A of k + 1 writes the other buffer.
 // Bit-identical to the K2 + K3 loop: a row sum is the thread-strided fma chain, warp butterfly and in-order warp sum of
-// matvec_seg_kernel (one column segment: ld <= 3072), the share tree is K2's group combine, phase B is K3's own code.
-// What crosses CTAs inside the kernel (u, w, products, per-CTA partials, the done flag) is read with L1-bypassing loads.
+// matvec_seg_kernel (one column segment: ld <= 3072); the share tree is K2's group combine; phase B evaluates, for
+// every virtual CTA c of K3's grid, exactly the per-thread accumulations and reduction trees of pg_vector_body (same
+// element helpers, same block-reduce shape), and the cross-CTA partials that K3 passes through memory stay in shared
+// memory.  CTA 0 works on the solver's own arrays and records state and history; the stopping test is evaluated
+// identically by every CTA, so all leave together.
 #pragma once
 #include "k3_vector.cuh"
 
@@ -20,13 +28,18 @@ constexpr int PK_RMAX = 16;   // rows per CTA (accumulators per thread)
 constexpr int PK_UMAX = 6;    // 128-bit operand slots per thread: ld <= 2 * PK_NT * PK_UMAX = 3072 columns
 constexpr int PK_SROUNDS = (2 * PK_NT * PK_UMAX / MV_GROUP + PK_NT / 64 - 1) / (PK_NT / 64);  // share rounds: 4 groups each
 
+constexpr int PK_VMAX = 2 * PK_NT * PK_UMAX / VP_ELEMS;   // virtual K3 CTAs: n <= 3072 -> at most 6
+constexpr int PK_NGRP_MAX = 2 * PK_NT * PK_UMAX / MV_GROUP;  // 48 share groups
+
 struct PersistArgs {
     const double* Q;        // n x ld, all rows on this GPU
     long long ld, n;
     int rows_per_cta;
-    double* prod;           // n per-row products u_r * w_r (scratch)
+    double* wbuf;           // 2 x ld : w = Q u, double-buffered by iteration parity
+    double* prod;           // 2 x ld : per-row products u_r * w_r, likewise
+    double* priv;           // (grid - 1) private copies of {x, g, d (nvars each), u (ld)} for CTAs 1..grid-1
     unsigned* gbar;         // grid barrier: [0] arrivals, [32] generation (separate 128-byte lines), zero between launches
-    VecArgs v;              // vector phase; v.gathered is the plain [w | shares] buffer of a single rank
+    VecArgs v;              // the solver's own arrays and state (CTA 0 works on them)
     long long k0;           // first iteration of this launch
     long long niter;        // iterations to run unless the stopping test fires first
 };
@@ -59,21 +72,22 @@ __device__ __forceinline__ void pk_backoff(unsigned long long spins) { (void)emu
 __device__ __forceinline__ double2 pk_ld_cg_f64x2(const double2* p) { return *p; }
 #endif
 
-// all CTAs of the (cooperatively launched, hence co-resident) grid; sense by generation, the last arriver re-arms
+// all CTAs of the (cooperatively launched, hence co-resident) grid; sense by generation, the last arriver re-arms.
+// The arrival is an acq_rel RMW at gpu scope (cumulative over the CTA's writes through the bar.sync before it), the
+// waiters poll with relaxed loads and acquire once.
 __device__ __forceinline__ void pk_grid_barrier(unsigned* bar, unsigned nblocks) {
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned* count = bar;
         unsigned* gen = bar + 32;
-        __threadfence();
-        const unsigned my_gen = pk_ld_acquire(gen);
+        const unsigned my_gen = *reinterpret_cast<volatile unsigned*>(gen);
         if (pk_arrive(count) == nblocks - 1) {
             *reinterpret_cast<volatile unsigned*>(count) = 0u;
             pk_st_release(gen, my_gen + 1u);
         } else {
-            for (unsigned long long spins = 0; pk_ld_acquire(gen) == my_gen; ++spins) pk_backoff(spins);
+            for (unsigned long long spins = 0; *reinterpret_cast<volatile unsigned*>(gen) == my_gen; ++spins) pk_backoff(spins);
+            (void)pk_ld_acquire(gen);
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -87,13 +101,23 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
 #endif
     __shared__ double red[PK_NT / 32][PK_RMAX];
     __shared__ double share_red[PK_SROUNDS][PK_NT / 32];
+    __shared__ double shares[PK_NGRP_MAX];
+    __shared__ double part[2][3][PK_VMAX];            // per-virtual-CTA partials, double-buffered by state parity (as K3's)
+    __shared__ double smq[PK_VMAX][PK_NT / 32][4];
+    __shared__ double sm[VP_NT / 32][4];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
     long long r1 = r0 + a.rows_per_cta;
     if (r1 > a.n) r1 = a.n;
     const int myrows = r1 > r0 ? (int)(r1 - r0) : 0;
     const int nvec = (int)(a.ld >> 1);
+    const long long n = a.n, nvars = a.v.svr ? 2 * n : n;
+    const int nctas = a.v.nctas;
+    const long long chunk = (n + nctas - 1) / nctas;
+    const unsigned rpr = (unsigned)a.v.rpr;
+    const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
     PGDeviceState* st = a.v.st;
+    const bool lead = blockIdx.x == 0;
 
     // ---- the CTA's rows, once: global -> shared (the matrix is read-only for the whole solve)
     {
@@ -102,22 +126,40 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
         const long long total = (long long)myrows * nvec;
         for (long long i = tid; i < total; i += PK_NT) dst[i] = ld_stream_f64x2(src + i);
     }
+    // ---- private copy of the iterate (CTA 0 keeps working on the solver's own arrays) and of K3's partials
+    VecArgs v = a.v;
+    if (!lead) {
+        double* base = a.priv + (size_t)(blockIdx.x - 1) * (size_t)(3 * nvars + a.ld);
+        v.x = base;
+        v.g = base + nvars;
+        v.d = base + 2 * nvars;
+        v.u = base + 3 * nvars;
+        for (long long i = tid; i < nvars; i += PK_NT) {
+            v.x[i] = a.v.x[i];
+            v.g[i] = a.v.g[i];
+            v.d[i] = a.v.d[i];
+        }
+        for (long long i = tid; i < a.ld; i += PK_NT) v.u[i] = a.v.u[i];
+    }
+    if (tid < 2 * 3 * PK_VMAX) {
+        const int par = tid / (3 * PK_VMAX), q3 = (tid / PK_VMAX) % 3, c = tid % PK_VMAX;
+        part[par][q3][c] = c < nctas ? a.v.part[(size_t)par * 3 * VP_MAXC + (size_t)q3 * VP_MAXC + c] : 0.0;
+    }
     __syncthreads();
 
-    const unsigned ngrp = (unsigned)((a.n + MV_GROUP - 1) / MV_GROUP);
-    for (long long it = 0; it < a.niter; ++it) {
-        const long long k = a.k0 + it;
+    long long k = a.k0;
+    for (long long it = 0; it < a.niter; ++it, ++k) {
+        double* wk = a.wbuf + (size_t)(k & 1) * a.ld;
+        double* pk = a.prod + (size_t)(k & 1) * a.ld;
         // ================= phase A: w = Q u for my rows (matvec_seg_kernel's arithmetic, one column segment) =================
-        double u_row = 0.0;
         if (myrows > 0) {
             double2 uv[PK_UMAX];
-            const double2* u2 = reinterpret_cast<const double2*>(a.v.u);
+            const double2* u2 = reinterpret_cast<const double2*>(v.u);
 #pragma unroll
             for (int m = 0; m < PK_UMAX; ++m) {
                 const int c = tid + m * PK_NT;
-                uv[m] = c < nvec ? pk_ld_cg_f64x2(u2 + c) : double2{0.0, 0.0};
+                uv[m] = c < nvec ? u2[c] : double2{0.0, 0.0};
             }
-            if (tid < myrows) u_row = __ldcg(a.v.u + r0 + tid);  // for the row's term of u'w below: in flight with the rest
             double acc[PK_RMAX];
 #pragma unroll
             for (int r = 0; r < PK_RMAX; ++r) acc[r] = 0.0;
@@ -140,56 +182,153 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
 #pragma unroll
             for (int r = 0; r < PK_RMAX; ++r) {
                 if (r < myrows) {  // uniform over the CTA
-                    double v = acc[r];
+                    double vv = acc[r];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0) red[wid][r] = v;
+                    for (int o = 16; o > 0; o >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, o);
+                    if (lane == 0) red[wid][r] = vv;
                 }
             }
         }
         __syncthreads();
         if (tid < myrows) {
-            double part = 0.0;
+            double p8 = 0.0;
 #pragma unroll
-            for (int kk = 0; kk < PK_NT / 32; ++kk) part += red[kk][tid];
-            double v = 0.0;
-            v += part;                                   // the segment combine of K2 with its single segment
+            for (int kk = 0; kk < PK_NT / 32; ++kk) p8 += red[kk][tid];
+            double w = 0.0;
+            w += p8;                                     // the segment combine of K2 with its single segment
             const long long rr = r0 + tid;
-            const_cast<double*>(a.v.gathered)[rr] = v;
-            a.prod[rr] = __dmul_rn(u_row, v);            // term of this row in its group's share of u'w
+            wk[rr] = w;
+            pk[rr] = __dmul_rn(v.u[rr], w);              // term of this row in its group's share of u'w
         }
         pk_grid_barrier(a.gbar, gridDim.x);
 
-        // ================= phase B: shares of u'w (K2's group combine) + K3's vector phase on the first nctas CTAs =================
-        if ((int)blockIdx.x < a.v.nctas) {
-            // warps 2p, 2p+1 take groups p, p + 4, ...: butterfly inside each warp, then warp 2p + warp 2p+1 (K2's tree);
-            // all loads first, so the rounds cost one memory round trip together
+        // ================= phase B (every CTA, on its own copy of the iterate) =================
+        // ---- shares of u'w: warps 2p, 2p+1 take groups p, p + 4, ...; butterfly inside each warp, then warp 2p + warp 2p+1
+        {
             double dv[PK_SROUNDS];
 #pragma unroll
             for (int r = 0; r < PK_SROUNDS; ++r) {
                 const unsigned grp = (unsigned)r * (PK_NT / 64) + (unsigned)(wid >> 1);
                 const long long rr = (long long)grp * MV_GROUP + (wid & 1) * 32 + lane;
-                dv[r] = (grp < ngrp && rr < a.n) ? __ldcg(a.prod + rr) : 0.0;
+                dv[r] = (grp < ngrp && rr < n) ? __ldcg(pk + rr) : 0.0;
             }
 #pragma unroll
             for (int r = 0; r < PK_SROUNDS; ++r) {
                 if ((unsigned)r * (PK_NT / 64) < ngrp) {  // uniform
-                    double v = dv[r];
+                    double vv = dv[r];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-                    if (lane == 0) share_red[r][wid] = v;
+                    for (int o = 16; o > 0; o >>= 1) vv = __dadd_rn(vv, __shfl_xor_sync(0xffffffffu, vv, o));
+                    if (lane == 0) share_red[r][wid] = vv;
                 }
             }
             __syncthreads();
             if ((unsigned)tid < ngrp) {
                 const int r = tid / (PK_NT / 64), p = tid % (PK_NT / 64);
-                const_cast<double*>(a.v.gathered)[a.v.rpr + tid] = __dadd_rn(share_red[r][2 * p], share_red[r][2 * p + 1]);
+                shares[tid] = __dadd_rn(share_red[r][2 * p], share_red[r][2 * p + 1]);
             }
             __syncthreads();
-            __threadfence_block();
-            pg_vector_body<VP_STEP>(a.v, k);
         }
-        pk_grid_barrier(a.gbar, gridDim.x);
-        if (*reinterpret_cast<volatile int*>(&st->done)) break;
+        // ---- K3's reductions over the whole problem (pg_vector_body, MODE == VP_STEP)
+        const double (*pr)[PK_VMAX] = part[k & 1];
+        double (*pw)[PK_VMAX] = part[(k + 1) & 1];
+        Quad r;
+        r.a = r.b = r.c = 0.0;
+        r.m = INFINITY;
+        if (tid < nctas) {
+            r.a = pr[0][tid];
+            r.b = pr[1][tid];
+            r.m = pr[2][tid];
+        }
+        {
+            // u'w: thread-strided over the groups, four per step (ngrp <= 48 < VP_NT: one step, one live term)
+            double v4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const unsigned bq = (unsigned)tid + (unsigned)e * VP_NT;
+                v4[e] = ((unsigned)tid < ngrp && bq < ngrp) ? shares[bq] : 0.0;
+            }
+            if ((unsigned)tid < ngrp) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) r.c = __dadd_rn(r.c, v4[e]);
+            }
+        }
+        r = block_reduce(r, sm);
+        const double s = r.a, f = 0.5 * r.b, mt = r.m, den = r.c;
+        const double ng = sqrt(s);
+        if (lead && tid == 0) {
+            if (k < a.v.hist_cap) {
+                a.v.hist_f[k] = f;
+                a.v.hist_ng[k] = ng;
+            }
+            st->f = f;
+            st->ng = ng;
+            st->s = s;
+            st->maxt = mt;
+            st->iter = k;
+        }
+        int stop = 0;
+        if (ng <= a.v.eps) stop = SVMB200_STATUS_OPTIMAL;
+        else if (k >= a.v.max_iter) stop = SVMB200_STATUS_STOPPED;
+        if (stop) {
+            if (lead && tid == 0) {
+                st->status = stop;
+                __threadfence();
+                st->done = 1;
+            }
+            break;
+        }
+        const double t = (den <= 1e-16) ? mt : fmin(__ddiv_rn(s, den), mt);
+        if (lead && tid == 0) {
+            st->t = t;
+            st->den = den;
+        }
+        // ---- update, new direction and the partials of the next state, virtual CTA by virtual CTA
+        VecArgs vw = v;           // w of this iteration: pg_load_elem reads it through `gathered` (single rank: index j)
+        vw.gathered = wk;
+        vw.gathered_ll = nullptr;
+#pragma unroll
+        for (int c = 0; c < PK_VMAX; ++c) {
+            if (c < nctas) {
+                const long long j0 = (long long)c * chunk;
+                const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
+                Quad acc;
+                acc.a = acc.b = acc.c = 0.0;
+                acc.m = INFINITY;
+                for (long long j = j0 + tid; j < j1; j += VP_NT) {
+                    const PGElem el = pg_load_elem<VP_STEP>(vw, j, n, rpr);
+                    pg_step_elem<VP_STEP>(vw, j, n, t, el, acc);
+                }
+                acc.a = warp_sum(acc.a);
+                acc.b = warp_sum(acc.b);
+                acc.c = warp_sum(acc.c);
+                acc.m = warp_min(acc.m);
+                if (lane == 0) {
+                    smq[c][wid][0] = acc.a;
+                    smq[c][wid][1] = acc.b;
+                    smq[c][wid][2] = acc.c;
+                    smq[c][wid][3] = acc.m;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < nctas) {   // the second half of block_reduce, for virtual CTA tid
+            double ra = 0.0, rb = 0.0, rm = INFINITY;
+#pragma unroll
+            for (int i = 0; i < VP_NT / 32; ++i) {
+                ra = __dadd_rn(ra, smq[tid][i][0]);
+                rb = __dadd_rn(rb, smq[tid][i][1]);
+                rm = fmin(rm, smq[tid][i][3]);
+            }
+            pw[0][tid] = ra;
+            pw[1][tid] = rb;
+            pw[2][tid] = rm;
+        }
+        __syncthreads();   // u, the partials and (CTA 0) the iterate are in place for the next phase A / reductions
+    }
+    // ---- the solver's own copy of K3's partials (the FINALISE launch and a later launch read them)
+    __syncthreads();
+    if (lead && tid < 2 * 3 * PK_VMAX) {
+        const int par = tid / (3 * PK_VMAX), q3 = (tid / PK_VMAX) % 3, c = tid % PK_VMAX;
+        if (c < nctas) a.v.part[(size_t)par * 3 * VP_MAXC + (size_t)q3 * VP_MAXC + c] = part[par][q3][c];
     }
 }

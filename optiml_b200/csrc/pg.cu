@@ -739,6 +739,8 @@ static int poll_wait(svmb200_pg* pg, int slot) {
 // A projected-gradient solve on one GPU whose matrix fits the shared memory of the SMs (n <= ~2 050 on a B200) runs as
 // ONE cooperative launch (k_persistent.cuh) instead of two launches per iteration.  Same bits; SVMB200_PERSISTENT=0
 // keeps the two-kernel loop (A/B), SVMB200_PERSISTENT_GRID overrides the grid size (tests on the host emulation).
+constexpr size_t PK_SMEM_MAX = 221 * 1024;  // dynamic part; the kernel's static arrays take ~4 KB of the 227 KB
+
 struct PersistPlan {
     int grid = 0, rows_per_cta = 0;
     size_t smem = 0;
@@ -757,7 +759,7 @@ static bool persistent_plan(const svmb200_pg* pg, int64_t budget, PersistPlan* p
     if (grid < 1 || grid < pg->nctas) return false;
     const int64_t rows = (pg->n + grid - 1) / grid;
     const size_t smem = (size_t)rows * pg->ld * sizeof(double);
-    if (rows > PK_RMAX || smem > 225 * 1024) return false;
+    if (rows > PK_RMAX || smem > PK_SMEM_MAX || pg->nctas > PK_VMAX) return false;
     plan->grid = grid;
     plan->rows_per_cta = (int)rows;
     plan->smem = smem;
@@ -766,19 +768,20 @@ static bool persistent_plan(const svmb200_pg* pg, int64_t budget, PersistPlan* p
 
 static int launch_persistent(svmb200_pg* pg, const PersistPlan& plan, int64_t niter) {
     svmb200_ctx* ctx = pg->ctx;
-    if (!ctx->matvec_scratch) ctx->matvec_scratch = new MatvecScratch();
-    MatvecScratch& s = *static_cast<MatvecScratch*>(ctx->matvec_scratch);
-    SVM_TRY(matvec_scratch_reserve(ctx, s, pg->n, pg->ld));
+    // scratch: two w buffers, two product buffers (ld each), grid - 1 private copies of {x, g, d, u}
+    const size_t per_cta = (size_t)(3 * pg->nvars + pg->ld);
+    const size_t doubles = 4 * (size_t)pg->ld + (size_t)(plan.grid - 1) * per_cta;
+    SVM_TRY(svm_scratch_reserve(ctx, &ctx->persist_buf, &ctx->persist_bytes, doubles * sizeof(double)));
     if (!ctx->gbar) {
         SVM_CUDA(cudaMalloc(&ctx->gbar, 256));
         SVM_CUDA(cudaMemsetAsync(ctx->gbar, 0, 256, ctx->stream));
     }
 #ifndef SVMB200_HOST_EMULATION
-    static size_t configured[64] = {};  // per-device opt-in to the dynamic shared memory size
+    static bool configured[64] = {};  // per-device opt-in to the dynamic shared memory size
     const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
-    if (configured[dev] < plan.smem) {
-        SVM_CUDA(cudaFuncSetAttribute(pg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        configured[dev] = 225 * 1024;
+    if (!configured[dev]) {
+        SVM_CUDA(cudaFuncSetAttribute(pg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM_MAX));
+        configured[dev] = true;
     }
 #endif
     PersistArgs a;
@@ -786,7 +789,9 @@ static int launch_persistent(svmb200_pg* pg, const PersistPlan& plan, int64_t ni
     a.ld = pg->ld;
     a.n = pg->n;
     a.rows_per_cta = plan.rows_per_cta;
-    a.prod = s.wpart;
+    a.wbuf = static_cast<double*>(ctx->persist_buf);
+    a.prod = a.wbuf + 2 * pg->ld;
+    a.priv = a.wbuf + 4 * pg->ld;
     a.gbar = ctx->gbar;
     a.v = make_vec_args(pg);
     a.k0 = pg->k_next;
