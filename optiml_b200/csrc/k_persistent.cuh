@@ -8,12 +8,15 @@
 //     phase A   w = Q u for the CTA's rows, from shared memory, into the w buffer of this iteration's parity;
 //               per-row products u_r w_r for the shares of u'w
 //     grid barrier
-//     phase B   EVERY CTA runs the whole O(n) vector phase on a private copy of x, g, d, u (the vectors are a few
-//               tens of KB; 148 copies live in L2): shares of u'w, reductions, step length, update, new direction.
-//               Nothing has to travel back before the next phase A, so there is no second barrier (a first version ran
-//               phase B on the nctas CTAs of K3's grid and paid two barriers: 13.6 us per iteration, barely better than
-//               two launches -- profiles/r2_s4_persistent_kernel_v1_ncu.txt).  The w / product buffers are double-
-//               buffered by iteration parity: a CTA that is already in phase A of k + 1 writes the other buffer.
+//     phase B   EVERY CTA runs the whole O(n) vector phase redundantly, with the iterate IN REGISTERS: a thread owns the
+//               same <= 8 variables for the whole solve (x, g, d, q, lb, ub: 48 doubles), per iteration it reads their
+//               w and writes the new direction to the CTA's private u.  Nothing has to travel back before the next
+//               phase A, so there is no second barrier (a first version ran phase B on the nctas CTAs of K3's grid and
+//               paid two barriers and K3's chain of memory latencies: 13.6 us per iteration, no better than two
+//               launches -- profiles/r2_s4_persistent_kernel_v1_ncu.txt).  The w / product buffers are double-buffered
+//               by iteration parity: a CTA that is already in phase A of k + 1 writes the other buffer.
+// Scope: projected gradient, plain layout without label-sign views, n <= 2048 (four virtual K3 CTAs of <= 512
+// variables) -- BASELINE config C1 and the folds / classes of small data sets; everything else takes the two-kernel loop.
 // Bit-identical to the K2 + K3 loop: a row sum is the thread-strided fma chain, warp butterfly and in-order warp sum of
 // matvec_seg_kernel (one column segment: ld <= 3072); the share tree is K2's group combine; phase B evaluates, for
 // every virtual CTA c of K3's grid, exactly the per-thread accumulations and reduction trees of pg_vector_body (same
@@ -28,7 +31,8 @@ constexpr int PK_RMAX = 16;   // rows per CTA (accumulators per thread)
 constexpr int PK_UMAX = 6;    // 128-bit operand slots per thread: ld <= 2 * PK_NT * PK_UMAX = 3072 columns
 constexpr int PK_SROUNDS = (2 * PK_NT * PK_UMAX / MV_GROUP + PK_NT / 64 - 1) / (PK_NT / 64);  // share rounds: 4 groups each
 
-constexpr int PK_VMAX = 2 * PK_NT * PK_UMAX / VP_ELEMS;   // virtual K3 CTAs: n <= 3072 -> at most 6
+constexpr int PK_VMAX = 4;                                 // virtual K3 CTAs (512 variables each): n <= 2048
+constexpr int PK_SLOTS = 2 * PK_VMAX;                      // variables per thread: two per virtual CTA
 constexpr int PK_NGRP_MAX = 2 * PK_NT * PK_UMAX / MV_GROUP;  // 48 share groups
 
 struct PersistArgs {
@@ -37,7 +41,7 @@ struct PersistArgs {
     int rows_per_cta;
     double* wbuf;           // 2 x ld : w = Q u, double-buffered by iteration parity
     double* prod;           // 2 x ld : per-row products u_r * w_r, likewise
-    double* priv;           // (grid - 1) private copies of {x, g, d (nvars each), u (ld)} for CTAs 1..grid-1
+    double* priv;           // (grid - 1) private copies of u (ld each) for CTAs 1..grid-1
     unsigned* gbar;         // grid barrier: [0] arrivals, [32] generation (separate 128-byte lines), zero between launches
     VecArgs v;              // the solver's own arrays and state (CTA 0 works on them)
     long long k0;           // first iteration of this launch
@@ -126,21 +130,32 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
         const long long total = (long long)myrows * nvec;
         for (long long i = tid; i < total; i += PK_NT) dst[i] = ld_stream_f64x2(src + i);
     }
-    // ---- private copy of the iterate (CTA 0 keeps working on the solver's own arrays) and of K3's partials
-    VecArgs v = a.v;
-    if (!lead) {
-        double* base = a.priv + (size_t)(blockIdx.x - 1) * (size_t)(3 * nvars + a.ld);
-        v.x = base;
-        v.g = base + nvars;
-        v.d = base + 2 * nvars;
-        v.u = base + 3 * nvars;
-        for (long long i = tid; i < nvars; i += PK_NT) {
-            v.x[i] = a.v.x[i];
-            v.g[i] = a.v.g[i];
-            v.d[i] = a.v.d[i];
+    // ---- the iterate in registers: slot s = 2 c + e is variable c * chunk + tid + 256 e of virtual K3 CTA c (the
+    // element a thread of K3's CTA c visits in its e-th loop trip); u in a private copy (CTA 0: the solver's own)
+    double* u_priv = lead ? a.v.u : a.priv + (size_t)(blockIdx.x - 1) * (size_t)a.ld;
+    long long slot_j[PK_SLOTS];
+    bool slot_on[PK_SLOTS];
+    double xs[PK_SLOTS], gs[PK_SLOTS], ds[PK_SLOTS], qv_[PK_SLOTS], lbs[PK_SLOTS], ubs[PK_SLOTS];
+#pragma unroll
+    for (int sl = 0; sl < PK_SLOTS; ++sl) {
+        const int c = sl >> 1, e = sl & 1;
+        const long long j0 = (long long)c * chunk;
+        const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
+        slot_j[sl] = j0 + tid + (long long)e * VP_NT;
+        slot_on[sl] = c < nctas && slot_j[sl] < j1;
+        xs[sl] = gs[sl] = ds[sl] = qv_[sl] = lbs[sl] = ubs[sl] = 0.0;
+        if (slot_on[sl]) {
+            const long long j = slot_j[sl];
+            xs[sl] = a.v.x[j];
+            gs[sl] = a.v.g[j];
+            ds[sl] = a.v.d[j];
+            qv_[sl] = a.v.q[j];
+            lbs[sl] = a.v.lb[j];
+            ubs[sl] = a.v.ub[j];
         }
-        for (long long i = tid; i < a.ld; i += PK_NT) v.u[i] = a.v.u[i];
     }
+    if (!lead)
+        for (long long i = tid; i < a.ld; i += PK_NT) u_priv[i] = a.v.u[i];
     if (tid < 2 * 3 * PK_VMAX) {
         const int par = tid / (3 * PK_VMAX), q3 = (tid / PK_VMAX) % 3, c = tid % PK_VMAX;
         part[par][q3][c] = c < nctas ? a.v.part[(size_t)par * 3 * VP_MAXC + (size_t)q3 * VP_MAXC + c] : 0.0;
@@ -154,7 +169,7 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
         // ================= phase A: w = Q u for my rows (matvec_seg_kernel's arithmetic, one column segment) =================
         if (myrows > 0) {
             double2 uv[PK_UMAX];
-            const double2* u2 = reinterpret_cast<const double2*>(v.u);
+            const double2* u2 = reinterpret_cast<const double2*>(u_priv);
 #pragma unroll
             for (int m = 0; m < PK_UMAX; ++m) {
                 const int c = tid + m * PK_NT;
@@ -198,11 +213,14 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
             w += p8;                                     // the segment combine of K2 with its single segment
             const long long rr = r0 + tid;
             wk[rr] = w;
-            pk[rr] = __dmul_rn(v.u[rr], w);              // term of this row in its group's share of u'w
+            pk[rr] = __dmul_rn(u_priv[rr], w);           // term of this row in its group's share of u'w
         }
         pk_grid_barrier(a.gbar, gridDim.x);
 
         // ================= phase B (every CTA, on its own copy of the iterate) =================
+        double wv[PK_SLOTS];
+#pragma unroll
+        for (int sl = 0; sl < PK_SLOTS; ++sl) wv[sl] = slot_on[sl] ? __ldcg(wk + slot_j[sl]) : 0.0;  // in flight under the shares
         // ---- shares of u'w: warps 2p, 2p+1 take groups p, p + 4, ...; butterfly inside each warp, then warp 2p + warp 2p+1
         {
             double dv[PK_SROUNDS];
@@ -282,30 +300,34 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
             st->t = t;
             st->den = den;
         }
-        // ---- update, new direction and the partials of the next state, virtual CTA by virtual CTA
-        VecArgs vw = v;           // w of this iteration: pg_load_elem reads it through `gathered` (single rank: index j)
-        vw.gathered = wk;
-        vw.gathered_ll = nullptr;
+        // ---- update, new direction and the partials of the next state (pg_step_elem, plain layout, no sign view), the
+        // two variables of virtual CTA c accumulated in K3's loop order, then the warp halves of its block reduce
 #pragma unroll
         for (int c = 0; c < PK_VMAX; ++c) {
-            if (c < nctas) {
-                const long long j0 = (long long)c * chunk;
-                const long long j1 = (j0 + chunk < n) ? (j0 + chunk) : n;
-                Quad acc;
-                acc.a = acc.b = acc.c = 0.0;
-                acc.m = INFINITY;
-                for (long long j = j0 + tid; j < j1; j += VP_NT) {
-                    const PGElem el = pg_load_elem<VP_STEP>(vw, j, n, rpr);
-                    pg_step_elem<VP_STEP>(vw, j, n, t, el, acc);
+            Quad acc;
+            acc.a = acc.b = acc.c = 0.0;
+            acc.m = INFINITY;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int sl = 2 * c + e;
+                if (slot_on[sl]) {
+                    const double x = axpy_rn(t, ds[sl], xs[sl]);
+                    const double g = axpy_rn(t, wv[sl], gs[sl]);
+                    const double dn = project_dir(g, x, lbs[sl], ubs[sl]);
+                    tail_accumulate(acc, dn, x, g, qv_[sl], lbs[sl], ubs[sl]);
+                    xs[sl] = x;
+                    gs[sl] = g;
+                    ds[sl] = dn;
+                    u_priv[slot_j[sl]] = dn;
                 }
+            }
+            if (c < nctas) {  // uniform
                 acc.a = warp_sum(acc.a);
                 acc.b = warp_sum(acc.b);
-                acc.c = warp_sum(acc.c);
                 acc.m = warp_min(acc.m);
                 if (lane == 0) {
                     smq[c][wid][0] = acc.a;
                     smq[c][wid][1] = acc.b;
-                    smq[c][wid][2] = acc.c;
                     smq[c][wid][3] = acc.m;
                 }
             }
@@ -325,7 +347,17 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
         }
         __syncthreads();   // u, the partials and (CTA 0) the iterate are in place for the next phase A / reductions
     }
-    // ---- the solver's own copy of K3's partials (the FINALISE launch and a later launch read them)
+    // ---- CTA 0 hands the iterate back; the solver's own copy of K3's partials (the FINALISE launch and a later launch
+    // read them)
+    if (lead) {
+#pragma unroll
+        for (int sl = 0; sl < PK_SLOTS; ++sl)
+            if (slot_on[sl]) {
+                a.v.x[slot_j[sl]] = xs[sl];
+                a.v.g[slot_j[sl]] = gs[sl];
+                a.v.d[slot_j[sl]] = ds[sl];
+            }
+    }
     __syncthreads();
     if (lead && tid < 2 * 3 * PK_VMAX) {
         const int par = tid / (3 * PK_VMAX), q3 = (tid / PK_VMAX) % 3, c = tid % PK_VMAX;

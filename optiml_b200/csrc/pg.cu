@@ -753,6 +753,7 @@ static bool persistent_plan(const svmb200_pg* pg, int64_t budget, PersistPlan* p
     }();
     const svmb200_ctx* ctx = pg->ctx;
     if (!enabled || pg->solver != 0 || ctx->nranks != 1 || pg->profile || budget < 8) return false;
+    if (pg->svr || pg->sgn != nullptr) return false;  // plain layout, no label-sign view (k_persistent.cuh)
     if (pg->ld > 2 * PK_NT * PK_UMAX || pg->nrows != pg->n) return false;
     int grid = ctx->sm_count;
     if (const char* ev = getenv("SVMB200_PERSISTENT_GRID")) grid = atoi(ev);
@@ -768,9 +769,8 @@ static bool persistent_plan(const svmb200_pg* pg, int64_t budget, PersistPlan* p
 
 static int launch_persistent(svmb200_pg* pg, const PersistPlan& plan, int64_t niter) {
     svmb200_ctx* ctx = pg->ctx;
-    // scratch: two w buffers, two product buffers (ld each), grid - 1 private copies of {x, g, d, u}
-    const size_t per_cta = (size_t)(3 * pg->nvars + pg->ld);
-    const size_t doubles = 4 * (size_t)pg->ld + (size_t)(plan.grid - 1) * per_cta;
+    // scratch: two w buffers, two product buffers, grid - 1 private copies of u (ld each)
+    const size_t doubles = 4 * (size_t)pg->ld + (size_t)(plan.grid - 1) * (size_t)pg->ld;
     SVM_TRY(svm_scratch_reserve(ctx, &ctx->persist_buf, &ctx->persist_bytes, doubles * sizeof(double)));
     if (!ctx->gbar) {
         SVM_CUDA(cudaMalloc(&ctx->gbar, 256));
