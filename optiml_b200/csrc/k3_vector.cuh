@@ -126,9 +126,13 @@ __device__ __forceinline__ double project_dir(double g, double x, double lb, dou
 __device__ __forceinline__ void tail_accumulate(Quad& a, double d, double x, double g, double q, double lb, double ub) {
     a.a = __dadd_rn(a.a, __dmul_rn(d, d));
     a.b = __dadd_rn(a.b, __dmul_rn(x, __dadd_rn(g, q)));
-    // projected_gradient.py:111-114 (correctly rounded IEEE division, exact min)
-    if (d > 0.0) a.m = fmin(a.m, __ddiv_rn(__dsub_rn(ub, x), d));
-    else if (d < 0.0) a.m = fmin(a.m, __ddiv_rn(__dsub_rn(lb, x), d));
+    // projected_gradient.py:111-114 (correctly rounded IEEE division, exact min): (ub - x) / d where d > 0, (lb - x) / d
+    // where d < 0, nothing where d == 0.  ONE branch-free division per variable -- the divide is a ~30-instruction dependent
+    // sequence, and with a branch per sign the compiler emitted two of them per variable and could not interleave the
+    // variables of a thread; same operands, same quotient, same bits.
+    const double num = __dsub_rn(d > 0.0 ? ub : lb, x);
+    const double quot = __ddiv_rn(num, d != 0.0 ? d : 1.0);
+    a.m = (d != 0.0) ? fmin(a.m, quot) : a.m;
 }
 
 // One variable (and, for the SVR block layout, its twin j + n) of the vector phase.  The operands do not depend on the

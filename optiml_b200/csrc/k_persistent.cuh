@@ -115,10 +115,9 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
     if (r1 > a.n) r1 = a.n;
     const int myrows = r1 > r0 ? (int)(r1 - r0) : 0;
     const int nvec = (int)(a.ld >> 1);
-    const long long n = a.n, nvars = a.v.svr ? 2 * n : n;
+    const long long n = a.n;
     const int nctas = a.v.nctas;
     const long long chunk = (n + nctas - 1) / nctas;
-    const unsigned rpr = (unsigned)a.v.rpr;
     const unsigned ngrp = (unsigned)((n + MV_GROUP - 1) / MV_GROUP);
     PGDeviceState* st = a.v.st;
     const bool lead = blockIdx.x == 0;
@@ -167,26 +166,29 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
         double* wk = a.wbuf + (size_t)(k & 1) * a.ld;
         double* pk = a.prod + (size_t)(k & 1) * a.ld;
         // ================= phase A: w = Q u for my rows (matvec_seg_kernel's arithmetic, one column segment) =================
+        double u_row = 0.0;
         if (myrows > 0) {
             double2 uv[PK_UMAX];
             const double2* u2 = reinterpret_cast<const double2*>(u_priv);
+            const int mcount = (nvec + PK_NT - 1) / PK_NT;   // operand slots in use (4 at n = 2000)
 #pragma unroll
             for (int m = 0; m < PK_UMAX; ++m) {
                 const int c = tid + m * PK_NT;
-                uv[m] = c < nvec ? u2[c] : double2{0.0, 0.0};
+                uv[m] = (m < mcount && c < nvec) ? u2[c] : double2{0.0, 0.0};
             }
+            if (tid < myrows) u_row = u_priv[r0 + tid];   // for the row's term of u'w below: in flight with the rest
             double acc[PK_RMAX];
 #pragma unroll
             for (int r = 0; r < PK_RMAX; ++r) acc[r] = 0.0;
 #pragma unroll
-            for (int r = 0; r < PK_RMAX; ++r) {
-                if (r < myrows) {
-                    const double2* row = reinterpret_cast<const double2*>(qs + (size_t)r * a.ld);
+            for (int m = 0; m < PK_UMAX; ++m) {
+                if (m < mcount) {  // uniform
+                    const int c = tid + m * PK_NT;
+                    const bool on = c < nvec;
 #pragma unroll
-                    for (int m = 0; m < PK_UMAX; ++m) {
-                        const int c = tid + m * PK_NT;
-                        if (c < nvec) {
-                            const double2 qv = row[c];
+                    for (int r = 0; r < PK_RMAX; ++r) {
+                        if (r < myrows && on) {
+                            const double2 qv = reinterpret_cast<const double2*>(qs + (size_t)r * a.ld)[c];
                             acc[r] = fma(qv.x, uv[m].x, acc[r]);
                             acc[r] = fma(qv.y, uv[m].y, acc[r]);
                         }
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
             w += p8;                                     // the segment combine of K2 with its single segment
             const long long rr = r0 + tid;
             wk[rr] = w;
-            pk[rr] = __dmul_rn(u_priv[rr], w);           // term of this row in its group's share of u'w
+            pk[rr] = __dmul_rn(u_row, w);                // term of this row in its group's share of u'w
         }
         pk_grid_barrier(a.gbar, gridDim.x);
 
