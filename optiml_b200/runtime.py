@@ -107,9 +107,13 @@ class Context:
         return float(ms.value)
 
     def launch_count(self):
+        """kernels launched through this context (and, for a solo context with a device group, through the group's)"""
         n = C.c_uint64(0)
         N.call('svmb200_launch_count', self.handle, C.byref(n))
-        return int(n.value)
+        total = int(n.value)
+        if self.group is not None:
+            total += sum(c.launch_count() for c in self.group.ctxs)
+        return total
 
     def info(self):
         sm, ma, mi = C.c_int(0), C.c_int(0), C.c_int(0)

@@ -40,8 +40,9 @@ Krows = O.gaussian_kernel(X[rows], X, gamma=1.0 / (X.shape[1] * X.var()))
 Krows[np.arange(len(rows)), rows] = 1.0                       # the self-Gram's exact diagonal (sklearn semantics)
 g_oracle = (ys[rows, None] * ys[None, :] * (Krows + 1.0)) @ m.alphas_ - 1.0
 sv_mask = m.alphas_ > 1e-6
-kdot_oracle = Krows[:, sv_mask] @ (m.alphas_[sv_mask] * ys[sv_mask])
-dec_oracle = kdot_oracle + m.intercept_
+# decision_function resolves gamma='scale' from the SUPPORT VECTORS (first argument of the kernel call, ml/svm/_base.py:286)
+Ksv = O.gaussian_kernel(X[sv_mask], X[rows], gamma=1.0 / (X.shape[1] * X[sv_mask].var()))
+dec_oracle = (m.alphas_[sv_mask] * ys[sv_mask]) @ Ksv + m.intercept_
 dec_dev = m.decision_function(X[rows])
 digest = hashlib.sha256(m.alphas_.tobytes()).hexdigest()
 digs = [None] * ctx.nranks
