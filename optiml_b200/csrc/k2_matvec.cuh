@@ -126,10 +126,26 @@ __global__ void __launch_bounds__(MV_NT, MV_MINB) matvec_seg_kernel(const Matvec
     if (a.fault != nullptr && *a.fault) return;  // the exchange is broken: nothing downstream will be used
     constexpr int R = MV_R, NT = MV_NT, U = MV_U;
     const unsigned items_per_group = (unsigned)(MV_BPG * a.nseg);
-    const unsigned group = blockIdx.x / items_per_group;
-    const unsigned within = blockIdx.x - group * items_per_group;
-    const unsigned rb_in_group = within / (unsigned)a.nseg;
-    const int seg = (int)(within - rb_in_group * (unsigned)a.nseg);
+    // Work items in launch order: all FULL column segments first, the short last segment (ld mod 8192 columns: 848 of
+    // them at n = 50 000, a tenth of an item) at the end of the grid.  The grid's tail -- SMs that run out of work while
+    // the last 256 KB items finish, ~half an item time, 2 % of a pass over a 1/8 shard -- is then filled with small
+    // items.  Which CTA computes an item never changes a bit: partials are combined per group in segment order.
+    const unsigned nbig = (a.ld % MV_SEG == 0 || a.nseg == 1) ? (unsigned)a.nseg : (unsigned)a.nseg - 1u;
+    const unsigned ngroups = gridDim.x / items_per_group;
+    const unsigned items_big = ngroups * (unsigned)MV_BPG * nbig;
+    unsigned group, rb_in_group;
+    int seg;
+    if (blockIdx.x < items_big) {
+        group = blockIdx.x / ((unsigned)MV_BPG * nbig);
+        const unsigned within = blockIdx.x - group * ((unsigned)MV_BPG * nbig);
+        rb_in_group = within / nbig;
+        seg = (int)(within - rb_in_group * nbig);
+    } else {
+        const unsigned idx = blockIdx.x - items_big;
+        group = idx / (unsigned)MV_BPG;
+        rb_in_group = idx - group * (unsigned)MV_BPG;
+        seg = a.nseg - 1;
+    }
     const long long row_base = (long long)group * MV_GROUP + (long long)rb_in_group * R;
     __shared__ double red[NT / 32][R];
     __shared__ unsigned is_last;
