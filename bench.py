@@ -472,7 +472,9 @@ def run_b200(args):
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
-        if tj.get('n') == n and tj.get('n_gpus', 1) == gpus:
+        if tj.get('n') == n and str(gpus) in tj.get('per_gpus', {}):
+            traffic = tj['per_gpus'][str(gpus)]['dram_bytes_per_launch']   # ncu on this GPU count's shard shape
+        elif tj.get('n') == n and tj.get('n_gpus', 1) == gpus:
             traffic = tj.get('dram_bytes_per_launch')
     line = {
         'metric': metric_name(args.config, n, d), 'value': value, 'unit': UNIT, 'n_gpus': gpus, 'steps': args.steps, 'warmup': args.warmup,
