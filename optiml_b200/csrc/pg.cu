@@ -784,6 +784,17 @@ static int launch_persistent(svmb200_pg* pg, const PersistPlan& plan, int64_t ni
         configured[dev] = true;
     }
 #endif
+#ifndef SVMB200_HOST_EMULATION
+    {
+        // a cooperative grid must be co-resident: one CTA of this size per SM, `grid` SMs (fails on a partitioned GPU)
+        int per_sm = 0;
+        SVM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_persistent_kernel, PK_NT, plan.smem));
+        if ((long long)per_sm * ctx->sm_count < plan.grid) {
+            svmb200_set_error("persistent loop: %d CTAs cannot be co-resident", plan.grid);
+            return SVMB200_ERR_STATE;
+        }
+    }
+#endif
     PersistArgs a;
     a.Q = pg->dQ;
     a.ld = pg->ld;
@@ -832,13 +843,16 @@ static int run_many(svmb200_pg* const* pgs, int count, int64_t max_new) {
         if (count == 1 && persistent_plan(p0, budget, &plan)) {
             // one cooperative launch runs the whole budget (it leaves early when the stopping test fires)
             const int64_t k0 = p0->k_next;
-            rc = launch_persistent(p0, plan, budget);
-            if (rc == SVMB200_OK) rc = poll_enqueue(p0, 0);
-            if (rc == SVMB200_OK) rc = poll_wait(p0, 0);
-            SVM_TRY(rc);
-            p0->k_next = p0->finished ? p0->st_host->iter : k0 + budget;
-            p0->last_passes += p0->k_next - k0;
-            budget = 0;
+            if (launch_persistent(p0, plan, budget) == SVMB200_OK) {
+                rc = poll_enqueue(p0, 0);
+                if (rc == SVMB200_OK) rc = poll_wait(p0, 0);
+                SVM_TRY(rc);
+                p0->k_next = p0->finished ? p0->st_host->iter : k0 + budget;
+                p0->last_passes += p0->k_next - k0;
+                budget = 0;
+            } else {
+                cudaGetLastError();  // the launch was refused (nothing ran): the two-kernel loop below takes over
+            }
         }
         while (budget > 0 && !p0->finished && rc == SVMB200_OK) {
             const int64_t nb = budget < BATCH ? budget : BATCH;
