@@ -356,6 +356,17 @@ def test_sass_carries_the_instructions_the_design_claims():
         if 'matvec_seg' in name:
             assert any(o.startswith('LDG.E.NA.128') or o.startswith('LDG.E.128') for o in ops), name
             assert sum(o == 'DFMA' for o in ops) >= 32, name
+        if 'matvec_seg' in name or '_vector_' in name:
+            # programmatic dependent launch: griddepcontrol.wait / launch_dependents at the top of every solver kernel
+            assert 'ACQBULK' in ops[:12] and 'PREEXIT' in ops[:40], name
+    # the persistent small-problem loop: matrix rows from shared memory, a grid barrier on a global atomic, no spills
+    pk = [ops for name, ops in pg.items() if 'pg_persistent_kernel' in name]
+    assert len(pk) == 1
+    assert sum(o.startswith('LDS') for o in pk[0]) >= 56 and any(o.startswith('ATOMG') for o in pk[0])
+    assert not any(o.startswith(('LDL', 'STL')) for o in pk[0])
+    # device-side variance / gather
+    dev = kernels('devmath.o')
+    assert any('pairwise_leaf_kernel' in n for n in dev) and any('gather_rows_kernel' in n for n in dev)
 
 
 def test_load_library_cannot_deadlock_on_a_finalizer():
