@@ -15,8 +15,8 @@
 //               paid two barriers and K3's chain of memory latencies: 13.6 us per iteration, no better than two
 //               launches -- profiles/r2_s4_persistent_kernel_v1_ncu.txt).  The w / product buffers are double-buffered
 //               by iteration parity: a CTA that is already in phase A of k + 1 writes the other buffer.
-// Scope: projected gradient, plain layout without label-sign views, n <= 2048 (four virtual K3 CTAs of <= 512
-// variables) -- BASELINE config C1 and the folds / classes of small data sets; everything else takes the two-kernel loop.
+// Scope: projected gradient, plain layout without label-sign views, n <= 2016 on 148 SMs (14 rows per CTA in 221 KB;
+// at most four virtual K3 CTAs of <= 512 variables) -- BASELINE config C1 and the folds / classes of small data sets; everything else takes the two-kernel loop.
 // Bit-identical to the K2 + K3 loop: a row sum is the thread-strided fma chain, warp butterfly and in-order warp sum of
 // matvec_seg_kernel (one column segment: ld <= 3072); the share tree is K2's group combine; phase B evaluates, for
 // every virtual CTA c of K3's grid, exactly the per-thread accumulations and reduction trees of pg_vector_body (same
@@ -31,7 +31,7 @@ constexpr int PK_RMAX = 16;   // rows per CTA (accumulators per thread)
 constexpr int PK_UMAX = 6;    // 128-bit operand slots per thread: ld <= 2 * PK_NT * PK_UMAX = 3072 columns
 constexpr int PK_SROUNDS = (2 * PK_NT * PK_UMAX / MV_GROUP + PK_NT / 64 - 1) / (PK_NT / 64);  // share rounds: 4 groups each
 
-constexpr int PK_VMAX = 4;                                 // virtual K3 CTAs (512 variables each): n <= 2048
+constexpr int PK_VMAX = 4;                                 // virtual K3 CTAs (512 variables each)
 constexpr int PK_SLOTS = 2 * PK_VMAX;                      // variables per thread: two per virtual CTA
 constexpr int PK_NGRP_MAX = 2 * PK_NT * PK_UMAX / MV_GROUP;  // 48 share groups
 

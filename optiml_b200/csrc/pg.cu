@@ -736,7 +736,7 @@ static int poll_wait(svmb200_pg* pg, int slot) {
 }
 
 // ------------------------------------------------------------------------------------------ persistent small-problem loop
-// A projected-gradient solve on one GPU whose matrix fits the shared memory of the SMs (n <= ~2 050 on a B200) runs as
+// A projected-gradient solve on one GPU whose matrix fits the shared memory of the SMs (n <= 2 016 on a B200) runs as
 // ONE cooperative launch (k_persistent.cuh) instead of two launches per iteration.  Same bits; SVMB200_PERSISTENT=0
 // keeps the two-kernel loop (A/B), SVMB200_PERSISTENT_GRID overrides the grid size (tests on the host emulation).
 constexpr size_t PK_SMEM_MAX = 221 * 1024;  // dynamic part; the kernel's static arrays take ~4 KB of the 227 KB

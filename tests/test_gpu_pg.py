@@ -176,13 +176,13 @@ def test_matvec_matches_numpy_and_is_row_order_independent():
 
 
 def test_persistent_loop_is_bit_identical_to_the_two_kernel_loop(monkeypatch):
-    """csrc/k_persistent.cuh on hardware: problems whose matrix fits the shared memory of the 148 SMs (n <= 2048, plain
-    layout) run as ONE cooperative launch; SVMB200_PERSISTENT_GRID=0 forces the K2 + K3 launch pairs -- same bits, on a run
+    """csrc/k_persistent.cuh on hardware: problems whose matrix fits the shared memory of the 148 SMs (n <= 2016: 14 rows of
+    2016 doubles per CTA; plain layout) run as ONE cooperative launch; SVMB200_PERSISTENT_GRID=0 forces the K2 + K3 launch pairs -- same bits, on a run
     that stops at the iteration limit, one that reaches optimality and the ragged sizes around the limits"""
     from optiml_b200.runtime import default_context
     ctx = default_context()
     rng = np.random.default_rng(8)
-    for n, iters in ((2000, 300), (2048, 40), (1531, 60), (257, 400), (9, 50)):
+    for n, iters in ((2000, 300), (2016, 40), (1531, 60), (257, 400), (9, 50)):
         G = rng.standard_normal((n + 5, n))
         Q, q, ub = G.T @ G / n, rng.standard_normal(n), rng.uniform(0.5, 2., n)
         runs = []
@@ -199,8 +199,8 @@ def test_persistent_loop_is_bit_identical_to_the_two_kernel_loop(monkeypatch):
         assert persistent[4:6] == two_kernel[4:6]
         for a, b in zip(two_kernel[:4], persistent[:4]):
             assert np.array_equal(a, b)
-    # just beyond the scope (n = 2049: five virtual vector CTAs): the two-kernel loop, silently
-    n = 2049
+    # just beyond the scope (n = 2032: 14 rows no longer fit 221 KB): the two-kernel loop, silently
+    n = 2032
     G = rng.standard_normal((n + 5, n))
     before = ctx.launch_count()
     solve(G.T @ G / n, rng.standard_normal(n), np.ones(n), max_iter=20)
