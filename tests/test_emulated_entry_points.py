@@ -89,3 +89,26 @@ def test_integration_md_stubs_run_against_the_emulated_library():
     x, g, hist, it, status = ns['projected_gradient'](Q, -np.ones(90), np.ones(90), max_iter=25)
     want = O.projected_gradient(Q, -np.ones(90), np.ones(90), max_iter=25)
     assert it == want.iter and status == want.status and np.abs(x - want.x).max() <= 1e-10
+
+
+def test_reference_arm_runs_the_unmodified_reference_on_the_same_config(capsys, monkeypatch):
+    """`bench.py --impl reference`: the UNMODIFIED reference (baseline/_ref, or the container's checkout) on the full
+    workload -- same `config` object as the GPU arm, `kind: "reference"`; when the host cannot hold the reference's
+    matrices it says so and falls back to the NumPy port on a row sample (`kind: "port"`)."""
+    import bench
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip('no reference copy (baseline/_ref or /root/reference)')
+    monkeypatch.setattr(sys, 'argv', ['bench.py', '--impl', 'reference', '--n', '700', '--max-iter', '1000', '--steps', '2', '--warmup', '1'])
+    bench.main()
+    line = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith('{')][-1])
+    assert line['impl'] == 'reference' and line['cpu_baseline']['kind'] == 'reference' and line['value'] > 0
+    assert 'UNMODIFIED reference' in line['cpu_baseline']['sample'] and line['cpu_baseline']['parts']['iters'] == 8
+    assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert line['higher_is_better'] is True and line['unit'] == bench.UNIT
+    # the GPU arm prints the identical config object for the same workload
+    assert line['config'] == bench.bench_config('C4', 700, 128, 1000, 1)
+    # not enough host memory for the reference's n x n matrices: labelled fallback to the port
+    monkeypatch.setattr(bench, 'available_host_bytes', lambda: 1 << 20)
+    r = bench.reference_measure('C4', 700, 1000, steps=1)
+    assert r['kind'] == 'port' and r['sample'].startswith('FALLBACK (host memory') and r['value'] > 0
