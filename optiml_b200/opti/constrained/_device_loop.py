@@ -148,13 +148,26 @@ class DeviceLoopMixin:
         f_hist, second = np.empty(self.iter + 1), np.empty(self.iter + 1)
         N.call('svmb200_pg_history', h, N.ptr(f_hist), N.ptr(second), C.byref(cnt))
         self.f_hist, self.ng_hist = f_hist[:cnt.value], second[:cnt.value]
-        if self._callback is not None:
+        if self._callback is not None and not self._extend_owner_history(self.f_hist):
             # replay the history-only callback: one call per callback point, in order
             final_f, final_iter = self.f_x, self.iter
             for k, fk in enumerate(self.f_hist):
                 self.iter, self.f_x = k, float(fk)
                 self._callback(self, *self.callback_args)
             self.iter, self.f_x = final_iter, final_f
+
+    def _extend_owner_history(self, values):
+        """The estimators' own callback (ml/svm/_base.py:289-293) appends one number per callback point to
+        ``train_loss_history``; when that is the callback, the 1001 Python calls of a replay are one ``list.extend``."""
+        cb = self._callback
+        owner = getattr(cb, '__self__', None)
+        if owner is None or not getattr(getattr(cb, '__func__', None), '_svmb200_history_only', False) or self.callback_args:
+            return False
+        hist = getattr(owner, 'train_loss_history', None)
+        if not isinstance(hist, list):
+            return False
+        hist.extend(np.asarray(values, dtype=np.float64).tolist())
+        return True
 
     def _minimize_stepwise(self, h, n):
         # generic callbacks / verbose / ndim <= 3 histories: synchronise at every callback point

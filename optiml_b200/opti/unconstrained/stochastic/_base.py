@@ -156,7 +156,7 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
         N.call('svmb200_pg_history', h, N.ptr(f_hist), N.ptr(pf_hist), C.byref(cnt))
         self.f_hist, self.pf_hist = f_hist[:cnt.value], pf_hist[:cnt.value]
         self.dgap = abs((self.primal_f_x - self.f_x) / max(abs(self.primal_f_x), 1))
-        if self._callback is not None:
+        if self._callback is not None and not self._extend_owner_history(self.pf_hist):   # the primal cost (ml/svm/_base.py:291)
             final = (self.iter, self.f_x, self.primal_f_x)
             for k, (fk, pk) in enumerate(zip(self.f_hist, self.pf_hist)):
                 self.iter, self.f_x, self.primal_f_x = k, float(fk), float(pk)
