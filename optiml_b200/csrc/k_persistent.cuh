@@ -27,7 +27,7 @@
 #include "k3_vector.cuh"
 
 constexpr int PK_NT = 256;
-constexpr int PK_RMAX = 16;   // rows per CTA (accumulators per thread)
+constexpr int PK_RMAX = 14;   // rows per CTA (accumulators per thread): ceil(2016 / 148)
 constexpr int PK_UMAX = 6;    // 128-bit operand slots per thread: ld <= 2 * PK_NT * PK_UMAX = 3072 columns
 constexpr int PK_SROUNDS = (2 * PK_NT * PK_UMAX / MV_GROUP + PK_NT / 64 - 1) / (PK_NT / 64);  // share rounds: 4 groups each
 
@@ -166,6 +166,10 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
         double* wk = a.wbuf + (size_t)(k & 1) * a.ld;
         double* pk = a.prod + (size_t)(k & 1) * a.ld;
         // ================= phase A: w = Q u for my rows (matvec_seg_kernel's arithmetic, one column segment) =================
+        // The GPU issues a warp's instructions in order: independent chains only overlap if they are interleaved in the
+        // PROGRAM.  Per-row / per-slot branches keep the compiler from doing that (v3 of this kernel spent 2.4 k cycles of
+        // an iteration in sixteen serialised butterflies), so the loops below are branch-free: rows beyond the CTA's own
+        // re-read its last row and are discarded, columns beyond the matrix multiply by a zero operand.
         double u_row = 0.0;
         if (myrows > 0) {
             double2 uv[PK_UMAX];
@@ -177,6 +181,10 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
                 uv[m] = (m < mcount && c < nvec) ? u2[c] : double2{0.0, 0.0};
             }
             if (tid < myrows) u_row = u_priv[r0 + tid];   // for the row's term of u'w below: in flight with the rest
+            const double2* q2 = reinterpret_cast<const double2*>(qs);
+            int roff[PK_RMAX];
+#pragma unroll
+            for (int r = 0; r < PK_RMAX; ++r) roff[r] = (r < myrows ? r : myrows - 1) * nvec;
             double acc[PK_RMAX];
 #pragma unroll
             for (int r = 0; r < PK_RMAX; ++r) acc[r] = 0.0;
@@ -184,26 +192,33 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
             for (int m = 0; m < PK_UMAX; ++m) {
                 if (m < mcount) {  // uniform
                     const int c = tid + m * PK_NT;
-                    const bool on = c < nvec;
+                    const int cc = c < nvec ? c : 0;   // (uv[m] is zero there)
 #pragma unroll
-                    for (int r = 0; r < PK_RMAX; ++r) {
-                        if (r < myrows && on) {
-                            const double2 qv = reinterpret_cast<const double2*>(qs + (size_t)r * a.ld)[c];
-                            acc[r] = fma(qv.x, uv[m].x, acc[r]);
-                            acc[r] = fma(qv.y, uv[m].y, acc[r]);
+                    for (int h = 0; h < 2; ++h) {
+                        double2 qv[PK_RMAX / 2];
+#pragma unroll
+                        for (int r = 0; r < PK_RMAX / 2; ++r) qv[r] = q2[roff[h * (PK_RMAX / 2) + r] + cc];
+#pragma unroll
+                        for (int r = 0; r < PK_RMAX / 2; ++r) {
+                            double& ar = acc[h * (PK_RMAX / 2) + r];
+                            ar = fma(qv[r].x, uv[m].x, ar);
+                            ar = fma(qv[r].y, uv[m].y, ar);
                         }
                     }
                 }
             }
-            // warp butterfly, then fixed-order sum over warps
+            // warp butterfly, level by level over all rows, then fixed-order sum over warps
 #pragma unroll
-            for (int r = 0; r < PK_RMAX; ++r) {
-                if (r < myrows) {  // uniform over the CTA
-                    double vv = acc[r];
+            for (int o = 16; o > 0; o >>= 1) {
+                double other[PK_RMAX];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, o);
-                    if (lane == 0) red[wid][r] = vv;
-                }
+                for (int r = 0; r < PK_RMAX; ++r) other[r] = __shfl_xor_sync(0xffffffffu, acc[r], o);
+#pragma unroll
+                for (int r = 0; r < PK_RMAX; ++r) acc[r] += other[r];
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < PK_RMAX; ++r) red[wid][r] = acc[r];
             }
         }
         __syncthreads();
@@ -233,13 +248,16 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
                 dv[r] = (grp < ngrp && rr < n) ? __ldcg(pk + rr) : 0.0;
             }
 #pragma unroll
-            for (int r = 0; r < PK_SROUNDS; ++r) {
-                if ((unsigned)r * (PK_NT / 64) < ngrp) {  // uniform
-                    double vv = dv[r];
+            for (int o = 16; o > 0; o >>= 1) {   // level by level over all rounds (see phase A)
+                double other[PK_SROUNDS];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) vv = __dadd_rn(vv, __shfl_xor_sync(0xffffffffu, vv, o));
-                    if (lane == 0) share_red[r][wid] = vv;
-                }
+                for (int r = 0; r < PK_SROUNDS; ++r) other[r] = __shfl_xor_sync(0xffffffffu, dv[r], o);
+#pragma unroll
+                for (int r = 0; r < PK_SROUNDS; ++r) dv[r] = __dadd_rn(dv[r], other[r]);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < PK_SROUNDS; ++r) share_red[r][wid] = dv[r];
             }
             __syncthreads();
             if ((unsigned)tid < ngrp) {
@@ -304,34 +322,47 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
         }
         // ---- update, new direction and the partials of the next state (pg_step_elem, plain layout, no sign view), the
         // two variables of virtual CTA c accumulated in K3's loop order, then the warp halves of its block reduce
+        Quad accq[PK_VMAX];
 #pragma unroll
         for (int c = 0; c < PK_VMAX; ++c) {
-            Quad acc;
-            acc.a = acc.b = acc.c = 0.0;
-            acc.m = INFINITY;
+            accq[c].a = accq[c].b = accq[c].c = 0.0;
+            accq[c].m = INFINITY;
+        }
+        double dnew[PK_SLOTS];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int sl = 2 * c + e;
-                if (slot_on[sl]) {
-                    const double x = axpy_rn(t, ds[sl], xs[sl]);
-                    const double g = axpy_rn(t, wv[sl], gs[sl]);
-                    const double dn = project_dir(g, x, lbs[sl], ubs[sl]);
-                    tail_accumulate(acc, dn, x, g, qv_[sl], lbs[sl], ubs[sl]);
-                    xs[sl] = x;
-                    gs[sl] = g;
-                    ds[sl] = dn;
-                    u_priv[slot_j[sl]] = dn;
-                }
+        for (int sl = 0; sl < PK_SLOTS; ++sl) {   // branch-free: idle slots hold zeros, add +0.0 to the sums and skip the min
+            const double x = axpy_rn(t, ds[sl], xs[sl]);
+            const double g = axpy_rn(t, wv[sl], gs[sl]);
+            const double dn = project_dir(g, x, lbs[sl], ubs[sl]);
+            const double mprev = accq[sl >> 1].m;
+            tail_accumulate(accq[sl >> 1], dn, x, g, qv_[sl], lbs[sl], ubs[sl]);
+            accq[sl >> 1].m = slot_on[sl] ? accq[sl >> 1].m : mprev;
+            xs[sl] = x;
+            gs[sl] = g;
+            ds[sl] = dn;
+            dnew[sl] = dn;
+        }
+#pragma unroll
+        for (int sl = 0; sl < PK_SLOTS; ++sl)
+            if (slot_on[sl]) u_priv[slot_j[sl]] = dnew[sl];
+        // the warp halves of K3's block reduce, all virtual CTAs level by level
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < PK_VMAX; ++c) {
+                const double oa = __shfl_xor_sync(0xffffffffu, accq[c].a, o), ob = __shfl_xor_sync(0xffffffffu, accq[c].b, o);
+                const double om = __shfl_xor_sync(0xffffffffu, accq[c].m, o);
+                accq[c].a = __dadd_rn(accq[c].a, oa);
+                accq[c].b = __dadd_rn(accq[c].b, ob);
+                accq[c].m = fmin(accq[c].m, om);
             }
-            if (c < nctas) {  // uniform
-                acc.a = warp_sum(acc.a);
-                acc.b = warp_sum(acc.b);
-                acc.m = warp_min(acc.m);
-                if (lane == 0) {
-                    smq[c][wid][0] = acc.a;
-                    smq[c][wid][1] = acc.b;
-                    smq[c][wid][3] = acc.m;
-                }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < PK_VMAX; ++c) {
+                smq[c][wid][0] = accq[c].a;
+                smq[c][wid][1] = accq[c].b;
+                smq[c][wid][3] = accq[c].m;
             }
         }
         __syncthreads();

@@ -386,8 +386,8 @@ def test_gram_tile_bands_cover_every_tile_once():
         dX.release()
 
 
-@pytest.mark.parametrize('n,grid,layout,order', [(70, 5, 'plain', 0), (600, 40, 'plain', 2), (1100, 70, 'plain', 1), (150, 11, 'svr', 1),
-                                                 (200, 13, 'plain', 0)])
+@pytest.mark.parametrize('n,grid,layout,order', [(70, 5, 'plain', 0), (600, 43, 'plain', 2), (1100, 79, 'plain', 1), (150, 11, 'svr', 1),
+                                                 (200, 15, 'plain', 0), (45, 4, 'plain', 0)])
 def test_persistent_loop_is_bit_identical_to_the_two_kernel_loop(monkeypatch, n, grid, layout, order):
     """k_persistent.cuh: the whole projected-gradient solve as ONE cooperative launch with the matrix in shared memory
     (what BASELINE config C1 runs on a B200) against the K2 + K3 launch pairs -- same iterates, histories, stopping
