@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(os.path.dirname(HERE), '_lib')
 LIB = os.path.join(LIB_DIR, 'libsvmb200.so')
 SOURCES = ['api.cu', 'pg.cu', 'gram.cu', 'comm.cu', 'hostmath.cu', 'devmath.cu']
-HEADERS = ['common.cuh', 'al_math.cuh', 'k2_matvec.cuh', 'k3_vector.cuh', os.path.join('..', '..', 'include', 'svmb200.h')]
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith('.cuh')) + [os.path.join('..', '..', 'include', 'svmb200.h')]  # every header
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall', '--fmad=true',
               '-Xcompiler', '-ffp-contract=off']  # host arithmetic (start point, variance) rounds like NumPy

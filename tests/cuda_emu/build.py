@@ -65,7 +65,7 @@ def build(force=False, defines=()):
     defines = tuple(defines)
     suffix = ''.join('_' + d.replace('SVMB200_', '').replace('=', '') for d in defines)
     lib = os.path.join(BUILD, f'libsvmb200_emu{suffix}.so')
-    common = [os.path.join(CSRC, h) for h in ('common.cuh', 'al_math.cuh', 'k2_matvec.cuh', 'k3_vector.cuh')] + \
+    common = [os.path.join(CSRC, h) for h in sorted(os.listdir(CSRC)) if h.endswith('.cuh')] + \
              [os.path.join(ROOT, 'include', 'svmb200.h'),
               os.path.join(HERE, 'include', 'cuda_runtime.h'), os.path.join(HERE, 'include', 'cudaTypedefs.h'),
               os.path.abspath(__file__)]
