@@ -82,6 +82,7 @@ extern "C" int svmb200_ctx_destroy(svmb200_ctx* ctx) {
         if (ctx->mp_buf) cudaFree(ctx->mp_buf);
         if (ctx->batch_buf) cudaFree(ctx->batch_buf);
         if (ctx->idx_buf) cudaFree(ctx->idx_buf);
+        if (ctx->gbar) cudaFree(ctx->gbar);
         if (ctx->persist_buf) cudaFree(ctx->persist_buf);
         svm_release_variance_cache(ctx);
         cudaStreamDestroy(ctx->stream);

@@ -57,8 +57,9 @@ struct svmb200_ctx {
     size_t batch_bytes = 0;
     // device-side X.var() (devmath.cu): leaf table of NumPy's pairwise tree, leaf sums, pinned staging -- cached per size
     void* var_cache = nullptr;
-    // persistent small-problem kernel (k_persistent.cuh): tagged w / product double buffers, fault flag, the CTAs' private u
-    void* persist_buf = nullptr;
+    // grid barrier of the persistent small-problem kernel (k_persistent.cuh): 256 zeroed bytes
+    unsigned* gbar = nullptr;
+    void* persist_buf = nullptr;   // w / product double buffers and the CTAs' private iterates
     size_t persist_bytes = 0;
     // row indices of a device gather (support vectors)
     void* idx_buf = nullptr;

@@ -4,17 +4,17 @@
 // BASELINE config C1 (n = 2 000: a 32 MB matrix) is launch-bound on the two-kernel loop: 14 us per iteration for ~1 us of
 // memory traffic ("hard parts").  148 SMs x 227 KB of shared memory hold 33 MB, so here ONE
 // cooperative kernel keeps the whole matrix on chip -- CTA b owns rows [b r, (b+1) r) and loads them once -- and runs all
-// iterations of the solve WITHOUT any grid-wide barrier:
-//     phase A   w = Q u for the CTA's rows, from shared memory, published as self-validating tagged entries (the format
-//               of the multi-GPU exchange) in the buffer of this iteration's parity; per-row products u_r w_r likewise
+// iterations of the solve with ONE grid barrier per iteration:
+//     phase A   w = Q u for the CTA's rows, from shared memory, into the w buffer of this iteration's parity;
+//               per-row products u_r w_r for the shares of u'w
+//     grid barrier
 //     phase B   EVERY CTA runs the whole O(n) vector phase redundantly, with the iterate IN REGISTERS: a thread owns the
 //               same <= 8 variables for the whole solve (x, g, d, q, lb, ub: 48 doubles), per iteration it reads their
 //               w and writes the new direction to the CTA's private u.  Nothing has to travel back before the next
 //               phase A, so there is no second barrier (a first version ran phase B on the nctas CTAs of K3's grid and
 //               paid two barriers and K3's chain of memory latencies: 13.6 us per iteration, no better than two
-//               launches -- profiles/r2_s4_persistent_kernel_v1_ncu.txt).  A reader spins on the tags of exactly the
-//               entries it needs, so there is no barrier at all; the buffers are double-buffered by iteration parity: a
-//               CTA cannot publish w of k + 2 before every CTA has published w of k + 1, i.e. has finished reading w of k.
+//               launches -- profiles/r2_s4_persistent_kernel_v1_ncu.txt).  The w / product buffers are double-buffered
+//               by iteration parity: a CTA that is already in phase A of k + 1 writes the other buffer.
 // Scope: projected gradient, plain layout without label-sign views, n <= 2016 on 148 SMs (14 rows per CTA in 221 KB;
 // at most four virtual K3 CTAs of <= 512 variables) -- BASELINE config C1 and the folds / classes of small data sets; everything else takes the two-kernel loop.
 // Bit-identical to the K2 + K3 loop: a row sum is the thread-strided fma chain, warp butterfly and in-order warp sum of
@@ -39,14 +39,62 @@ struct PersistArgs {
     const double* Q;        // n x ld, all rows on this GPU
     long long ld, n;
     int rows_per_cta;
-    ulonglong2* wbuf;       // 2 x ld tagged entries: w = Q u, double-buffered by iteration parity
-    ulonglong2* prod;       // 2 x ld tagged entries: per-row products u_r * w_r, likewise
-    int* fault;             // raised by a reader whose wait for an entry expired (never, unless a CTA died)
+    double* wbuf;           // 2 x ld : w = Q u, double-buffered by iteration parity
+    double* prod;           // 2 x ld : per-row products u_r * w_r, likewise
     double* priv;           // (grid - 1) private copies of u (ld each) for CTAs 1..grid-1
+    unsigned* gbar;         // grid barrier: [0] arrivals, [32] generation (separate 128-byte lines), zero between launches
     VecArgs v;              // the solver's own arrays and state (CTA 0 works on them)
     long long k0;           // first iteration of this launch
     long long niter;        // iterations to run unless the stopping test fires first
 };
+
+#ifndef SVMB200_HOST_EMULATION
+__device__ __forceinline__ unsigned pk_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pk_st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned pk_arrive(unsigned* p) {
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+    return old;
+}
+__device__ __forceinline__ void pk_backoff(unsigned long long) {}
+__device__ __forceinline__ double2 pk_ld_cg_f64x2(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    return r;
+}
+#else
+__device__ __forceinline__ unsigned pk_ld_acquire(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void pk_st_release(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned pk_arrive(unsigned* p) { return __atomic_fetch_add(p, 1u, __ATOMIC_ACQ_REL); }
+__device__ __forceinline__ void pk_backoff(unsigned long long spins) { (void)emu::spin_wait(spins); }
+__device__ __forceinline__ double2 pk_ld_cg_f64x2(const double2* p) { return *p; }
+#endif
+
+// all CTAs of the (cooperatively launched, hence co-resident) grid; sense by generation, the last arriver re-arms.
+// The arrival is an acq_rel RMW at gpu scope (cumulative over the CTA's writes through the bar.sync before it), the
+// waiters poll with relaxed loads and acquire once.
+__device__ __forceinline__ void pk_grid_barrier(unsigned* bar, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* count = bar;
+        unsigned* gen = bar + 32;
+        const unsigned my_gen = *reinterpret_cast<volatile unsigned*>(gen);
+        if (pk_arrive(count) == nblocks - 1) {
+            *reinterpret_cast<volatile unsigned*>(count) = 0u;
+            pk_st_release(gen, my_gen + 1u);
+        } else {
+            for (unsigned long long spins = 0; *reinterpret_cast<volatile unsigned*>(gen) == my_gen; ++spins) pk_backoff(spins);
+            (void)pk_ld_acquire(gen);
+        }
+    }
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistArgs a) {
 #ifndef SVMB200_HOST_EMULATION
@@ -115,9 +163,8 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
 
     long long k = a.k0;
     for (long long it = 0; it < a.niter; ++it, ++k) {
-        ulonglong2* wk = a.wbuf + (size_t)(k & 1) * a.ld;
-        ulonglong2* pk = a.prod + (size_t)(k & 1) * a.ld;
-        const unsigned tag = (unsigned)(k + 1);   // never 0; the buffers are cleared before every launch
+        double* wk = a.wbuf + (size_t)(k & 1) * a.ld;
+        double* pk = a.prod + (size_t)(k & 1) * a.ld;
         // ================= phase A: w = Q u for my rows (matvec_seg_kernel's arithmetic, one column segment) =================
         // The GPU issues a warp's instructions in order: independent chains only overlap if they are interleaved in the
         // PROGRAM.  Per-row / per-slot branches keep the compiler from doing that (v3 of this kernel spent 2.4 k cycles of
@@ -182,17 +229,15 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
             double w = 0.0;
             w += p8;                                     // the segment combine of K2 with its single segment
             const long long rr = r0 + tid;
-            ll_store(wk + rr, w, tag);
-            ll_store(pk + rr, __dmul_rn(u_row, w), tag);   // term of this row in its group's share of u'w
+            wk[rr] = w;
+            pk[rr] = __dmul_rn(u_row, w);                // term of this row in its group's share of u'w
         }
-        // NO grid barrier: w and the products travel as self-validating tagged entries (the 16-byte {lo32 | tag, hi32 | tag}
-        // format of the multi-GPU exchange, k2_matvec.cuh); a reader spins on exactly the entries it needs.  A barrier cost
-        // ~3 k of the 18 k cycles of an iteration (arrive + release + poll, three L2 round trips), the tagged load one.
+        pk_grid_barrier(a.gbar, gridDim.x);
 
         // ================= phase B (every CTA, on its own copy of the iterate) =================
         double wv[PK_SLOTS];
 #pragma unroll
-        for (int sl = 0; sl < PK_SLOTS; ++sl) wv[sl] = slot_on[sl] ? ll_load(wk + slot_j[sl], tag, a.fault) : 0.0;
+        for (int sl = 0; sl < PK_SLOTS; ++sl) wv[sl] = slot_on[sl] ? __ldcg(wk + slot_j[sl]) : 0.0;  // in flight under the shares
         // ---- shares of u'w: warps 2p, 2p+1 take groups p, p + 4, ...; butterfly inside each warp, then warp 2p + warp 2p+1
         {
             double dv[PK_SROUNDS];
@@ -200,7 +245,7 @@ __global__ void __launch_bounds__(PK_NT, 1) pg_persistent_kernel(const PersistAr
             for (int r = 0; r < PK_SROUNDS; ++r) {
                 const unsigned grp = (unsigned)r * (PK_NT / 64) + (unsigned)(wid >> 1);
                 const long long rr = (long long)grp * MV_GROUP + (wid & 1) * 32 + lane;
-                dv[r] = (grp < ngrp && rr < n) ? ll_load(pk + rr, tag, a.fault) : 0.0;
+                dv[r] = (grp < ngrp && rr < n) ? __ldcg(pk + rr) : 0.0;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {   // level by level over all rounds (see phase A)

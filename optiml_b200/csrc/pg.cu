@@ -769,12 +769,13 @@ static bool persistent_plan(const svmb200_pg* pg, int64_t budget, PersistPlan* p
 
 static int launch_persistent(svmb200_pg* pg, const PersistPlan& plan, int64_t niter) {
     svmb200_ctx* ctx = pg->ctx;
-    // scratch: two w buffers and two product buffers of tagged 16-byte entries (cleared: tags restart with every launch),
-    // a fault flag, grid - 1 private copies of u (ld doubles each)
-    const size_t entry_bytes = 4 * (size_t)pg->ld * sizeof(ulonglong2);
-    const size_t bytes = entry_bytes + 256 + (size_t)(plan.grid - 1) * (size_t)pg->ld * sizeof(double);
-    SVM_TRY(svm_scratch_reserve(ctx, &ctx->persist_buf, &ctx->persist_bytes, bytes));
-    SVM_CUDA(cudaMemsetAsync(ctx->persist_buf, 0, entry_bytes + 256, ctx->stream));
+    // scratch: two w buffers, two product buffers, grid - 1 private copies of u (ld each)
+    const size_t doubles = 4 * (size_t)pg->ld + (size_t)(plan.grid - 1) * (size_t)pg->ld;
+    SVM_TRY(svm_scratch_reserve(ctx, &ctx->persist_buf, &ctx->persist_bytes, doubles * sizeof(double)));
+    if (!ctx->gbar) {
+        SVM_CUDA(cudaMalloc(&ctx->gbar, 256));
+        SVM_CUDA(cudaMemsetAsync(ctx->gbar, 0, 256, ctx->stream));
+    }
 #ifndef SVMB200_HOST_EMULATION
     static bool configured[64] = {};  // per-device opt-in to the dynamic shared memory size
     const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
@@ -799,10 +800,10 @@ static int launch_persistent(svmb200_pg* pg, const PersistPlan& plan, int64_t ni
     a.ld = pg->ld;
     a.n = pg->n;
     a.rows_per_cta = plan.rows_per_cta;
-    a.wbuf = static_cast<ulonglong2*>(ctx->persist_buf);
+    a.wbuf = static_cast<double*>(ctx->persist_buf);
     a.prod = a.wbuf + 2 * pg->ld;
-    a.fault = reinterpret_cast<int*>(static_cast<unsigned char*>(ctx->persist_buf) + entry_bytes);
-    a.priv = reinterpret_cast<double*>(static_cast<unsigned char*>(ctx->persist_buf) + entry_bytes + 256);
+    a.priv = a.wbuf + 4 * pg->ld;
+    a.gbar = ctx->gbar;
     a.v = make_vec_args(pg);
     a.k0 = pg->k_next;
     a.niter = niter;
@@ -846,15 +847,6 @@ static int run_many(svmb200_pg* const* pgs, int count, int64_t max_new) {
                 rc = poll_enqueue(p0, 0);
                 if (rc == SVMB200_OK) rc = poll_wait(p0, 0);
                 SVM_TRY(rc);
-                {
-                    int fault = 0;  // a CTA whose wait for a tagged entry expired (k_persistent.cuh): never, unless one died
-                    const size_t off = 4 * (size_t)p0->ld * sizeof(ulonglong2);
-                    SVM_CUDA(cudaMemcpy(&fault, static_cast<unsigned char*>(p0->ctx->persist_buf) + off, sizeof(int), cudaMemcpyDeviceToHost));
-                    if (fault) {
-                        svmb200_set_error("persistent loop: a CTA stopped publishing its rows");
-                        return SVMB200_ERR_STATE;
-                    }
-                }
                 p0->k_next = p0->finished ? p0->st_host->iter : k0 + budget;
                 p0->last_passes += p0->k_next - k0;
                 budget = 0;

@@ -269,20 +269,11 @@ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
 }
 
 bool spin_wait(unsigned long long spins) {
-    // NB one clock per host thread, not per fiber: good enough for a 20 s bound
     static thread_local std::chrono::steady_clock::time_point t0;
     if (spins == 0) t0 = std::chrono::steady_clock::now();
     if ((spins & 63) == 63) {
         sched_yield();
         if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) return true;
-    }
-    // What the waiter polls may be produced by ANOTHER THREAD OF THE SAME BLOCK that has not run yet (fibers run until
-    // they block; on the GPU its warp simply runs concurrently): let the block's other fibers run.  The wait counts as
-    // progress -- the producer may live in another block / rank (another host thread), which the block-local deadlock
-    // detector cannot see; a real deadlock ends in the 20 s bound above.
-    if (g_run != nullptr && g_run->current >= 0) {
-        g_run->fibers[g_run->current].progressed = true;
-        yield_to_scheduler();
     }
     return false;
 }
