@@ -2,6 +2,7 @@
 // segmentation and a TMA-bulk (cp.async.bulk + mbarrier) variant on a 20 GB and a 2.5 GB matrix.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o mv_sweep mv_sweep.cu
 #include <cuda_runtime.h>
+#include <string.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -298,6 +299,29 @@ int main(int argc, char** argv) {
     // reference points: device copy bandwidth (read+write) on 8 GB
     { double* b; CK(cudaMalloc(&b, (size_t)4e9)); timeit("cudaMemcpy D2D 4 GB (r+w bytes)", 8e9, [&]() { cudaMemcpyAsync(b, Q, (size_t)4e9, cudaMemcpyDeviceToDevice); });
       timeit("copy kernel 4 GB (r+w bytes)", 8e9, [&]() { copyk<<<148 * 16, 512>>>((const double2*)Q, (double2*)b, (size_t)4e9 / 16); }); CK(cudaFree(b)); }
+    if (argc > 1 && strcmp(argv[1], "shard") == 0) {
+        // round 2: the pass over a 1/8 row shard (6272 x 50000 = 2.5 GB) is the least efficient piece of the 8-GPU loop
+        // (6.6-6.8 TB/s against 7.0-7.2 on the full matrix): smaller work items for a shorter ramp and tail?
+        const long long nrows = 6272;
+        const char* tag = "[shard 6272]";
+        g_sustain = 2000;
+        run_ldg<4, 256, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<2, 256, 8, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<2, 256, 4, 16, 0, 0, 4>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<2, 256, 4, 16, 0, 0, 6>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<4, 256, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
+        run_ldg<2, 256, 8, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 4096);
+        run_ldg<4, 128, 4, 16, 0, 0, 6>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<2, 128, 8, 16, 0, 0, 6>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<1, 256, 16, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        run_ldg<4, 256, 4, 16, 0, 0, 3>(tag, Q, ld, nrows, u, w, wpart, cnt, 8192);
+        const long long full = 50000;
+        g_sustain = 300;
+        run_ldg<4, 256, 4, 16, 0, 0, 3>("[full 50000]", Q, ld, full, u, w, wpart, cnt, 8192);
+        run_ldg<2, 256, 8, 16, 0, 0, 3>("[full 50000]", Q, ld, full, u, w, wpart, cnt, 8192);
+        run_ldg<2, 256, 4, 16, 0, 0, 4>("[full 50000]", Q, ld, full, u, w, wpart, cnt, 8192);
+        return 0;
+    }
     for (int pass = 0; pass < 2; ++pass) {
         const long long nrows = pass == 0 ? 50000 : 6250;
         const char* tag = pass == 0 ? "[20GB]" : "[2.5GB]";
