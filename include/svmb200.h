@@ -127,6 +127,18 @@ int64_t svmb200_padded_ld(int64_t ncols);
  * Replaces the three products of projected_gradient.py:82,121 (opti/_base.py:282,291).          */
 int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld, const double* du, double* dw);
 
+/* ---- K2s: the same product from the UPPER TRIANGLE of a symmetric matrix (opt-in) -----------
+ * dw[i] = sum_j dQ[i][j] * du[j] for a symmetric n x n matrix, streaming 4 n^2 bytes instead of 8 n^2: every element
+ * above the diagonal blocks is used for its row and, transposed, for its column.  The lower triangle is never read.
+ * Replaces the same `Q.dot(d)` (projected_gradient.py:113) for the Hessians of the SVM dual, which are symmetric by
+ * construction (ml/svm/_base.py:554, 1098-1099).  Reproducible run to run; NOT bit-identical to svmb200_matvec
+ * (another summation order), which is why solvers use it only on request:
+ *   svmb200_ctx_set_symmetric(ctx, 1)  (initial value: environment variable SVMB200_SYMMETRIC)  makes every solver
+ *   created afterwards that holds the WHOLE matrix on one rank take its products this way; sharded solvers and
+ *   lockstep batches keep the full pass.  svmb200_pg_is_symmetric reports what a solver does.                      */
+int svmb200_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, const double* du, double* dw);
+int svmb200_ctx_set_symmetric(svmb200_ctx* ctx, int on);
+
 /* ---- K2+K3(+K4): projected-gradient solve of the box-constrained QP -------------------------
  * Replaces  BoxConstrainedQuadraticOptimizer.__init__ (opti/constrained/_base.py:59-73) +
  * ProjectedGradient.minimize (opti/constrained/projected_gradient.py:76-143).
@@ -164,6 +176,7 @@ int svmb200_pg_stats(svmb200_pg* pg, float* ms, int64_t* passes, float* matvec_m
 int svmb200_pg_set_profile(svmb200_pg* pg, int on);
 int svmb200_pg_stats_ex(svmb200_pg* pg, float* matvec_ms, float* comm_ms, float* vector_ms);
 int svmb200_pg_profile_samples(svmb200_pg* pg, int64_t* samples);
+int svmb200_pg_is_symmetric(svmb200_pg* pg, int* on);   /* 1: products from the upper triangle (K2s above) */
 int svmb200_pg_device_x(svmb200_pg* pg, double** dx); /* device pointer of the iterate (nvars)     */
 int svmb200_pg_destroy(svmb200_pg* pg);
 

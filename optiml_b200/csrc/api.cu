@@ -1,5 +1,6 @@
 // Context, memory and host-pointer entry points of the svmb200 C ABI.
 #include "common.cuh"
+#include <stdlib.h>
 #include <algorithm>
 
 static thread_local char g_err[1024] = "";
@@ -55,7 +56,18 @@ extern "C" int svmb200_ctx_create(int device, svmb200_ctx** out) {
         delete ctx;
         return SVMB200_ERR_CUDA;
     }
+    if (const char* ev = getenv("SVMB200_SYMMETRIC")) ctx->symmetric = atoi(ev) != 0;
     *out = ctx;
+    return SVMB200_OK;
+}
+
+// Opt-in: solvers created on this context from now on read only the upper triangle of their matrix (half the HBM bytes per
+// iteration; K2s, k2_symv.cuh).  The caller asserts symmetry -- every Hessian of the SVM dual is symmetric
+// (optiml/ml/svm/_base.py:554, 1098-1099).  Applies to solvers that hold the whole matrix on one rank; sharded solvers and
+// lockstep batches keep the full pass.
+extern "C" int svmb200_ctx_set_symmetric(svmb200_ctx* ctx, int on) {
+    SVM_CHECK_ARG(ctx != nullptr, "null context");
+    ctx->symmetric = on != 0;
     return SVMB200_OK;
 }
 

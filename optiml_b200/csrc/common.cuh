@@ -61,6 +61,9 @@ struct svmb200_ctx {
     unsigned* gbar = nullptr;
     void* persist_buf = nullptr;   // w / product double buffers and the CTAs' private iterates
     size_t persist_bytes = 0;
+    // opt-in: solvers created on this context take their products from the upper triangle of the (symmetric) matrix
+    // (K2s, k2_symv.cuh); svmb200_ctx_set_symmetric, initial value from SVMB200_SYMMETRIC
+    bool symmetric = false;
     // row indices of a device gather (support vectors)
     void* idx_buf = nullptr;
     size_t idx_bytes = 0;

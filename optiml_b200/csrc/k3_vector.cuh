@@ -147,32 +147,47 @@ struct PGElem {
     double x2, q2, lb2, ub2, d2, g2;
 };
 
+// the operands that the PREVIOUS vector launch (or the host, before INIT) left behind: everything but w
 template <int MODE>
-__device__ __forceinline__ PGElem pg_load_elem(const VecArgs& a, long long j, long long n, unsigned rpr) {
+__device__ __forceinline__ PGElem pg_load_elem_own(const VecArgs& a, long long j, long long n) {
     PGElem e;
-    const unsigned rk = (unsigned)j / rpr;
-    e.w = gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
-    e.x = a.x[j];
+    e.w = 0.0;
+    // x, d, g change every iteration and are read here possibly BEFORE griddepcontrol.wait: L2 loads (no L1 line of an
+    // earlier launch can be served); q and the bounds are constants of the solve
+    e.x = __ldcg(a.x + j);
     e.q = a.q[j];
     e.lb = a.lb[j];
     e.ub = a.ub[j];
     e.d = e.g = 0.0;
     if (MODE != VP_INIT) {
-        e.d = a.d[j];
-        e.g = a.g[j];
+        e.d = __ldcg(a.d + j);
+        e.g = __ldcg(a.g + j);
     }
     e.x2 = e.q2 = e.lb2 = e.ub2 = e.d2 = e.g2 = 0.0;
     if (a.svr) {
         const long long i2 = j + n;
-        e.x2 = a.x[i2];
+        e.x2 = __ldcg(a.x + i2);
         e.q2 = a.q[i2];
         e.lb2 = a.lb[i2];
         e.ub2 = a.ub[i2];
         if (MODE != VP_INIT) {
-            e.d2 = a.d[i2];
-            e.g2 = a.g[i2];
+            e.d2 = __ldcg(a.d + i2);
+            e.g2 = __ldcg(a.g + i2);
         }
     }
+    return e;
+}
+
+// w_j of the product this launch consumes (written by the matvec launch in front of it / by the peers)
+__device__ __forceinline__ double pg_load_w(const VecArgs& a, long long j, unsigned rpr) {
+    const unsigned rk = (unsigned)j / rpr;
+    return gathered_at(a, (size_t)rk * a.stride + ((unsigned)j - rk * rpr));
+}
+
+template <int MODE>
+__device__ __forceinline__ PGElem pg_load_elem(const VecArgs& a, long long j, long long n, unsigned rpr) {
+    PGElem e = pg_load_elem_own<MODE>(a, j, n);
+    e.w = pg_load_w(a, j, rpr);
     return e;
 }
 
@@ -230,12 +245,25 @@ __device__ __forceinline__ void pg_vector_body(const VecArgs& a, const long long
     const double* part_r = a.part + (size_t)(k & 1) * 3 * VP_MAXC;
     double* part_w = a.part + (size_t)((MODE == VP_INIT ? k : k + 1) & 1) * 3 * VP_MAXC;
 
+    // Operands first.  Everything but w was left behind by the PREVIOUS vector launch, which had completed before the
+    // matvec launch in front of this one even started -- so those loads are issued BEFORE griddepcontrol.wait: this grid is
+    // scheduled while the matvec grid drains (programmatic dependent launch) and its operands are in flight by the time
+    // the product is complete.  w and the shares of u'w are read after the wait.
     PGElem pre[PG_PREFETCH];
     if (MODE != VP_FINALISE) {
 #pragma unroll
         for (int e = 0; e < PG_PREFETCH; ++e) {
             const long long j = j0 + tid + (long long)e * VP_NT;
-            if (j < j1) pre[e] = pg_load_elem<MODE>(a, j, n, rpr);
+            if (j < j1) pre[e] = pg_load_elem_own<MODE>(a, j, n);
+        }
+    }
+    pdl_wait();               // the product this launch consumes must be complete and visible
+    pdl_launch_dependents();  // the next product may be scheduled behind us; it waits for our completion itself
+    if (MODE != VP_FINALISE) {
+#pragma unroll
+        for (int e = 0; e < PG_PREFETCH; ++e) {
+            const long long j = j0 + tid + (long long)e * VP_NT;
+            if (j < j1) pre[e].w = pg_load_w(a, j, rpr);
         }
     }
     double t = 0.0;
@@ -695,9 +723,7 @@ __device__ __forceinline__ void al_vector_body(const VecArgs& a, const ALArgs& a
 // blocks live in device memory.  A problem that has finished ignores the launches that follow (its `done` flag).
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) pg_vector_kernel(const VecArgs a, const long long k) {
-    pdl_wait();               // the product this launch consumes (and the previous vector launch) must be complete
-    pdl_launch_dependents();  // the next product may be scheduled behind us; it waits for our completion itself
-    pg_vector_body<MODE>(a, k);
+    pg_vector_body<MODE>(a, k);   // griddepcontrol.wait / launch_dependents sit inside, behind the operand prefetch
 }
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) fw_vector_kernel(const VecArgs a, const long long k) {
@@ -724,9 +750,7 @@ __device__ __forceinline__ VecArgs batch_args(const VecArgs* __restrict__ args, 
 template <int MODE>
 __global__ void __launch_bounds__(VP_NT) pg_vector_batch_kernel(const VecArgs* __restrict__ args, const long long k,
                                                                 const unsigned tag, const int parity) {
-    pdl_wait();
-    pdl_launch_dependents();
-    const VecArgs a = batch_args(args, tag, parity);
+    const VecArgs a = batch_args(args, tag, parity);   // argument blocks: written by a copy long before this launch
     pg_vector_body<MODE>(a, k);
 }
 template <int MODE>

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "al_math.cuh"
 #include "k2_matvec.cuh"   // K2, K2 x NB (device code)
+#include "k2_symv.cuh"     // K2s: one pass over the upper triangle of a symmetric matrix (opt-in)
 #include "k3_vector.cuh"   // K3 vector phases and kernel entry points (device code)
 #include "k_persistent.cuh"  // the whole loop in one cooperative kernel, matrix in shared memory (small problems)
 #include <math.h>
@@ -24,6 +25,13 @@ struct MatvecScratch {
     double* wpart = nullptr;
     unsigned* tickets = nullptr;
     size_t wpart_elems = 0, ticket_elems = 0;
+    // symmetric pass (K2s): row / column partials and the work list of the (n, ld) it was last built for
+    double* sy_rowpart = nullptr;
+    double* sy_colpart = nullptr;
+    int2* sy_items = nullptr;
+    size_t sy_row_elems = 0, sy_col_elems = 0, sy_item_cap = 0;
+    int64_t sy_n = -1, sy_ld = -1, sy_nitems = 0;
+    std::vector<int2> sy_host_items;
 };
 
 static int matvec_scratch_reserve(svmb200_ctx* ctx, MatvecScratch& s, int64_t nrows, int64_t ld, int nvec = 1) {
@@ -110,11 +118,96 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
     return SVMB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------ K2s launcher
+// w = Q u from the upper triangle of the symmetric n x n matrix dQ (see k2_symv.cuh); same outputs as launch_matvec
+// (w, and the shares of u'w per 64-row group when du_rows / ddenpart are given).  One rank, whole matrix.
+static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, const double* du, double* dw,
+                       const double* du_rows, double* ddenpart, const int* d_done) {
+    using S = SymvDefault;
+    if (n <= 0) return SVMB200_OK;
+    if (ld % 2 != 0 || ld < n) {
+        svmb200_set_error("symv: ld must be even and at least n");
+        return SVMB200_ERR_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(dQ) & 15) || (reinterpret_cast<uintptr_t>(du) & 15)) {
+        svmb200_set_error("symv: operands must be 16-byte aligned");
+        return SVMB200_ERR_ARG;
+    }
+    if (!ctx->matvec_scratch) ctx->matvec_scratch = new MatvecScratch();
+    MatvecScratch& s = *static_cast<MatvecScratch*>(ctx->matvec_scratch);
+    const int64_t nbands = (n + S::BH - 1) / S::BH;
+    const int64_t n_pad = round_up64(n, 16);
+    const int64_t nseg_max = 1 + symv_npanels(n, 0, S::BH, S::BW);
+    if (s.sy_n != n || s.sy_ld != ld) {
+        std::vector<int2>& items = s.sy_host_items;
+        symv_build_items<S>(n, ld, items);
+        const size_t need_r = (size_t)nseg_max * n_pad, need_c = (size_t)nbands * ld;
+        if (need_r > s.sy_row_elems || need_c > s.sy_col_elems || items.size() > s.sy_item_cap) {
+            SVM_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (s.sy_rowpart) cudaFree(s.sy_rowpart);
+            if (s.sy_colpart) cudaFree(s.sy_colpart);
+            if (s.sy_items) cudaFree(s.sy_items);
+            s.sy_rowpart = s.sy_colpart = nullptr;
+            s.sy_items = nullptr;
+            s.sy_row_elems = s.sy_col_elems = s.sy_item_cap = 0;
+            s.sy_n = s.sy_ld = -1;
+            SVM_CUDA(cudaMalloc(&s.sy_rowpart, need_r * sizeof(double)));
+            s.sy_row_elems = need_r;
+            SVM_CUDA(cudaMalloc(&s.sy_colpart, need_c * sizeof(double)));
+            s.sy_col_elems = need_c;
+            SVM_CUDA(cudaMalloc(&s.sy_items, items.size() * sizeof(int2)));
+            s.sy_item_cap = items.size();
+        }
+        SVM_CUDA(cudaMemcpyAsync(s.sy_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        SVM_CUDA(cudaStreamSynchronize(ctx->stream));  // once per problem size; the list stays valid for every later pass
+        s.sy_n = n;
+        s.sy_ld = ld;
+        s.sy_nitems = (int64_t)items.size();
+    }
+    SymvArgs a;
+    a.Q = dQ;
+    a.ld = ld;
+    a.n = n;
+    a.n_pad = n_pad;
+    a.u = du;
+    a.rowpart = s.sy_rowpart;
+    a.colpart = s.sy_colpart;
+    a.items = s.sy_items;
+    a.done = d_done;
+    SVM_CUDA(svm_launch_chained(symv_tile_kernel<S>, dim3((unsigned)s.sy_nitems), dim3(SY_NT), ctx->stream, a));
+    SymvCombineArgs c;
+    c.rowpart = s.sy_rowpart;
+    c.colpart = s.sy_colpart;
+    c.ld = ld;
+    c.n = n;
+    c.n_pad = n_pad;
+    c.BH = S::BH;
+    c.BW = S::BW;
+    c.u_rows = du_rows;
+    c.w = dw;
+    c.denpart = ddenpart;
+    c.done = d_done;
+    const int64_t ngroups = (n + MV_GROUP - 1) / MV_GROUP;
+    SVM_CUDA(svm_launch_chained(symv_combine_kernel, dim3((unsigned)ngroups), dim3(MV_GROUP), ctx->stream, c));
+    ctx->launches += 2;
+    return SVMB200_OK;
+}
+
+// w = Q u for a symmetric n x n matrix from its upper triangle (the lower one is never read)
+extern "C" int svmb200_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, const double* du, double* dw) {
+    SVM_TRY(svm_use(ctx));
+    SVM_CHECK_ARG(dQ != nullptr && du != nullptr && dw != nullptr && n >= 0, "bad argument");
+    return launch_symv(ctx, dQ, n, ld, du, dw, nullptr, nullptr, nullptr);
+}
+
 void svm_release_matvec_scratch(svmb200_ctx* ctx) {
     if (ctx->matvec_scratch) {
         MatvecScratch* s = static_cast<MatvecScratch*>(ctx->matvec_scratch);
         if (s->wpart) cudaFree(s->wpart);
         if (s->tickets) cudaFree(s->tickets);
+        if (s->sy_rowpart) cudaFree(s->sy_rowpart);
+        if (s->sy_colpart) cudaFree(s->sy_colpart);
+        if (s->sy_items) cudaFree(s->sy_items);
         delete s;
         ctx->matvec_scratch = nullptr;
     }
@@ -249,6 +342,7 @@ struct svmb200_pg {
     double *x = nullptr, *g = nullptr, *d = nullptr, *u = nullptr, *w = nullptr;  // w: gathered [P][stride]
     int64_t stride = 0;  // rows_per_rank results + rows_per_rank / MV_GROUP shares of u'w
     bool p2p = false;           // fused exchange through the peer arena instead of ncclAllGather
+    bool symmetric = false;     // products from the upper triangle only (K2s; one rank holding the whole matrix)
     unsigned long long cur_seq = 0;  // sequence number of the product the next vector kernel consumes
     int nctas = 1;
     double *q = nullptr, *lb = nullptr, *ub = nullptr;
@@ -361,8 +455,12 @@ static int pg_product(svmb200_pg* pg, bool timed) {
         if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
     } else {
         double* wshard = pg->w + (size_t)ctx->rank * pg->stride;
-        SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wshard, pg->u + pg->row0,
-                              wshard + pg->rows_per_rank, &pg->st->done));
+        if (pg->symmetric) {
+            SVM_TRY(launch_symv(ctx, pg->dQ, pg->n, pg->ld, pg->u, wshard, pg->u, wshard + pg->rows_per_rank, &pg->st->done));
+        } else {
+            SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wshard, pg->u + pg->row0,
+                                  wshard + pg->rows_per_rank, &pg->st->done));
+        }
         if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
         if (ctx->nranks > 1) SVM_TRY(svm_comm_allgather(ctx, pg->w, pg->stride));
     }
@@ -509,6 +607,7 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     const bool every_rank_owns_rows = (int64_t)(P - 1) * rpr < n;
     pg->p2p = ctx->p2p_enabled && P > 1 && every_rank_owns_rows &&
               ARENA_DATA_OFF + 2 * (size_t)pg->stride * P * sizeof(ulonglong2) <= ctx->arena_bytes;
+    pg->symmetric = ctx->symmetric && P == 1 && row0 == 0 && nrows == n;
     pg->nctas = (int)((n + VP_ELEMS - 1) / VP_ELEMS);
     if (pg->nctas > VP_MAXC) pg->nctas = VP_MAXC;
     if (pg->nctas < 1) pg->nctas = 1;
@@ -1264,6 +1363,14 @@ extern "C" int svmb200_pg_profile_samples(svmb200_pg* pg, int64_t* samples) {
 extern "C" int svmb200_pg_set_profile(svmb200_pg* pg, int on) {
     SVM_CHECK_ARG(pg != nullptr, "null solver");
     pg->profile = on != 0;
+    return SVMB200_OK;
+}
+
+// 1 when the solver's products come from the upper triangle alone (svmb200_ctx_set_symmetric was on at its creation and
+// it holds the whole matrix on one rank)
+extern "C" int svmb200_pg_is_symmetric(svmb200_pg* pg, int* on) {
+    SVM_CHECK_ARG(pg != nullptr && on != nullptr, "null argument");
+    *on = pg->symmetric ? 1 : 0;
     return SVMB200_OK;
 }
 

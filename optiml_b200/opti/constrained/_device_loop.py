@@ -76,6 +76,9 @@ class DeviceLoopMixin:
                                        *self._extra_create_args(), C.byref(hh)))
         if profile:
             N.call('svmb200_pg_set_profile', h, 1)
+        sym = C.c_int(0)
+        N.call('svmb200_pg_is_symmetric', h, C.byref(sym))
+        self.symmetric_pass = bool(sym.value)   # products from the upper triangle only (runtime.use_symmetric_pass)
         return h, n
 
     @staticmethod

@@ -102,6 +102,9 @@ class StochasticOptimizer(DeviceLoopMixin, Optimizer):
             float(k['offset']), float(self.tol), int(self.epochs), C.byref(hh)))
         if profile:
             N.call('svmb200_pg_set_profile', h, 1)
+        sym = C.c_int(0)
+        N.call('svmb200_pg_is_symmetric', h, C.byref(sym))
+        self.symmetric_pass = bool(sym.value)
         return h, n
 
     def _pull_state(self, h, n):

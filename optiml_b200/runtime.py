@@ -37,6 +37,8 @@ class Context:
         # large device buffers (the Hessian shard) are recycled between fits: cudaMalloc/cudaFree of
         # tens of GB costs ~0.1 s each, more than the Gram build itself
         self._pool = []  # (nbytes, device pointer), oldest first
+        if _symmetric is not None:
+            N.call('svmb200_ctx_set_symmetric', h, int(_symmetric))
         self._finalizer = weakref.finalize(self, N.load_library().svmb200_ctx_destroy, h)
 
     # ---------------------------------------------------------------- memory
@@ -455,6 +457,23 @@ def hessian_from_host(ctx, Q):
     if ctx.group is not None and ctx.group.wants(np.shape(Q)[0]):
         return GroupHessian.from_host(ctx.group, Q)
     return DeviceHessian.from_host(ctx, Q)
+
+
+_symmetric = None   # None: the library's default (environment variable SVMB200_SYMMETRIC, else off)
+
+
+def use_symmetric_pass(on=True):
+    """Opt in to (or out of) the symmetric pass: solvers that hold their whole Hessian on one GPU take every product
+    ``Q d`` from the UPPER TRIANGLE of the matrix alone -- half the HBM bytes per iteration, about twice the iterations
+    per second on a bandwidth-bound fit.  Every Hessian of the SVM dual is symmetric, so this is always valid for the
+    estimators; for a hand-made ``Quadratic`` the caller vouches for it.  The iterate is reproducible run to run but
+    follows another summation order than the default pass, so it is NOT bit-identical to it (well-conditioned problems
+    stay far inside the 1e-8 of ``north_star``; the default keeps the bit-exact contract).  ``SVMB200_SYMMETRIC=1`` in
+    the environment does the same without a code change."""
+    global _symmetric
+    _symmetric = bool(on)
+    if _default_ctx is not None:
+        N.call('svmb200_ctx_set_symmetric', _default_ctx.handle, int(_symmetric))
 
 
 _devices = None

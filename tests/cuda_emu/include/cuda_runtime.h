@@ -29,6 +29,9 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct alignas(16) double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+struct alignas(8) int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 struct alignas(16) ulonglong2 { unsigned long long x, y; };
 
 namespace emu {

@@ -427,3 +427,36 @@ def test_persistent_loop_is_bit_identical_to_the_two_kernel_loop(monkeypatch, n,
         assert persistent[5] == 'optimal' and persistent[4] < iters
     for a, b in zip(two_kernel[:4], persistent[:4]):
         assert np.array_equal(a, b)
+
+
+# --------------------------------------------------------------------------------------------- symmetric pass (K2s)
+# (the same checks run on the B200 in tests/test_gpu_symmetric.py with the shipped tile shape)
+import symv_checks as SY   # noqa: E402
+
+# small tile shapes so that a few hundred rows cover several bands, ragged last bands and narrow last panels:
+#   BH = TR * NRB rows per band, BW = 512 * NCH columns per panel
+_SYMV_SMALL = ('SVMB200_SYMV_TR=4', 'SVMB200_SYMV_NRB=2', 'SVMB200_SYMV_NCH=1', 'SVMB200_SYMV_LB=2')      # 8 x 512
+_SYMV_TALL = ('SVMB200_SYMV_TR=16', 'SVMB200_SYMV_NRB=4', 'SVMB200_SYMV_NCH=2', 'SVMB200_SYMV_LB=8')      # 64 x 1024
+_SYMV_WIDE32 = ('SVMB200_SYMV_TR=32', 'SVMB200_SYMV_NRB=2', 'SVMB200_SYMV_NCH=1', 'SVMB200_SYMV_LB=16')   # 64 x 512
+
+
+@pytest.mark.parametrize('n,defines', [(70, _SYMV_SMALL), (600, _SYMV_SMALL), (1100, _SYMV_TALL), (200, _SYMV_WIDE32),
+                                       (643, _SYMV_WIDE32), (130, ())])
+def test_symmetric_pass_product(n, defines):
+    w0 = SY.check_symmetric_product(emu_probe, n, defines=defines)
+    w1 = SY.check_symmetric_product(emu_probe, n, defines=defines, order=2, seed=n)   # other thread / block schedule
+    assert np.array_equal(w0, w1)
+
+
+@pytest.mark.parametrize('n,bh,defines', [(333, 8, _SYMV_SMALL), (700, 64, _SYMV_TALL), (300, 128, ())])
+def test_symmetric_pass_never_reads_below_the_diagonal_blocks(n, bh, defines):
+    SY.check_lower_triangle_is_never_read(emu_probe, n, bh, defines=defines, order=1)
+
+
+def test_symmetric_pass_solvers_follow_the_default_pass():
+    SY.check_symmetric_solves(emu_probe, n=150, max_iter=25, defines=_SYMV_SMALL)
+    SY.check_symmetric_solves(emu_probe, n=90, max_iter=12, defines=_SYMV_TALL, order=2, seed=4)
+
+
+def test_symmetric_pass_estimators():
+    SY.check_symmetric_fit(emu_probe, n=120, defines=_SYMV_SMALL)

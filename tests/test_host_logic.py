@@ -356,9 +356,23 @@ def test_sass_carries_the_instructions_the_design_claims():
         if 'matvec_seg' in name:
             assert any(o.startswith('LDG.E.NA.128') or o.startswith('LDG.E.128') for o in ops), name
             assert sum(o == 'DFMA' for o in ops) >= 32, name
-        if 'matvec_seg' in name or '_vector_' in name:
-            # programmatic dependent launch: griddepcontrol.wait / launch_dependents at the top of every solver kernel
+        if 'matvec_seg' in name or 'symv_' in name:
+            # programmatic dependent launch: griddepcontrol.wait / launch_dependents at the top of every product kernel
             assert 'ACQBULK' in ops[:12] and 'PREEXIT' in ops[:40], name
+        if '_vector_' in name:
+            # the vector kernels too; the projected-gradient ones issue the loads of their own operands (left behind by
+            # the previous vector launch) BEFORE griddepcontrol.wait
+            assert 'ACQBULK' in ops and 'PREEXIT' in ops, name
+            if 'pg_vector_kernel' in name or 'pg_vector_batch_kernel' in name:
+                first_wait = ops.index('ACQBULK')
+                assert any(o.startswith('LDG') for o in ops[:first_wait]), name
+    # the symmetric pass: 128-bit streaming loads, column and row sums (4 DFMA per load), no spills, two CTAs per SM
+    sy = [ops for name, ops in pg.items() if 'symv_tile_kernel' in name]
+    assert len(sy) == 1
+    assert sum(o.startswith('LDG.E.NA.128') or o.startswith('LDG.E.128') for o in sy[0]) >= 64
+    assert sum(o == 'DFMA' for o in sy[0]) >= 256 and sum(o.startswith('SHFL') for o in sy[0]) >= 62
+    assert not any(o.startswith(('LDL', 'STL')) for o in sy[0])
+    assert any('symv_combine_kernel' in name for name in pg)
     # the persistent small-problem loop: matrix rows from shared memory, a grid barrier on a global atomic, no spills
     pk = [ops for name, ops in pg.items() if 'pg_persistent_kernel' in name]
     assert len(pk) == 1
