@@ -59,6 +59,11 @@ def parse_args():
     ap.add_argument('--n', type=int, default=None, help='override the sample count (debug)')
     ap.add_argument('--max-iter', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--symmetric', action='store_true',
+                    help='run the whole bench with the opt-in symmetric pass (K2s: products from the upper triangle of Q '
+                         'alone); without it the default full pass is benched and, on one GPU, a short symmetric-pass leg '
+                         'is added to the line as "symmetric_pass"')
+    ap.add_argument('--no-symmetric-leg', action='store_true')
     ap.add_argument('--devices', default=None,
                     help="ONE process driving several GPUs (comma-separated indices or 'all'): the single-process device "
                          "group instead of torchrun ranks; not a driver mode, used to compare the two launch models")
@@ -346,6 +351,66 @@ def parity_block(args, m, n):
     return out
 
 
+def symv_streamed_bytes(n):
+    import ctypes as C
+    from optiml_b200 import _native as N
+    b = C.c_int64(0)
+    N.call('svmb200_symv_geometry', int(n), int(N.padded_ld(n)), C.byref(b), None, None, None)
+    return int(b.value)
+
+
+def symmetric_leg(args, ctx, make_model, X, y, dX, n, peak):
+    """The same fits with the opt-in symmetric pass (runtime.use_symmetric_pass): device-resident leg + end-to-end leg, two
+    fits each after one warm-up, its own parity block against the reference's golden run and its own roofline (bytes =
+    what K2s streams, 4 n^2 + the diagonal blocks' lower halves)."""
+    from optiml_b200.runtime import use_symmetric_pass
+    use_symmetric_pass(True)
+    try:
+        m = make_model().fit(X, y, X_device=dX)
+        m.obj.release()
+        ctx.sync()
+        fits = max(1, min(args.steps, 2))
+        iters, mv_ms, samples, pg_ms, vec_ms = 0, 0.0, 0, 0.0, 0.0
+        launches0 = ctx.launch_count()
+        ctx.timer_start()
+        for _ in range(fits):
+            m = make_model().fit(X, y, X_device=dX)
+            iters += m.optimizer.iter
+            mv_ms += m.optimizer.matvec_ms
+            vec_ms += m.optimizer.vector_ms
+            samples += m.optimizer.profile_samples
+            pg_ms += m.optimizer.device_ms
+            m.obj.release()
+        ctx.sync()
+        dev_ms = ctx.timer_stop_ms()
+        launches = ctx.launch_count() - launches0
+        t0 = time.perf_counter()
+        e2e_iters = 0
+        for _ in range(fits):
+            m = make_model(False).fit(X, y)
+            e2e_iters += m.optimizer.iter
+            m.obj.release()
+        ctx.sync()
+        e2e_s = time.perf_counter() - t0
+        assert m.optimizer.symmetric_pass
+        streamed = float(symv_streamed_bytes(n))
+        avg_ms = mv_ms / max(samples, 1)
+        achieved = streamed / (avg_ms / 1e3) / 1e9
+        return {'what': 'the same workload with runtime.use_symmetric_pass(True) / SVMB200_SYMMETRIC=1: every product Q d read '
+                        'from the upper triangle of Q alone (K2s); reproducible, not bit-identical to the default pass',
+                'value': iters / (dev_ms / 1e3), 'unit': UNIT, 'fits': fits, 'fit_s': dev_ms / fits / 1e3,
+                'e2e': {'value': e2e_iters / e2e_s, 'unit': UNIT, 'fit_s': e2e_s / fits},
+                'pg_its_per_s': iters / (pg_ms / 1e3),
+                'per_iteration_us': {'product (tile pass + combine)': 1e3 * avg_ms, 'vector_phase': 1e3 * vec_ms / max(samples, 1)},
+                'roofline': {'bound': 'hbm', 'kernel': 'symv_tile_kernel + symv_combine_kernel (K2s)', 'achieved': achieved, 'peak': peak,
+                             'unit': 'GB/s', 'frac': achieved / peak, 'bytes_per_launch': streamed,
+                             'full_matrix_equivalent_gbs': 8.0 * n * n / (avg_ms / 1e3) / 1e9,
+                             'frac_of_dram_theoretical': achieved / 8184.0},
+                'gpu_launches': int(launches), 'parity': parity_block(args, m, n)}
+    finally:
+        use_symmetric_pass(False)
+
+
 def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -374,6 +439,9 @@ def run_b200(args):
         use_devices(devs)
         group_size = len(devs)
     ctx = default_context()
+    if args.symmetric:
+        from optiml_b200.runtime import use_symmetric_pass
+        use_symmetric_pass(True)
     spec, X0, y0 = make_config(args.config, n=args.n)
     n, d = X0.shape
     X = pinned_array(X0.shape)
@@ -459,12 +527,21 @@ def run_b200(args):
     h2d = X.nbytes + 8 * n + 4 * 8 * nvars + 8 * n  # X, label signs, q/lb/ub/x0, intercept mask vector
     d2h = 2 * 8 * nvars + 2 * 8 * (args.max_iter + 1) + 8 * n  # alpha, gradient, f/|d| history, masked product
 
+    sym_used = bool(getattr(m.optimizer, 'symmetric_pass', False))
+    sym_leg = None
+    if world == 1 and group_size == 1 and not args.symmetric and not args.no_symmetric_leg:
+        sym_leg = symmetric_leg(args, ctx, make_model, X, y, dX, n, measured_peak()[0])
     if rank != 0:
         return
     parity = parity_block(args, m, n)
     peak, peak_src = measured_peak()
     gpus = world * group_size
     bytes_per_launch = 8.0 * n * n / gpus
+    kernel_name = 'matvec_seg_kernel (K2)'
+    if sym_used:
+        # K2s streams the upper triangle in band geometry (diagonal blocks in full): these are its algorithmic bytes
+        bytes_per_launch = float(symv_streamed_bytes(n))
+        kernel_name = 'symv_tile_kernel + symv_combine_kernel (K2s, upper triangle; the timed pair)'
     mv_avg_ms = mv_ms / max(mv_samples, 1)  # CUDA events bracket one K2 launch in 16 (they serialise programmatic launches)
     achieved = bytes_per_launch / (mv_avg_ms / 1e3) / 1e9
     traffic = None
@@ -496,7 +573,7 @@ def run_b200(args):
         'per_iteration_us': {'matvec': 1e3 * mv_ms / max(mv_samples, 1), 'allgather': 1e3 * comm_ms / max(mv_samples, 1),
                              'vector_phase': 1e3 * vec_ms / max(mv_samples, 1),
                              'pg_loop_total': 1e3 * pg_ms / max(mv_launches, 1)},
-        'roofline': {'bound': 'hbm', 'kernel': 'matvec_seg_kernel (K2)', 'achieved': achieved, 'peak': peak,
+        'roofline': {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                      'bytes_per_launch': bytes_per_launch, 'avg_launch_ms': mv_avg_ms, 'launches_timed': mv_samples, 'launches_total': mv_launches,
                      'dram_theoretical_gbs': 8184.0, 'frac_of_dram_theoretical': achieved / 8184.0,
@@ -506,6 +583,14 @@ def run_b200(args):
                 'fit_s': e2e_s / args.steps, 'step_wall_s': e2e_steps, 'api': 'optiml_b200.ml.svm.DualSVC.fit(X_host_pinned, y_host)'},
         'gpu_launches': int(launches), 'clocks': clocks,
     }
+    line['product_pass'] = 'symmetric (K2s: upper triangle of Q only, opt-in)' if sym_used else 'full (K2: every row of Q, the default)'
+    if sym_used:
+        line['hbm_gbps_pg_loop'] = bytes_per_launch * mv_launches / (pg_ms / 1e3) / 1e9
+        line['frac_of_8TBps_nominal'] = line['hbm_gbps_pg_loop'] / gpus / 8000.0
+        line['roofline']['traffic'] = None
+        line['roofline']['full_matrix_equivalent_gbs'] = 8.0 * n * n / (mv_avg_ms / 1e3) / 1e9
+    if sym_leg is not None:
+        line['symmetric_pass'] = sym_leg
     if world == 1 and not args.no_cpu_baseline:
         # release the GPU arm's host copies first: the reference needs ~4.6 x 8 n^2 bytes of host memory
         r = reference_measure(args.config, n, args.max_iter)

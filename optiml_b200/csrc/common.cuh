@@ -125,11 +125,11 @@ static inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
-static inline cudaError_t svm_launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+static inline cudaError_t svm_launch_chained_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -137,6 +137,10 @@ static inline cudaError_t svm_launch_chained(void (*kernel)(KArgs...), dim3 grid
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t svm_launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    return svm_launch_chained_smem(kernel, grid, block, 0, stream, args...);
 }
 template <typename Arg>
 static inline cudaError_t svm_launch_cooperative(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Arg arg) {
@@ -152,9 +156,13 @@ static inline cudaError_t svm_launch_cooperative(void (*kernel)(Arg), dim3 grid,
 static inline void pdl_wait() {}
 static inline void pdl_launch_dependents() {}
 template <typename... KArgs, typename... Args>
-static inline cudaError_t svm_launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t, Args... args) {
-    emu::launch(grid, block, 0, [=]() { kernel(KArgs(args)...); });
+static inline cudaError_t svm_launch_chained_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args... args) {
+    emu::launch(grid, block, smem, [=]() { kernel(KArgs(args)...); });
     return cudaSuccess;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t svm_launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    return svm_launch_chained_smem(kernel, grid, block, 0, stream, args...);
 }
 #endif
 

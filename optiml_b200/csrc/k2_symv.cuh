@@ -37,24 +37,28 @@ constexpr int SY_CHUNK = 2 * SY_NT;  // columns one pass of the CTA's threads co
 #define SVMB200_SYMV_NCH 4     // 512-column chunks per panel
 #endif
 #ifndef SVMB200_SYMV_LB
-#define SVMB200_SYMV_LB 8      // 128-bit loads per batch; two batches are in flight
+#define SVMB200_SYMV_LB 8      // 128-bit copies per batch
+#endif
+#ifndef SVMB200_SYMV_STAGES
+#define SVMB200_SYMV_STAGES 3  // batches in flight per thread (ring depth)
 #endif
 #ifndef SVMB200_SYMV_MINB
 #define SVMB200_SYMV_MINB 2    // CTAs per SM the register budget is cut for
 #endif
 
-template <int TR_, int NRB_, int NCH_, int LB_, int MINB_>
+template <int TR_, int NRB_, int NCH_, int LB_, int MINB_, int STAGES_ = 3>
 struct SymvShape {
-    static constexpr int TR = TR_, NRB = NRB_, NCH = NCH_, LB = LB_, MINB = MINB_;
+    static constexpr int TR = TR_, NRB = NRB_, NCH = NCH_, LB = LB_, MINB = MINB_, STAGES = STAGES_;
+    static constexpr int RING_BYTES = STAGES_ * LB_ * SY_NT * 16;   // dynamic shared memory: the copy ring
     static constexpr int BH = TR_ * NRB_;          // rows per band
     static constexpr int BW = SY_CHUNK * NCH_;     // columns per panel
     static constexpr int NBATCH = NCH_ * TR_ / LB_;  // load batches per sub-block
     static_assert((TR_ & (TR_ - 1)) == 0 && TR_ >= 2 && TR_ <= 32, "TR: a power of two up to 32");
-    static_assert(TR_ % LB_ == 0 && NBATCH % 2 == 0, "batches must tile a sub-block, an even number of them");
+    static_assert(TR_ % LB_ == 0, "batches must tile a sub-block");
     static_assert(BH % MV_GROUP == 0 || MV_GROUP % BH == 0, "bands and 64-row groups must nest");
     static_assert(BH % 2 == 0, "panels start on 16-byte boundaries");
 };
-using SymvDefault = SymvShape<SVMB200_SYMV_TR, SVMB200_SYMV_NRB, SVMB200_SYMV_NCH, SVMB200_SYMV_LB, SVMB200_SYMV_MINB>;
+using SymvDefault = SymvShape<SVMB200_SYMV_TR, SVMB200_SYMV_NRB, SVMB200_SYMV_NCH, SVMB200_SYMV_LB, SVMB200_SYMV_MINB, SVMB200_SYMV_STAGES>;
 
 // panels of band `band`: columns (band+1) BH ... n - 1 in steps of BW (columns >= n meet u = 0: nothing to add)
 __host__ __device__ inline long long symv_npanels(long long n, long long band, int BH, int BW) {
@@ -113,13 +117,36 @@ __device__ __forceinline__ double symv_warp_rows(double (&v)[TR], const int lane
     return v[0];
 }
 
+// ---- the matrix stream: cp.async (16 bytes, L2 only) into a ring of thread-private shared-memory slots.  Every thread
+// keeps STAGES batches of LB copies in flight without holding a register for them -- the in-flight bytes per SM
+// (CTAs x 256 threads x STAGES x LB x 16 B, ~190 KB) are what a 7 TB/s stream needs at ~1.5 us of loaded latency; with the
+// data held in registers the same kernel stalled at 6.2 TB/s for every tile shape (profiles/r2_sy2_symv_sweep.log).
+// A slot is written and read by ONE thread, so there is no block-wide barrier anywhere in the stream: completion is the
+// thread's own cp.async.wait_group, and a slot is refilled only after the FMAs that consumed it have been issued.
+#ifndef SVMB200_HOST_EMULATION
+__device__ __forceinline__ void sy_cp_async16(double2* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sy_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void sy_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+#else
+__device__ __forceinline__ void sy_cp_async16(double2* smem_dst, const double* gsrc) { *smem_dst = *reinterpret_cast<const double2*>(gsrc); }
+__device__ __forceinline__ void sy_cp_async_commit() {}
+template <int PENDING>
+__device__ __forceinline__ void sy_cp_async_wait() {}
+#endif
+
 template <class S, bool COLS>
 __device__ __forceinline__ void symv_item(const SymvArgs& a, const long long r0, const long long c0, const int width,
                                           const int band, const int seg, const double* ush,
-                                          double (*red)[SY_NT / 32][S::TR]) {
-    constexpr int TR = S::TR, NRB = S::NRB, NCH = S::NCH, LB = S::LB, NBATCH = S::NBATCH, BPC = TR / LB;
+                                          double (*wsum)[S::BH], double2* ring) {
+    constexpr int TR = S::TR, NCH = S::NCH, LB = S::LB, NBATCH = S::NBATCH, BPC = TR / LB, ST = S::STAGES;
+    static_assert(ST >= 2 && ST <= NBATCH, "ring depth: between 2 batches and one sub-block");
     const int tid = (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nch = (width + SY_CHUNK - 1) / SY_CHUNK;  // chunks this item has (a diagonal block or a last panel: fewer)
+    const int rows = (int)(a.n - r0 < S::BH ? a.n - r0 : S::BH);
+    const int nrb = (rows + TR - 1) / TR;               // sub-blocks this item has (the last band: fewer)
     // the thread's columns, relative to c0; a column beyond the item reads column 0 of it against u = 0
     int coff[NCH];
     bool cok[NCH];
@@ -133,67 +160,69 @@ __device__ __forceinline__ void symv_item(const SymvArgs& a, const long long r0,
 #pragma unroll
     for (int k = 0; k < NCH; ++k) colacc[k] = make_double2(0.0, 0.0);
     const double* __restrict__ ucol = a.u + c0;
+    const double* __restrict__ qitem = a.Q + r0 * a.ld + c0;
+    double2* const myring = ring + tid;   // ring[slot][j][thread]
 
-    // rows of sub-block rb: clamped to the last row of the matrix (a valid read; ush is zero there and the row sum is dropped)
-    auto load_batch = [&](const double* qb, const int last, const int b, double2 (&q)[LB]) {
+    // batch b of sub-block rb -> ring slot; rows beyond the matrix re-read its last row (a valid address; ush is zero
+    // there and the row sum is dropped).  Always commits, so that the group count per step is constant.
+    auto issue = [&](const int rb, const int b, const int slot) {
         const int k = b / BPC, rbase = (b % BPC) * LB;
+        if (rb < nrb && k < nch) {
+            const int last = (rows - rb * TR < TR ? rows - rb * TR : TR) - 1;
+            const double* qb = qitem + (long long)(rb * TR) * a.ld + coff[k];
 #pragma unroll
-        for (int j = 0; j < LB; ++j) {
-            const int r = rbase + j < last ? rbase + j : last;
-            q[j] = ld_stream_f64x2(reinterpret_cast<const double2*>(qb + (long long)r * a.ld + coff[k]));
+            for (int j = 0; j < LB; ++j) {
+                const int r = rbase + j < last ? rbase + j : last;
+                sy_cp_async16(myring + (slot * LB + j) * SY_NT, qb + (long long)r * a.ld);
+            }
         }
+        sy_cp_async_commit();
     };
 
-    double2 q[2][LB];
-    {
-        const long long rows_left = a.n - r0;
-        load_batch(a.Q + r0 * a.ld + c0, (int)(rows_left < TR ? rows_left : TR) - 1, 0, q[0]);
-    }
+#pragma unroll
+    for (int b = 0; b < ST; ++b) issue(0, b, b);
+    int slot = 0;
 #pragma unroll 1
-    for (int rb = 0; rb < NRB; ++rb) {
-        const long long rbase = r0 + (long long)rb * TR;
-        if (rbase >= a.n) break;
-        const long long rows_left = a.n - rbase;
-        const int last = (int)(rows_left < TR ? rows_left : TR) - 1;
-        const double* qb = a.Q + rbase * a.ld + c0;
-        const bool more = rb + 1 < NRB && rbase + TR < a.n;
+    for (int rb = 0; rb < nrb; ++rb) {
         double rowacc[TR];
 #pragma unroll
         for (int r = 0; r < TR; ++r) rowacc[r] = 0.0;
 #pragma unroll
         for (int b = 0; b < NBATCH; ++b) {
-            if (b + 1 < NBATCH) {
-                if ((b + 1) / BPC < nch) load_batch(qb, last, b + 1, q[(b + 1) & 1]);
-            } else if (more) {  // the first batch of the next sub-block, in flight across the reduction below
-                const long long nleft = rows_left - TR;
-                load_batch(qb + (long long)TR * a.ld, (int)(nleft < TR ? nleft : TR) - 1, 0, q[0]);
-            }
+            sy_cp_async_wait<ST - 1>();   // the oldest batch in flight -- the one consumed now -- has landed
             const int k = b / BPC, rb0 = (b % BPC) * LB;
-            if (k >= nch) continue;  // uniform over the CTA
-            double2 uc = __ldg(reinterpret_cast<const double2*>(ucol + coff[k]));
-            if (!cok[k]) uc = make_double2(0.0, 0.0);
+            if (k < nch) {  // uniform over the CTA
+                double2 uc = __ldg(reinterpret_cast<const double2*>(ucol + coff[k]));
+                if (!cok[k]) uc = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int j = 0; j < LB; ++j) {
-                const double2 v = q[b & 1][j];
-                rowacc[rb0 + j] = fma(v.x, uc.x, rowacc[rb0 + j]);
-                rowacc[rb0 + j] = fma(v.y, uc.y, rowacc[rb0 + j]);
-                if (COLS) {
-                    const double ur = ush[rb * TR + rb0 + j];
-                    colacc[k].x = fma(v.x, ur, colacc[k].x);
-                    colacc[k].y = fma(v.y, ur, colacc[k].y);
+                for (int j = 0; j < LB; ++j) {
+                    const double2 v = myring[(slot * LB + j) * SY_NT];
+                    rowacc[rb0 + j] = fma(v.x, uc.x, rowacc[rb0 + j]);
+                    rowacc[rb0 + j] = fma(v.y, uc.y, rowacc[rb0 + j]);
+                    if (COLS) {
+                        const double ur = ush[rb * TR + rb0 + j];
+                        colacc[k].x = fma(v.x, ur, colacc[k].x);
+                        colacc[k].y = fma(v.y, ur, colacc[k].y);
+                    }
                 }
             }
+            // refill the slot just consumed with the batch ST steps ahead (it may belong to the next sub-block)
+            if (b + ST < NBATCH) issue(rb, b + ST, slot);
+            else issue(rb + 1, b + ST - NBATCH, slot);
+            slot = slot + 1 == ST ? 0 : slot + 1;
         }
-        // row sums of the sub-block: lanes, then warps in index order
+        // row sums of the sub-block over the warp's lanes; the warps meet once per item, not once per sub-block, so a
+        // warp that reduces never holds up the stream of the others
         const double tot = symv_warp_rows<TR>(rowacc, lane);
-        if (lane < TR) red[rb & 1][wid][lane] = tot;
-        __syncthreads();
-        if (tid < TR && tid <= last) {
-            double v = 0.0;
+        if (lane < TR) wsum[wid][rb * TR + lane] = tot;
+    }
+    sy_cp_async_wait<0>();
+    __syncthreads();
+    for (int i = tid; i < rows; i += SY_NT) {   // warps in index order
+        double v = 0.0;
 #pragma unroll
-            for (int w = 0; w < SY_NT / 32; ++w) v += red[rb & 1][w][tid];
-            a.rowpart[(size_t)seg * a.n_pad + rbase + tid] = v;
-        }
+        for (int w = 0; w < SY_NT / 32; ++w) v += wsum[w][i];
+        a.rowpart[(size_t)seg * a.n_pad + r0 + i] = v;
     }
     if (COLS) {
 #pragma unroll
@@ -209,8 +238,14 @@ __global__ void __launch_bounds__(SY_NT, S::MINB) symv_tile_kernel(const SymvArg
     pdl_launch_dependents();
     if (a.done != nullptr && *a.done) return;
     constexpr int BH = S::BH, BW = S::BW;
+#ifndef SVMB200_HOST_EMULATION
+    extern __shared__ __align__(16) unsigned char sy_smem_raw[];
+    double2* ring = reinterpret_cast<double2*>(sy_smem_raw);
+#else
+    double2* ring = reinterpret_cast<double2*>(emu::dynamic_smem());
+#endif
     __shared__ double ush[BH];
-    __shared__ double red[2][SY_NT / 32][S::TR];
+    __shared__ double wsum[SY_NT / 32][BH];   // row sums per warp
     const int2 it = a.items[blockIdx.x];
     const long long r0 = (long long)it.x * BH;
     for (int i = (int)threadIdx.x; i < BH; i += SY_NT) ush[i] = r0 + i < a.n ? a.u[r0 + i] : 0.0;
@@ -218,17 +253,21 @@ __global__ void __launch_bounds__(SY_NT, S::MINB) symv_tile_kernel(const SymvArg
     if (it.y == 0) {
         long long c1 = r0 + BH;
         if (c1 > a.ld) c1 = a.ld;
-        symv_item<S, false>(a, r0, r0, (int)(c1 - r0), it.x, 0, ush, red);
+        symv_item<S, false>(a, r0, r0, (int)(c1 - r0), it.x, 0, ush, wsum, ring);
     } else {
         const long long c0 = r0 + BH + (long long)(it.y - 1) * BW;
         long long c1 = c0 + BW;
         if (c1 > a.ld) c1 = a.ld;
-        symv_item<S, true>(a, r0, c0, (int)(c1 - c0), it.x, it.y, ush, red);
+        symv_item<S, true>(a, r0, c0, (int)(c1 - c0), it.x, it.y, ush, wsum, ring);
     }
 }
 
-// w[r] = row sums of r's band in item order + column sums of the bands above it in band order; one CTA per 64-row group,
-// which also leaves the group's share of u'w where K2 leaves it (same tree: butterfly inside each warp, warp 0 + warp 1)
+// w[r] = row sums of r's band in item order + column sums of the bands above it; one CTA per 64-row group, which also
+// leaves the group's share of u'w where K2 leaves it (same tree: butterfly inside each warp, warp 0 + warp 1).  The
+// column sums of a row (up to n / BH of them, each a separate cache line) are split over SY_CPARTS threads in contiguous
+// ranges -- a single thread would spend n / BH / 8 memory round trips on them -- and joined in a fixed tree.
+constexpr int SY_CPARTS = 8;
+
 struct SymvCombineArgs {
     const double* rowpart;
     const double* colpart;
@@ -240,36 +279,55 @@ struct SymvCombineArgs {
     const int* done;
 };
 
-__global__ void __launch_bounds__(MV_GROUP) symv_combine_kernel(const SymvCombineArgs a) {
+__global__ void __launch_bounds__(MV_GROUP * SY_CPARTS) symv_combine_kernel(const SymvCombineArgs a) {
     pdl_wait();
     pdl_launch_dependents();
     if (a.done != nullptr && *a.done) return;
+    __shared__ double part[SY_CPARTS][MV_GROUP];
     __shared__ double red[2];
-    const long long rr = (long long)blockIdx.x * MV_GROUP + threadIdx.x;
-    double dv = 0.0;
+    const int t = (int)threadIdx.x % MV_GROUP, p = (int)threadIdx.x / MV_GROUP;   // warps share a part
+    // the last groups have the most column sums to add: they go first, the short ones fill the tail of the grid
+    const unsigned group = gridDim.x - 1u - blockIdx.x;
+    const long long rr = (long long)group * MV_GROUP + t;
+    double v = 0.0;
     if (rr < a.n) {
         const long long band = rr / a.BH;
-        const int nseg = 1 + (int)symv_npanels(a.n, band, a.BH, a.BW);
-        double v = 0.0;
-        for (int s = 0; s < nseg; ++s) v += __ldcg(a.rowpart + (size_t)s * a.n_pad + rr);
+        const long long per = (band + SY_CPARTS - 1) / SY_CPARTS;
+        long long I = p * per, I1 = I + per;
+        if (I1 > band) I1 = band;
         const double* cp = a.colpart + rr;
-        long long I = 0;
-        for (; I + 8 <= band; I += 8) {
-            double t[8];
+        for (; I + 16 <= I1; I += 16) {
+            double tt[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = __ldcg(cp + (size_t)(I + j) * a.ld);
+            for (int j = 0; j < 16; ++j) tt[j] = __ldcg(cp + (size_t)(I + j) * a.ld);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v += t[j];
+            for (int j = 0; j < 16; ++j) v += tt[j];
         }
-        for (; I < band; ++I) v += __ldcg(cp + (size_t)I * a.ld);
-        a.w[rr] = v;
-        if (a.u_rows != nullptr) dv = __dmul_rn(a.u_rows[rr], v);
+        for (; I < I1; ++I) v += __ldcg(cp + (size_t)I * a.ld);
+        if (p == 0) {   // the row sums of the band's own items go in front of part 0 ... after its column sums
+            const int nseg = 1 + (int)symv_npanels(a.n, band, a.BH, a.BW);
+            double rs = 0.0;
+            for (int s = 0; s < nseg; ++s) rs += __ldcg(a.rowpart + (size_t)s * a.n_pad + rr);
+            v = rs + v;
+        }
+    }
+    part[p][t] = v;
+    __syncthreads();
+    double dv = 0.0;
+    if (p == 0 && rr < a.n) {
+        static_assert(SY_CPARTS == 8, "the join below is written for eight parts");
+        const double w = ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) +
+                         ((part[4][t] + part[5][t]) + (part[6][t] + part[7][t]));
+        a.w[rr] = w;
+        if (a.u_rows != nullptr) dv = __dmul_rn(a.u_rows[rr], w);
     }
     if (a.denpart != nullptr) {
+        if (p == 0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dv = __dadd_rn(dv, __shfl_xor_sync(0xffffffffu, dv, o));
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dv;
+            for (int o = 16; o > 0; o >>= 1) dv = __dadd_rn(dv, __shfl_xor_sync(0xffffffffu, dv, o));
+            if ((t & 31) == 0) red[t >> 5] = dv;
+        }
         __syncthreads();
-        if (threadIdx.x == 0) a.denpart[blockIdx.x] = __dadd_rn(red[0], red[1]);
+        if (threadIdx.x == 0) a.denpart[group] = __dadd_rn(red[0], red[1]);
     }
 }

@@ -174,7 +174,13 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     a.colpart = s.sy_colpart;
     a.items = s.sy_items;
     a.done = d_done;
-    SVM_CUDA(svm_launch_chained(symv_tile_kernel<S>, dim3((unsigned)s.sy_nitems), dim3(SY_NT), ctx->stream, a));
+    static bool attr_set[64] = {};   // per device: the ring needs more than the default 48 KB of dynamic shared memory
+    if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {
+        SVM_CUDA(cudaFuncSetAttribute(symv_tile_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::RING_BYTES));
+        attr_set[ctx->device] = true;
+    }
+    SVM_CUDA(svm_launch_chained_smem(symv_tile_kernel<S>, dim3((unsigned)s.sy_nitems), dim3(SY_NT), (size_t)S::RING_BYTES,
+                                     ctx->stream, a));
     SymvCombineArgs c;
     c.rowpart = s.sy_rowpart;
     c.colpart = s.sy_colpart;
@@ -188,7 +194,7 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     c.denpart = ddenpart;
     c.done = d_done;
     const int64_t ngroups = (n + MV_GROUP - 1) / MV_GROUP;
-    SVM_CUDA(svm_launch_chained(symv_combine_kernel, dim3((unsigned)ngroups), dim3(MV_GROUP), ctx->stream, c));
+    SVM_CUDA(svm_launch_chained(symv_combine_kernel, dim3((unsigned)ngroups), dim3(MV_GROUP * SY_CPARTS), ctx->stream, c));
     ctx->launches += 2;
     return SVMB200_OK;
 }
@@ -198,6 +204,29 @@ extern "C" int svmb200_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64
     SVM_TRY(svm_use(ctx));
     SVM_CHECK_ARG(dQ != nullptr && du != nullptr && dw != nullptr && n >= 0, "bad argument");
     return launch_symv(ctx, dQ, n, ld, du, dw, nullptr, nullptr, nullptr);
+}
+
+// bytes of the matrix one symmetric pass streams (diagonal blocks in full + everything to their right) and the shape of
+// its tiles -- what a roofline of K2s is computed from
+extern "C" int svmb200_symv_geometry(int64_t n, int64_t ld, int64_t* streamed_bytes, int64_t* band_rows, int64_t* panel_cols,
+                                     int64_t* items) {
+    using S = SymvDefault;
+    SVM_CHECK_ARG(n >= 0 && ld >= n, "bad argument");
+    std::vector<int2> list;
+    symv_build_items<S>(n, ld, list);
+    int64_t elems = 0;
+    for (const int2& it : list) {
+        const int64_t r0 = (int64_t)it.x * S::BH, rows = n - r0 < S::BH ? n - r0 : S::BH;
+        const int64_t c0 = it.y == 0 ? r0 : r0 + S::BH + (int64_t)(it.y - 1) * S::BW;
+        int64_t c1 = it.y == 0 ? r0 + S::BH : c0 + S::BW;
+        if (c1 > ld) c1 = ld;
+        elems += rows * (c1 - c0);
+    }
+    if (streamed_bytes) *streamed_bytes = 8 * elems;
+    if (band_rows) *band_rows = S::BH;
+    if (panel_cols) *panel_cols = S::BW;
+    if (items) *items = (int64_t)list.size();
+    return SVMB200_OK;
 }
 
 void svm_release_matvec_scratch(svmb200_ctx* ctx) {

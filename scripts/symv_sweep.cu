@@ -70,15 +70,16 @@ void run_shape(const Bufs& b, int reps) {
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, symv_tile_kernel<S>));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, symv_tile_kernel<S>, SY_NT, 0));
+    CK(cudaFuncSetAttribute(symv_tile_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::RING_BYTES));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, symv_tile_kernel<S>, SY_NT, S::RING_BYTES));
     CK(cudaMemset(b.w, 0xFF, b.n * 8));
     auto both = [&]() {
-        CK(svm_launch_chained(symv_tile_kernel<S>, dim3((unsigned)items.size()), dim3(SY_NT), (cudaStream_t)0, a));
-        CK(svm_launch_chained(symv_combine_kernel, dim3(ngroups), dim3(MV_GROUP), (cudaStream_t)0, c));
+        CK(svm_launch_chained_smem(symv_tile_kernel<S>, dim3((unsigned)items.size()), dim3(SY_NT), (size_t)S::RING_BYTES, (cudaStream_t)0, a));
+        CK(svm_launch_chained(symv_combine_kernel, dim3(ngroups), dim3(MV_GROUP * SY_CPARTS), (cudaStream_t)0, c));
     };
     const float ms_both = time_launches(reps, both);
-    const float ms_tile = time_launches(reps, [&]() { CK(svm_launch_chained(symv_tile_kernel<S>, dim3((unsigned)items.size()), dim3(SY_NT), (cudaStream_t)0, a)); });
-    const float ms_comb = time_launches(reps, [&]() { CK(svm_launch_chained(symv_combine_kernel, dim3(ngroups), dim3(MV_GROUP), (cudaStream_t)0, c)); });
+    const float ms_tile = time_launches(reps, [&]() { CK(svm_launch_chained_smem(symv_tile_kernel<S>, dim3((unsigned)items.size()), dim3(SY_NT), (size_t)S::RING_BYTES, (cudaStream_t)0, a)); });
+    const float ms_comb = time_launches(reps, [&]() { CK(svm_launch_chained(symv_combine_kernel, dim3(ngroups), dim3(MV_GROUP * SY_CPARTS), (cudaStream_t)0, c)); });
     // correctness against the full pass
     std::vector<double> w(b.n), wr(b.n);
     CK(cudaMemcpy(w.data(), b.w, b.n * 8, cudaMemcpyDeviceToHost));
@@ -96,9 +97,9 @@ void run_shape(const Bufs& b, int reps) {
         const long long c1 = std::min<long long>(b.ld, it.y == 0 ? r0 + S::BH : c0 + S::BW);
         elems += (double)rows * (double)(c1 - c0);
     }
-    printf("TR%-2d NRB%-2d NCH%d LB%-2d mb%d  BH%-3d BW%-4d items %5zu regs %3d occ %d | pass+combine %8.4f ms  tile %8.4f ms (%7.1f GB/s streamed)  "
+    printf("TR%-2d NRB%-2d NCH%d LB%-2d mb%d st%d BH%-3d BW%-4d items %5zu regs %3d occ %d | pass+combine %8.4f ms  tile %8.4f ms (%7.1f GB/s streamed)  "
            "combine %7.4f ms | vs full-pass bytes: %7.1f GB/s-equivalent | max|dw| %.2e (|w| %.1e)\n",
-           S::TR, S::NRB, S::NCH, S::LB, S::MINB, S::BH, S::BW, items.size(), fa.numRegs, occ, ms_both, ms_tile, 8.0 * elems / ms_tile / 1e6,
+           S::TR, S::NRB, S::NCH, S::LB, S::MINB, S::STAGES, S::BH, S::BW, items.size(), fa.numRegs, occ, ms_both, ms_tile, 8.0 * elems / ms_tile / 1e6,
            ms_comb, 8.0 * (double)b.n * (double)b.ld / ms_both / 1e6, maxd, maxw);
     fflush(stdout);
 }
@@ -141,18 +142,19 @@ int main(int argc, char** argv) {
     const unsigned nitems = (unsigned)(ngroups * MV_BPG * nseg);
     const float ms_full = time_launches(reps / 2 + 1, [&]() { CK(svm_launch_chained(matvec_seg_kernel<false>, dim3(nitems), dim3(MV_NT), (cudaStream_t)0, m)); });
     printf("n = %lld  ld = %lld   full pass (K2): %8.4f ms  %7.1f GB/s\n", n, ld, ms_full, 8.0 * n * ld / ms_full / 1e6);
-    run_shape<SymvShape<16, 8, 4, 8, 2>>(b, reps);
-    run_shape<SymvShape<16, 16, 4, 8, 2>>(b, reps);
-    run_shape<SymvShape<16, 8, 2, 8, 2>>(b, reps);
-    run_shape<SymvShape<16, 4, 4, 8, 2>>(b, reps);
-    run_shape<SymvShape<16, 8, 4, 16, 1>>(b, reps);
-    run_shape<SymvShape<32, 4, 4, 8, 1>>(b, reps);
-    run_shape<SymvShape<32, 4, 2, 16, 1>>(b, reps);
-    run_shape<SymvShape<32, 8, 4, 16, 1>>(b, reps);
-    run_shape<SymvShape<8, 16, 4, 8, 2>>(b, reps);
-    run_shape<SymvShape<8, 16, 4, 4, 3>>(b, reps);
-    run_shape<SymvShape<16, 8, 2, 4, 3>>(b, reps);
-    run_shape<SymvShape<16, 8, 4, 4, 3>>(b, reps);
-    run_shape<SymvShape<16, 8, 4, 8, 2>>(b, reps);
+    run_shape<SymvDefault>(b, reps);
+    if (argc > 3 && strcmp(argv[3], "one") == 0) return 0;   // profiling runs: the shipped shape only
+    run_shape<SymvShape<16, 8, 4, 8, 2, 2>>(b, reps);
+    run_shape<SymvShape<16, 8, 4, 4, 3, 4>>(b, reps);
+    run_shape<SymvShape<16, 8, 4, 8, 3, 2>>(b, reps);
+    run_shape<SymvShape<16, 8, 4, 4, 2, 6>>(b, reps);
+    run_shape<SymvShape<16, 8, 4, 8, 1, 6>>(b, reps);
+    run_shape<SymvShape<8, 16, 4, 8, 3, 2>>(b, reps);
+    run_shape<SymvShape<16, 16, 4, 8, 2, 3>>(b, reps);
+    run_shape<SymvShape<16, 8, 2, 8, 2, 3>>(b, reps);
+    run_shape<SymvShape<32, 4, 4, 8, 2, 3>>(b, reps);
+    run_shape<SymvShape<32, 8, 4, 8, 2, 3>>(b, reps);
+    run_shape<SymvShape<16, 8, 8, 8, 2, 3>>(b, reps);
+    run_shape<SymvShape<16, 8, 4, 8, 2, 3>>(b, reps);
     return 0;
 }

@@ -435,9 +435,11 @@ import symv_checks as SY   # noqa: E402
 
 # small tile shapes so that a few hundred rows cover several bands, ragged last bands and narrow last panels:
 #   BH = TR * NRB rows per band, BW = 512 * NCH columns per panel
-_SYMV_SMALL = ('SVMB200_SYMV_TR=4', 'SVMB200_SYMV_NRB=2', 'SVMB200_SYMV_NCH=1', 'SVMB200_SYMV_LB=2')      # 8 x 512
+_SYMV_SMALL = ('SVMB200_SYMV_TR=4', 'SVMB200_SYMV_NRB=2', 'SVMB200_SYMV_NCH=1', 'SVMB200_SYMV_LB=2',
+               'SVMB200_SYMV_STAGES=2')                                                                    # 8 x 512
 _SYMV_TALL = ('SVMB200_SYMV_TR=16', 'SVMB200_SYMV_NRB=4', 'SVMB200_SYMV_NCH=2', 'SVMB200_SYMV_LB=8')      # 64 x 1024
-_SYMV_WIDE32 = ('SVMB200_SYMV_TR=32', 'SVMB200_SYMV_NRB=2', 'SVMB200_SYMV_NCH=1', 'SVMB200_SYMV_LB=16')   # 64 x 512
+_SYMV_WIDE32 = ('SVMB200_SYMV_TR=32', 'SVMB200_SYMV_NRB=2', 'SVMB200_SYMV_NCH=1', 'SVMB200_SYMV_LB=16',
+                'SVMB200_SYMV_STAGES=2')                                                                   # 64 x 512
 
 
 @pytest.mark.parametrize('n,defines', [(70, _SYMV_SMALL), (600, _SYMV_SMALL), (1100, _SYMV_TALL), (200, _SYMV_WIDE32),
