@@ -60,39 +60,151 @@ struct SymvShape {
 };
 using SymvDefault = SymvShape<SVMB200_SYMV_TR, SVMB200_SYMV_NRB, SVMB200_SYMV_NCH, SVMB200_SYMV_LB, SVMB200_SYMV_MINB, SVMB200_SYMV_STAGES>;
 
-// panels of band `band`: columns (band+1) BH ... n - 1 in steps of BW (columns >= n meet u = 0: nothing to add)
-__host__ __device__ inline long long symv_npanels(long long n, long long band, int BH, int BW) {
-    const long long first = (band + 1) * BH;
-    return first >= n ? 0 : (n - first + BW - 1) / BW;
+// ------------------------------------------------------------------------------------------ the plan of a pass
+// One rank (P = 1) works through the upper triangle of the whole matrix.  With the matrix cut into P row blocks
+// (svmb200_shard_rows, rank r holds block r in full), the P x P grid of blocks is symmetric as well, and every pair of
+// off-diagonal blocks (p, q), (q, p) needs ONE of them: rank p takes block (p, q) for the (P - 1) / 2 ranks q that follow
+// it cyclically, and for an even P the pair at distance P / 2 is halved (the lower rank takes the first h columns of
+// its block, the upper rank the rows from h on of its own, h = half the upper rank's rows rounded down to a band) -- every
+// rank streams the same share, half of its block row.  What a rank computes from block (p, q):
+//     row sums     -> its own rows                         (rowpart, as on one rank)
+//     column sums  -> rows of rank q: reduced over its bands and SENT to q   (symv_send_kernel -> q's inbox, tagged entries)
+// and its diagonal block is a small one-rank problem.  The owner of a row adds, in a fixed order, the row sums of its
+// own items, the column sums of its own bands above the row and the column sums it was sent (ascending sender rank) --
+// symv_combine_kernel -- and publishes the finished product exactly as K2 does (own w, or tagged entries into every
+// rank's gathered buffer), so the vector kernels do not know which pass fed them.
+struct SymvItem {
+    int lr0;     // first LOCAL row of the band
+    int c0;      // first column
+    int width;   // columns (even; a last panel is narrower than BW)
+    int seg;     // slot of the item's row sums in rowpart
+    int cols;    // 1: column sums too (everything but a diagonal block)
+};
+struct SymvSend {
+    int dest;    // owner of the columns
+    int c0;      // first column
+    int ncols;   // columns (= rows of dest) covered
+    int lr0;     // local row of dest that column c0 is
+    int band0, band1;   // local bands whose column sums are added
+};
+struct SymvRecv {
+    int src;       // sending rank
+    int lr0, lr1;  // my local rows it sends column sums for
+};
+struct SymvPlan {
+    std::vector<SymvItem> items;   // large items first
+    std::vector<int> nseg;         // per local band: items (= row-sum slots) of the band
+    std::vector<SymvSend> sends;
+    std::vector<SymvRecv> recvs;   // ascending sender
+    int nseg_max = 0;
+    long long row0 = 0, nrows = 0, nbands = 0, streamed_elems = 0;
+};
+
+inline void symv_block(long long n, long long rpr, int r, long long* row0, long long* nrows) {
+    long long r0 = (long long)r * rpr;
+    if (r0 > n) r0 = n;
+    *row0 = r0;
+    *nrows = n - r0 < rpr ? n - r0 : rpr;
 }
 
-// work list of an n x n pass: full panels first, then the narrow last panels, the diagonal blocks at the end -- the SMs
-// that run out of large items fill the tail of the grid with small ones (the order never changes a bit of the result)
+// does rank p read (part of) block (p, q)?  *c_lo, *c_hi: the columns (relative to block q's first); *b_lo: first local
+// band of p that takes part
 template <class S>
-inline void symv_build_items(long long n, long long ld, std::vector<int2>& items) {
-    const long long nbands = (n + S::BH - 1) / S::BH;
-    items.clear();
-    for (int pass = 0; pass < 2; ++pass) {
-        for (long long I = 0; I < nbands; ++I) {
-            const long long np = symv_npanels(n, I, S::BH, S::BW);
-            for (long long p = 0; p < np; ++p) {
-                const long long c0 = (I + 1) * S::BH + p * S::BW;
-                const bool full = c0 + S::BW <= ld && (I + 1) * S::BH <= n;
-                if (full == (pass == 0)) items.push_back(make_int2((int)I, (int)(p + 1)));
-            }
+inline bool symv_takes(long long n, long long rpr, int P, int p, int q, long long* c_lo, long long* c_hi, long long* b_lo) {
+    long long row0q, nrq, row0p, nrp;
+    symv_block(n, rpr, q, &row0q, &nrq);
+    symv_block(n, rpr, p, &row0p, &nrp);
+    *c_lo = 0;
+    *c_hi = nrq;
+    *b_lo = 0;
+    if (p == q || nrq <= 0 || nrp <= 0) return false;
+    const int d = ((q - p) % P + P) % P;
+    if (2 * d < P) return true;
+    if (2 * d > P) return false;
+    // the halved pair: lo = min(p, q) reads the first h columns of (lo, hi); hi reads its rows from h on of (hi, lo)
+    const int hi = p > q ? p : q;
+    long long row0h, nrh;
+    symv_block(n, rpr, hi, &row0h, &nrh);
+    const long long h = nrh / 2 / S::BH * S::BH;
+    if (p < q) {
+        *c_hi = h;
+        return h > 0;
+    }
+    *b_lo = h / S::BH;
+    return true;
+}
+
+template <class S>
+inline void symv_build_plan(long long n, long long ld, int rank, int P, long long rpr, SymvPlan& plan) {
+    plan = SymvPlan();
+    symv_block(n, rpr, rank, &plan.row0, &plan.nrows);
+    const long long row0 = plan.row0, nrows = plan.nrows;
+    plan.nbands = (nrows + S::BH - 1) / S::BH;
+    plan.nseg.assign((size_t)plan.nbands, 0);
+    // the last block also owns the padding columns [n, ld): they meet u = 0, and the width of a panel stays even
+    auto block_end = [&](int r) {
+        long long r0, nr;
+        symv_block(n, rpr, r, &r0, &nr);
+        return r == P - 1 ? ld : r0 + nr;
+    };
+    std::vector<SymvItem> big, small, diag;
+    auto add_range = [&](long long I, long long c_begin, long long c_end) {   // panels of band I over columns [c_begin, c_end)
+        const long long rows = nrows - I * S::BH < S::BH ? nrows - I * S::BH : S::BH;
+        for (long long c = c_begin; c < c_end && c < n; c += S::BW) {   // a panel that starts at or beyond n meets u = 0 only
+            const long long w = c_end - c < S::BW ? c_end - c : S::BW;
+            SymvItem it = {(int)(I * S::BH), (int)c, (int)w, plan.nseg[(size_t)I]++, 1};
+            (w == S::BW && rows == S::BH ? big : small).push_back(it);
+            plan.streamed_elems += rows * w;
+        }
+    };
+    for (long long I = 0; I < plan.nbands; ++I) {
+        const long long rows = nrows - I * S::BH < S::BH ? nrows - I * S::BH : S::BH;
+        const long long g0 = row0 + I * S::BH;
+        long long dend = g0 + S::BH;   // the diagonal block, clipped to this rank's block
+        if (dend > block_end(rank)) dend = block_end(rank);
+        SymvItem d = {(int)(I * S::BH), (int)g0, (int)(dend - g0), plan.nseg[(size_t)I]++, 0};
+        diag.push_back(d);
+        plan.streamed_elems += rows * (dend - g0);
+        add_range(I, dend, block_end(rank));
+        for (int k = 1; k < P; ++k) {
+            const int q = (rank + k) % P;
+            long long c_lo, c_hi, b_lo, row0q, nrq;
+            if (!symv_takes<S>(n, rpr, P, rank, q, &c_lo, &c_hi, &b_lo) || I < b_lo) continue;
+            symv_block(n, rpr, q, &row0q, &nrq);
+            const long long cend = c_hi == nrq ? block_end(q) : row0q + c_hi;
+            add_range(I, row0q + c_lo, cend);
         }
     }
-    for (long long I = 0; I < nbands; ++I) items.push_back(make_int2((int)I, 0));
+    plan.items = big;
+    plan.items.insert(plan.items.end(), small.begin(), small.end());
+    plan.items.insert(plan.items.end(), diag.begin(), diag.end());
+    for (int v : plan.nseg) plan.nseg_max = v > plan.nseg_max ? v : plan.nseg_max;
+    for (int q = 0; q < P; ++q) {
+        long long c_lo, c_hi, b_lo, row0q, nrq;
+        symv_block(n, rpr, q, &row0q, &nrq);
+        if (symv_takes<S>(n, rpr, P, rank, q, &c_lo, &c_hi, &b_lo) && b_lo < plan.nbands) {
+            SymvSend sd = {q, (int)(row0q + c_lo), (int)(c_hi - c_lo), (int)c_lo, (int)b_lo, (int)plan.nbands};
+            plan.sends.push_back(sd);
+        }
+        long long nbq, row0me, nrme;
+        symv_block(n, rpr, rank, &row0me, &nrme);
+        nbq = (nrq + S::BH - 1) / S::BH;
+        if (symv_takes<S>(n, rpr, P, q, rank, &c_lo, &c_hi, &b_lo) && b_lo < nbq) {
+            SymvRecv rv = {q, (int)c_lo, (int)c_hi};
+            plan.recvs.push_back(rv);
+        }
+    }
 }
 
 struct SymvArgs {
-    const double* Q;     // n x ld, symmetric in its leading n x n block
-    long long ld, n, n_pad;
+    const double* Q;     // this rank's rows x ld; the whole matrix is symmetric
+    long long ld, nrows, row0, n_pad;
     const double* u;     // ld entries, zero beyond n
-    double* rowpart;     // [1 + max panels][n_pad]
-    double* colpart;     // [bands][ld]
-    const int2* items;   // {band, seg}: the work list, large items first
+    double* rowpart;     // [max items per band][n_pad]
+    double* colpart;     // [local bands][ld]
+    const SymvItem* items;
     const int* done;
+    const int* fault;    // the context's sticky exchange-fault flag, or null
 };
 
 // sums v[i] over the 32 lanes for all i < TR at once: the butterfly halves the set of rows a lane is responsible for at
@@ -145,7 +257,7 @@ __device__ __forceinline__ void symv_item(const SymvArgs& a, const long long r0,
     static_assert(ST >= 2 && ST <= NBATCH, "ring depth: between 2 batches and one sub-block");
     const int tid = (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nch = (width + SY_CHUNK - 1) / SY_CHUNK;  // chunks this item has (a diagonal block or a last panel: fewer)
-    const int rows = (int)(a.n - r0 < S::BH ? a.n - r0 : S::BH);
+    const int rows = (int)(a.nrows - r0 < S::BH ? a.nrows - r0 : S::BH);   // r0: first LOCAL row of the band
     const int nrb = (rows + TR - 1) / TR;               // sub-blocks this item has (the last band: fewer)
     // the thread's columns, relative to c0; a column beyond the item reads column 0 of it against u = 0
     int coff[NCH];
@@ -237,7 +349,8 @@ __global__ void __launch_bounds__(SY_NT, S::MINB) symv_tile_kernel(const SymvArg
     pdl_wait();               // u (and the done flag) come from the vector launch before this one
     pdl_launch_dependents();
     if (a.done != nullptr && *a.done) return;
-    constexpr int BH = S::BH, BW = S::BW;
+    if (a.fault != nullptr && *a.fault) return;  // the exchange is broken: nothing downstream will be used
+    constexpr int BH = S::BH;
 #ifndef SVMB200_HOST_EMULATION
     extern __shared__ __align__(16) unsigned char sy_smem_raw[];
     double2* ring = reinterpret_cast<double2*>(sy_smem_raw);
@@ -246,19 +359,52 @@ __global__ void __launch_bounds__(SY_NT, S::MINB) symv_tile_kernel(const SymvArg
 #endif
     __shared__ double ush[BH];
     __shared__ double wsum[SY_NT / 32][BH];   // row sums per warp
-    const int2 it = a.items[blockIdx.x];
-    const long long r0 = (long long)it.x * BH;
-    for (int i = (int)threadIdx.x; i < BH; i += SY_NT) ush[i] = r0 + i < a.n ? a.u[r0 + i] : 0.0;
+    const SymvItem it = a.items[blockIdx.x];
+    const long long r0 = it.lr0;
+    for (int i = (int)threadIdx.x; i < BH; i += SY_NT) ush[i] = r0 + i < a.nrows ? a.u[a.row0 + r0 + i] : 0.0;
     __syncthreads();
-    if (it.y == 0) {
-        long long c1 = r0 + BH;
-        if (c1 > a.ld) c1 = a.ld;
-        symv_item<S, false>(a, r0, r0, (int)(c1 - r0), it.x, 0, ush, wsum, ring);
-    } else {
-        const long long c0 = r0 + BH + (long long)(it.y - 1) * BW;
-        long long c1 = c0 + BW;
-        if (c1 > a.ld) c1 = a.ld;
-        symv_item<S, true>(a, r0, c0, (int)(c1 - c0), it.x, it.y, ush, wsum, ring);
+    if (it.cols) symv_item<S, true>(a, r0, it.c0, it.width, it.lr0 / BH, it.seg, ush, wsum, ring);
+    else symv_item<S, false>(a, r0, it.c0, it.width, it.lr0 / BH, it.seg, ush, wsum, ring);
+}
+
+// ---- column sums that belong to other ranks' rows: added over this rank's bands (band order) and stored into the
+// owner's inbox as tagged entries (k2_matvec.cuh, ll_store).  One thread per column.
+struct SymvSendArgs {
+    const double* colpart;
+    long long ld;
+    int nsend;
+    SymvSend sends[SVM_MAX_RANKS];
+    ulonglong2* inbox[SVM_MAX_RANKS];   // per send: this rank's slot in the destination's inbox (entry of its local row 0)
+    unsigned tag;
+    const int* done;
+    const int* fault;
+};
+
+__global__ void __launch_bounds__(256) symv_send_kernel(const SymvSendArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (a.done != nullptr && *a.done) return;
+    if (a.fault != nullptr && *a.fault) return;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int s = 0; s < a.nsend; ++s) {
+        const SymvSend sd = a.sends[s];
+        if (idx >= sd.ncols) {
+            idx -= sd.ncols;
+            continue;
+        }
+        const double* cp = a.colpart + sd.c0 + idx;
+        double v = 0.0;
+        int I = sd.band0;
+        for (; I + 16 <= sd.band1; I += 16) {
+            double t[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) t[j] = __ldcg(cp + (size_t)(I + j) * a.ld);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v += t[j];
+        }
+        for (; I < sd.band1; ++I) v += __ldcg(cp + (size_t)I * a.ld);
+        ll_store(a.inbox[s] + sd.lr0 + idx, v, a.tag);
+        return;
     }
 }
 
@@ -271,31 +417,44 @@ constexpr int SY_CPARTS = 8;
 struct SymvCombineArgs {
     const double* rowpart;
     const double* colpart;
-    long long ld, n, n_pad;
-    int BH, BW;
-    const double* u_rows;   // u at the rows, or null
-    double* w;
+    long long ld, nrows, row0, n_pad;
+    int BH;
+    const int* nseg;        // per local band: row-sum slots in use
+    const double* u_rows;   // u at this rank's rows, or null
+    double* w;              // nrows results (no exchange)
     double* denpart;        // one per 64-row group, or null
     const int* done;
+    // column sums sent by other ranks (sharded pass): inbox + (src * rpr + local row), tagged entries
+    int nrecv;
+    SymvRecv recvs[SVM_MAX_RANKS];
+    const ulonglong2* inbox;
+    long long rpr;
+    unsigned tag;
+    int* fault;
+    // fused exchange of the finished product (nranks_x > 0), as in MatvecArgs
+    int nranks_x;
+    long long share_off;    // slot of the first u'w share relative to the slot of row 0
+    ulonglong2* peer_w[SVM_MAX_RANKS];
 };
 
 __global__ void __launch_bounds__(MV_GROUP * SY_CPARTS) symv_combine_kernel(const SymvCombineArgs a) {
     pdl_wait();
     pdl_launch_dependents();
     if (a.done != nullptr && *a.done) return;
+    if (a.fault != nullptr && *a.fault) return;
     __shared__ double part[SY_CPARTS][MV_GROUP];
     __shared__ double red[2];
     const int t = (int)threadIdx.x % MV_GROUP, p = (int)threadIdx.x / MV_GROUP;   // warps share a part
     // the last groups have the most column sums to add: they go first, the short ones fill the tail of the grid
     const unsigned group = gridDim.x - 1u - blockIdx.x;
-    const long long rr = (long long)group * MV_GROUP + t;
+    const long long rr = (long long)group * MV_GROUP + t;   // local row
     double v = 0.0;
-    if (rr < a.n) {
+    if (rr < a.nrows) {
         const long long band = rr / a.BH;
         const long long per = (band + SY_CPARTS - 1) / SY_CPARTS;
         long long I = p * per, I1 = I + per;
         if (I1 > band) I1 = band;
-        const double* cp = a.colpart + rr;
+        const double* cp = a.colpart + a.row0 + rr;
         for (; I + 16 <= I1; I += 16) {
             double tt[16];
 #pragma unroll
@@ -304,8 +463,8 @@ __global__ void __launch_bounds__(MV_GROUP * SY_CPARTS) symv_combine_kernel(cons
             for (int j = 0; j < 16; ++j) v += tt[j];
         }
         for (; I < I1; ++I) v += __ldcg(cp + (size_t)I * a.ld);
-        if (p == 0) {   // the row sums of the band's own items go in front of part 0 ... after its column sums
-            const int nseg = 1 + (int)symv_npanels(a.n, band, a.BH, a.BW);
+        if (p == 0) {   // the row sums of the band's own items go in front of part 0
+            const int nseg = a.nseg[band];
             double rs = 0.0;
             for (int s = 0; s < nseg; ++s) rs += __ldcg(a.rowpart + (size_t)s * a.n_pad + rr);
             v = rs + v;
@@ -314,11 +473,19 @@ __global__ void __launch_bounds__(MV_GROUP * SY_CPARTS) symv_combine_kernel(cons
     part[p][t] = v;
     __syncthreads();
     double dv = 0.0;
-    if (p == 0 && rr < a.n) {
+    if (p == 0 && rr < a.nrows) {
         static_assert(SY_CPARTS == 8, "the join below is written for eight parts");
-        const double w = ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) +
-                         ((part[4][t] + part[5][t]) + (part[6][t] + part[7][t]));
-        a.w[rr] = w;
+        double w = ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) +
+                   ((part[4][t] + part[5][t]) + (part[6][t] + part[7][t]));
+        for (int s = 0; s < a.nrecv; ++s) {   // ascending sender
+            const SymvRecv rv = a.recvs[s];
+            if (rr >= rv.lr0 && rr < rv.lr1) w += ll_load(a.inbox + (size_t)rv.src * a.rpr + rr, a.tag, a.fault);
+        }
+        if (a.nranks_x > 0) {
+            for (int q = 0; q < a.nranks_x; ++q) ll_store(a.peer_w[q] + rr, w, a.tag);   // NVLink stores (one is local)
+        } else {
+            a.w[rr] = w;
+        }
         if (a.u_rows != nullptr) dv = __dmul_rn(a.u_rows[rr], w);
     }
     if (a.denpart != nullptr) {
@@ -328,6 +495,13 @@ __global__ void __launch_bounds__(MV_GROUP * SY_CPARTS) symv_combine_kernel(cons
             if ((t & 31) == 0) red[t >> 5] = dv;
         }
         __syncthreads();
-        if (threadIdx.x == 0) a.denpart[group] = __dadd_rn(red[0], red[1]);
+        if (threadIdx.x == 0) {
+            const double tot = __dadd_rn(red[0], red[1]);
+            if (a.nranks_x > 0) {
+                for (int q = 0; q < a.nranks_x; ++q) ll_store(a.peer_w[q] + a.share_off + group, tot, a.tag);
+            } else {
+                a.denpart[group] = tot;
+            }
+        }
     }
 }

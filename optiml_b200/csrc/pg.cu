@@ -25,13 +25,15 @@ struct MatvecScratch {
     double* wpart = nullptr;
     unsigned* tickets = nullptr;
     size_t wpart_elems = 0, ticket_elems = 0;
-    // symmetric pass (K2s): row / column partials and the work list of the (n, ld) it was last built for
+    // symmetric pass (K2s): row / column partials and the plan of the (n, ld, rank, ranks) it was last built for
     double* sy_rowpart = nullptr;
     double* sy_colpart = nullptr;
-    int2* sy_items = nullptr;
-    size_t sy_row_elems = 0, sy_col_elems = 0, sy_item_cap = 0;
-    int64_t sy_n = -1, sy_ld = -1, sy_nitems = 0;
-    std::vector<int2> sy_host_items;
+    SymvItem* sy_items = nullptr;
+    int* sy_nseg = nullptr;
+    size_t sy_row_elems = 0, sy_col_elems = 0, sy_item_cap = 0, sy_nseg_cap = 0;
+    int64_t sy_n = -1, sy_ld = -1;
+    int sy_rank = -1, sy_P = -1;
+    SymvPlan sy_plan;
 };
 
 static int matvec_scratch_reserve(svmb200_ctx* ctx, MatvecScratch& s, int64_t nrows, int64_t ld, int nvec = 1) {
@@ -119,10 +121,17 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
 }
 
 // ------------------------------------------------------------------------------------------ K2s launcher
-// w = Q u from the upper triangle of the symmetric n x n matrix dQ (see k2_symv.cuh); same outputs as launch_matvec
-// (w, and the shares of u'w per 64-row group when du_rows / ddenpart are given).  One rank, whole matrix.
-static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, const double* du, double* dw,
-                       const double* du_rows, double* ddenpart, const int* d_done) {
+// w = Q u from the upper triangle of the symmetric matrix (see k2_symv.cuh); same outputs as launch_matvec (w, and the
+// shares of u'w per 64-row group when du_rows / ddenpart are given).  One rank holding the whole matrix, or the ranks of
+// a fused peer exchange (xt != null): `phase` 1 = tile pass + the column sums for the other ranks, 2 = combine (waits
+// for the column sums of the others), 0 = both.  A single host thread that drives several ranks issues phase 1 for all
+// of them before phase 2 (the host emulation runs launches synchronously; on hardware the order is immaterial).
+constexpr size_t symv_inbox_bytes(int64_t rpr, int P) { return (size_t)P * (size_t)rpr * sizeof(ulonglong2); }
+static size_t symv_inbox_off(const svmb200_ctx* ctx) { return ctx->arena_bytes / 2; }
+
+static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t rpr, const double* du, double* dw,
+                       const double* du_rows, double* ddenpart, const int* d_done, const ExchangeTargets* xt = nullptr,
+                       unsigned long long seq = 0, int phase = 0) {
     using S = SymvDefault;
     if (n <= 0) return SVMB200_OK;
     if (ld % 2 != 0 || ld < n) {
@@ -133,69 +142,119 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
         svmb200_set_error("symv: operands must be 16-byte aligned");
         return SVMB200_ERR_ARG;
     }
+    const int P = xt ? xt->nranks : 1, rank = xt ? ctx->rank : 0;
     if (!ctx->matvec_scratch) ctx->matvec_scratch = new MatvecScratch();
     MatvecScratch& s = *static_cast<MatvecScratch*>(ctx->matvec_scratch);
-    const int64_t nbands = (n + S::BH - 1) / S::BH;
-    const int64_t n_pad = round_up64(n, 16);
-    const int64_t nseg_max = 1 + symv_npanels(n, 0, S::BH, S::BW);
-    if (s.sy_n != n || s.sy_ld != ld) {
-        std::vector<int2>& items = s.sy_host_items;
-        symv_build_items<S>(n, ld, items);
-        const size_t need_r = (size_t)nseg_max * n_pad, need_c = (size_t)nbands * ld;
-        if (need_r > s.sy_row_elems || need_c > s.sy_col_elems || items.size() > s.sy_item_cap) {
+    if (s.sy_n != n || s.sy_ld != ld || s.sy_rank != rank || s.sy_P != P) {
+        SymvPlan& plan = s.sy_plan;
+        symv_build_plan<S>(n, ld, rank, P, P == 1 ? n : rpr, plan);
+        const size_t n_pad = (size_t)round_up64(plan.nrows, 16);
+        const size_t need_r = (size_t)plan.nseg_max * n_pad, need_c = (size_t)plan.nbands * ld;
+        if (need_r > s.sy_row_elems || need_c > s.sy_col_elems || plan.items.size() > s.sy_item_cap ||
+            plan.nseg.size() > s.sy_nseg_cap) {
             SVM_CUDA(cudaStreamSynchronize(ctx->stream));
             if (s.sy_rowpart) cudaFree(s.sy_rowpart);
             if (s.sy_colpart) cudaFree(s.sy_colpart);
             if (s.sy_items) cudaFree(s.sy_items);
+            if (s.sy_nseg) cudaFree(s.sy_nseg);
             s.sy_rowpart = s.sy_colpart = nullptr;
             s.sy_items = nullptr;
-            s.sy_row_elems = s.sy_col_elems = s.sy_item_cap = 0;
+            s.sy_nseg = nullptr;
+            s.sy_row_elems = s.sy_col_elems = s.sy_item_cap = s.sy_nseg_cap = 0;
             s.sy_n = s.sy_ld = -1;
-            SVM_CUDA(cudaMalloc(&s.sy_rowpart, need_r * sizeof(double)));
+            SVM_CUDA(cudaMalloc(&s.sy_rowpart, (need_r ? need_r : 1) * sizeof(double)));
             s.sy_row_elems = need_r;
-            SVM_CUDA(cudaMalloc(&s.sy_colpart, need_c * sizeof(double)));
+            SVM_CUDA(cudaMalloc(&s.sy_colpart, (need_c ? need_c : 1) * sizeof(double)));
             s.sy_col_elems = need_c;
-            SVM_CUDA(cudaMalloc(&s.sy_items, items.size() * sizeof(int2)));
-            s.sy_item_cap = items.size();
+            SVM_CUDA(cudaMalloc(&s.sy_items, (plan.items.size() + 1) * sizeof(SymvItem)));
+            s.sy_item_cap = plan.items.size();
+            SVM_CUDA(cudaMalloc(&s.sy_nseg, (plan.nseg.size() + 1) * sizeof(int)));
+            s.sy_nseg_cap = plan.nseg.size();
         }
-        SVM_CUDA(cudaMemcpyAsync(s.sy_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-        SVM_CUDA(cudaStreamSynchronize(ctx->stream));  // once per problem size; the list stays valid for every later pass
+        if (!plan.items.empty())
+            SVM_CUDA(cudaMemcpyAsync(s.sy_items, plan.items.data(), plan.items.size() * sizeof(SymvItem), cudaMemcpyHostToDevice, ctx->stream));
+        if (!plan.nseg.empty())
+            SVM_CUDA(cudaMemcpyAsync(s.sy_nseg, plan.nseg.data(), plan.nseg.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        SVM_CUDA(cudaStreamSynchronize(ctx->stream));  // once per problem size; the tables stay valid for every later pass
         s.sy_n = n;
         s.sy_ld = ld;
-        s.sy_nitems = (int64_t)items.size();
+        s.sy_rank = rank;
+        s.sy_P = P;
     }
-    SymvArgs a;
-    a.Q = dQ;
-    a.ld = ld;
-    a.n = n;
-    a.n_pad = n_pad;
-    a.u = du;
-    a.rowpart = s.sy_rowpart;
-    a.colpart = s.sy_colpart;
-    a.items = s.sy_items;
-    a.done = d_done;
-    static bool attr_set[64] = {};   // per device: the ring needs more than the default 48 KB of dynamic shared memory
-    if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {
-        SVM_CUDA(cudaFuncSetAttribute(symv_tile_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::RING_BYTES));
-        attr_set[ctx->device] = true;
+    const SymvPlan& plan = s.sy_plan;
+    if (plan.nrows <= 0) return SVMB200_OK;
+    const long long n_pad = round_up64(plan.nrows, 16);
+    const int* fault = xt ? reinterpret_cast<const int*>(ctx->arena + ARENA_LOCAL_OFF + 8) : nullptr;
+    const unsigned tag = xt ? xt->tag : 0u;
+    const size_t inbox_par = xt ? symv_inbox_off(ctx) + (size_t)(seq & 1) * symv_inbox_bytes(rpr, P) : 0;
+    if (phase == 0 || phase == 1) {
+        SymvArgs a;
+        a.Q = dQ;
+        a.ld = ld;
+        a.nrows = plan.nrows;
+        a.row0 = plan.row0;
+        a.n_pad = n_pad;
+        a.u = du;
+        a.rowpart = s.sy_rowpart;
+        a.colpart = s.sy_colpart;
+        a.items = s.sy_items;
+        a.done = d_done;
+        a.fault = fault;
+        static bool attr_set[64] = {};   // per device: the ring needs more than the default 48 KB of dynamic shared memory
+        if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {
+            SVM_CUDA(cudaFuncSetAttribute(symv_tile_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::RING_BYTES));
+            attr_set[ctx->device] = true;
+        }
+        SVM_CUDA(svm_launch_chained_smem(symv_tile_kernel<S>, dim3((unsigned)plan.items.size()), dim3(SY_NT),
+                                         (size_t)S::RING_BYTES, ctx->stream, a));
+        ctx->launches++;
+        if (!plan.sends.empty()) {
+            SymvSendArgs sa = {};
+            sa.colpart = s.sy_colpart;
+            sa.ld = ld;
+            sa.nsend = (int)plan.sends.size();
+            long long total = 0;
+            for (int i = 0; i < sa.nsend; ++i) {
+                sa.sends[i] = plan.sends[(size_t)i];
+                sa.inbox[i] = reinterpret_cast<ulonglong2*>(ctx->peer_arena[plan.sends[(size_t)i].dest] + inbox_par) + (size_t)rank * rpr;
+                total += plan.sends[(size_t)i].ncols;
+            }
+            sa.tag = tag;
+            sa.done = d_done;
+            sa.fault = fault;
+            SVM_CUDA(svm_launch_chained(symv_send_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), ctx->stream, sa));
+            ctx->launches++;
+        }
     }
-    SVM_CUDA(svm_launch_chained_smem(symv_tile_kernel<S>, dim3((unsigned)s.sy_nitems), dim3(SY_NT), (size_t)S::RING_BYTES,
-                                     ctx->stream, a));
-    SymvCombineArgs c;
-    c.rowpart = s.sy_rowpart;
-    c.colpart = s.sy_colpart;
-    c.ld = ld;
-    c.n = n;
-    c.n_pad = n_pad;
-    c.BH = S::BH;
-    c.BW = S::BW;
-    c.u_rows = du_rows;
-    c.w = dw;
-    c.denpart = ddenpart;
-    c.done = d_done;
-    const int64_t ngroups = (n + MV_GROUP - 1) / MV_GROUP;
-    SVM_CUDA(svm_launch_chained(symv_combine_kernel, dim3((unsigned)ngroups), dim3(MV_GROUP * SY_CPARTS), ctx->stream, c));
-    ctx->launches += 2;
+    if (phase == 0 || phase == 2) {
+        SymvCombineArgs c = {};
+        c.rowpart = s.sy_rowpart;
+        c.colpart = s.sy_colpart;
+        c.ld = ld;
+        c.nrows = plan.nrows;
+        c.row0 = plan.row0;
+        c.n_pad = n_pad;
+        c.BH = S::BH;
+        c.nseg = s.sy_nseg;
+        c.u_rows = du_rows;
+        c.w = dw;
+        c.denpart = ddenpart;
+        c.done = d_done;
+        c.nrecv = (int)plan.recvs.size();
+        for (int i = 0; i < c.nrecv; ++i) c.recvs[i] = plan.recvs[(size_t)i];
+        c.inbox = xt ? reinterpret_cast<const ulonglong2*>(ctx->arena + inbox_par) : nullptr;
+        c.rpr = rpr;
+        c.tag = tag;
+        c.fault = const_cast<int*>(fault);
+        if (xt != nullptr) {
+            c.nranks_x = xt->nranks;
+            c.share_off = (long long)(ddenpart - dw);
+            for (int r = 0; r < xt->nranks; ++r) c.peer_w[r] = xt->peer_w[r];
+        }
+        const int64_t ngroups = (plan.nrows + MV_GROUP - 1) / MV_GROUP;
+        SVM_CUDA(svm_launch_chained(symv_combine_kernel, dim3((unsigned)ngroups), dim3(MV_GROUP * SY_CPARTS), ctx->stream, c));
+        ctx->launches++;
+    }
     return SVMB200_OK;
 }
 
@@ -203,7 +262,7 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
 extern "C" int svmb200_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, const double* du, double* dw) {
     SVM_TRY(svm_use(ctx));
     SVM_CHECK_ARG(dQ != nullptr && du != nullptr && dw != nullptr && n >= 0, "bad argument");
-    return launch_symv(ctx, dQ, n, ld, du, dw, nullptr, nullptr, nullptr);
+    return launch_symv(ctx, dQ, n, ld, n, du, dw, nullptr, nullptr, nullptr);
 }
 
 // bytes of the matrix one symmetric pass streams (diagonal blocks in full + everything to their right) and the shape of
@@ -212,20 +271,12 @@ extern "C" int svmb200_symv_geometry(int64_t n, int64_t ld, int64_t* streamed_by
                                      int64_t* items) {
     using S = SymvDefault;
     SVM_CHECK_ARG(n >= 0 && ld >= n, "bad argument");
-    std::vector<int2> list;
-    symv_build_items<S>(n, ld, list);
-    int64_t elems = 0;
-    for (const int2& it : list) {
-        const int64_t r0 = (int64_t)it.x * S::BH, rows = n - r0 < S::BH ? n - r0 : S::BH;
-        const int64_t c0 = it.y == 0 ? r0 : r0 + S::BH + (int64_t)(it.y - 1) * S::BW;
-        int64_t c1 = it.y == 0 ? r0 + S::BH : c0 + S::BW;
-        if (c1 > ld) c1 = ld;
-        elems += rows * (c1 - c0);
-    }
-    if (streamed_bytes) *streamed_bytes = 8 * elems;
+    SymvPlan plan;
+    symv_build_plan<S>(n, ld, 0, 1, n, plan);
+    if (streamed_bytes) *streamed_bytes = 8 * plan.streamed_elems;
+    if (items) *items = (int64_t)plan.items.size();
     if (band_rows) *band_rows = S::BH;
     if (panel_cols) *panel_cols = S::BW;
-    if (items) *items = (int64_t)list.size();
     return SVMB200_OK;
 }
 
@@ -237,6 +288,7 @@ void svm_release_matvec_scratch(svmb200_ctx* ctx) {
         if (s->sy_rowpart) cudaFree(s->sy_rowpart);
         if (s->sy_colpart) cudaFree(s->sy_colpart);
         if (s->sy_items) cudaFree(s->sy_items);
+        if (s->sy_nseg) cudaFree(s->sy_nseg);
         delete s;
         ctx->matvec_scratch = nullptr;
     }
@@ -453,11 +505,17 @@ static int launch_vec(svmb200_pg* pg, long long k) {
 
 static cudaEvent_t pooled_event(svmb200_ctx* ctx);
 
-static int pg_product(svmb200_pg* pg, bool timed) {
+// phase: 0 = the whole product; 1 / 2 = its two halves when a single host thread drives several ranks of a symmetric
+// sharded solve (tile pass + sends for every rank first, then every rank's combine); for every other solver phase 1 is the
+// whole product and phase 2 nothing
+static int pg_product(svmb200_pg* pg, bool timed, int phase = 0) {
     // w[row0 : row0+nrows] = Q_shard u, then all ranks exchange their shards (K4)
     svmb200_ctx* ctx = pg->ctx;
+    const bool split = pg->symmetric && pg->p2p;
+    if (phase == 2 && !split) return SVMB200_OK;
+    if (phase == 1 && !split) phase = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-    if (timed) {
+    if (timed && phase != 2) {
         e0 = pooled_event(ctx);
         e1 = pooled_event(ctx);
         e2 = pooled_event(ctx);
@@ -466,12 +524,18 @@ static int pg_product(svmb200_pg* pg, bool timed) {
             return SVMB200_ERR_CUDA;
         }
         SVM_CUDA(cudaEventRecord(e0, ctx->stream));
+        pg->mv_ev.push_back(e0);
+        pg->mv_ev.push_back(e1);
+        pg->mv_ev.push_back(e2);
+    } else if (timed) {   // second half of a split product: the events of the first half
+        e1 = pg->mv_ev[pg->mv_ev.size() - 2];
+        e2 = pg->mv_ev[pg->mv_ev.size() - 1];
     }
     if (pg->p2p) {
         // K2 + K4 fused: results go straight into every rank's gathered buffer (parity = seq & 1)
         ExchangeTargets xt;
         xt.nranks = ctx->nranks;
-        const unsigned long long seq = ++ctx->xseq;
+        const unsigned long long seq = phase == 2 ? pg->cur_seq : ++ctx->xseq;
         pg->cur_seq = seq;
         xt.tag = exchange_tag(seq);
         const size_t bufbytes = (size_t)pg->stride * ctx->nranks * sizeof(ulonglong2);
@@ -479,13 +543,19 @@ static int pg_product(svmb200_pg* pg, bool timed) {
         for (int r = 0; r < ctx->nranks; ++r) xt.peer_w[r] = reinterpret_cast<ulonglong2*>(ctx->peer_arena[r] + slot);
         // the plain pointers only carry the slot geometry (w at [0, rpr), shares at [rpr, stride)) in this mode
         double* geom = reinterpret_cast<double*>(ctx->arena);
-        SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, geom, pg->u + pg->row0, geom + pg->rows_per_rank,
-                              &pg->st->done, &xt));
-        if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
+        if (pg->symmetric) {
+            SVM_TRY(launch_symv(ctx, pg->dQ, pg->n, pg->ld, pg->rows_per_rank, pg->u, geom, pg->u + pg->row0,
+                                geom + pg->rows_per_rank, &pg->st->done, &xt, seq, phase));
+        } else {
+            SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, geom, pg->u + pg->row0, geom + pg->rows_per_rank,
+                                  &pg->st->done, &xt));
+        }
+        if (e1 && phase != 1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
     } else {
         double* wshard = pg->w + (size_t)ctx->rank * pg->stride;
         if (pg->symmetric) {
-            SVM_TRY(launch_symv(ctx, pg->dQ, pg->n, pg->ld, pg->u, wshard, pg->u, wshard + pg->rows_per_rank, &pg->st->done));
+            SVM_TRY(launch_symv(ctx, pg->dQ, pg->n, pg->ld, pg->n, pg->u, wshard, pg->u, wshard + pg->rows_per_rank,
+                                &pg->st->done));
         } else {
             SVM_TRY(launch_matvec(ctx, pg->dQ, pg->nrows, pg->ld, pg->u, wshard, pg->u + pg->row0,
                                   wshard + pg->rows_per_rank, &pg->st->done));
@@ -493,13 +563,8 @@ static int pg_product(svmb200_pg* pg, bool timed) {
         if (e1) SVM_CUDA(cudaEventRecord(e1, ctx->stream));
         if (ctx->nranks > 1) SVM_TRY(svm_comm_allgather(ctx, pg->w, pg->stride));
     }
-    if (e2) {
-        SVM_CUDA(cudaEventRecord(e2, ctx->stream));
-        pg->mv_ev.push_back(e0);
-        pg->mv_ev.push_back(e1);
-        pg->mv_ev.push_back(e2);
-    }
-    pg->last_passes++;
+    if (e2 && phase != 1) SVM_CUDA(cudaEventRecord(e2, ctx->stream));
+    if (phase != 2) pg->last_passes++;
     return SVMB200_OK;
 }
 
@@ -636,7 +701,12 @@ static int bcqp_create(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     const bool every_rank_owns_rows = (int64_t)(P - 1) * rpr < n;
     pg->p2p = ctx->p2p_enabled && P > 1 && every_rank_owns_rows &&
               ARENA_DATA_OFF + 2 * (size_t)pg->stride * P * sizeof(ulonglong2) <= ctx->arena_bytes;
-    pg->symmetric = ctx->symmetric && P == 1 && row0 == 0 && nrows == n;
+    // symmetric pass: one rank with the whole matrix, or the ranks of a fused peer exchange whose arena also holds the
+    // inboxes of the column sums (two parities x P senders x rows_per_rank tagged entries in its upper half)
+    pg->symmetric = ctx->symmetric &&
+                    ((P == 1 && row0 == 0 && nrows == n) ||
+                     (pg->p2p && ARENA_DATA_OFF + 2 * (size_t)pg->stride * P * sizeof(ulonglong2) <= symv_inbox_off(ctx) &&
+                      symv_inbox_off(ctx) % 16 == 0 && 2 * symv_inbox_bytes(rpr, P) <= ctx->arena_bytes - symv_inbox_off(ctx)));
     pg->nctas = (int)((n + VP_ELEMS - 1) / VP_ELEMS);
     if (pg->nctas > VP_MAXC) pg->nctas = VP_MAXC;
     if (pg->nctas < 1) pg->nctas = 1;
@@ -988,10 +1058,11 @@ static int run_many(svmb200_pg* const* pgs, int count, int64_t max_new) {
                 // profiling events serialise the programmatic launches around them: sample one iteration in PROFILE_STRIDE
                 // (rank 0 only)
                 const bool sample = p0->profile && (p0->k_next % PROFILE_STRIDE) == 0;
-                for (int r = 0; r < count && rc == SVMB200_OK; ++r) {
-                    if (count > 1) rc = svm_use(pgs[r]->ctx);
-                    if (rc == SVMB200_OK) rc = pg_product(pgs[r], sample && r == 0);
-                }
+                for (int ph = count > 1 ? 1 : 0; ph <= (count > 1 ? 2 : 0) && rc == SVMB200_OK; ++ph)
+                    for (int r = 0; r < count && rc == SVMB200_OK; ++r) {
+                        if (count > 1) rc = svm_use(pgs[r]->ctx);
+                        if (rc == SVMB200_OK) rc = pg_product(pgs[r], sample && r == 0, ph);
+                    }
                 for (int r = 0; r < count && rc == SVMB200_OK; ++r) {
                     if (count > 1) rc = svm_use(pgs[r]->ctx);
                     if (rc == SVMB200_OK) rc = launch_vec<VP_STEP>(pgs[r], pgs[r]->k_next);
@@ -1040,10 +1111,11 @@ static int run_many(svmb200_pg* const* pgs, int count, int64_t max_new) {
             // make the state at callback point k_next visible (f, |d|, stopping tests); the augmented Lagrangian
             // needs w = Q xe for that (value and gradient at xe), the box-constrained solvers carry g along
             if (p0->solver == 2)
-                for (int r = 0; r < count; ++r) {
-                    SVM_TRY(svm_use(pgs[r]->ctx));
-                    SVM_TRY(pg_product(pgs[r], false));
-                }
+                for (int ph = count > 1 ? 1 : 0; ph <= (count > 1 ? 2 : 0); ++ph)
+                    for (int r = 0; r < count; ++r) {
+                        SVM_TRY(svm_use(pgs[r]->ctx));
+                        SVM_TRY(pg_product(pgs[r], false, ph));
+                    }
             for (int r = 0; r < count; ++r) {
                 SVM_TRY(svm_use(pgs[r]->ctx));
                 SVM_TRY(launch_vec<VP_FINALISE>(pgs[r], pgs[r]->k_next));
@@ -1103,10 +1175,11 @@ extern "C" int svmb200_pg_start_group(svmb200_pg* const* pgs, int count) {
     SVM_TRY(check_group(pgs, count));
     for (int r = 0; r < count; ++r) SVM_CHECK_ARG(pgs[r]->deferred_start, "solver already started");
     if (pgs[0]->solver != 2)
-        for (int r = 0; r < count; ++r) {
-            SVM_TRY(svm_use(pgs[r]->ctx));
-            SVM_TRY(pg_product(pgs[r], false));
-        }
+        for (int ph = 1; ph <= 2; ++ph)
+            for (int r = 0; r < count; ++r) {
+                SVM_TRY(svm_use(pgs[r]->ctx));
+                SVM_TRY(pg_product(pgs[r], false, ph));
+            }
     for (int r = 0; r < count; ++r) {
         SVM_TRY(svm_use(pgs[r]->ctx));
         SVM_TRY(launch_vec<VP_INIT>(pgs[r], 0));

@@ -474,6 +474,9 @@ def use_symmetric_pass(on=True):
     _symmetric = bool(on)
     if _default_ctx is not None:
         N.call('svmb200_ctx_set_symmetric', _default_ctx.handle, int(_symmetric))
+        if _default_ctx.group is not None:   # one process, N GPUs: the pass is sharded over the group's contexts
+            for c in _default_ctx.group.ctxs:
+                N.call('svmb200_ctx_set_symmetric', c.handle, int(_symmetric))
 
 
 _devices = None

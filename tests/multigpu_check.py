@@ -84,6 +84,8 @@ def main():
         dist.barrier()
     if int(os.environ.get('SVMB200_CHECK_STRESS', '600')) > 0:
         ok = back_to_back_stress(dist, runtime, ctx, rank, world, local_rank, int(os.environ.get('SVMB200_CHECK_STRESS', '600'))) and ok
+    if os.environ.get('SVMB200_CHECK_SYMMETRIC', '1') == '1':
+        ok = symmetric_cases(dist, runtime, ctx, rank, world, local_rank) and ok
     if os.environ.get('SVMB200_CHECK_SHARED_GRAM', '0') == '1':
         ok = shared_gram_cases(dist, runtime, ctx, rank, world, local_rank) and ok
     flag = torch.tensor([1 if ok else 0], device='cuda')
@@ -157,6 +159,95 @@ def back_to_back_stress(dist, runtime, ctx, rank, world, local_rank, solves):
         dist.barrier()
     os.environ.pop('SVMB200_P2P_CREATE_BARRIER', None)
     return ok
+
+
+def symmetric_cases(dist, runtime, ctx, rank, world, local_rank):
+    """The opt-in symmetric pass on row blocks (K2s sharded: every pair of off-diagonal blocks read once, column sums sent
+    to the other owner as tagged entries): all ranks end with the same bits, repeats are bit-identical, the iterate is
+    within rounding of the default pass on one GPU, config C1 meets the reference's golden run; a mixed back-to-back
+    sequence of symmetric and default solves of alternating sizes shares the arena without a stall."""
+    from optiml_b200.configs import make_config
+    from optiml_b200.ml.svm import DualSVC, DualSVR
+    from optiml_b200.ml.svm.kernels import GaussianKernel, PolyKernel
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import FrankWolfe, ProjectedGradient
+    from optiml_b200.runtime import DeviceHessian
+    cases = [
+        ('C1', None, lambda: DualSVC(kernel=GaussianKernel(), C=1)),
+        ('C4', 8192 + 37, lambda: DualSVC(kernel=GaussianKernel(), C=1, max_iter=200)),
+        ('C4', 20000, lambda: DualSVC(kernel=GaussianKernel(), C=1, max_iter=100)),
+        ('C2', 3003, lambda: DualSVR(kernel=PolyKernel(degree=3), epsilon=0.1, C=1, max_iter=60)),
+        ('C1', 1500, lambda: DualSVC(kernel=GaussianKernel(), C=1, optimizer=FrankWolfe, max_iter=120)),
+    ]
+    ok = True
+    for cfg, n, mk in cases:
+        spec, X, y = make_config(cfg, n=n)
+        runtime.use_symmetric_pass(True)
+        try:
+            digests = []
+            for rep in range(2):
+                m = mk().fit(X, y)
+                digests.append(hashlib.sha256(m.alphas_.tobytes() + np.float64(m.intercept_).tobytes()).hexdigest())
+                used = bool(m.optimizer.symmetric_pass)
+                if rep == 0:
+                    m.obj.release()
+        finally:
+            runtime.use_symmetric_pass(False)
+        every = [None] * world
+        dist.all_gather_object(every, (digests[0], digests[1], used))
+        same = len(set(e[0] for e in every)) == 1 and all(e[0] == e[1] for e in every)
+        used_everywhere = all(e[2] for e in every)
+        m.obj.release()
+        if rank == 0:
+            solo = runtime.Context(device=local_rank)
+            runtime.set_default_context(solo)
+            try:
+                m1 = mk().fit(X, y)   # default full pass on one GPU
+                close = bool(np.abs(m1.alphas_ - m.alphas_).max() <= (1e-9 if cfg != 'C2' else 1e-6)
+                             and abs(m1.intercept_ - m.intercept_) <= 1e-8 and not m1.optimizer.symmetric_pass)
+                if cfg != 'C2':
+                    close = close and bool(np.array_equal(m1.support_, m.support_))
+                dmax = float(np.abs(m1.alphas_ - m.alphas_).max())
+                m1.obj.release()
+            finally:
+                runtime.set_default_context(ctx)
+            golden_ok = None
+            if cfg == 'C1' and n is None:
+                g = np.load(os.path.join(ROOT, 'tests', 'golden', 'c1_svc_gaussian.npz'))
+                golden_ok = bool(np.abs(m.alphas_ - g['alphas']).max() <= 1e-8 and np.array_equal(m.support_, g['support']))
+            print(f'[multigpu N={world}] symmetric pass {cfg} n={len(y)} iters={m.optimizer.iter} used_on_all_ranks={used_everywhere} '
+                  f'ranks_identical_and_repeatable={same} max|dalpha| vs 1-GPU full pass={dmax:.2e} close={close} golden={golden_ok}',
+                  flush=True)
+            ok = ok and same and used_everywhere and close and (golden_ok is not False)
+        dist.barrier()
+    # mixed sequence: symmetric and default solves of alternating sizes back to back (the inboxes live in the upper half of
+    # the arena, the gathered buffers of both kinds in the lower half)
+    rng = np.random.default_rng(3)
+    sizes = [900, 2048 + 5, 1333, 4096]
+    problems = []
+    for n in sizes:
+        G = rng.standard_normal((n + 5, n))
+        problems.append((G.T @ G / n, rng.standard_normal(n), np.full(n, 1.5)))
+    hess = [DeviceHessian.from_host(ctx, Q) for Q, _, _ in problems]
+    quads = [Quadratic(h, q) for h, (_, q, _) in zip(hess, problems)]
+    first, stable = {}, True
+    for i in range(240):
+        j, sym, it = i % len(problems), (i // 2) % 2 == 0, (3, 7, 1, 5, 12)[i % 5]
+        runtime.use_symmetric_pass(sym)
+        s = ProjectedGradient(quad=quads[j], ub=problems[j][2], max_iter=it).minimize()
+        stable = stable and s.symmetric_pass is sym
+        dg = hashlib.sha256(s.x.tobytes()).hexdigest()
+        stable = stable and first.setdefault((j, sym, it), dg) == dg
+    runtime.use_symmetric_pass(False)
+    for h in hess:
+        h.release()
+    every = [None] * world
+    dist.all_gather_object(every, (repr(sorted(first.items())), stable))
+    same = len(set(b for b, _ in every)) == 1 and all(st for _, st in every)
+    if rank == 0:
+        print(f'[multigpu N={world}] symmetric pass: 240 back-to-back solves alternating with the default pass, sizes {sizes}: '
+              f'repeats_bit_identical_on_all_ranks={same}', flush=True)
+    return ok and same
 
 
 def shared_gram_cases(dist, runtime, ctx, rank, world, local_rank):

@@ -442,3 +442,130 @@ def test_single_process_group_under_sklearn_meta_estimators(device_group):
         ovr = OneVsRestClassifier(DualSVC(kernel=GaussianKernel(), C=1, max_iter=15)).fit(X, y3)
         assert len(ovr.estimators_) == 3 and ovr.score(X, y3) > 0.6
         assert all(type(e.obj.device_hessian()).__name__ == 'GroupHessian' for e in ovr.estimators_)
+
+
+# ---------------------------------------------------------------------------------------------- symmetric pass, sharded
+# (K2s on row blocks: every pair of off-diagonal blocks is read once, by one of its two owners; the column sums travel
+# to the other owner as tagged entries -- optiml_b200/csrc/k2_symv.cuh)
+import symv_checks as SY   # noqa: E402
+
+_SYMV_SMALL = ('SVMB200_SYMV_TR=4', 'SVMB200_SYMV_NRB=2', 'SVMB200_SYMV_NCH=1', 'SVMB200_SYMV_LB=2', 'SVMB200_SYMV_STAGES=2')
+_SYMV_B32 = ('SVMB200_SYMV_TR=16', 'SVMB200_SYMV_NRB=2', 'SVMB200_SYMV_NCH=1', 'SVMB200_SYMV_LB=8', 'SVMB200_SYMV_STAGES=2')
+
+
+@pytest.mark.parametrize('kind,layout,n,nranks,defines', [
+    ('pg', 'plain', 200, 2, _SYMV_SMALL),     # the halved pair only
+    ('pg', 'plain', 380, 3, _SYMV_SMALL),     # odd rank count: whole blocks only
+    ('pg', 'plain', 500, 4, _SYMV_SMALL),     # whole blocks and halved pairs, ragged last block
+    ('pg', 'svr', 460, 4, _SYMV_B32),         # 128-row blocks of 32-row bands, SVR block Hessian
+    ('fw', 'plain', 330, 3, _SYMV_B32), ('adam', 'plain', 200, 2, _SYMV_SMALL),
+    ('pg', 'plain', 600, 5, _SYMV_B32),
+])
+def test_sharded_symmetric_pass_follows_the_one_rank_solve(kind, layout, n, nranks, defines):
+    """every rank ends with the SAME bits (the finished product is published once, by its owner), and the iterate stays
+    within rounding of the default full pass on one rank"""
+    rng = np.random.default_rng(n + nranks)
+    M = S.psd(rng, n)
+    nv = 2 * n if layout == 'svr' else n
+    q, ub = rng.standard_normal(nv), np.full(nv, 1.5)
+    max_iter = 10
+    flags = []
+
+    def body(ctx):
+        H = shard_hessian(ctx, M, layout)
+        state = solve(kind, H, q, ub, max_iter)
+        return state
+
+    with emulated_device(defines=defines, order=2, seed=n) as lib:
+        one = run_ranks(1, 'nccl', body)[0]
+        with SY.symmetric_pass():
+            gathers = lib.emu_allgather_calls()
+            many = run_ranks(nranks, 'p2p', body)
+            assert lib.emu_allgather_calls() - gathers == nranks   # the creation barrier only: no collective per iteration
+            again = run_ranks(nranks, 'p2p', body)
+            sym_one = run_ranks(1, 'nccl', body)[0]
+    for rank_state in many[1:]:
+        for a, b in zip(many[0], rank_state):
+            assert np.array_equal(a, b)
+    for a, b in zip(many[0], again[0]):
+        assert np.array_equal(a, b)          # reproducible run to run
+    for a, b, c in zip(one, many[0], sym_one):
+        scale = max(1.0, np.abs(a).max())
+        assert np.abs(np.asarray(a, dtype=float) - np.asarray(b, dtype=float)).max() <= 1e-10 * scale
+        assert np.abs(np.asarray(a, dtype=float) - np.asarray(c, dtype=float)).max() <= 1e-10 * scale
+
+
+def test_sharded_symmetric_pass_really_runs_and_reads_half(monkeypatch):
+    """the solver reports the mode, and every rank's plan covers each unordered pair of rows exactly once (checked on the
+    host plan through the product itself: a matrix with NaN in every block a rank must not read)"""
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import ProjectedGradient
+    rng = np.random.default_rng(5)
+    n, nranks = 500, 4
+    M = S.psd(rng, n)
+    q, ub = rng.standard_normal(n), np.full(n, 1.5)
+    rpr = 128
+    seen = []
+
+    def body(ctx):
+        H = shard_hessian(ctx, M)
+        # poison what this rank must not touch: the lower triangle of its diagonal block below the 8-row bands, and every
+        # block at cyclic distance > P/2 behind ... simply: blocks (p, q) with (q - p) mod P in {3} are read by q, not p
+        block = np.zeros((max(H.nrows, 1), H.ld))
+        block[:H.nrows, :n] = M[H.row0:H.row0 + H.nrows]
+        p = H.row0 // rpr
+        for qq in range(nranks):
+            if (qq - p) % nranks == 3:
+                block[:H.nrows, qq * rpr:min(n, (qq + 1) * rpr)] = np.nan
+        rows, cols = np.indices((H.nrows, n))
+        own = (cols >= H.row0) & (cols < H.row0 + H.nrows) & (cols - H.row0 < (rows // 8) * 8)
+        block[:H.nrows, :n][own] = np.nan
+        ctx.h2d(H.matrix.dptr, block)
+        s = ProjectedGradient(quad=Quadratic(H, q), ub=ub, max_iter=6)
+        s.minimize()
+        seen.append(s.symmetric_pass)
+        return [np.asarray(s.x), np.asarray(s.g_x)]
+
+    with emulated_device(defines=_SYMV_SMALL):
+        with SY.symmetric_pass():
+            many = run_ranks(nranks, 'p2p', body)
+    assert seen == [True] * nranks
+    from oracle import svm_oracle as O
+    want = O.projected_gradient(M, q, ub, max_iter=6)
+    for st in many:
+        assert np.all(np.isfinite(st[0])) and np.abs(st[0] - want.x).max() <= 1e-10
+
+
+def test_single_process_group_with_the_symmetric_pass(device_group):
+    """one host thread drives all ranks: the tile passes and sends of every rank are issued before any rank's combine"""
+    runtime = device_group
+    from optiml_b200.ml.svm import DualSVC, DualSVR
+    from optiml_b200.ml.svm.kernels import GaussianKernel, PolyKernel
+    from optiml_b200.opti.constrained import FrankWolfe
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((420, 5))
+    y = (X[:, 0] + 0.2 * rng.standard_normal(420) > 0).astype(int)
+    t = X @ rng.standard_normal(5)
+    makers = [lambda: DualSVC(kernel=GaussianKernel(), C=1, max_iter=30),
+              lambda: DualSVR(kernel=PolyKernel(degree=2), C=1, max_iter=20),
+              lambda: DualSVC(kernel=GaussianKernel(), C=1, max_iter=20, optimizer=FrankWolfe)]
+
+    def fit_all(expect_sym):
+        out = []
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            for mk in makers:
+                m = mk()
+                m.fit(X, t if isinstance(m, DualSVR) else y)
+                assert m.optimizer.symmetric_pass is expect_sym
+                out.append((type(m.obj.device_hessian()).__name__, m.alphas_.copy(), m.intercept_, m.support_.copy()))
+                m.obj.release()
+        return out
+
+    with SY.symmetric_pass():
+        grouped = fit_all(True)
+    assert all(g[0] == 'GroupHessian' for g in grouped)
+    runtime.use_devices(None)
+    solo = fit_all(False)
+    for g, s in zip(grouped, solo):
+        assert np.abs(g[1] - s[1]).max() <= 1e-10 and abs(g[2] - s[2]) <= 1e-9 and np.array_equal(g[3], s[3])
