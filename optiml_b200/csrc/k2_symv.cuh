@@ -23,6 +23,8 @@
 // which rounding it follows.
 #pragma once
 #include "k2_matvec.cuh"
+#include <algorithm>
+#include <utility>
 
 constexpr int SY_NT = 256;
 constexpr int SY_CHUNK = 2 * SY_NT;  // columns one pass of the CTA's threads covers
@@ -134,8 +136,34 @@ inline bool symv_takes(long long n, long long rpr, int P, int p, int q, long lon
     return true;
 }
 
+// list scheduling of item costs (in launch order) on `slots` resident CTAs: the finish time of the pass
+inline double symv_makespan(const std::vector<double>& cost, int slots) {
+    std::vector<double> heap((size_t)slots, 0.0);   // min-heap of slot finish times
+    auto sift = [&](size_t i) {
+        for (;;) {
+            size_t l = 2 * i + 1, r = l + 1, m = i;
+            if (l < heap.size() && heap[l] < heap[m]) m = l;
+            if (r < heap.size() && heap[r] < heap[m]) m = r;
+            if (m == i) return;
+            std::swap(heap[i], heap[m]);
+            i = m;
+        }
+    };
+    double end = 0.0;
+    for (double c : cost) {
+        heap[0] += c;
+        if (heap[0] > end) end = heap[0];
+        sift(0);
+    }
+    return end;
+}
+
+// `slots`: CTAs of the tile kernel that are resident at a time (2 per SM).  A rank of an 8-GPU solve has only ~2 waves of
+// full-size items: the finish time would be set by the last, nearly empty wave.  The plan therefore cuts the panels at the
+// end of the list into halves and quarters (still whole 512-column chunks) so that the grid ends on small items; how
+// many is chosen by simulating the CTA scheduler (items start in list order on the first free slot).
 template <class S>
-inline void symv_build_plan(long long n, long long ld, int rank, int P, long long rpr, SymvPlan& plan) {
+inline void symv_build_plan(long long n, long long ld, int rank, int P, long long rpr, SymvPlan& plan, int slots = 296) {
     plan = SymvPlan();
     symv_block(n, rpr, rank, &plan.row0, &plan.nrows);
     const long long row0 = plan.row0, nrows = plan.nrows;
@@ -147,37 +175,92 @@ inline void symv_build_plan(long long n, long long ld, int rank, int P, long lon
         symv_block(n, rpr, r, &r0, &nr);
         return r == P - 1 ? ld : r0 + nr;
     };
-    std::vector<SymvItem> big, small, diag;
-    auto add_range = [&](long long I, long long c_begin, long long c_end) {   // panels of band I over columns [c_begin, c_end)
-        const long long rows = nrows - I * S::BH < S::BH ? nrows - I * S::BH : S::BH;
-        for (long long c = c_begin; c < c_end && c < n; c += S::BW) {   // a panel that starts at or beyond n meets u = 0 only
-            const long long w = c_end - c < S::BW ? c_end - c : S::BW;
-            SymvItem it = {(int)(I * S::BH), (int)c, (int)w, plan.nseg[(size_t)I]++, 1};
-            (w == S::BW && rows == S::BH ? big : small).push_back(it);
-            plan.streamed_elems += rows * w;
-        }
-    };
+    auto band_rows = [&](long long I) { return nrows - I * S::BH < S::BH ? nrows - I * S::BH : S::BH; };
+    std::vector<SymvItem> full, rest, diag;   // seg is assigned at the end, in list order
     for (long long I = 0; I < plan.nbands; ++I) {
-        const long long rows = nrows - I * S::BH < S::BH ? nrows - I * S::BH : S::BH;
         const long long g0 = row0 + I * S::BH;
         long long dend = g0 + S::BH;   // the diagonal block, clipped to this rank's block
         if (dend > block_end(rank)) dend = block_end(rank);
-        SymvItem d = {(int)(I * S::BH), (int)g0, (int)(dend - g0), plan.nseg[(size_t)I]++, 0};
+        SymvItem d = {(int)(I * S::BH), (int)g0, (int)(dend - g0), 0, 0};
         diag.push_back(d);
-        plan.streamed_elems += rows * (dend - g0);
-        add_range(I, dend, block_end(rank));
+        // column intervals of the band: the rest of its own block and the blocks (or half block) it reads; blocks that
+        // follow each other are one interval -- panels do not care whose rows their columns are
+        std::vector<std::pair<long long, long long>> iv;
+        if (dend < block_end(rank)) iv.push_back({dend, block_end(rank)});
         for (int k = 1; k < P; ++k) {
             const int q = (rank + k) % P;
             long long c_lo, c_hi, b_lo, row0q, nrq;
             if (!symv_takes<S>(n, rpr, P, rank, q, &c_lo, &c_hi, &b_lo) || I < b_lo) continue;
             symv_block(n, rpr, q, &row0q, &nrq);
-            const long long cend = c_hi == nrq ? block_end(q) : row0q + c_hi;
-            add_range(I, row0q + c_lo, cend);
+            iv.push_back({row0q + c_lo, c_hi == nrq ? block_end(q) : row0q + c_hi});
+        }
+        std::sort(iv.begin(), iv.end());
+        std::vector<std::pair<long long, long long>> merged;
+        for (const auto& v : iv) {
+            if (!merged.empty() && merged.back().second == v.first) merged.back().second = v.second;
+            else merged.push_back(v);
+        }
+        for (const auto& v : merged) {
+            for (long long c = v.first; c < v.second && c < n; c += S::BW) {   // a panel that starts at or beyond n meets u = 0 only
+                const long long w = v.second - c < S::BW ? v.second - c : S::BW;
+                SymvItem it = {(int)(I * S::BH), (int)c, (int)w, 0, 1};
+                (w == S::BW && band_rows(I) == S::BH ? full : rest).push_back(it);
+            }
         }
     }
-    plan.items = big;
-    plan.items.insert(plan.items.end(), small.begin(), small.end());
-    plan.items.insert(plan.items.end(), diag.begin(), diag.end());
+    // ---- grade the tail: keep a whole number of waves of full panels, cut the others into halves / quarters
+    const double overhead = 8192.0;   // start-up of an item (first copies, u of the rows, the final barrier) in elements
+    auto cost_of = [&](const SymvItem& it) { return (double)band_rows(it.lr0 / S::BH) * it.width + overhead; };
+    auto build = [&](size_t keep, double f4, std::vector<SymvItem>& out) {
+        out.clear();
+        const size_t nf = full.size();
+        if (keep > nf) keep = nf;
+        const bool can2 = S::NCH % 2 == 0, can4 = S::NCH % 4 == 0;
+        const size_t n4 = can4 ? (size_t)(f4 * (double)(nf - keep)) : 0;
+        for (size_t i = 0; i < nf; ++i) {
+            const SymvItem& it = full[i];
+            const int parts = i < keep ? 1 : (i >= nf - n4 ? 4 : (can2 ? 2 : 1));
+            for (int p = 0; p < parts; ++p) {
+                SymvItem piece = it;
+                piece.width = it.width / parts;
+                piece.c0 = it.c0 + p * piece.width;
+                out.push_back(piece);
+            }
+        }
+        // largest first (the ragged items sit between the whole panels and their pieces), diagonal blocks at the end
+        out.insert(out.end(), rest.begin(), rest.end());
+        std::stable_sort(out.begin(), out.end(), [&](const SymvItem& a, const SymvItem& b) { return cost_of(a) > cost_of(b); });
+        out.insert(out.end(), diag.begin(), diag.end());
+    };
+    const size_t nslots = (size_t)(slots > 0 ? slots : 1), waves = full.size() / nslots;
+    std::vector<size_t> keeps = {full.size(), waves * nslots};
+    if (waves >= 1) keeps.push_back((waves - 1) * nslots);
+    for (size_t k = 1; k <= 24; ++k)   // and in steps of an eighth of a wave below the total (up to three waves)
+        if (k * (nslots / 8 + 1) < full.size()) keeps.push_back(full.size() - k * (nslots / 8 + 1));
+    const double f4s[] = {0.0, 0.25, 0.5, 0.75, 1.0};
+    double best = -1.0;
+    std::vector<SymvItem> cand;
+    for (size_t keep : keeps) {
+        for (double f4 : f4s) {
+            build(keep, f4, cand);
+            std::vector<double> cost;
+            cost.reserve(cand.size());
+            for (const SymvItem& it : cand) cost.push_back(cost_of(it));
+            const double t = symv_makespan(cost, (int)nslots);
+#ifdef SYMV_PLAN_DEBUG
+            printf("keep %zu f4 %.2f items %zu makespan %.0f\n", keep, f4, cand.size(), t);
+#endif
+            if (best < 0.0 || t < best * (1.0 - 1e-9)) {
+                best = t;
+                plan.items = cand;
+            }
+            if (keep == full.size()) break;   // nothing to cut
+        }
+    }
+    for (SymvItem& it : plan.items) {
+        it.seg = plan.nseg[(size_t)(it.lr0 / S::BH)]++;
+        plan.streamed_elems += band_rows(it.lr0 / S::BH) * it.width;
+    }
     for (int v : plan.nseg) plan.nseg_max = v > plan.nseg_max ? v : plan.nseg_max;
     for (int q = 0; q < P; ++q) {
         long long c_lo, c_hi, b_lo, row0q, nrq;

@@ -147,7 +147,7 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     MatvecScratch& s = *static_cast<MatvecScratch*>(ctx->matvec_scratch);
     if (s.sy_n != n || s.sy_ld != ld || s.sy_rank != rank || s.sy_P != P) {
         SymvPlan& plan = s.sy_plan;
-        symv_build_plan<S>(n, ld, rank, P, P == 1 ? n : rpr, plan);
+        symv_build_plan<S>(n, ld, rank, P, P == 1 ? n : rpr, plan, S::MINB * (ctx->sm_count > 0 ? ctx->sm_count : 148));
         const size_t n_pad = (size_t)round_up64(plan.nrows, 16);
         const size_t need_r = (size_t)plan.nseg_max * n_pad, need_c = (size_t)plan.nbands * ld;
         if (need_r > s.sy_row_elems || need_c > s.sy_col_elems || plan.items.size() > s.sy_item_cap ||
