@@ -359,18 +359,18 @@ def symv_streamed_bytes(n):
     return int(b.value)
 
 
-def symmetric_leg(args, ctx, make_model, X, y, dX, n, peak):
+def symmetric_leg(args, ctx, make_model, X, y, dX, n, peak, barrier, max_over_ranks, gpus):
     """The same fits with the opt-in symmetric pass (runtime.use_symmetric_pass): device-resident leg + end-to-end leg, two
     fits each after one warm-up, its own parity block against the reference's golden run and its own roofline (bytes =
-    what K2s streams, 4 n^2 + the diagonal blocks' lower halves)."""
+    what K2s streams per GPU: half the matrix + the lower halves of the diagonal blocks).  Every rank takes part."""
     from optiml_b200.runtime import use_symmetric_pass
     use_symmetric_pass(True)
     try:
         m = make_model().fit(X, y, X_device=dX)
         m.obj.release()
-        ctx.sync()
         fits = max(1, min(args.steps, 2))
         iters, mv_ms, samples, pg_ms, vec_ms = 0, 0.0, 0, 0.0, 0.0
+        barrier()
         launches0 = ctx.launch_count()
         ctx.timer_start()
         for _ in range(fits):
@@ -381,8 +381,8 @@ def symmetric_leg(args, ctx, make_model, X, y, dX, n, peak):
             samples += m.optimizer.profile_samples
             pg_ms += m.optimizer.device_ms
             m.obj.release()
-        ctx.sync()
-        dev_ms = ctx.timer_stop_ms()
+        barrier()
+        dev_ms = max_over_ranks(ctx.timer_stop_ms())
         launches = ctx.launch_count() - launches0
         t0 = time.perf_counter()
         e2e_iters = 0
@@ -390,21 +390,23 @@ def symmetric_leg(args, ctx, make_model, X, y, dX, n, peak):
             m = make_model(False).fit(X, y)
             e2e_iters += m.optimizer.iter
             m.obj.release()
-        ctx.sync()
-        e2e_s = time.perf_counter() - t0
-        assert m.optimizer.symmetric_pass
-        streamed = float(symv_streamed_bytes(n))
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        used = bool(m.optimizer.symmetric_pass)
+        streamed = float(symv_streamed_bytes(n)) / gpus   # the ranks stream equal shares (within a band)
         avg_ms = mv_ms / max(samples, 1)
         achieved = streamed / (avg_ms / 1e3) / 1e9
         return {'what': 'the same workload with runtime.use_symmetric_pass(True) / SVMB200_SYMMETRIC=1: every product Q d read '
-                        'from the upper triangle of Q alone (K2s); reproducible, not bit-identical to the default pass',
-                'value': iters / (dev_ms / 1e3), 'unit': UNIT, 'fits': fits, 'fit_s': dev_ms / fits / 1e3,
+                        'from the upper triangle of Q alone (K2s; on row blocks every pair of off-diagonal blocks is read by '
+                        'one of its two owners); reproducible, not bit-identical to the default pass',
+                'used': used, 'value': iters / (dev_ms / 1e3), 'unit': UNIT, 'fits': fits, 'fit_s': dev_ms / fits / 1e3,
                 'e2e': {'value': e2e_iters / e2e_s, 'unit': UNIT, 'fit_s': e2e_s / fits},
                 'pg_its_per_s': iters / (pg_ms / 1e3),
-                'per_iteration_us': {'product (tile pass + combine)': 1e3 * avg_ms, 'vector_phase': 1e3 * vec_ms / max(samples, 1)},
-                'roofline': {'bound': 'hbm', 'kernel': 'symv_tile_kernel + symv_combine_kernel (K2s)', 'achieved': achieved, 'peak': peak,
-                             'unit': 'GB/s', 'frac': achieved / peak, 'bytes_per_launch': streamed,
-                             'full_matrix_equivalent_gbs': 8.0 * n * n / (avg_ms / 1e3) / 1e9,
+                'per_iteration_us': {'product (tile pass + sends + combine)': 1e3 * avg_ms,
+                                     'vector_phase': 1e3 * vec_ms / max(samples, 1)},
+                'roofline': {'bound': 'hbm', 'kernel': 'symv_tile_kernel (+ symv_send_kernel, symv_combine_kernel) (K2s)',
+                             'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                             'bytes_per_launch': streamed, 'full_matrix_equivalent_gbs': 8.0 * n * n / gpus / (avg_ms / 1e3) / 1e9,
                              'frac_of_dram_theoretical': achieved / 8184.0},
                 'gpu_launches': int(launches), 'parity': parity_block(args, m, n)}
     finally:
@@ -529,8 +531,9 @@ def run_b200(args):
 
     sym_used = bool(getattr(m.optimizer, 'symmetric_pass', False))
     sym_leg = None
-    if world == 1 and group_size == 1 and not args.symmetric and not args.no_symmetric_leg:
-        sym_leg = symmetric_leg(args, ctx, make_model, X, y, dX, n, measured_peak()[0])
+    if not args.symmetric and not args.no_symmetric_leg:
+        sym_leg = symmetric_leg(args, ctx, make_model, X, y, dX, n, measured_peak()[0], barrier, max_over_ranks,
+                                world * group_size)
     if rank != 0:
         return
     parity = parity_block(args, m, n)
@@ -540,7 +543,7 @@ def run_b200(args):
     kernel_name = 'matvec_seg_kernel (K2)'
     if sym_used:
         # K2s streams the upper triangle in band geometry (diagonal blocks in full): these are its algorithmic bytes
-        bytes_per_launch = float(symv_streamed_bytes(n))
+        bytes_per_launch = float(symv_streamed_bytes(n)) / gpus
         kernel_name = 'symv_tile_kernel + symv_combine_kernel (K2s, upper triangle; the timed pair)'
     mv_avg_ms = mv_ms / max(mv_samples, 1)  # CUDA events bracket one K2 launch in 16 (they serialise programmatic launches)
     achieved = bytes_per_launch / (mv_avg_ms / 1e3) / 1e9

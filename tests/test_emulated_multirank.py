@@ -569,3 +569,40 @@ def test_single_process_group_with_the_symmetric_pass(device_group):
     solo = fit_all(False)
     for g, s in zip(grouped, solo):
         assert np.abs(g[1] - s[1]).max() <= 1e-10 and abs(g[2] - s[2]) <= 1e-9 and np.array_equal(g[3], s[3])
+
+
+def test_symmetric_and_default_solves_share_the_arena_back_to_back():
+    """eight ranks, problems of alternating sizes and passes back to back: a size that leaves the last rank without rows
+    takes the all-gather (and the full pass) even when the symmetric pass is requested; everything else alternates
+    between the two fused exchanges, whose regions live in the two halves of the arena.  No stall, every repeat
+    bit-identical on every rank."""
+    from optiml_b200 import runtime
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.constrained import ProjectedGradient
+    rng = np.random.default_rng(8)
+    nranks = 8
+    sizes = (450, 667, 1000, 1400)    # 667: 128-row blocks, ranks 6 and 7 own nothing
+    problems = [(S.psd(rng, n), rng.standard_normal(n), np.full(n, 1.5)) for n in sizes]
+    fused = [(nranks - 1) * (-(-(-(-n // nranks)) // 64) * 64) < n for n in sizes]
+    assert fused == [True, False, True, True]
+
+    def body(ctx):
+        quads = [Quadratic(shard_hessian(ctx, M), q) for M, q, _ in problems]
+        out, flags = [], []
+        for i in range(40):
+            j, sym, it = i % len(problems), (i // 2) % 2 == 0, (2, 5, 1, 3, 4)[i % 5]
+            N.call('svmb200_ctx_set_symmetric', ctx.handle, int(sym))
+            s = ProjectedGradient(quad=quads[j], ub=problems[j][2], max_iter=it).minimize()
+            flags.append(s.symmetric_pass == (sym and fused[j]))
+            out.append(((j, sym, it), s.x.copy()))
+        assert all(flags)
+        return out
+
+    with emulated_device(defines=_SYMV_SMALL):
+        many = run_ranks(nranks, 'p2p', body)
+    first = {}
+    for key, x in many[0]:
+        assert np.array_equal(first.setdefault(key, x), x)
+    for state in many[1:]:
+        for (ka, xa), (kb, xb) in zip(many[0], state):
+            assert ka == kb and np.array_equal(xa, xb)

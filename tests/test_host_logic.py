@@ -366,13 +366,15 @@ def test_sass_carries_the_instructions_the_design_claims():
             if 'pg_vector_kernel' in name or 'pg_vector_batch_kernel' in name:
                 first_wait = ops.index('ACQBULK')
                 assert any(o.startswith('LDG') for o in ops[:first_wait]), name
-    # the symmetric pass: 128-bit streaming loads, column and row sums (4 DFMA per load), no spills, two CTAs per SM
+    # the symmetric pass: the matrix arrives by 16-byte cp.async copies that bypass L1 (LDGSTS) into thread-private ring
+    # slots read back with LDS.128; column and row sums (4 DFMA per copy), warp-transposed row reduction, no spills
     sy = [ops for name, ops in pg.items() if 'symv_tile_kernel' in name]
     assert len(sy) == 1
-    assert sum(o.startswith('LDG.E.NA.128') or o.startswith('LDG.E.128') for o in sy[0]) >= 64
+    assert sum(o.startswith('LDGSTS.E.BYPASS.128') for o in sy[0]) >= 128 and sum(o == 'LDGDEPBAR' for o in sy[0]) >= 16
+    assert sum(o.startswith('LDS.128') for o in sy[0]) >= 128
     assert sum(o == 'DFMA' for o in sy[0]) >= 256 and sum(o.startswith('SHFL') for o in sy[0]) >= 62
     assert not any(o.startswith(('LDL', 'STL')) for o in sy[0])
-    assert any('symv_combine_kernel' in name for name in pg)
+    assert any('symv_combine_kernel' in name for name in pg) and any('symv_send_kernel' in name for name in pg)
     # the persistent small-problem loop: matrix rows from shared memory, a grid barrier on a global atomic, no spills
     pk = [ops for name, ops in pg.items() if 'pg_persistent_kernel' in name]
     assert len(pk) == 1
