@@ -532,8 +532,11 @@ def run_b200(args):
     sym_used = bool(getattr(m.optimizer, 'symmetric_pass', False))
     sym_leg = None
     if not args.symmetric and not args.no_symmetric_leg:
-        sym_leg = symmetric_leg(args, ctx, make_model, X, y, dX, n, measured_peak()[0], barrier, max_over_ranks,
-                                world * group_size)
+        try:
+            sym_leg = symmetric_leg(args, ctx, make_model, X, y, dX, n, measured_peak()[0], barrier, max_over_ranks,
+                                    world * group_size)
+        except Exception as exc:   # the extra leg must never cost the line of the default pass
+            sym_leg = {'error': repr(exc)}
     if rank != 0:
         return
     parity = parity_block(args, m, n)
