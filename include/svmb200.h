@@ -138,6 +138,7 @@ int svmb200_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int64_t ld
  *   lockstep batches keep the full pass.  svmb200_pg_is_symmetric reports what a solver does.                      */
 int svmb200_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, const double* du, double* dw);
 int svmb200_ctx_set_symmetric(svmb200_ctx* ctx, int on);
+int svmb200_ctx_get_symmetric(svmb200_ctx* ctx, int* on);
 /* what one symmetric pass over an n x n matrix streams (bytes: diagonal blocks in full + everything to their right) and
  * its tile geometry (rows per band, columns per panel, work items) -- for rooflines; any output pointer may be NULL */
 int svmb200_symv_geometry(int64_t n, int64_t ld, int64_t* streamed_bytes, int64_t* band_rows, int64_t* panel_cols,

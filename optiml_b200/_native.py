@@ -81,6 +81,7 @@ PROTOTYPES = {
     'svmb200_pg_is_symmetric': [c_vp, C.POINTER(C.c_int)],
     'svmb200_symv': [c_vp, c_vp, i64, i64, c_vp, c_vp],
     'svmb200_ctx_set_symmetric': [c_vp, C.c_int],
+    'svmb200_ctx_get_symmetric': [c_vp, C.POINTER(C.c_int)],
     'svmb200_symv_geometry': [i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
     'svmb200_pg_destroy': [c_vp],
     'svmb200_copy_peer': [c_vp, c_vp, c_vp, c_vp, C.c_size_t],

@@ -71,6 +71,12 @@ extern "C" int svmb200_ctx_set_symmetric(svmb200_ctx* ctx, int on) {
     return SVMB200_OK;
 }
 
+extern "C" int svmb200_ctx_get_symmetric(svmb200_ctx* ctx, int* on) {
+    SVM_CHECK_ARG(ctx != nullptr && on != nullptr, "null argument");
+    *on = ctx->symmetric ? 1 : 0;
+    return SVMB200_OK;
+}
+
 int svm_scratch_reserve(svmb200_ctx* ctx, void** buf, size_t* have, size_t need) {
     if (*have >= need) return SVMB200_OK;
     SVM_CUDA(cudaStreamSynchronize(ctx->stream));

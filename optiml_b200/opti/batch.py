@@ -49,9 +49,23 @@ def minimize_batch(solvers):
         return solvers
     lib = N.load_library()
     created = []
+    # a lockstep batch streams the matrix with the multi-vector FULL pass: its solvers are created with the symmetric
+    # pass (runtime.use_symmetric_pass) switched off, so that their first product follows the same order as the rest
+    ctxs = {}
+    for s in solvers:
+        c = getattr(s.f.device_hessian(), 'ctx', None)
+        if c is not None and id(c) not in ctxs:
+            was = C.c_int(0)
+            N.call('svmb200_ctx_get_symmetric', c.handle, C.byref(was))
+            ctxs[id(c)] = (c, was.value)
+            N.call('svmb200_ctx_set_symmetric', c.handle, 0)
     try:
-        for s in solvers:
-            created.append(s._create(False))
+        try:
+            for s in solvers:
+                created.append(s._create(False))
+        finally:
+            for c, was in ctxs.values():
+                N.call('svmb200_ctx_set_symmetric', c.handle, was)
         count = len(created)
         handles = (C.c_void_p * count)(*[h.value for h, _ in created])
         iters, statuses = (C.c_int64 * count)(), (C.c_int * count)()

@@ -25,7 +25,8 @@ for rep in range(2):
                intercept=m.intercept_, its_per_s=m.optimizer.iter / (m.optimizer.device_ms / 1e3),
                matvec_us=1e3 * m.optimizer.matvec_ms / max(m.optimizer.profile_samples, 1),
                hbm_gbps_per_gpu=8.0 * n * n / ctx.nranks / (m.optimizer.matvec_ms / max(m.optimizer.profile_samples, 1) / 1e3) / 1e9,
-               hessian_gb_per_gpu=8.0 * n * n / ctx.nranks / 1e9)
+               hessian_gb_per_gpu=8.0 * n * n / ctx.nranks / 1e9,
+               symmetric_pass=bool(m.optimizer.symmetric_pass))   # SVMB200_SYMMETRIC=1: hbm_gbps_per_gpu is then the FULL-matrix equivalent
     if rep == 0:
         m.obj.release()
 fh = np.array(m.train_loss_history)

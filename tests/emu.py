@@ -51,6 +51,10 @@ def emulated_device(order=0, seed=1, defines=()):
     try:
         yield lib
     finally:
+        # device objects that sit in reference cycles (estimator <-> optimizer <-> bound callback) are finalised by the cyclic
+        # collector, whenever it runs: run it now, while their buffers still belong to THIS library and this context
+        import gc
+        gc.collect()
         ctx = runtime._default_ctx
         if ctx is not None:
             ctx.trim()

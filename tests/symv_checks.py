@@ -138,6 +138,9 @@ def check_symmetric_solves(device, n=150, max_iter=30, **dev_kw):
             svr = ProjectedGradient(quad=Quadratic(H, q2), ub=np.ones(2 * n), max_iter=max_iter).minimize()
             assert svr.symmetric_pass is sym
             res[sym] = (pg.x.copy(), np.asarray(pg.f_hist).copy(), fw.x.copy(), svr.x.copy())
+            for s in (pg, fw, svr):
+                s.f.release()   # device buffers go back while their context is alive (the emulated one ends with the block)
+            del pg, fw, svr, H
             probe.assert_clean()
     for a, b in zip(res[False], res[True]):
         assert np.abs(a - b).max() <= 1e-10 * max(1.0, np.abs(a).max())
@@ -165,6 +168,9 @@ def check_symmetric_fit(device, n=120, **dev_kw):
             assert svc.optimizer.symmetric_pass is sym and svr.optimizer.symmetric_pass is sym
             out[sym] = (svc.alphas_.copy(), svc.support_.copy(), svc.decision_function(X[:20]).copy(),
                         svr.alphas_.copy(), svr.predict(Xr[:20]).copy())
+            svc.obj.release()
+            svr.obj.release()
+            del svc, svr
             probe.assert_clean()
     a, b = out[False], out[True]
     assert np.abs(a[0] - b[0]).max() <= 1e-10

@@ -8,6 +8,7 @@ entries straight into every rank's arena, K3 waits on them).  The property asser
 shards.  What the emulation cannot show: memory ordering over NVLink, timing.
 """
 import ctypes as C
+import gc
 import threading
 import time
 import warnings
@@ -44,6 +45,7 @@ def run_ranks(nranks, exchange, body):
             else:
                 assert ctx.exchange == ('nccl' if nranks > 1 else 'none')
             results[rank] = body(ctx)
+            gc.collect()   # cyclic garbage of the body holds device buffers of this context: finalise it before the context goes
             assert N.load_library().emu_sticky_error() == 0
             gate.wait(timeout=120)   # nobody tears its arena down while a peer may still store into it
             ctx._finalizer()
