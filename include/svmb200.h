@@ -143,6 +143,11 @@ int svmb200_ctx_get_symmetric(svmb200_ctx* ctx, int* on);
  * its tile geometry (rows per band, columns per panel, work items) -- for rooflines; any output pointer may be NULL */
 int svmb200_symv_geometry(int64_t n, int64_t ld, int64_t* streamed_bytes, int64_t* band_rows, int64_t* panel_cols,
                           int64_t* items);
+/* the work plan of rank `rank` of `nranks` row blocks on a GPU with sm_count SMs: bands (the last ones of a shard may be
+ * short ones, a quarter of the height, so that the grid ends on small items), how many of them are short, work items, and
+ * the simulated finish time of the grid over a perfectly balanced one -- for tests and tuning                        */
+int svmb200_symv_plan_info(int64_t n, int64_t ld, int rank, int nranks, int sm_count, int64_t* bands, int64_t* short_bands,
+                           int64_t* items, double* finish_over_ideal);
 
 /* ---- K2+K3(+K4): projected-gradient solve of the box-constrained QP -------------------------
  * Replaces  BoxConstrainedQuadraticOptimizer.__init__ (opti/constrained/_base.py:59-73) +

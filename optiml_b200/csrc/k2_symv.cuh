@@ -41,6 +41,9 @@ constexpr int SY_CHUNK = 2 * SY_NT;  // columns one pass of the CTA's threads co
 #ifndef SVMB200_SYMV_LB
 #define SVMB200_SYMV_LB 8      // 128-bit copies per batch
 #endif
+#ifndef SVMB200_SYMV_PLAN_OVERHEAD
+#define SVMB200_SYMV_PLAN_OVERHEAD 8192.0   // cost of starting an item, in matrix elements (the planner's model; ~3 us)
+#endif
 #ifndef SVMB200_SYMV_STAGES
 #define SVMB200_SYMV_STAGES 3  // batches in flight per thread (ring depth)
 #endif
@@ -77,6 +80,8 @@ using SymvDefault = SymvShape<SVMB200_SYMV_TR, SVMB200_SYMV_NRB, SVMB200_SYMV_NC
 // rank's gathered buffer), so the vector kernels do not know which pass fed them.
 struct SymvItem {
     int lr0;     // first LOCAL row of the band
+    int rows;    // rows of the band (BH; the short bands at the end of a shard: SH; a last band may be ragged)
+    int band;    // index of the band (row of colpart, entry of nseg)
     int c0;      // first column
     int width;   // columns (even; a last panel is narrower than BW)
     int seg;     // slot of the item's row sums in rowpart
@@ -96,9 +101,11 @@ struct SymvRecv {
 struct SymvPlan {
     std::vector<SymvItem> items;   // large items first
     std::vector<int> nseg;         // per local band: items (= row-sum slots) of the band
+    std::vector<int> band_lr0;     // per local band: its first local row (+ one entry: nrows)
+    std::vector<int> band_of_unit; // band of every `unit` rows (band boundaries are multiples of unit)
     std::vector<SymvSend> sends;
     std::vector<SymvRecv> recvs;   // ascending sender
-    int nseg_max = 0;
+    int nseg_max = 0, unit = 1;
     long long row0 = 0, nrows = 0, nbands = 0, streamed_elems = 0;
 };
 
@@ -159,120 +166,148 @@ inline double symv_makespan(const std::vector<double>& cost, int slots) {
 }
 
 // `slots`: CTAs of the tile kernel that are resident at a time (2 per SM).  A rank of an 8-GPU solve has only ~2 waves of
-// full-size items: the finish time would be set by the last, nearly empty wave.  The plan therefore cuts the panels at the
-// end of the list into halves and quarters (still whole 512-column chunks) so that the grid ends on small items; how
-// many is chosen by simulating the CTA scheduler (items start in list order on the first free slot).
+// full-size items: the finish time would be set by the last, nearly empty wave.  The plan therefore ends the grid on small
+// items: the last `s` bands of the shard are cut into SHORT bands of SH = BH / 4 rows, and the panels at the end of the list
+// into halves and quarters (still whole 512-column chunks).  How many of each is chosen by simulating the CTA scheduler
+// (items start in list order, largest first, on the first free slot).  Band boundaries up to half the shard stay multiples
+// of BH, which is what the halved block pair of an even rank count is cut at (symv_takes).
 template <class S>
 inline void symv_build_plan(long long n, long long ld, int rank, int P, long long rpr, SymvPlan& plan, int slots = 296) {
     plan = SymvPlan();
     symv_block(n, rpr, rank, &plan.row0, &plan.nrows);
     const long long row0 = plan.row0, nrows = plan.nrows;
-    plan.nbands = (nrows + S::BH - 1) / S::BH;
-    plan.nseg.assign((size_t)plan.nbands, 0);
+    constexpr int SH = S::BH / 4 >= S::TR ? S::BH / 4 : S::TR;   // rows of a short band
+    plan.unit = SH;
     // the last block also owns the padding columns [n, ld): they meet u = 0, and the width of a panel stays even
     auto block_end = [&](int r) {
         long long r0, nr;
         symv_block(n, rpr, r, &r0, &nr);
         return r == P - 1 ? ld : r0 + nr;
     };
-    auto band_rows = [&](long long I) { return nrows - I * S::BH < S::BH ? nrows - I * S::BH : S::BH; };
-    std::vector<SymvItem> full, rest, diag;   // seg is assigned at the end, in list order
-    for (long long I = 0; I < plan.nbands; ++I) {
-        const long long g0 = row0 + I * S::BH;
-        long long dend = g0 + S::BH;   // the diagonal block, clipped to this rank's block
-        if (dend > block_end(rank)) dend = block_end(rank);
-        SymvItem d = {(int)(I * S::BH), (int)g0, (int)(dend - g0), 0, 0};
-        diag.push_back(d);
-        // column intervals of the band: the rest of its own block and the blocks (or half block) it reads; blocks that
-        // follow each other are one interval -- panels do not care whose rows their columns are
-        std::vector<std::pair<long long, long long>> iv;
-        if (dend < block_end(rank)) iv.push_back({dend, block_end(rank)});
-        for (int k = 1; k < P; ++k) {
-            const int q = (rank + k) % P;
-            long long c_lo, c_hi, b_lo, row0q, nrq;
-            if (!symv_takes<S>(n, rpr, P, rank, q, &c_lo, &c_hi, &b_lo) || I < b_lo) continue;
-            symv_block(n, rpr, q, &row0q, &nrq);
-            iv.push_back({row0q + c_lo, c_hi == nrq ? block_end(q) : row0q + c_hi});
-        }
-        std::sort(iv.begin(), iv.end());
-        std::vector<std::pair<long long, long long>> merged;
-        for (const auto& v : iv) {
-            if (!merged.empty() && merged.back().second == v.first) merged.back().second = v.second;
-            else merged.push_back(v);
-        }
-        for (const auto& v : merged) {
-            for (long long c = v.first; c < v.second && c < n; c += S::BW) {   // a panel that starts at or beyond n meets u = 0 only
-                const long long w = v.second - c < S::BW ? v.second - c : S::BW;
-                SymvItem it = {(int)(I * S::BH), (int)c, (int)w, 0, 1};
-                (w == S::BW && band_rows(I) == S::BH ? full : rest).push_back(it);
-            }
-        }
-    }
-    // ---- grade the tail: keep a whole number of waves of full panels, cut the others into halves / quarters
-    const double overhead = 8192.0;   // start-up of an item (first copies, u of the rows, the final barrier) in elements
-    auto cost_of = [&](const SymvItem& it) { return (double)band_rows(it.lr0 / S::BH) * it.width + overhead; };
-    auto build = [&](size_t keep, double f4, std::vector<SymvItem>& out) {
-        out.clear();
-        const size_t nf = full.size();
-        if (keep > nf) keep = nf;
-        const bool can2 = S::NCH % 2 == 0, can4 = S::NCH % 4 == 0;
-        const size_t n4 = can4 ? (size_t)(f4 * (double)(nf - keep)) : 0;
-        for (size_t i = 0; i < nf; ++i) {
-            const SymvItem& it = full[i];
-            const int parts = i < keep ? 1 : (i >= nf - n4 ? 4 : (can2 ? 2 : 1));
-            for (int p = 0; p < parts; ++p) {
-                SymvItem piece = it;
-                piece.width = it.width / parts;
-                piece.c0 = it.c0 + p * piece.width;
-                out.push_back(piece);
-            }
-        }
-        // largest first (the ragged items sit between the whole panels and their pieces), diagonal blocks at the end
-        out.insert(out.end(), rest.begin(), rest.end());
-        std::stable_sort(out.begin(), out.end(), [&](const SymvItem& a, const SymvItem& b) { return cost_of(a) > cost_of(b); });
-        out.insert(out.end(), diag.begin(), diag.end());
-    };
-    const size_t nslots = (size_t)(slots > 0 ? slots : 1), waves = full.size() / nslots;
-    std::vector<size_t> keeps = {full.size(), waves * nslots};
-    if (waves >= 1) keeps.push_back((waves - 1) * nslots);
-    for (size_t k = 1; k <= 24; ++k)   // and in steps of an eighth of a wave below the total (up to three waves)
-        if (k * (nslots / 8 + 1) < full.size()) keeps.push_back(full.size() - k * (nslots / 8 + 1));
-    const double f4s[] = {0.0, 0.25, 0.5, 0.75, 1.0};
+    const double overhead = SVMB200_SYMV_PLAN_OVERHEAD;   // start-up of an item (first copies, u of the rows, the final barrier) in elements
+    auto cost_of = [&](const SymvItem& it) { return (double)it.rows * it.width + overhead; };
+    const long long full_bands = nrows / S::BH;
+    std::vector<long long> shorts = {0};   // how many of the last full bands become short ones
+    for (long long sb : {1, 2, 4, 8, 16})
+        if (SH < S::BH && sb <= full_bands / 2) shorts.push_back(sb);
     double best = -1.0;
-    std::vector<SymvItem> cand;
-    for (size_t keep : keeps) {
-        for (double f4 : f4s) {
-            build(keep, f4, cand);
-            std::vector<double> cost;
-            cost.reserve(cand.size());
-            for (const SymvItem& it : cand) cost.push_back(cost_of(it));
-            const double t = symv_makespan(cost, (int)nslots);
-#ifdef SYMV_PLAN_DEBUG
-            printf("keep %zu f4 %.2f items %zu makespan %.0f\n", keep, f4, cand.size(), t);
-#endif
-            if (best < 0.0 || t < best * (1.0 - 1e-9)) {
-                best = t;
-                plan.items = cand;
+    std::vector<int> best_lr0;
+    for (long long sb : shorts) {
+        // ---- band layout
+        std::vector<int> lr0s;
+        const long long tall_rows = (full_bands - sb) * S::BH + (sb == 0 ? nrows - full_bands * S::BH : 0);
+        for (long long r = 0; r < tall_rows; r += S::BH) lr0s.push_back((int)r);
+        for (long long r = tall_rows; r < nrows; r += SH) lr0s.push_back((int)r);
+        lr0s.push_back((int)nrows);
+        const long long nb = (long long)lr0s.size() - 1;
+        std::vector<SymvItem> full, rest, diag;   // seg is assigned at the end, in list order
+        for (long long I = 0; I < nb; ++I) {
+            const int lr0 = lr0s[(size_t)I], rows = lr0s[(size_t)I + 1] - lr0;
+            const long long g0 = row0 + lr0;
+            long long dend = g0 + rows;   // the diagonal block: rows x rows, clipped to this rank's block (never active: rows end there)
+            if (dend % 2) dend += 1;      // an odd last row count: the pair's second column is padding (u = 0) or the next row's, see below
+            if (dend > block_end(rank)) dend = block_end(rank);
+            SymvItem d = {lr0, rows, (int)I, (int)g0, (int)(dend - g0), 0, 0};
+            diag.push_back(d);
+            // column intervals of the band: the rest of its own block and the blocks (or half block) it reads; blocks that
+            // follow each other are one interval -- panels do not care whose rows their columns are
+            std::vector<std::pair<long long, long long>> iv;
+            if (dend < block_end(rank)) iv.push_back({dend, block_end(rank)});
+            for (int k = 1; k < P; ++k) {
+                const int q = (rank + k) % P;
+                long long c_lo, c_hi, b_lo, row0q, nrq;
+                if (!symv_takes<S>(n, rpr, P, rank, q, &c_lo, &c_hi, &b_lo) || lr0 < b_lo * S::BH) continue;
+                symv_block(n, rpr, q, &row0q, &nrq);
+                iv.push_back({row0q + c_lo, c_hi == nrq ? block_end(q) : row0q + c_hi});
             }
-            if (keep == full.size()) break;   // nothing to cut
+            std::sort(iv.begin(), iv.end());
+            std::vector<std::pair<long long, long long>> merged;
+            for (const auto& v : iv) {
+                if (!merged.empty() && merged.back().second == v.first) merged.back().second = v.second;
+                else merged.push_back(v);
+            }
+            for (const auto& v : merged) {
+                for (long long c = v.first; c < v.second && c < n; c += S::BW) {   // a panel that starts at or beyond n meets u = 0 only
+                    const long long w = v.second - c < S::BW ? v.second - c : S::BW;
+                    SymvItem it = {lr0, rows, (int)I, (int)c, (int)w, 0, 1};
+                    (w == S::BW && rows == S::BH ? full : rest).push_back(it);
+                }
+            }
+        }
+        // ---- grade the tail: keep a whole number of waves of full panels, cut the others into halves / quarters; the
+        // full-width panels of the short bands may be cut likewise
+        auto build = [&](size_t keep, double f4, int short_parts, std::vector<SymvItem>& out) {
+            out.clear();
+            const size_t nf = full.size();
+            if (keep > nf) keep = nf;
+            const bool can2 = S::NCH % 2 == 0, can4 = S::NCH % 4 == 0;
+            const size_t n4 = can4 ? (size_t)(f4 * (double)(nf - keep)) : 0;
+            auto push_parts = [&](const SymvItem& it, int parts) {
+                for (int p = 0; p < parts; ++p) {
+                    SymvItem piece = it;
+                    piece.width = it.width / parts;
+                    piece.c0 = it.c0 + p * piece.width;
+                    out.push_back(piece);
+                }
+            };
+            for (size_t i = 0; i < nf; ++i) push_parts(full[i], i < keep ? 1 : (i >= nf - n4 ? 4 : (can2 ? 2 : 1)));
+            for (const SymvItem& it : rest) {
+                const bool whole_short = it.width == S::BW && it.rows < S::BH;
+                push_parts(it, whole_short && ((short_parts == 2 && can2) || (short_parts == 4 && can4)) ? short_parts : 1);
+            }
+            // largest first (the ragged items sit between the whole panels and their pieces), diagonal blocks at the end
+            std::stable_sort(out.begin(), out.end(), [&](const SymvItem& a, const SymvItem& b) { return cost_of(a) > cost_of(b); });
+            out.insert(out.end(), diag.begin(), diag.end());
+        };
+        const size_t nslots = (size_t)(slots > 0 ? slots : 1), waves = full.size() / nslots;
+        std::vector<size_t> keeps = {full.size(), waves * nslots};
+        if (waves >= 1) keeps.push_back((waves - 1) * nslots);
+        for (size_t k = 1; k <= 24; ++k)   // and in steps of an eighth of a wave below the total (up to three waves)
+            if (k * (nslots / 8 + 1) < full.size()) keeps.push_back(full.size() - k * (nslots / 8 + 1));
+        const double f4s[] = {0.0, 0.5, 1.0};
+        std::vector<SymvItem> cand;
+        for (int short_parts : {1, 2, 4}) {
+            if (sb == 0 && short_parts > 1) break;
+            for (size_t keep : keeps) {
+                for (double f4 : f4s) {
+                    build(keep, f4, short_parts, cand);
+                    std::vector<double> cost;
+                    cost.reserve(cand.size());
+                    for (const SymvItem& it : cand) cost.push_back(cost_of(it));
+                    const double t = symv_makespan(cost, (int)nslots);
+#ifdef SYMV_PLAN_DEBUG
+                    printf("short %lld x%d keep %zu f4 %.2f items %zu makespan %.0f\n", sb, short_parts, keep, f4, cand.size(), t);
+#endif
+                    if (best < 0.0 || t < best * (1.0 - 1e-3)) {   // a finer plan must pay for itself
+                        best = t;
+                        plan.items = cand;
+                        best_lr0 = lr0s;
+                    }
+                    if (keep == full.size()) break;   // nothing to cut
+                }
+            }
         }
     }
+    plan.band_lr0 = best_lr0;
+    plan.nbands = (long long)best_lr0.size() - 1;
+    plan.nseg.assign((size_t)plan.nbands, 0);
+    plan.band_of_unit.assign((size_t)((nrows + SH - 1) / SH), 0);
+    for (long long I = 0; I < plan.nbands; ++I)
+        for (long long r = best_lr0[(size_t)I]; r < best_lr0[(size_t)I + 1]; r += SH) plan.band_of_unit[(size_t)(r / SH)] = (int)I;
     for (SymvItem& it : plan.items) {
-        it.seg = plan.nseg[(size_t)(it.lr0 / S::BH)]++;
-        plan.streamed_elems += band_rows(it.lr0 / S::BH) * it.width;
+        it.seg = plan.nseg[(size_t)it.band]++;
+        plan.streamed_elems += (long long)it.rows * it.width;
     }
     for (int v : plan.nseg) plan.nseg_max = v > plan.nseg_max ? v : plan.nseg_max;
     for (int q = 0; q < P; ++q) {
         long long c_lo, c_hi, b_lo, row0q, nrq;
         symv_block(n, rpr, q, &row0q, &nrq);
-        if (symv_takes<S>(n, rpr, P, rank, q, &c_lo, &c_hi, &b_lo) && b_lo < plan.nbands) {
+        // (the first b_lo bands of a shard are BH rows tall -- short bands only come after its middle -- so b_lo is a band index)
+        if (symv_takes<S>(n, rpr, P, rank, q, &c_lo, &c_hi, &b_lo) && b_lo * S::BH < nrows) {
             SymvSend sd = {q, (int)(row0q + c_lo), (int)(c_hi - c_lo), (int)c_lo, (int)b_lo, (int)plan.nbands};
             plan.sends.push_back(sd);
         }
-        long long nbq, row0me, nrme;
-        symv_block(n, rpr, rank, &row0me, &nrme);
-        nbq = (nrq + S::BH - 1) / S::BH;
-        if (symv_takes<S>(n, rpr, P, q, rank, &c_lo, &c_hi, &b_lo) && b_lo < nbq) {
+        if (symv_takes<S>(n, rpr, P, q, rank, &c_lo, &c_hi, &b_lo) && b_lo * S::BH < nrq) {
             SymvRecv rv = {q, (int)c_lo, (int)c_hi};
             plan.recvs.push_back(rv);
         }
@@ -333,14 +368,14 @@ __device__ __forceinline__ void sy_cp_async_wait() {}
 #endif
 
 template <class S, bool COLS>
-__device__ __forceinline__ void symv_item(const SymvArgs& a, const long long r0, const long long c0, const int width,
-                                          const int band, const int seg, const double* ush,
+__device__ __forceinline__ void symv_item(const SymvArgs& a, const long long r0, const int rows, const long long c0,
+                                          const int width, const int band, const int seg, const double* ush,
                                           double (*wsum)[S::BH], double2* ring) {
     constexpr int TR = S::TR, NCH = S::NCH, LB = S::LB, NBATCH = S::NBATCH, BPC = TR / LB, ST = S::STAGES;
     static_assert(ST >= 2 && ST <= NBATCH, "ring depth: between 2 batches and one sub-block");
     const int tid = (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nch = (width + SY_CHUNK - 1) / SY_CHUNK;  // chunks this item has (a diagonal block or a last panel: fewer)
-    const int rows = (int)(a.nrows - r0 < S::BH ? a.nrows - r0 : S::BH);   // r0: first LOCAL row of the band
+    // r0: first LOCAL row of the band, rows: its height (<= BH)
     const int nrb = (rows + TR - 1) / TR;               // sub-blocks this item has (the last band: fewer)
     // the thread's columns, relative to c0; a column beyond the item reads column 0 of it against u = 0
     int coff[NCH];
@@ -444,10 +479,10 @@ __global__ void __launch_bounds__(SY_NT, S::MINB) symv_tile_kernel(const SymvArg
     __shared__ double wsum[SY_NT / 32][BH];   // row sums per warp
     const SymvItem it = a.items[blockIdx.x];
     const long long r0 = it.lr0;
-    for (int i = (int)threadIdx.x; i < BH; i += SY_NT) ush[i] = r0 + i < a.nrows ? a.u[a.row0 + r0 + i] : 0.0;
+    for (int i = (int)threadIdx.x; i < BH; i += SY_NT) ush[i] = i < it.rows ? a.u[a.row0 + r0 + i] : 0.0;
     __syncthreads();
-    if (it.cols) symv_item<S, true>(a, r0, it.c0, it.width, it.lr0 / BH, it.seg, ush, wsum, ring);
-    else symv_item<S, false>(a, r0, it.c0, it.width, it.lr0 / BH, it.seg, ush, wsum, ring);
+    if (it.cols) symv_item<S, true>(a, r0, it.rows, it.c0, it.width, it.band, it.seg, ush, wsum, ring);
+    else symv_item<S, false>(a, r0, it.rows, it.c0, it.width, it.band, it.seg, ush, wsum, ring);
 }
 
 // ---- column sums that belong to other ranks' rows: added over this rank's bands (band order) and stored into the
@@ -501,7 +536,8 @@ struct SymvCombineArgs {
     const double* rowpart;
     const double* colpart;
     long long ld, nrows, row0, n_pad;
-    int BH;
+    int unit;               // rows per entry of band_of_unit
+    const int* band_of_unit;   // band of every `unit` local rows
     const int* nseg;        // per local band: row-sum slots in use
     const double* u_rows;   // u at this rank's rows, or null
     double* w;              // nrows results (no exchange)
@@ -533,7 +569,7 @@ __global__ void __launch_bounds__(MV_GROUP * SY_CPARTS) symv_combine_kernel(cons
     const long long rr = (long long)group * MV_GROUP + t;   // local row
     double v = 0.0;
     if (rr < a.nrows) {
-        const long long band = rr / a.BH;
+        const long long band = a.band_of_unit[rr / a.unit];
         const long long per = (band + SY_CPARTS - 1) / SY_CPARTS;
         long long I = p * per, I1 = I + per;
         if (I1 > band) I1 = band;

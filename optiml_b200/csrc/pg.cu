@@ -29,7 +29,7 @@ struct MatvecScratch {
     double* sy_rowpart = nullptr;
     double* sy_colpart = nullptr;
     SymvItem* sy_items = nullptr;
-    int* sy_nseg = nullptr;
+    int* sy_nseg = nullptr;     // per band: row-sum slots; behind them: band of every `unit` rows
     size_t sy_row_elems = 0, sy_col_elems = 0, sy_item_cap = 0, sy_nseg_cap = 0;
     int64_t sy_n = -1, sy_ld = -1;
     int sy_rank = -1, sy_P = -1;
@@ -129,6 +129,17 @@ static int launch_matvec(svmb200_ctx* ctx, const double* dQ, int64_t nrows, int6
 constexpr size_t symv_inbox_bytes(int64_t rpr, int P) { return (size_t)P * (size_t)rpr * sizeof(ulonglong2); }
 static size_t symv_inbox_off(const svmb200_ctx* ctx) { return ctx->arena_bytes / 2; }
 
+// resident CTAs of the tile kernel the planner balances the grid for (a build-time override exists for the tests on the host
+// emulation, whose problems are far too small to fill 296 slots)
+static int symv_plan_slots(int sm_count) {
+#ifdef SVMB200_SYMV_PLAN_SLOTS
+    (void)sm_count;
+    return SVMB200_SYMV_PLAN_SLOTS;
+#else
+    return SymvDefault::MINB * (sm_count > 0 ? sm_count : 148);
+#endif
+}
+
 static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld, int64_t rpr, const double* du, double* dw,
                        const double* du_rows, double* ddenpart, const int* d_done, const ExchangeTargets* xt = nullptr,
                        unsigned long long seq = 0, int phase = 0) {
@@ -147,11 +158,11 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
     MatvecScratch& s = *static_cast<MatvecScratch*>(ctx->matvec_scratch);
     if (s.sy_n != n || s.sy_ld != ld || s.sy_rank != rank || s.sy_P != P) {
         SymvPlan& plan = s.sy_plan;
-        symv_build_plan<S>(n, ld, rank, P, P == 1 ? n : rpr, plan, S::MINB * (ctx->sm_count > 0 ? ctx->sm_count : 148));
+        symv_build_plan<S>(n, ld, rank, P, P == 1 ? n : rpr, plan, symv_plan_slots(ctx->sm_count));
         const size_t n_pad = (size_t)round_up64(plan.nrows, 16);
         const size_t need_r = (size_t)plan.nseg_max * n_pad, need_c = (size_t)plan.nbands * ld;
-        if (need_r > s.sy_row_elems || need_c > s.sy_col_elems || plan.items.size() > s.sy_item_cap ||
-            plan.nseg.size() > s.sy_nseg_cap) {
+        const size_t need_t = plan.nseg.size() + plan.band_of_unit.size();
+        if (need_r > s.sy_row_elems || need_c > s.sy_col_elems || plan.items.size() > s.sy_item_cap || need_t > s.sy_nseg_cap) {
             SVM_CUDA(cudaStreamSynchronize(ctx->stream));
             if (s.sy_rowpart) cudaFree(s.sy_rowpart);
             if (s.sy_colpart) cudaFree(s.sy_colpart);
@@ -168,13 +179,16 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
             s.sy_col_elems = need_c;
             SVM_CUDA(cudaMalloc(&s.sy_items, (plan.items.size() + 1) * sizeof(SymvItem)));
             s.sy_item_cap = plan.items.size();
-            SVM_CUDA(cudaMalloc(&s.sy_nseg, (plan.nseg.size() + 1) * sizeof(int)));
-            s.sy_nseg_cap = plan.nseg.size();
+            SVM_CUDA(cudaMalloc(&s.sy_nseg, (need_t + 1) * sizeof(int)));
+            s.sy_nseg_cap = need_t;
         }
         if (!plan.items.empty())
             SVM_CUDA(cudaMemcpyAsync(s.sy_items, plan.items.data(), plan.items.size() * sizeof(SymvItem), cudaMemcpyHostToDevice, ctx->stream));
         if (!plan.nseg.empty())
             SVM_CUDA(cudaMemcpyAsync(s.sy_nseg, plan.nseg.data(), plan.nseg.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (!plan.band_of_unit.empty())
+            SVM_CUDA(cudaMemcpyAsync(s.sy_nseg + plan.nseg.size(), plan.band_of_unit.data(), plan.band_of_unit.size() * sizeof(int),
+                                     cudaMemcpyHostToDevice, ctx->stream));
         SVM_CUDA(cudaStreamSynchronize(ctx->stream));  // once per problem size; the tables stay valid for every later pass
         s.sy_n = n;
         s.sy_ld = ld;
@@ -234,7 +248,8 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
         c.nrows = plan.nrows;
         c.row0 = plan.row0;
         c.n_pad = n_pad;
-        c.BH = S::BH;
+        c.unit = plan.unit;
+        c.band_of_unit = s.sy_nseg + plan.nseg.size();
         c.nseg = s.sy_nseg;
         c.u_rows = du_rows;
         c.w = dw;
@@ -277,6 +292,32 @@ extern "C" int svmb200_symv_geometry(int64_t n, int64_t ld, int64_t* streamed_by
     if (items) *items = (int64_t)plan.items.size();
     if (band_rows) *band_rows = S::BH;
     if (panel_cols) *panel_cols = S::BW;
+    return SVMB200_OK;
+}
+
+static int64_t rows_per_rank(int64_t n, int nranks);
+
+// the plan of rank `rank` of `nranks` (svmb200_shard_rows blocks) for the shipped tile shape: bands (tall + short), work items,
+// ratio of the simulated finish time to a perfectly balanced one -- for tests and tuning; any output pointer may be NULL
+extern "C" int svmb200_symv_plan_info(int64_t n, int64_t ld, int rank, int nranks, int sm_count, int64_t* bands,
+                                      int64_t* short_bands, int64_t* items, double* finish_over_ideal) {
+    using S = SymvDefault;
+    SVM_CHECK_ARG(n >= 0 && ld >= n && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
+    SymvPlan plan;
+    const int slots = symv_plan_slots(sm_count);
+    symv_build_plan<S>(n, ld, rank, nranks, nranks == 1 ? n : rows_per_rank(n, nranks), plan, slots);
+    int64_t nshort = 0;
+    for (int64_t I = 0; I + 1 < plan.nbands; ++I) nshort += plan.band_lr0[(size_t)I + 1] - plan.band_lr0[(size_t)I] < S::BH;
+    std::vector<double> cost;
+    double total = 0.0;
+    for (const SymvItem& it : plan.items) {
+        cost.push_back((double)it.rows * it.width + SVMB200_SYMV_PLAN_OVERHEAD);
+        total += cost.back();
+    }
+    if (bands) *bands = plan.nbands;
+    if (short_bands) *short_bands = nshort;
+    if (items) *items = (int64_t)plan.items.size();
+    if (finish_over_ideal) *finish_over_ideal = total > 0.0 ? symv_makespan(cost, slots) / (total / slots) : 1.0;
     return SVMB200_OK;
 }
 

@@ -38,7 +38,8 @@ __global__ void fill_vec(double* u, long long n, long long ld) {
 struct Bufs {
     double *Q, *u, *w, *wref, *wpart, *rowpart, *colpart, *den;
     unsigned* tickets;
-    int2* items;
+    SymvItem* items;
+    int* tables;
     long long n, ld;
 };
 
@@ -60,12 +61,28 @@ static float time_launches(int reps, const std::function<void()>& f) {
 
 template <class S>
 void run_shape(const Bufs& b, int reps) {
-    std::vector<int2> items;
-    symv_build_items<S>(b.n, b.ld, items);
-    CK(cudaMemcpy(b.items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    SymvPlan plan;
+    symv_build_plan<S>(b.n, b.ld, 0, 1, b.n, plan, 2 * 148);
+    const std::vector<SymvItem>& items = plan.items;
+    CK(cudaMemcpy(b.items, items.data(), items.size() * sizeof(SymvItem), cudaMemcpyHostToDevice));
+    std::vector<int> tables = plan.nseg;
+    tables.insert(tables.end(), plan.band_of_unit.begin(), plan.band_of_unit.end());
+    CK(cudaMemcpy(b.tables, tables.data(), tables.size() * sizeof(int), cudaMemcpyHostToDevice));
     const long long n_pad = (b.n + 15) / 16 * 16;
-    SymvArgs a{b.Q, b.ld, b.n, n_pad, b.u, b.rowpart, b.colpart, b.items, nullptr};
-    SymvCombineArgs c{b.rowpart, b.colpart, b.ld, b.n, n_pad, S::BH, S::BW, b.u, b.w, b.den, nullptr};
+    SymvArgs a{b.Q, b.ld, b.n, 0, n_pad, b.u, b.rowpart, b.colpart, b.items, nullptr, nullptr};
+    SymvCombineArgs c = {};
+    c.rowpart = b.rowpart;
+    c.colpart = b.colpart;
+    c.ld = b.ld;
+    c.nrows = b.n;
+    c.row0 = 0;
+    c.n_pad = n_pad;
+    c.unit = plan.unit;
+    c.nseg = b.tables;
+    c.band_of_unit = b.tables + plan.nseg.size();
+    c.u_rows = b.u;
+    c.w = b.w;
+    c.denpart = b.den;
     const unsigned ngroups = (unsigned)((b.n + MV_GROUP - 1) / MV_GROUP);
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, symv_tile_kernel<S>));
@@ -89,14 +106,7 @@ void run_shape(const Bufs& b, int reps) {
         maxd = std::max(maxd, std::fabs(w[i] - wr[i]));
         maxw = std::max(maxw, std::fabs(wr[i]));
     }
-    // bytes the pass has to stream: the upper triangle in band geometry
-    double elems = 0;
-    for (const int2& it : items) {
-        const long long r0 = (long long)it.x * S::BH, rows = std::min<long long>(S::BH, b.n - r0);
-        const long long c0 = it.y == 0 ? r0 : r0 + S::BH + (long long)(it.y - 1) * S::BW;
-        const long long c1 = std::min<long long>(b.ld, it.y == 0 ? r0 + S::BH : c0 + S::BW);
-        elems += (double)rows * (double)(c1 - c0);
-    }
+    const double elems = (double)plan.streamed_elems;   // the upper triangle in band geometry
     printf("TR%-2d NRB%-2d NCH%d LB%-2d mb%d st%d BH%-3d BW%-4d items %5zu regs %3d occ %d | pass+combine %8.4f ms  tile %8.4f ms (%7.1f GB/s streamed)  "
            "combine %7.4f ms | vs full-pass bytes: %7.1f GB/s-equivalent | max|dw| %.2e (|w| %.1e)\n",
            S::TR, S::NRB, S::NCH, S::LB, S::MINB, S::STAGES, S::BH, S::BW, items.size(), fa.numRegs, occ, ms_both, ms_tile, 8.0 * elems / ms_tile / 1e6,
@@ -121,9 +131,10 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&b.wpart, (size_t)nseg * n_pad * 8));
     CK(cudaMalloc(&b.tickets, (n / MV_GROUP + 1) * 4));
     CK(cudaMemset(b.tickets, 0, (n / MV_GROUP + 1) * 4));
-    CK(cudaMalloc(&b.rowpart, (size_t)(2 + ld / SY_CHUNK) * n_pad * 8));   // enough for BW >= 512
-    CK(cudaMalloc(&b.colpart, (size_t)((n + 31) / 32) * ld * 8));           // enough for BH >= 32
-    CK(cudaMalloc(&b.items, (size_t)((n + 31) / 32) * (2 + ld / SY_CHUNK) * sizeof(int2)));
+    CK(cudaMalloc(&b.rowpart, (size_t)(4 + 2 * ld / SY_CHUNK) * n_pad * 8));   // enough for BW >= 512, cut panels included
+    CK(cudaMalloc(&b.colpart, (size_t)((n + 31) / 32 + 64) * ld * 8));      // enough for BH >= 32 and the short bands
+    CK(cudaMalloc(&b.items, (size_t)((n + 31) / 32) * (2 + ld / SY_CHUNK) * sizeof(SymvItem)));
+    CK(cudaMalloc(&b.tables, (size_t)(n + 64) * sizeof(int)));
     fill_sym<<<148 * 8, 256>>>(b.Q, n, ld);
     fill_vec<<<148, 256>>>(b.u, n, ld);
     CK(cudaDeviceSynchronize());

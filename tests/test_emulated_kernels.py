@@ -462,3 +462,24 @@ def test_symmetric_pass_solvers_follow_the_default_pass():
 
 def test_symmetric_pass_estimators():
     SY.check_symmetric_fit(emu_probe, n=120, defines=_SYMV_SMALL)
+
+
+_SYMV_FEW_SLOTS = _SYMV_TALL + ('SVMB200_SYMV_PLAN_SLOTS=5', 'SVMB200_SYMV_PLAN_OVERHEAD=64.0')   # the planner balances for 5
+# resident CTAs and a start-up cost scaled down with the tiles: tail grading pays at test sizes
+
+
+def test_symmetric_pass_with_short_bands_and_cut_panels():
+    """With few resident CTAs the plan ends a shard on short bands (a quarter of the height) and cuts panels into halves:
+    same product, bit for bit reproducible under another schedule, lower triangle still unread"""
+    import ctypes as C
+    from optiml_b200 import _native as N
+    n = 1100
+    with emulated_device(defines=_SYMV_FEW_SLOTS):
+        bands, short, items, ratio = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
+        N.call('svmb200_symv_plan_info', n, N.padded_ld(n), 0, 1, 148, C.byref(bands), C.byref(short), C.byref(items), C.byref(ratio))
+        assert short.value >= 3 and bands.value > -(-n // 64) and ratio.value < 1.15
+    w0 = SY.check_symmetric_product(emu_probe, n, defines=_SYMV_FEW_SLOTS)
+    w1 = SY.check_symmetric_product(emu_probe, n, defines=_SYMV_FEW_SLOTS, order=2, seed=3)
+    assert np.array_equal(w0, w1)
+    SY.check_lower_triangle_is_never_read(emu_probe, 700, 64, defines=_SYMV_FEW_SLOTS)
+    SY.check_symmetric_solves(emu_probe, n=300, max_iter=10, defines=_SYMV_FEW_SLOTS)

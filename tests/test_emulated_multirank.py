@@ -608,3 +608,32 @@ def test_symmetric_and_default_solves_share_the_arena_back_to_back():
     for state in many[1:]:
         for (ka, xa), (kb, xb) in zip(many[0], state):
             assert ka == kb and np.array_equal(xa, xb)
+
+
+_SYMV_B32_FEW_SLOTS = _SYMV_B32 + ('SVMB200_SYMV_PLAN_SLOTS=4', 'SVMB200_SYMV_PLAN_OVERHEAD=64.0')
+
+
+@pytest.mark.parametrize('n,nranks', [(900, 4), (700, 3)])
+def test_sharded_symmetric_pass_with_short_bands(n, nranks):
+    """the planner cuts the end of every shard into short bands (few resident CTAs assumed): the halved block pair, the sends
+    and the owners' combines must agree on the band tables"""
+    import ctypes as C
+    rng = np.random.default_rng(n)
+    M = S.psd(rng, n)
+    q, ub = rng.standard_normal(n), np.full(n, 1.5)
+
+    def body(ctx):
+        return solve('pg', shard_hessian(ctx, M), q, ub, 8)
+
+    with emulated_device(defines=_SYMV_B32_FEW_SLOTS):
+        short = C.c_int64()
+        N.call('svmb200_symv_plan_info', n, N.padded_ld(n), 1, nranks, 148, None, C.byref(short), None, None)
+        assert short.value >= 3
+        one = run_ranks(1, 'nccl', body)[0]
+        with SY.symmetric_pass():
+            many = run_ranks(nranks, 'p2p', body)
+    for state in many[1:]:
+        for a, b in zip(many[0], state):
+            assert np.array_equal(a, b)
+    for a, b in zip(one, many[0]):
+        assert np.abs(np.asarray(a, dtype=float) - np.asarray(b, dtype=float)).max() <= 1e-10 * max(1.0, np.abs(a).max())
