@@ -114,6 +114,24 @@ void run_shape(const Bufs& b, int reps) {
     fflush(stdout);
 }
 
+// the tile pass of ONE rank of a P-rank solve, timed alone on this GPU (the plan, the shard's rows, no peers needed)
+template <class S>
+void run_rank(const Bufs& b, int reps, int P, int r, int slots) {
+    const long long rpr = ((b.n + P - 1) / P + 63) / 64 * 64;
+    SymvPlan plan;
+    symv_build_plan<S>(b.n, b.ld, r, P, rpr, plan, slots);
+    CK(cudaMemcpy(b.items, plan.items.data(), plan.items.size() * sizeof(SymvItem), cudaMemcpyHostToDevice));
+    const long long n_pad = (plan.nrows + 15) / 16 * 16;
+    SymvArgs a{b.Q + plan.row0 * b.ld, b.ld, plan.nrows, plan.row0, n_pad, b.u, b.rowpart, b.colpart, b.items, nullptr, nullptr};
+    CK(cudaFuncSetAttribute(symv_tile_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::RING_BYTES));
+    const float ms = time_launches(reps, [&]() { CK(svm_launch_chained_smem(symv_tile_kernel<S>, dim3((unsigned)plan.items.size()), dim3(SY_NT), (size_t)S::RING_BYTES, (cudaStream_t)0, a)); });
+    int nshort = 0;
+    for (long long I = 0; I + 1 < plan.nbands; ++I) nshort += plan.band_lr0[I + 1] - plan.band_lr0[I] < S::BH;
+    printf("rank %d of %d (planned for %d slots): bands %lld (%d short) items %zu streamed %.4f GB | tile %8.4f ms = %7.1f GB/s\n", r, P, slots,
+           plan.nbands, nshort, plan.items.size(), 8.0 * plan.streamed_elems / 1e9, ms, 8.0 * plan.streamed_elems / ms / 1e6);
+    fflush(stdout);
+}
+
 int main(int argc, char** argv) {
     const long long n = argc > 1 ? atoll(argv[1]) : 50000;
     const int reps = argc > 2 ? atoi(argv[2]) : 100;
@@ -155,6 +173,14 @@ int main(int argc, char** argv) {
     printf("n = %lld  ld = %lld   full pass (K2): %8.4f ms  %7.1f GB/s\n", n, ld, ms_full, 8.0 * n * ld / ms_full / 1e6);
     run_shape<SymvDefault>(b, reps);
     if (argc > 3 && strcmp(argv[3], "one") == 0) return 0;   // profiling runs: the shipped shape only
+    if (argc > 4 && strcmp(argv[3], "shard") == 0) {         // the tile pass of single ranks of a P-rank solve
+        const int P = atoi(argv[4]);
+        for (int r : {0, P / 2, P - 1}) {
+            run_rank<SymvDefault>(b, reps, P, r, 296);        // the graded plan
+            run_rank<SymvDefault>(b, reps, P, r, 1 << 20);    // everything in "one wave": no grading (whole panels, tall bands)
+        }
+        return 0;
+    }
     run_shape<SymvShape<16, 8, 4, 8, 2, 2>>(b, reps);
     run_shape<SymvShape<16, 8, 4, 4, 3, 4>>(b, reps);
     run_shape<SymvShape<16, 8, 4, 8, 3, 2>>(b, reps);
