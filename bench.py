@@ -406,11 +406,24 @@ def symmetric_leg(args, ctx, make_model, X, y, dX, n, peak, barrier, max_over_ra
                                      'vector_phase': 1e3 * vec_ms / max(samples, 1)},
                 'roofline': {'bound': 'hbm', 'kernel': 'symv_tile_kernel (+ symv_send_kernel, symv_combine_kernel) (K2s)',
                              'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                             'traffic': symv_traffic(n, gpus),
                              'bytes_per_launch': streamed, 'full_matrix_equivalent_gbs': 8.0 * n * n / gpus / (avg_ms / 1e3) / 1e9,
                              'frac_of_dram_theoretical': achieved / 8184.0},
                 'gpu_launches': int(launches), 'parity': parity_block(args, m, n)}
     finally:
         use_symmetric_pass(False)
+
+
+def symv_traffic(n, gpus):
+    """DRAM bytes per product of the symmetric pass from the committed ncu capture (profiles/symv_traffic.json), or None"""
+    tpath = os.path.join(ROOT, 'profiles', 'symv_traffic.json')
+    if not os.path.exists(tpath):
+        return None
+    with open(tpath) as fh:
+        tj = json.load(fh)
+    if tj.get('n') == n and str(gpus) in tj.get('per_gpus', {}):
+        return tj['per_gpus'][str(gpus)]['dram_bytes_per_launch']
+    return None
 
 
 def run_b200(args):
@@ -593,7 +606,7 @@ def run_b200(args):
     if sym_used:
         line['hbm_gbps_pg_loop'] = bytes_per_launch * mv_launches / (pg_ms / 1e3) / 1e9
         line['frac_of_8TBps_nominal'] = line['hbm_gbps_pg_loop'] / gpus / 8000.0
-        line['roofline']['traffic'] = None
+        line['roofline']['traffic'] = symv_traffic(n, gpus)
         line['roofline']['full_matrix_equivalent_gbs'] = 8.0 * n * n / (mv_avg_ms / 1e3) / 1e9
     if sym_leg is not None:
         line['symmetric_pass'] = sym_leg
