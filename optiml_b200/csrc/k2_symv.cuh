@@ -389,7 +389,14 @@ __device__ __forceinline__ void symv_item(const SymvArgs& a, const long long r0,
     double2 colacc[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) colacc[k] = make_double2(0.0, 0.0);
-    const double* __restrict__ ucol = a.u + c0;
+    // u at the thread's columns: the same for every sub-block of the item, so it is fetched ONCE, up front -- as a load in
+    // front of every batch it was the top stall of the first ring version (an exposed L2 round trip per 8 rows)
+    double2 ucs[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        ucs[k] = make_double2(0.0, 0.0);
+        if (cok[k]) ucs[k] = __ldg(reinterpret_cast<const double2*>(a.u + c0 + coff[k]));
+    }
     const double* __restrict__ qitem = a.Q + r0 * a.ld + c0;
     double2* const myring = ring + tid;   // ring[slot][j][thread]
 
@@ -422,8 +429,7 @@ __device__ __forceinline__ void symv_item(const SymvArgs& a, const long long r0,
             sy_cp_async_wait<ST - 1>();   // the oldest batch in flight -- the one consumed now -- has landed
             const int k = b / BPC, rb0 = (b % BPC) * LB;
             if (k < nch) {  // uniform over the CTA
-                double2 uc = __ldg(reinterpret_cast<const double2*>(ucol + coff[k]));
-                if (!cok[k]) uc = make_double2(0.0, 0.0);
+                const double2 uc = ucs[k];
 #pragma unroll
                 for (int j = 0; j < LB; ++j) {
                     const double2 v = myring[(slot * LB + j) * SY_NT];
