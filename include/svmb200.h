@@ -148,6 +148,10 @@ int svmb200_symv_geometry(int64_t n, int64_t ld, int64_t* streamed_bytes, int64_
  * the simulated finish time of the grid over a perfectly balanced one -- for tests and tuning                        */
 int svmb200_symv_plan_info(int64_t n, int64_t ld, int rank, int nranks, int sm_count, int64_t* bands, int64_t* short_bands,
                            int64_t* items, double* finish_over_ideal);
+/* the work items of that plan: seven ints each {first local row, rows, band, first column, columns, row-sum slot, 1 if the
+ * item also feeds column sums}; *count items (items7 may be NULL to ask for the count), *row0 = first row of the block   */
+int svmb200_symv_plan_items(int64_t n, int64_t ld, int rank, int nranks, int sm_count, int32_t* items7, int64_t capacity,
+                            int64_t* count, int64_t* row0);
 
 /* ---- K2+K3(+K4): projected-gradient solve of the box-constrained QP -------------------------
  * Replaces  BoxConstrainedQuadraticOptimizer.__init__ (opti/constrained/_base.py:59-73) +

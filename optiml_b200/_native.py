@@ -83,6 +83,7 @@ PROTOTYPES = {
     'svmb200_ctx_set_symmetric': [c_vp, C.c_int],
     'svmb200_ctx_get_symmetric': [c_vp, C.POINTER(C.c_int)],
     'svmb200_symv_geometry': [i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
+    'svmb200_symv_plan_items': [i64, i64, C.c_int, C.c_int, C.c_int, c_vp, i64, C.POINTER(i64), C.POINTER(i64)],
     'svmb200_symv_plan_info': [i64, i64, C.c_int, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
                                C.POINTER(C.c_double)],
     'svmb200_pg_destroy': [c_vp],

@@ -321,6 +321,28 @@ extern "C" int svmb200_symv_plan_info(int64_t n, int64_t ld, int rank, int nrank
     return SVMB200_OK;
 }
 
+// the work items of that plan, seven ints each {first local row, rows, band, first column, columns, row-sum slot, 1 if the
+// item also feeds column sums}, and the first global row of the rank's block -- so that a test can check, on the host, that
+// the plans of all ranks cover every pair of rows exactly once
+extern "C" int svmb200_symv_plan_items(int64_t n, int64_t ld, int rank, int nranks, int sm_count, int32_t* items7, int64_t capacity,
+                                       int64_t* count, int64_t* row0) {
+    using S = SymvDefault;
+    SVM_CHECK_ARG(n >= 0 && ld >= n && nranks >= 1 && rank >= 0 && rank < nranks && count != nullptr, "bad argument");
+    SymvPlan plan;
+    symv_build_plan<S>(n, ld, rank, nranks, nranks == 1 ? n : rows_per_rank(n, nranks), plan, symv_plan_slots(sm_count));
+    *count = (int64_t)plan.items.size();
+    if (row0) *row0 = plan.row0;
+    if (items7 != nullptr) {
+        SVM_CHECK_ARG(capacity >= *count, "items7 is too small");
+        for (size_t i = 0; i < plan.items.size(); ++i) {
+            const SymvItem& it = plan.items[i];
+            const int32_t v[7] = {it.lr0, it.rows, it.band, it.c0, it.width, it.seg, it.cols};
+            memcpy(items7 + 7 * i, v, sizeof(v));
+        }
+    }
+    return SVMB200_OK;
+}
+
 void svm_release_matvec_scratch(svmb200_ctx* ctx) {
     if (ctx->matvec_scratch) {
         MatvecScratch* s = static_cast<MatvecScratch*>(ctx->matvec_scratch);

@@ -637,3 +637,22 @@ def test_sharded_symmetric_pass_with_short_bands(n, nranks):
             assert np.array_equal(a, b)
     for a, b in zip(one, many[0]):
         assert np.abs(np.asarray(a, dtype=float) - np.asarray(b, dtype=float)).max() <= 1e-10 * max(1.0, np.abs(a).max())
+
+
+@pytest.mark.parametrize('n,nranks,defines', [(1100, 1, _SYMV_B32_FEW_SLOTS), (900, 4, _SYMV_B32_FEW_SLOTS), (700, 3, _SYMV_B32_FEW_SLOTS),
+                                              (1000, 2, _SYMV_B32_FEW_SLOTS), (1400, 8, _SYMV_SMALL), (1000, 8, _SYMV_B32_FEW_SLOTS)])
+def test_graded_plans_cover_every_pair_of_rows_exactly_once(n, nranks, defines):
+    """the coverage property of tests/test_host_logic.py on plans that DO end on short bands and cut panels (few resident CTAs
+    assumed, small tiles)"""
+    import ctypes as C
+    from test_host_logic import _symv_plan_cover
+    with emulated_device(defines=defines):
+        if 'SVMB200_SYMV_PLAN_SLOTS=4' in defines:
+            shorts = []
+            for r in range(nranks):
+                short = C.c_int64()
+                N.call('svmb200_symv_plan_info', n, N.padded_ld(n), r, nranks, 148, None, C.byref(short), None, None)
+                shorts.append(short.value)
+            assert max(shorts) >= 1, shorts
+        count, _ = _symv_plan_cover(N.call, n, nranks)
+    assert count.min() == 1 and count.max() == 1

@@ -401,3 +401,50 @@ def test_load_library_cannot_deadlock_on_a_finalizer():
     t.start()
     t.join(timeout=10)
     assert not t.is_alive() and done == [lib]
+
+
+def _symv_plan_cover(lib_call, n, nranks):
+    """count[i, j] = how often the plans of all ranks account for the ordered pair (row i, column j) of an n x n matrix"""
+    import ctypes as C
+    from optiml_b200 import _native as N
+    ld = N.padded_ld(n)
+    count = np.zeros((n, n), dtype=np.int16)
+    streamed = 0
+    for r in range(nranks):
+        cnt, row0 = C.c_int64(0), C.c_int64(0)
+        lib_call('svmb200_symv_plan_items', n, ld, r, nranks, 148, None, 0, C.byref(cnt), C.byref(row0))
+        items = np.zeros((max(cnt.value, 1), 7), dtype=np.int32)
+        lib_call('svmb200_symv_plan_items', n, ld, r, nranks, 148, items.ctypes.data_as(C.c_void_p), int(cnt.value), C.byref(cnt),
+                 C.byref(row0))
+        seen_slots = set()
+        for lr0, rows, band, c0, width, seg, cols in items[:cnt.value]:
+            assert rows > 0 and width > 0 and width % 2 == 0 and c0 % 2 == 0 and c0 + width <= ld
+            assert (band, seg) not in seen_slots   # every item has its own row-sum slot
+            seen_slots.add((band, seg))
+            i0, i1 = row0.value + lr0, row0.value + lr0 + rows
+            j0, j1 = c0, min(c0 + width, n)
+            assert i1 <= n
+            streamed += rows * width
+            if j1 <= j0:
+                continue
+            count[i0:i1, j0:j1] += 1
+            if cols:                      # the element also stands for its transpose
+                assert j0 >= i1 or j1 <= i0   # a panel never touches its own rows' diagonal
+                count[j0:j1, i0:i1] += 1
+    return count, streamed
+
+
+@pytest.mark.parametrize('n,nranks', [(130, 1), (1500, 1), (2049, 1), (700, 2), (1000, 3), (1500, 4), (1999, 4), (2600, 5),
+                                      (4000, 8), (3101, 8), (2304, 6)])
+def test_symmetric_pass_plans_cover_every_pair_of_rows_exactly_once(n, nranks):
+    """The work plans of the opt-in symmetric pass (csrc/k2_symv.cuh, shipped tile shape), all ranks together: every ordered
+    pair (i, j) is accounted for exactly once -- by a diagonal block, by a panel, or by a panel's transpose -- whatever the
+    rank count (whole blocks, the halved pair of an even count), the ragged last block and the graded tail (short bands, cut
+    panels); and what is streamed is about half the matrix."""
+    from optiml_b200 import _native as N
+    rpr = -(-(-(-n // nranks)) // 64) * 64
+    if nranks > 1 and (nranks - 1) * rpr >= n:
+        pytest.skip('the last rank owns no rows: such a solve takes the all-gather and the full pass')
+    count, streamed = _symv_plan_cover(N.call, n, nranks)
+    assert count.min() == 1 and count.max() == 1
+    assert streamed <= 0.5 * n * N.padded_ld(n) + 130 * N.padded_ld(n) * 1.0 + 64 * n   # half + diagonal blocks + padding
