@@ -187,9 +187,18 @@ inline void symv_build_plan(long long n, long long ld, int rank, int P, long lon
     const double overhead = SVMB200_SYMV_PLAN_OVERHEAD;   // start-up of an item (first copies, u of the rows, the final barrier) in elements
     auto cost_of = [&](const SymvItem& it) { return (double)it.rows * it.width + overhead; };
     const long long full_bands = nrows / S::BH;
+    // A grid of many waves has no tail worth grading (one GPU at C4: 15 waves, < 1 % to gain) -- and simulating hundreds of
+    // candidate plans of thousands of items would cost more host time than it can save: the wide search is for short grids.
+    long long est_items = 0;
+    {
+        const long long span = (P == 1 ? n / 2 : n / 2);   // columns a band reads, on average
+        est_items = full_bands * ((span + S::BW - 1) / S::BW);
+    }
+    const bool wide_search = est_items < 8ll * (slots > 0 ? slots : 1);
     std::vector<long long> shorts = {0};   // how many of the last full bands become short ones
-    for (long long sb : {1, 2, 4, 8, 16})
-        if (SH < S::BH && sb <= full_bands / 2) shorts.push_back(sb);
+    if (wide_search)
+        for (long long sb : {1, 2, 4, 8})
+            if (SH < S::BH && sb <= full_bands / 2) shorts.push_back(sb);
     double best = -1.0;
     std::vector<int> best_lr0;
     for (long long sb : shorts) {
@@ -262,11 +271,12 @@ inline void symv_build_plan(long long n, long long ld, int rank, int P, long lon
         const size_t nslots = (size_t)(slots > 0 ? slots : 1), waves = full.size() / nslots;
         std::vector<size_t> keeps = {full.size(), waves * nslots};
         if (waves >= 1) keeps.push_back((waves - 1) * nslots);
-        for (size_t k = 1; k <= 24; ++k)   // and in steps of an eighth of a wave below the total (up to three waves)
-            if (k * (nslots / 8 + 1) < full.size()) keeps.push_back(full.size() - k * (nslots / 8 + 1));
-        const double f4s[] = {0.0, 0.5, 1.0};
+        if (wide_search)
+            for (size_t k = 1; k <= 8; ++k)   // and in steps of a quarter of a wave below the total (up to two waves)
+                if (k * (nslots / 4 + 1) < full.size()) keeps.push_back(full.size() - k * (nslots / 4 + 1));
+        const double f4s[] = {0.0, 1.0};
         std::vector<SymvItem> cand;
-        for (int short_parts : {1, 2, 4}) {
+        for (int short_parts : {1, 4}) {
             if (sb == 0 && short_parts > 1) break;
             for (size_t keep : keeps) {
                 for (double f4 : f4s) {

@@ -653,6 +653,6 @@ def test_graded_plans_cover_every_pair_of_rows_exactly_once(n, nranks, defines):
                 short = C.c_int64()
                 N.call('svmb200_symv_plan_info', n, N.padded_ld(n), r, nranks, 148, None, C.byref(short), None, None)
                 shorts.append(short.value)
-            assert max(shorts) >= 1, shorts
+            assert nranks == 1 or max(shorts) >= 1, shorts   # (a grid of many waves is not graded: nothing to gain)
         count, _ = _symv_plan_cover(N.call, n, nranks)
     assert count.min() == 1 and count.max() == 1
