@@ -173,6 +173,33 @@ int main(int argc, char** argv) {
     printf("n = %lld  ld = %lld   full pass (K2): %8.4f ms  %7.1f GB/s\n", n, ld, ms_full, 8.0 * n * ld / ms_full / 1e6);
     run_shape<SymvDefault>(b, reps);
     if (argc > 3 && strcmp(argv[3], "one") == 0) return 0;   // profiling runs: the shipped shape only
+    if (argc > 3 && strcmp(argv[3], "bands") == 0) {          // band height / ring depth around the shipped shape
+        run_shape<SymvShape<16, 8, 4, 8, 2, 2>>(b, reps);
+        run_shape<SymvShape<16, 16, 4, 8, 2, 2>>(b, reps);
+        run_shape<SymvShape<16, 12, 4, 8, 2, 2>>(b, reps);
+        run_shape<SymvShape<16, 16, 4, 4, 2, 4>>(b, reps);
+        run_shape<SymvDefault>(b, reps);
+        run_shape<SymvShape<16, 16, 4, 8, 2, 2>>(b, reps);
+        return 0;
+    }
+    if (argc > 3 && strcmp(argv[3], "bands2") == 0) {         // batch size / ring depth / band height, full matrix and shards
+#define BOTH(...)                                         \
+    run_shape<SymvShape<__VA_ARGS__>>(b, reps);           \
+    run_rank<SymvShape<__VA_ARGS__>>(b, 2 * reps, 8, 0, 296); \
+    run_rank<SymvShape<__VA_ARGS__>>(b, 2 * reps, 4, 0, 296);
+        BOTH(16, 8, 4, 8, 2, 3)
+        BOTH(16, 16, 4, 4, 2, 4)
+        BOTH(16, 16, 4, 4, 2, 5)
+        BOTH(16, 16, 4, 2, 2, 8)
+        BOTH(16, 16, 4, 2, 2, 10)
+        BOTH(16, 8, 4, 4, 2, 6)
+        BOTH(16, 8, 4, 4, 2, 4)
+        BOTH(16, 24, 4, 4, 2, 4)
+        BOTH(16, 16, 4, 4, 2, 4)
+        BOTH(16, 8, 4, 8, 2, 3)
+#undef BOTH
+        return 0;
+    }
     if (argc > 4 && strcmp(argv[3], "shard") == 0) {         // the tile pass of single ranks of a P-rank solve
         const int P = atoi(argv[4]);
         for (int r : {0, P / 2, P - 1}) {
