@@ -483,3 +483,50 @@ def test_symmetric_pass_with_short_bands_and_cut_panels():
     assert np.array_equal(w0, w1)
     SY.check_lower_triangle_is_never_read(emu_probe, 700, 64, defines=_SYMV_FEW_SLOTS)
     SY.check_symmetric_solves(emu_probe, n=300, max_iter=10, defines=_SYMV_FEW_SLOTS)
+
+
+def test_symmetric_switches(monkeypatch):
+    """the three ways to opt in: runtime.use_symmetric_pass (contexts that exist and contexts created later), the
+    environment variable read when a context is created, the C entry point; lockstep batches keep the full pass"""
+    import ctypes as C
+    from optiml_b200 import _native as N, runtime
+    from optiml_b200.opti import Quadratic
+    from optiml_b200.opti.batch import minimize_batch
+    from optiml_b200.opti.constrained import ProjectedGradient
+
+    def state(ctx):
+        on = C.c_int(-1)
+        N.call('svmb200_ctx_get_symmetric', ctx.handle, C.byref(on))
+        return on.value
+
+    saved = runtime._symmetric
+    try:
+        with emulated_device():
+            runtime._symmetric = None
+            monkeypatch.delenv('SVMB200_SYMMETRIC', raising=False)
+            assert state(runtime.Context(device=0)) == 0                 # off by default
+            monkeypatch.setenv('SVMB200_SYMMETRIC', '1')
+            assert state(runtime.Context(device=0)) == 1                 # environment variable, read at creation
+            monkeypatch.delenv('SVMB200_SYMMETRIC')
+            ctx = runtime.default_context()
+            assert state(ctx) == 0
+            runtime.use_symmetric_pass()                                 # the context that exists ...
+            assert state(ctx) == 1 and state(runtime.Context(device=0)) == 1   # ... and those created later
+            rng = np.random.default_rng(2)
+            Q, q, ub = _psd(rng, 80), rng.standard_normal(80), np.ones(80)
+            shared = S.upload_shared(Q)
+            signs = [np.where(rng.random(80) < 0.5, 1.0, -1.0) for _ in range(3)]
+            solvers = [ProjectedGradient(quad=Quadratic(shared.with_signs(s), q), ub=ub, max_iter=5) for s in signs]
+            minimize_batch(solvers)
+            assert all(s.batch_size_ == 3 and not s.symmetric_pass for s in solvers)   # batches: the multi-vector full pass
+            assert state(ctx) == 1                                       # ... and the switch is back afterwards
+            single = ProjectedGradient(quad=Quadratic(Q, q), ub=ub, max_iter=5)
+            single.profile = True
+            assert single.minimize().symmetric_pass
+            runtime.use_symmetric_pass(False)
+            assert state(ctx) == 0
+            for s in solvers + [single]:
+                s.f.release()
+            shared.release()
+    finally:
+        runtime._symmetric = saved
