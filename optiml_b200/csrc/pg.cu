@@ -215,9 +215,10 @@ static int launch_symv(svmb200_ctx* ctx, const double* dQ, int64_t n, int64_t ld
         a.done = d_done;
         a.fault = fault;
         static bool attr_set[64] = {};   // per device: the ring needs more than the default 48 KB of dynamic shared memory
-        if (ctx->device >= 0 && ctx->device < 64 && !attr_set[ctx->device]) {
+        const bool tracked = ctx->device >= 0 && ctx->device < 64;
+        if (!tracked || !attr_set[ctx->device]) {
             SVM_CUDA(cudaFuncSetAttribute(symv_tile_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::RING_BYTES));
-            attr_set[ctx->device] = true;
+            if (tracked) attr_set[ctx->device] = true;
         }
         SVM_CUDA(svm_launch_chained_smem(symv_tile_kernel<S>, dim3((unsigned)plan.items.size()), dim3(SY_NT),
                                          (size_t)S::RING_BYTES, ctx->stream, a));
